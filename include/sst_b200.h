@@ -1,0 +1,113 @@
+/*
+ * sst_b200.h — C-ABI of the B200 mass-explanation library (libsst_b200.so).
+ *
+ * The reference (SpectrSeqTools 0.1.2) has no FFI/plugin interface: its hot path is three Python
+ * functions and one table builder.  Each entry point below names the reference function it replaces
+ * (paths relative to /root/reference/spectrseqtools); spectrseqtools_b200/_cabi.py is the ctypes
+ * binding, INTEGRATION.md shows the stub a reference maintainer would add.
+ *
+ * Conventions: plain pointers and sizes only; every function returns an SST_* code (0 = ok) unless
+ * noted; sst_last_error(ctx) gives the text of the last failure.  A context owns one CUDA stream on one
+ * device and is not thread-safe; tables belong to the context that made them.  Host pointers may be
+ * pageable or pinned (sst_host_alloc gives pinned memory); all calls are synchronous on return.
+ * Integer masses are in table units (1 mDa for the stock alphabet).  The float -> integer conversions of
+ * mass_explanation.py:107-114 stay on the host (Python) so they match CPython bit for bit.
+ */
+#ifndef SST_B200_H
+#define SST_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct sst_ctx sst_ctx;
+typedef struct sst_table sst_table;
+
+enum {
+    SST_OK = 0,
+    SST_ERR_CUDA = 1,          /* a CUDA runtime call failed (text in sst_last_error) */
+    SST_ERR_NO_DEVICE = 2,     /* no sm_100 GPU / wrong architecture: the product has no CPU fallback */
+    SST_ERR_BAD_ARG = 3,       /* -> ValueError */
+    SST_ERR_COMPRESSION = 4,   /* unsupported cells-per-word -> ValueError (mass_table.py:285-289) */
+    SST_ERR_TOO_MANY_ROWS = 5, /* more than 128 table rows */
+    SST_ERR_TOO_DEEP = 6,      /* a composition could exceed 96 nucleotides */
+    SST_ERR_NOMEM = 7,         /* result or scratch does not fit in device memory -> MemoryError */
+    SST_ERR_MEMO_FULL = 8,     /* first-visit map too small: call again with a larger memo_capacity */
+    SST_ERR_STATE = 9          /* fetch without a preceding run */
+};
+
+/* per-peak budget modes for sst_explain (see DESIGN.md "Budget semantics") */
+enum { SST_MODE_FREE = 0, SST_MODE_EXACT = 1, SST_MODE_MEMO = 2 };
+/* per-peak status bits written by sst_explain_fetch */
+enum { SST_STATUS_ZERO_IN_WINDOW = 1, SST_STATUS_OUT_OF_TABLE = 2 };
+/* sst_is_valid results */
+enum { SST_VALID_NO = 0, SST_VALID_YES = 1, SST_VALID_OUT_OF_TABLE = 2 };
+#define SST_BUDGET_INF (1 << 30)
+
+/* kernel slots of sst_kernel_ms */
+enum {
+    SST_K_BUILD = 0, SST_K_TRANSPOSE, SST_K_IS_VALID, SST_K_WINDOW_COUNT, SST_K_WINDOW_FILL, SST_K_PHASE_A,
+    SST_K_ENUM_COUNT, SST_K_ENUM_FILL, SST_K_SCAN, SST_K_PEAK_OFFSETS, SST_K_COUNT_
+};
+
+/* ---- context ---- */
+int sst_ctx_create(int device, sst_ctx** out);
+void sst_ctx_destroy(sst_ctx* ctx);
+const char* sst_last_error(const sst_ctx* ctx);
+int sst_device_info(sst_ctx* ctx, int* sm_count, int* cc_major, int* cc_minor, uint64_t* free_bytes, uint64_t* total_bytes);
+void* sst_host_alloc(sst_ctx* ctx, size_t bytes); /* pinned host memory, NULL on failure */
+void sst_host_free(sst_ctx* ctx, void* p);
+/* CUDA-event stopwatch on the context's stream (what bench.py times with) */
+int sst_timer_start(sst_ctx* ctx);
+int sst_timer_stop(sst_ctx* ctx, float* ms);
+/* device time of each kernel family accumulated since the last sst_stats_reset, and launches made */
+int sst_stats_reset(sst_ctx* ctx);
+int sst_kernel_ms(sst_ctx* ctx, float* ms /* [SST_K_COUNT_] */, uint64_t* launches /* [SST_K_COUNT_] */);
+/* write `bytes` of device scratch (L2 flush between timed iterations) */
+int sst_flush_l2(sst_ctx* ctx, size_t bytes);
+
+/* ---- DP table: replaces set_up_bit_table (mass_table.py:207-248) and load_dp_table (:319-340) ----
+ * weights[0] must be 0, the rest strictly ascending, every non-zero weight >= 32; R <= 128.
+ * compression must be 32 (uint64 cells); last_col_mask is numpy's value of
+ * full << 2*(max_col - (max_mass+1) % max_col) (mass_table.py:246), computed by the caller.
+ * with_masks != 0 also builds the mass-major row masks the enumerator needs. */
+int sst_table_build(sst_ctx* ctx, const int64_t* weights, int R, int64_t max_mass, int compression,
+                    uint64_t last_col_mask, int with_masks, sst_table** out);
+/* adopt a table computed elsewhere (row-major R x C uint64, reference layout) */
+int sst_table_upload(sst_ctx* ctx, const uint64_t* host_table, const int64_t* weights, int R, int64_t C, sst_table** out);
+/* run the build kernels again into the same buffers (benchmarking) */
+int sst_table_rebuild(sst_ctx* ctx, sst_table* t);
+int sst_table_info(const sst_table* t, int* R, int64_t* C, float* build_ms, float* transpose_ms);
+int sst_table_download(sst_ctx* ctx, const sst_table* t, uint64_t* host_out /* R*C */);
+int sst_table_download_masks(sst_ctx* ctx, const sst_table* t, int64_t first_mass, int64_t n, uint32_t* host_out /* n*4 */);
+void sst_table_destroy(sst_ctx* ctx, sst_table* t);
+
+/* ---- validity: replaces is_valid_mass (mass_explanation.py:45-89) for P (target, threshold) pairs ---- */
+int sst_is_valid(sst_ctx* ctx, const sst_table* t, const int64_t* target, const int64_t* thr, int64_t P,
+                 uint8_t* out /* P, SST_VALID_* */);
+
+/* ---- enumeration: replaces explain_mass_with_table (mass_explanation.py:92-203) for P peaks ----
+ * max_mods[p]: global modification budget (SST_BUDGET_INF = unbounded); mode[p]: SST_MODE_*;
+ * ind[r] = round(max_len * rate_r), is_mod[r]: per-row budget data shared by the batch (length R).
+ * rec_width: bytes per composition record (multiple of 8, >= longest possible composition).
+ * memo_capacity: slots of the first-visit map (0 = default); only used when some mode is MEMO.
+ * Results stay on the device until sst_explain_fetch / the next run. */
+int sst_explain(sst_ctx* ctx, const sst_table* t, const int64_t* target, const int64_t* thr, const int32_t* max_mods,
+                const uint8_t* mode, int64_t P, const int32_t* ind, const uint8_t* is_mod, int rec_width,
+                uint64_t memo_capacity, uint64_t* n_roots, uint64_t* n_comps);
+/* the same in two halves, so that the kernel-only time can be measured with inputs resident in HBM */
+int sst_explain_stage(sst_ctx* ctx, const sst_table* t, const int64_t* target, const int64_t* thr, const int32_t* max_mods,
+                      const uint8_t* mode, int64_t P, const int32_t* ind, const uint8_t* is_mod);
+int sst_explain_run(sst_ctx* ctx, const sst_table* t, int rec_width, uint64_t memo_capacity, uint64_t* n_roots,
+                    uint64_t* n_comps);
+/* status[P]; peak_off[P+1] (compositions of peak p are records peak_off[p] .. peak_off[p+1]);
+ * recs[n_comps * rec_width]: row indices in ascending order, 0-padded.  Any pointer may be NULL. */
+int sst_explain_fetch(sst_ctx* ctx, uint8_t* status, uint64_t* peak_off, uint8_t* recs);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SST_B200_H */

@@ -1,0 +1,279 @@
+"""ctypes binding of libsst_b200.so (include/sst_b200.h) plus a small object layer on top.
+
+There is NO CPU fallback: if the shared library is missing, or the machine has no sm_100 GPU, every
+entry point raises ``DeviceUnavailable`` with the reason.  ``load()`` alone (symbol check) works
+without a GPU so that CPU-only CI can verify the ABI.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import pathlib
+import threading
+import weakref
+from typing import Dict, Optional, Sequence, Tuple
+
+import numpy as np
+
+_HERE = pathlib.Path(__file__).resolve().parent
+LIB_PATH = _HERE / "libsst_b200.so"
+
+# error codes (include/sst_b200.h)
+SST_OK, SST_ERR_CUDA, SST_ERR_NO_DEVICE, SST_ERR_BAD_ARG, SST_ERR_COMPRESSION = 0, 1, 2, 3, 4
+SST_ERR_TOO_MANY_ROWS, SST_ERR_TOO_DEEP, SST_ERR_NOMEM, SST_ERR_MEMO_FULL, SST_ERR_STATE = 5, 6, 7, 8, 9
+MODE_FREE, MODE_EXACT, MODE_MEMO = 0, 1, 2
+STATUS_ZERO_IN_WINDOW, STATUS_OUT_OF_TABLE = 1, 2
+VALID_NO, VALID_YES, VALID_OUT_OF_TABLE = 0, 1, 2
+BUDGET_INF = 1 << 30
+KERNEL_SLOTS = ["build", "transpose", "is_valid", "window_count", "window_fill", "phase_a", "enum_count",
+                "enum_fill", "scan", "peak_offsets"]
+
+EXPORTS = [
+    "sst_ctx_create", "sst_ctx_destroy", "sst_last_error", "sst_device_info", "sst_host_alloc", "sst_host_free",
+    "sst_timer_start", "sst_timer_stop", "sst_stats_reset", "sst_kernel_ms", "sst_flush_l2",
+    "sst_table_build", "sst_table_upload", "sst_table_rebuild", "sst_table_info", "sst_table_download",
+    "sst_table_download_masks", "sst_table_destroy", "sst_is_valid", "sst_explain", "sst_explain_stage",
+    "sst_explain_run", "sst_explain_fetch",
+]
+
+
+class DeviceUnavailable(RuntimeError):
+    """The CUDA library or a B200-class GPU is missing; the product path has no CPU fallback."""
+
+
+class TableTooSmall(NotImplementedError):
+    """A probed mass lies beyond the table (the reference raises NotImplementedError here)."""
+
+
+_lib: Optional[C.CDLL] = None
+_lock = threading.Lock()
+
+
+def load() -> C.CDLL:
+    """dlopen the library and declare signatures.  Needs no GPU."""
+    global _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not LIB_PATH.exists():
+            raise DeviceUnavailable(
+                f"{LIB_PATH} not built: run `python -c 'import __graft_entry__ as g; g.build()'` (nvcc, sm_100a). "
+                "spectrseqtools_b200 has no CPU fallback.")
+        lib = C.CDLL(str(LIB_PATH))
+        vp, i64p, u64p, u8p, i32p, u32p, fp = C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p
+        sig = {
+            "sst_ctx_create": (C.c_int, [C.c_int, C.POINTER(vp)]),
+            "sst_ctx_destroy": (None, [vp]),
+            "sst_last_error": (C.c_char_p, [vp]),
+            "sst_device_info": (C.c_int, [vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
+            "sst_host_alloc": (vp, [vp, C.c_size_t]),
+            "sst_host_free": (None, [vp, vp]),
+            "sst_timer_start": (C.c_int, [vp]),
+            "sst_timer_stop": (C.c_int, [vp, C.POINTER(C.c_float)]),
+            "sst_stats_reset": (C.c_int, [vp]),
+            "sst_kernel_ms": (C.c_int, [vp, fp, u64p]),
+            "sst_flush_l2": (C.c_int, [vp, C.c_size_t]),
+            "sst_table_build": (C.c_int, [vp, i64p, C.c_int, C.c_int64, C.c_int, C.c_uint64, C.c_int, C.POINTER(vp)]),
+            "sst_table_upload": (C.c_int, [vp, u64p, i64p, C.c_int, C.c_int64, C.POINTER(vp)]),
+            "sst_table_rebuild": (C.c_int, [vp, vp]),
+            "sst_table_info": (C.c_int, [vp, C.POINTER(C.c_int), C.POINTER(C.c_int64), C.POINTER(C.c_float), C.POINTER(C.c_float)]),
+            "sst_table_download": (C.c_int, [vp, vp, u64p]),
+            "sst_table_download_masks": (C.c_int, [vp, vp, C.c_int64, C.c_int64, u32p]),
+            "sst_table_destroy": (None, [vp, vp]),
+            "sst_is_valid": (C.c_int, [vp, vp, i64p, i64p, C.c_int64, u8p]),
+            "sst_explain": (C.c_int, [vp, vp, i64p, i64p, i32p, u8p, C.c_int64, i32p, u8p, C.c_int, C.c_uint64, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
+            "sst_explain_stage": (C.c_int, [vp, vp, i64p, i64p, i32p, u8p, C.c_int64, i32p, u8p]),
+            "sst_explain_run": (C.c_int, [vp, vp, C.c_int, C.c_uint64, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
+            "sst_explain_fetch": (C.c_int, [vp, u8p, u64p, u8p]),
+        }
+        for name in EXPORTS:
+            fn = getattr(lib, name)  # AttributeError here = ABI drift
+            fn.restype, fn.argtypes = sig[name]
+        _lib = lib
+        return lib
+
+
+def _p(a: Optional[np.ndarray]):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _arr(x, dtype) -> np.ndarray:
+    return np.ascontiguousarray(x, dtype=dtype)
+
+
+class Context:
+    """One CUDA stream on one device + scratch.  Not thread-safe."""
+
+    def __init__(self, device: int = 0):
+        lib = load()
+        h = C.c_void_p()
+        rc = lib.sst_ctx_create(int(device), C.byref(h))
+        if rc != SST_OK:
+            raise DeviceUnavailable(
+                f"no usable sm_100 (B200) GPU at index {device} (sst_ctx_create rc={rc}); "
+                "spectrseqtools_b200 has no CPU fallback.")
+        self._lib, self._h, self.device = lib, h, int(device)
+        self._finalizer = weakref.finalize(self, lib.sst_ctx_destroy, h)
+
+    # -- plumbing
+    def _check(self, rc: int):
+        if rc == SST_OK:
+            return
+        msg = (self._lib.sst_last_error(self._h) or b"").decode(errors="replace")
+        if rc in (SST_ERR_BAD_ARG, SST_ERR_COMPRESSION, SST_ERR_TOO_MANY_ROWS):
+            raise ValueError(msg)
+        if rc == SST_ERR_TOO_DEEP:
+            raise NotImplementedError(msg)
+        if rc == SST_ERR_NOMEM:
+            raise MemoryError(msg)
+        if rc == SST_ERR_MEMO_FULL:
+            raise MemoFull(msg)
+        raise RuntimeError(f"libsst_b200 rc={rc}: {msg}")
+
+    def device_info(self) -> dict:
+        sm, ma, mi = C.c_int(), C.c_int(), C.c_int()
+        fr, to = C.c_uint64(), C.c_uint64()
+        self._check(self._lib.sst_device_info(self._h, C.byref(sm), C.byref(ma), C.byref(mi), C.byref(fr), C.byref(to)))
+        return dict(sm_count=sm.value, cc=(ma.value, mi.value), free_bytes=fr.value, total_bytes=to.value)
+
+    def pinned_empty(self, shape, dtype) -> np.ndarray:
+        """numpy array on page-locked host memory (freed when the array is garbage collected)."""
+        dtype = np.dtype(dtype)
+        n = int(np.prod(shape)) * dtype.itemsize
+        ptr = self._lib.sst_host_alloc(self._h, max(n, 1))
+        if not ptr:
+            raise MemoryError(f"cudaHostAlloc({n}) failed")
+        buf = (C.c_uint8 * max(n, 1)).from_address(ptr)
+        arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+        weakref.finalize(buf, self._lib.sst_host_free, self._h, C.c_void_p(ptr))
+        return arr
+
+    def timer_start(self):
+        self._check(self._lib.sst_timer_start(self._h))
+
+    def timer_stop(self) -> float:
+        ms = C.c_float()
+        self._check(self._lib.sst_timer_stop(self._h, C.byref(ms)))
+        return float(ms.value)
+
+    def stats_reset(self):
+        self._check(self._lib.sst_stats_reset(self._h))
+
+    def kernel_stats(self) -> Dict[str, Tuple[float, int]]:
+        ms = np.zeros(len(KERNEL_SLOTS), dtype=np.float32)
+        n = np.zeros(len(KERNEL_SLOTS), dtype=np.uint64)
+        self._check(self._lib.sst_kernel_ms(self._h, _p(ms), _p(n)))
+        return {k: (float(ms[i]), int(n[i])) for i, k in enumerate(KERNEL_SLOTS)}
+
+    def flush_l2(self, nbytes: int = 256 << 20):
+        self._check(self._lib.sst_flush_l2(self._h, int(nbytes)))
+
+    # -- tables
+    def build_table(self, weights: Sequence[int], max_mass: int, compression: int, last_col_mask: int,
+                    with_masks: bool = True) -> "DeviceTable":
+        w = _arr(weights, np.int64)
+        h = C.c_void_p()
+        self._check(self._lib.sst_table_build(self._h, _p(w), len(w), int(max_mass), int(compression),
+                                              C.c_uint64(last_col_mask), 1 if with_masks else 0, C.byref(h)))
+        return DeviceTable(self, h, w)
+
+    def upload_table(self, table: np.ndarray, weights: Sequence[int]) -> "DeviceTable":
+        if table.dtype != np.uint64 or table.ndim != 2:
+            raise ValueError("only uint64 tables (32 masses per cell) can be adopted by the device path")
+        t = np.ascontiguousarray(table)
+        w = _arr(weights, np.int64)
+        if len(w) != t.shape[0]:
+            raise ValueError("one weight per table row expected")
+        h = C.c_void_p()
+        self._check(self._lib.sst_table_upload(self._h, _p(t), _p(w), t.shape[0], t.shape[1], C.byref(h)))
+        return DeviceTable(self, h, w)
+
+    # -- hot path
+    def is_valid(self, table: "DeviceTable", target, thr) -> np.ndarray:
+        t, h = _arr(target, np.int64), _arr(thr, np.int64)
+        out = np.empty(len(t), dtype=np.uint8)
+        self._check(self._lib.sst_is_valid(self._h, table._h, _p(t), _p(h), len(t), _p(out)))
+        return out
+
+    def explain_stage(self, table: "DeviceTable", target, thr, max_mods, mode, ind, is_mod):
+        t, h = _arr(target, np.int64), _arr(thr, np.int64)
+        mm, mo = _arr(max_mods, np.int32), _arr(mode, np.uint8)
+        iv, im = _arr(ind, np.int32), _arr(is_mod, np.uint8)
+        if not (len(t) == len(h) == len(mm) == len(mo)):
+            raise ValueError("per-peak arrays differ in length")
+        if len(iv) != table.R or len(im) != table.R:
+            raise ValueError("ind / is_mod need one entry per table row")
+        self._check(self._lib.sst_explain_stage(self._h, table._h, _p(t), _p(h), _p(mm), _p(mo), len(t), _p(iv), _p(im)))
+        self._staged_P = len(t)
+
+    def explain_run(self, table: "DeviceTable", rec_width: int, memo_capacity: int = 0) -> Tuple[int, int]:
+        nr, nc = C.c_uint64(), C.c_uint64()
+        self._check(self._lib.sst_explain_run(self._h, table._h, int(rec_width), C.c_uint64(memo_capacity), C.byref(nr), C.byref(nc)))
+        self._last = (int(nr.value), int(nc.value), int(rec_width))
+        return int(nr.value), int(nc.value)
+
+    def explain_fetch(self, want_records: bool = True, out_recs: Optional[np.ndarray] = None):
+        P = self._staged_P
+        _nr, nc, W = self._last
+        status = np.empty(P, dtype=np.uint8)
+        off = np.empty(P + 1, dtype=np.uint64)
+        recs = None
+        if want_records:
+            recs = out_recs if out_recs is not None else np.empty((nc, W), dtype=np.uint8)
+            if recs.size < nc * W:
+                raise ValueError("record buffer too small")
+        self._check(self._lib.sst_explain_fetch(self._h, _p(status), _p(off), _p(recs) if (recs is not None and nc) else None))
+        return status, off.astype(np.int64), recs
+
+
+class MemoFull(RuntimeError):
+    pass
+
+
+class DeviceTable:
+    """Device-resident 2-bit table (+ mass-major row masks)."""
+
+    def __init__(self, ctx: Context, handle, weights: np.ndarray):
+        self.ctx, self._h, self.weights = ctx, handle, weights
+        R, Cc, b, t = C.c_int(), C.c_int64(), C.c_float(), C.c_float()
+        ctx._lib.sst_table_info(handle, C.byref(R), C.byref(Cc), C.byref(b), C.byref(t))
+        self.R, self.C = R.value, Cc.value
+        self._finalizer = weakref.finalize(self, ctx._lib.sst_table_destroy, ctx._h, handle)
+
+    @property
+    def limit(self) -> int:
+        return self.C * 32
+
+    def timings(self) -> Tuple[float, float]:
+        b, t = C.c_float(), C.c_float()
+        self.ctx._lib.sst_table_info(self._h, None, None, C.byref(b), C.byref(t))
+        return float(b.value), float(t.value)
+
+    def rebuild(self):
+        self.ctx._check(self.ctx._lib.sst_table_rebuild(self.ctx._h, self._h))
+
+    def download(self, out: Optional[np.ndarray] = None) -> np.ndarray:
+        if out is None:
+            out = np.empty((self.R, self.C), dtype=np.uint64)
+        self.ctx._check(self.ctx._lib.sst_table_download(self.ctx._h, self._h, _p(out)))
+        return out
+
+    def download_masks(self, first_mass: int, n: int) -> np.ndarray:
+        out = np.empty((n, 4), dtype=np.uint32)
+        self.ctx._check(self.ctx._lib.sst_table_download_masks(self.ctx._h, self._h, int(first_mass), int(n), _p(out)))
+        return out
+
+
+_contexts: Dict[int, Context] = {}
+
+
+def default_device() -> int:
+    return int(os.environ.get("SST_DEVICE", os.environ.get("LOCAL_RANK", "0")))
+
+
+def context(device: Optional[int] = None) -> Context:
+    d = default_device() if device is None else int(device)
+    ctx = _contexts.get(d)
+    if ctx is None:
+        ctx = _contexts[d] = Context(d)
+    return ctx

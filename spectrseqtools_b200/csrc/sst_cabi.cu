@@ -1,0 +1,667 @@
+// C-ABI of libsst_b200.so (declared in include/sst_b200.h): context, device tables, kernel launches.
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <new>
+#include <vector>
+
+#include "../../include/sst_b200.h"
+#include "sst_common.cuh"
+#include "sst_explain.cuh"
+#include "sst_table.cuh"
+
+using namespace sst;
+
+namespace {
+
+struct DevBuf {  // grow-only device scratch
+    void* p = nullptr;
+    size_t cap = 0;
+};
+
+}  // namespace
+
+struct sst_table {
+    uint64_t* tbl = nullptr;
+    uint4* H = nullptr;
+    int32_t* d_weights = nullptr;
+    int32_t* d_step = nullptr;
+    int32_t* d_shift = nullptr;
+    int* d_flags = nullptr;  // n_tiles + 1 ints; the last one is the ticket
+    int R = 0;
+    int64_t C = 0;
+    int n_tiles = 0;
+    int64_t step_min = 0;
+    int64_t w_min = 0;
+    uint64_t last_mask = ~0ULL;
+    float build_ms = 0.f, transpose_ms = 0.f;
+    bool built_here = false;
+};
+
+struct sst_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaDeviceProp prop{};
+    char err[512] = {0};
+    cudaEvent_t ev_a = nullptr, ev_b = nullptr;    // user stopwatch
+    cudaEvent_t kev[2 * 16] = {nullptr};            // per-launch brackets
+    float k_ms[SST_K_COUNT_] = {0};
+    uint64_t k_launches[SST_K_COUNT_] = {0};
+    bool time_kernels = true;
+    // staged peak batch
+    int64_t P = 0;
+    int R_staged = 0;
+    DevBuf d_target, d_thr, d_maxmods, d_mode, d_ind, d_ismod, d_memo_peaks;
+    int n_memo = 0;
+    int64_t window_total = 0;  // sum of window sizes (upper bound for the number of roots)
+    int64_t max_hi = 0;
+    // results
+    DevBuf d_status, d_nroots, d_rootoff, d_rootv, d_rootpeak, d_cnt, d_compoff, d_peakoff, d_recs, d_blocksums;
+    DevBuf d_memo_keys, d_memo_alive, d_memo_top, d_memo_misc, d_flush;
+    uint64_t n_roots = 0, n_comps = 0;
+    int rec_width = 0;
+    bool have_result = false;
+};
+
+namespace {
+
+int fail(sst_ctx* ctx, int code, const char* fmt, ...) {
+    if (ctx) {
+        va_list ap;
+        va_start(ap, fmt);
+        vsnprintf(ctx->err, sizeof ctx->err, fmt, ap);
+        va_end(ap);
+    }
+    return code;
+}
+
+#define CK(call)                                                                                          \
+    do {                                                                                                  \
+        cudaError_t e_ = (call);                                                                          \
+        if (e_ != cudaSuccess)                                                                            \
+            return fail(ctx, e_ == cudaErrorMemoryAllocation ? SST_ERR_NOMEM : SST_ERR_CUDA, "%s: %s (%s:%d)", #call, \
+                        cudaGetErrorString(e_), __FILE__, __LINE__);                                      \
+    } while (0)
+
+int reserve(sst_ctx* ctx, DevBuf& b, size_t bytes) {
+    if (bytes <= b.cap && b.p) return SST_OK;
+    if (b.p) CK(cudaFree(b.p));
+    b.p = nullptr;
+    b.cap = 0;
+    size_t want = bytes < 256 ? 256 : bytes;
+    want += want / 8;  // a little headroom so that slowly growing batches do not reallocate each time
+    cudaError_t e = cudaMalloc(&b.p, want);
+    if (e != cudaSuccess) {
+        b.p = nullptr;
+        cudaGetLastError();
+        return fail(ctx, SST_ERR_NOMEM, "cudaMalloc of %zu bytes failed: %s", want, cudaGetErrorString(e));
+    }
+    b.cap = want;
+    return SST_OK;
+}
+
+struct KTimer {  // brackets one kernel family with events on the context stream
+    sst_ctx* ctx;
+    int slot;
+    KTimer(sst_ctx* c, int s) : ctx(c), slot(s) {
+        if (ctx->time_kernels) cudaEventRecord(ctx->kev[0], ctx->stream);
+    }
+    void stop(uint64_t launches = 1) {
+        ctx->k_launches[slot] += launches;
+        if (ctx->time_kernels) {
+            cudaEventRecord(ctx->kev[1], ctx->stream);
+            cudaEventSynchronize(ctx->kev[1]);
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, ctx->kev[0], ctx->kev[1]);
+            ctx->k_ms[slot] += ms;
+        }
+    }
+};
+
+// exclusive scan of n uint64 -> out[n+1]
+int scan_u64(sst_ctx* ctx, const unsigned long long* in, int64_t n, unsigned long long* out) {
+    if (n == 0) {
+        CK(cudaMemsetAsync(out, 0, sizeof(unsigned long long), ctx->stream));
+        return SST_OK;
+    }
+    const int64_t n_blocks = (n + kScanBlock - 1) / kScanBlock;
+    int rc = reserve(ctx, ctx->d_blocksums, (size_t)n_blocks * 8);
+    if (rc) return rc;
+    auto* bs = (unsigned long long*)ctx->d_blocksums.p;
+    KTimer kt(ctx, SST_K_SCAN);
+    k_scan_partials<<<(unsigned)n_blocks, kScanThreads, 0, ctx->stream>>>(in, n, bs);
+    k_scan_block_sums<<<1, kScanThreads, 0, ctx->stream>>>(bs, n_blocks);
+    k_scan_final<<<(unsigned)n_blocks, kScanThreads, 0, ctx->stream>>>(in, n, bs, out);
+    kt.stop(3);
+    CK(cudaGetLastError());
+    return SST_OK;
+}
+
+int launch_build(sst_ctx* ctx, sst_table* t) {
+    const int NW = kBuildWarps;
+    KTimer kt(ctx, SST_K_BUILD);
+    cudaEvent_t e0 = ctx->kev[2], e1 = ctx->kev[3];
+    CK(cudaEventRecord(e0, ctx->stream));
+    if (t->step_min >= kTileWords) {
+        CK(cudaMemsetAsync(t->d_flags, 0, (size_t)(t->n_tiles + 1) * sizeof(int), ctx->stream));
+        const int rpw = (t->R - 1 + NW - 1) / NW;
+        // tiles further apart than this never wait on each other
+        int64_t indep = (t->step_min - (kTileWords - 1)) / kTileWords;
+        if (indep < 1) indep = 1;
+        int occ = 1;
+        auto launch = [&](auto kern) -> cudaError_t {
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NW * 32, 0);
+            if (occ < 1) occ = 1;
+            int64_t grid = (int64_t)ctx->prop.multiProcessorCount * occ;
+            if (grid > indep) grid = indep;
+            if (grid > t->n_tiles) grid = t->n_tiles;
+            if (grid < 1) grid = 1;
+            kern<<<(unsigned)grid, NW * 32, 0, ctx->stream>>>(t->tbl, t->R, t->C, t->d_step, t->d_shift, t->last_mask,
+                                                              t->n_tiles, t->step_min, t->d_flags, t->d_flags + t->n_tiles);
+            return cudaGetLastError();
+        };
+        cudaError_t e;
+        if (rpw <= 2) e = launch(k_build_table<2>);
+        else if (rpw <= 4) e = launch(k_build_table<4>);
+        else if (rpw <= 8) e = launch(k_build_table<8>);
+        else e = launch(k_build_table<16>);
+        CK(e);
+    } else {
+        k_build_table_small<<<1, 1024, 0, ctx->stream>>>(t->tbl, t->R, t->C, t->d_step, t->d_shift, t->last_mask);
+        CK(cudaGetLastError());
+    }
+    CK(cudaEventRecord(e1, ctx->stream));
+    kt.stop(1);
+    CK(cudaEventSynchronize(e1));
+    CK(cudaEventElapsedTime(&t->build_ms, e0, e1));
+    return SST_OK;
+}
+
+int launch_transpose(sst_ctx* ctx, sst_table* t) {
+    if (!t->H) return SST_OK;
+    KTimer kt(ctx, SST_K_TRANSPOSE);
+    cudaEvent_t e0 = ctx->kev[2], e1 = ctx->kev[3];
+    CK(cudaEventRecord(e0, ctx->stream));
+    k_transpose_masks<<<(unsigned)t->n_tiles, 256, 0, ctx->stream>>>(t->tbl, t->R, t->C, t->H);
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(e1, ctx->stream));
+    kt.stop(1);
+    CK(cudaEventSynchronize(e1));
+    CK(cudaEventElapsedTime(&t->transpose_ms, e0, e1));
+    return SST_OK;
+}
+
+int alloc_table(sst_ctx* ctx, sst_table* t, const int64_t* weights, int R, int64_t C, bool with_masks) {
+    if (R < 1 || R > kMaxRows) return fail(ctx, SST_ERR_TOO_MANY_ROWS, "table has %d rows; at most %d are supported", R, kMaxRows);
+    if (weights[0] != 0) return fail(ctx, SST_ERR_BAD_ARG, "weights[0] must be 0");
+    for (int i = 1; i < R; i++)
+        if (weights[i] <= weights[i - 1]) return fail(ctx, SST_ERR_BAD_ARG, "weights must be strictly ascending");
+    if (C < 1 || C * 32 >= ((int64_t)1 << 31)) return fail(ctx, SST_ERR_BAD_ARG, "table width %lld words out of range", (long long)C);
+    t->R = R;
+    t->C = C;
+    t->n_tiles = (int)((C + kTileWords - 1) / kTileWords);
+    std::vector<int32_t> w(R), st(R), sh(R);
+    int64_t step_min = C + 1, w_min = 0;
+    for (int i = 0; i < R; i++) {
+        w[i] = (int32_t)weights[i];
+        st[i] = (int32_t)(weights[i] / 32);
+        sh[i] = (int32_t)(weights[i] % 32);
+        if (i >= 1 && st[i] < step_min) step_min = st[i];
+        if (i == 1) w_min = weights[i];
+    }
+    if (R == 1) step_min = C + 1;
+    t->step_min = step_min;
+    t->w_min = w_min;
+    CK(cudaMalloc(&t->tbl, (size_t)R * (size_t)C * 8));
+    CK(cudaMalloc(&t->d_weights, (size_t)kMaxRows * 4));
+    CK(cudaMalloc(&t->d_step, (size_t)kMaxRows * 4));
+    CK(cudaMalloc(&t->d_shift, (size_t)kMaxRows * 4));
+    CK(cudaMalloc(&t->d_flags, (size_t)(t->n_tiles + 1) * sizeof(int)));
+    CK(cudaMemcpyAsync(t->d_weights, w.data(), (size_t)R * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(t->d_step, st.data(), (size_t)R * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(t->d_shift, sh.data(), (size_t)R * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));  // the host vectors go out of scope
+    if (with_masks) CK(cudaMalloc(&t->H, (size_t)C * 32 * sizeof(uint4)));
+    return SST_OK;
+}
+
+void free_table(sst_table* t) {
+    if (!t) return;
+    cudaFree(t->tbl);
+    cudaFree(t->H);
+    cudaFree(t->d_weights);
+    cudaFree(t->d_step);
+    cudaFree(t->d_shift);
+    cudaFree(t->d_flags);
+    delete t;
+}
+
+TableView view_of(const sst_table* t) {
+    TableView tv;
+    tv.tbl = t->tbl;
+    tv.H = t->H;
+    tv.weights = t->d_weights;
+    tv.R = t->R;
+    tv.C = t->C;
+    return tv;
+}
+
+}  // namespace
+
+extern "C" {
+
+int sst_ctx_create(int device, sst_ctx** out) {
+    *out = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0 || device < 0 || device >= n) {
+        cudaGetLastError();
+        return SST_ERR_NO_DEVICE;
+    }
+    sst_ctx* ctx = new (std::nothrow) sst_ctx();
+    if (!ctx) return SST_ERR_NOMEM;
+    ctx->device = device;
+    if (cudaSetDevice(device) != cudaSuccess || cudaGetDeviceProperties(&ctx->prop, device) != cudaSuccess) {
+        delete ctx;
+        return SST_ERR_NO_DEVICE;
+    }
+    if (ctx->prop.major != 10) {  // the fatbin only holds sm_100a code
+        delete ctx;
+        return SST_ERR_NO_DEVICE;
+    }
+    cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+    cudaEventCreate(&ctx->ev_a);
+    cudaEventCreate(&ctx->ev_b);
+    for (auto& e : ctx->kev) cudaEventCreate(&e);
+    *out = ctx;
+    return SST_OK;
+}
+
+void sst_ctx_destroy(sst_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    DevBuf* bufs[] = {&ctx->d_target, &ctx->d_thr, &ctx->d_maxmods, &ctx->d_mode, &ctx->d_ind, &ctx->d_ismod,
+                      &ctx->d_memo_peaks, &ctx->d_status, &ctx->d_nroots, &ctx->d_rootoff, &ctx->d_rootv,
+                      &ctx->d_rootpeak, &ctx->d_cnt, &ctx->d_compoff, &ctx->d_peakoff, &ctx->d_recs,
+                      &ctx->d_blocksums, &ctx->d_memo_keys, &ctx->d_memo_alive, &ctx->d_memo_top,
+                      &ctx->d_memo_misc, &ctx->d_flush};
+    for (DevBuf* b : bufs) cudaFree(b->p);
+    cudaEventDestroy(ctx->ev_a);
+    cudaEventDestroy(ctx->ev_b);
+    for (auto& e : ctx->kev) cudaEventDestroy(e);
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+const char* sst_last_error(const sst_ctx* ctx) { return ctx ? ctx->err : "no context (no usable sm_100 GPU?)"; }
+
+int sst_device_info(sst_ctx* ctx, int* sm_count, int* cc_major, int* cc_minor, uint64_t* free_bytes, uint64_t* total_bytes) {
+    CK(cudaSetDevice(ctx->device));
+    size_t f = 0, t = 0;
+    CK(cudaMemGetInfo(&f, &t));
+    if (sm_count) *sm_count = ctx->prop.multiProcessorCount;
+    if (cc_major) *cc_major = ctx->prop.major;
+    if (cc_minor) *cc_minor = ctx->prop.minor;
+    if (free_bytes) *free_bytes = f;
+    if (total_bytes) *total_bytes = t;
+    return SST_OK;
+}
+
+void* sst_host_alloc(sst_ctx* ctx, size_t bytes) {
+    void* p = nullptr;
+    cudaSetDevice(ctx->device);
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    return p;
+}
+
+void sst_host_free(sst_ctx* ctx, void* p) {
+    (void)ctx;
+    if (p) cudaFreeHost(p);
+}
+
+int sst_timer_start(sst_ctx* ctx) {
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaEventRecord(ctx->ev_a, ctx->stream));
+    return SST_OK;
+}
+
+int sst_timer_stop(sst_ctx* ctx, float* ms) {
+    CK(cudaEventRecord(ctx->ev_b, ctx->stream));
+    CK(cudaEventSynchronize(ctx->ev_b));
+    CK(cudaEventElapsedTime(ms, ctx->ev_a, ctx->ev_b));
+    return SST_OK;
+}
+
+int sst_stats_reset(sst_ctx* ctx) {
+    memset(ctx->k_ms, 0, sizeof ctx->k_ms);
+    memset(ctx->k_launches, 0, sizeof ctx->k_launches);
+    return SST_OK;
+}
+
+int sst_kernel_ms(sst_ctx* ctx, float* ms, uint64_t* launches) {
+    for (int i = 0; i < SST_K_COUNT_; i++) {
+        if (ms) ms[i] = ctx->k_ms[i];
+        if (launches) launches[i] = ctx->k_launches[i];
+    }
+    return SST_OK;
+}
+
+int sst_flush_l2(sst_ctx* ctx, size_t bytes) {
+    CK(cudaSetDevice(ctx->device));
+    int rc = reserve(ctx, ctx->d_flush, bytes);
+    if (rc) return rc;
+    CK(cudaMemsetAsync(ctx->d_flush.p, 0x5a, bytes, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return SST_OK;
+}
+
+int sst_table_build(sst_ctx* ctx, const int64_t* weights, int R, int64_t max_mass, int compression,
+                    uint64_t last_col_mask, int with_masks, sst_table** out) {
+    *out = nullptr;
+    CK(cudaSetDevice(ctx->device));
+    if (compression != 32)
+        return fail(ctx, SST_ERR_COMPRESSION, "compression %d: the device table packs 32 masses per uint64 cell only", compression);
+    if (max_mass < 0) return fail(ctx, SST_ERR_BAD_ARG, "max_mass must be >= 0");
+    for (int i = 1; i < R; i++)
+        if (weights[i] < 32) return fail(ctx, SST_ERR_BAD_ARG, "weight %lld < 32: the in-place word loop of the reference is not a closed form there", (long long)weights[i]);
+    const int64_t C = (max_mass + 1 + 31) / 32;
+    sst_table* t = new (std::nothrow) sst_table();
+    if (!t) return fail(ctx, SST_ERR_NOMEM, "host allocation failed");
+    int rc = alloc_table(ctx, t, weights, R, C, with_masks != 0);
+    if (rc) {
+        free_table(t);
+        return rc;
+    }
+    t->last_mask = last_col_mask;
+    t->built_here = true;
+    rc = launch_build(ctx, t);
+    if (!rc) rc = launch_transpose(ctx, t);
+    if (rc) {
+        free_table(t);
+        return rc;
+    }
+    *out = t;
+    return SST_OK;
+}
+
+int sst_table_upload(sst_ctx* ctx, const uint64_t* host_table, const int64_t* weights, int R, int64_t C, sst_table** out) {
+    *out = nullptr;
+    CK(cudaSetDevice(ctx->device));
+    sst_table* t = new (std::nothrow) sst_table();
+    if (!t) return fail(ctx, SST_ERR_NOMEM, "host allocation failed");
+    int rc = alloc_table(ctx, t, weights, R, C, true);
+    if (rc) {
+        free_table(t);
+        return rc;
+    }
+    cudaError_t e = cudaMemcpyAsync(t->tbl, host_table, (size_t)R * (size_t)C * 8, cudaMemcpyHostToDevice, ctx->stream);
+    if (e != cudaSuccess) {
+        free_table(t);
+        return fail(ctx, SST_ERR_CUDA, "table upload: %s", cudaGetErrorString(e));
+    }
+    rc = launch_transpose(ctx, t);
+    if (rc) {
+        free_table(t);
+        return rc;
+    }
+    *out = t;
+    return SST_OK;
+}
+
+int sst_table_rebuild(sst_ctx* ctx, sst_table* t) {
+    CK(cudaSetDevice(ctx->device));
+    if (!t->built_here) return fail(ctx, SST_ERR_STATE, "an uploaded table cannot be rebuilt");
+    int rc = launch_build(ctx, t);
+    if (!rc) rc = launch_transpose(ctx, t);
+    return rc;
+}
+
+int sst_table_info(const sst_table* t, int* R, int64_t* C, float* build_ms, float* transpose_ms) {
+    if (R) *R = t->R;
+    if (C) *C = t->C;
+    if (build_ms) *build_ms = t->build_ms;
+    if (transpose_ms) *transpose_ms = t->transpose_ms;
+    return SST_OK;
+}
+
+int sst_table_download(sst_ctx* ctx, const sst_table* t, uint64_t* host_out) {
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMemcpyAsync(host_out, t->tbl, (size_t)t->R * (size_t)t->C * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return SST_OK;
+}
+
+int sst_table_download_masks(sst_ctx* ctx, const sst_table* t, int64_t first_mass, int64_t n, uint32_t* host_out) {
+    CK(cudaSetDevice(ctx->device));
+    if (!t->H) return fail(ctx, SST_ERR_STATE, "table was built without row masks");
+    if (first_mass < 0 || n < 0 || first_mass + n > t->C * 32) return fail(ctx, SST_ERR_BAD_ARG, "mask range out of table");
+    CK(cudaMemcpyAsync(host_out, t->H + first_mass, (size_t)n * 16, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return SST_OK;
+}
+
+void sst_table_destroy(sst_ctx* ctx, sst_table* t) {
+    if (ctx) {
+        cudaSetDevice(ctx->device);
+        cudaStreamSynchronize(ctx->stream);
+    }
+    free_table(t);
+}
+
+int sst_is_valid(sst_ctx* ctx, const sst_table* t, const int64_t* target, const int64_t* thr, int64_t P, uint8_t* out) {
+    CK(cudaSetDevice(ctx->device));
+    if (P <= 0) return SST_OK;
+    int rc;
+    if ((rc = reserve(ctx, ctx->d_target, (size_t)P * 8))) return rc;
+    if ((rc = reserve(ctx, ctx->d_thr, (size_t)P * 8))) return rc;
+    if ((rc = reserve(ctx, ctx->d_status, (size_t)P))) return rc;
+    ctx->have_result = false;  // the scratch is shared with the enumerator
+    CK(cudaMemcpyAsync(ctx->d_target.p, target, (size_t)P * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->d_thr.p, thr, (size_t)P * 8, cudaMemcpyHostToDevice, ctx->stream));
+    KTimer kt(ctx, SST_K_IS_VALID);
+    k_is_valid<<<(unsigned)((P + 255) / 256), 256, 0, ctx->stream>>>(view_of(t), (const int64_t*)ctx->d_target.p,
+                                                                     (const int64_t*)ctx->d_thr.p, P, (uint8_t*)ctx->d_status.p);
+    kt.stop(1);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(out, ctx->d_status.p, (size_t)P, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return SST_OK;
+}
+
+int sst_explain_stage(sst_ctx* ctx, const sst_table* t, const int64_t* target, const int64_t* thr, const int32_t* max_mods,
+                      const uint8_t* mode, int64_t P, const int32_t* ind, const uint8_t* is_mod) {
+    CK(cudaSetDevice(ctx->device));
+    ctx->have_result = false;
+    if (P < 0) return fail(ctx, SST_ERR_BAD_ARG, "negative peak count");
+    if (!t->H) return fail(ctx, SST_ERR_STATE, "table was built without row masks");
+    int rc;
+    const size_t p8 = (size_t)(P ? P : 1) * 8;
+    if ((rc = reserve(ctx, ctx->d_target, p8))) return rc;
+    if ((rc = reserve(ctx, ctx->d_thr, p8))) return rc;
+    if ((rc = reserve(ctx, ctx->d_maxmods, p8 / 2))) return rc;
+    if ((rc = reserve(ctx, ctx->d_mode, p8 / 8))) return rc;
+    if ((rc = reserve(ctx, ctx->d_ind, (size_t)kMaxRows * 4))) return rc;
+    if ((rc = reserve(ctx, ctx->d_ismod, (size_t)kMaxRows))) return rc;
+    std::vector<uint32_t> memo_peaks;
+    int64_t window_total = 0, max_hi = 0;
+    for (int64_t p = 0; p < P; p++) {
+        if (mode[p] == SST_MODE_MEMO) memo_peaks.push_back((uint32_t)p);
+        else if (mode[p] != SST_MODE_FREE && mode[p] != SST_MODE_EXACT) return fail(ctx, SST_ERR_BAD_ARG, "peak %lld: unknown mode %d", (long long)p, (int)mode[p]);
+        if (thr[p] >= 0) {
+            int64_t hi = target[p] + thr[p], lo = target[p] - thr[p];
+            if (hi > max_hi) max_hi = hi;
+            int64_t a = lo < 1 ? 1 : lo, b = hi < t->C * 32 - 1 ? hi : t->C * 32 - 1;
+            if (b >= a) window_total += b - a + 1;
+        }
+    }
+    if (P) {
+        CK(cudaMemcpyAsync(ctx->d_target.p, target, (size_t)P * 8, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(ctx->d_thr.p, thr, (size_t)P * 8, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(ctx->d_maxmods.p, max_mods, (size_t)P * 4, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(ctx->d_mode.p, mode, (size_t)P, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    CK(cudaMemcpyAsync(ctx->d_ind.p, ind, (size_t)t->R * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->d_ismod.p, is_mod, (size_t)t->R, cudaMemcpyHostToDevice, ctx->stream));
+    ctx->n_memo = (int)memo_peaks.size();
+    if (ctx->n_memo) {
+        if ((rc = reserve(ctx, ctx->d_memo_peaks, memo_peaks.size() * 4))) return rc;
+        CK(cudaMemcpyAsync(ctx->d_memo_peaks.p, memo_peaks.data(), memo_peaks.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->P = P;
+    ctx->R_staged = t->R;
+    ctx->window_total = window_total;
+    ctx->max_hi = max_hi;
+    return SST_OK;
+}
+
+int sst_explain_run(sst_ctx* ctx, const sst_table* t, int rec_width, uint64_t memo_capacity, uint64_t* n_roots,
+                    uint64_t* n_comps) {
+    CK(cudaSetDevice(ctx->device));
+    ctx->have_result = false;
+    const int64_t P = ctx->P;
+    if (ctx->R_staged != t->R) return fail(ctx, SST_ERR_STATE, "staged batch belongs to a table with %d rows", ctx->R_staged);
+    if (rec_width < 8 || rec_width % 8 || rec_width > kMaxDepth) return fail(ctx, SST_ERR_BAD_ARG, "rec_width %d must be a multiple of 8 in [8, %d]", rec_width, kMaxDepth);
+    if (t->w_min > 0) {  // longest composition any in-table window value can have
+        const int64_t cap = t->C * 32 - 1;
+        const int64_t deepest = (ctx->max_hi < cap ? ctx->max_hi : cap) / t->w_min;
+        if (deepest > kMaxDepth) return fail(ctx, SST_ERR_TOO_DEEP, "a composition may need %lld nucleotides (limit %d)", (long long)deepest, kMaxDepth);
+        if (deepest > rec_width) return fail(ctx, SST_ERR_BAD_ARG, "a composition may need %lld nucleotides but rec_width is %d", (long long)deepest, rec_width);
+    }
+    int rc;
+    if ((rc = reserve(ctx, ctx->d_status, (size_t)(P ? P : 1)))) return rc;
+    if ((rc = reserve(ctx, ctx->d_nroots, (size_t)(P + 1) * 8))) return rc;
+    if ((rc = reserve(ctx, ctx->d_rootoff, (size_t)(P + 2) * 8))) return rc;
+    if ((rc = reserve(ctx, ctx->d_peakoff, (size_t)(P + 2) * 8))) return rc;
+    TableView tv = view_of(t);
+    RowMeta meta{(const int32_t*)ctx->d_ind.p, (const uint8_t*)ctx->d_ismod.p};
+    PeakBatch pk{(const int64_t*)ctx->d_target.p, (const int64_t*)ctx->d_thr.p, (const int32_t*)ctx->d_maxmods.p,
+                 (const uint8_t*)ctx->d_mode.p, P};
+    auto* d_nroots = (unsigned long long*)ctx->d_nroots.p;
+    auto* d_rootoff = (unsigned long long*)ctx->d_rootoff.p;
+    auto* d_peakoff = (unsigned long long*)ctx->d_peakoff.p;
+    const unsigned pgrid = (unsigned)((P + 127) / 128);
+
+    unsigned long long roots = 0;
+    if (P) {
+        KTimer kt(ctx, SST_K_WINDOW_COUNT);
+        k_window_roots<false><<<pgrid, 128, 0, ctx->stream>>>(tv, pk, (uint8_t*)ctx->d_status.p, d_nroots, nullptr, nullptr);
+        kt.stop(1);
+        CK(cudaGetLastError());
+    }
+    if ((rc = scan_u64(ctx, d_nroots, P, d_rootoff))) return rc;
+    CK(cudaMemcpyAsync(&roots, d_rootoff + P, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if ((rc = reserve(ctx, ctx->d_rootv, (size_t)(roots + 1) * 4))) return rc;
+    if ((rc = reserve(ctx, ctx->d_rootpeak, (size_t)(roots + 1) * 4))) return rc;
+    if ((rc = reserve(ctx, ctx->d_cnt, (size_t)(roots + 1) * 8))) return rc;
+    if ((rc = reserve(ctx, ctx->d_compoff, (size_t)(roots + 2) * 8))) return rc;
+    auto* d_rootv = (uint32_t*)ctx->d_rootv.p;
+    auto* d_rootpeak = (uint32_t*)ctx->d_rootpeak.p;
+    auto* d_cnt = (unsigned long long*)ctx->d_cnt.p;
+    auto* d_compoff = (unsigned long long*)ctx->d_compoff.p;
+    if (roots) {
+        KTimer kt(ctx, SST_K_WINDOW_FILL);
+        k_window_roots<true><<<pgrid, 128, 0, ctx->stream>>>(tv, pk, nullptr, d_rootoff, d_rootv, d_rootpeak);
+        kt.stop(1);
+        CK(cudaGetLastError());
+    }
+
+    MemoMap mp{};
+    if (ctx->n_memo) {
+        uint64_t cap = memo_capacity ? memo_capacity : ((uint64_t)1 << 20);
+        uint64_t pow2 = 1024;
+        while (pow2 < cap) pow2 <<= 1;
+        if (pow2 > ((uint64_t)1 << 31)) return fail(ctx, SST_ERR_NOMEM, "memo capacity %llu too large", (unsigned long long)cap);
+        if ((rc = reserve(ctx, ctx->d_memo_keys, pow2 * 8))) return rc;
+        if ((rc = reserve(ctx, ctx->d_memo_alive, pow2 * 16))) return rc;
+        if ((rc = reserve(ctx, ctx->d_memo_top, pow2 * 4))) return rc;
+        if ((rc = reserve(ctx, ctx->d_memo_misc, 64))) return rc;
+        CK(cudaMemsetAsync(ctx->d_memo_keys.p, 0, pow2 * 8, ctx->stream));
+        CK(cudaMemsetAsync(ctx->d_memo_alive.p, 0, pow2 * 16, ctx->stream));
+        CK(cudaMemsetAsync(ctx->d_memo_top.p, 0, pow2 * 4, ctx->stream));
+        CK(cudaMemsetAsync(ctx->d_memo_misc.p, 0, 64, ctx->stream));
+        mp.keys = (unsigned long long*)ctx->d_memo_keys.p;
+        mp.alive = (uint4*)ctx->d_memo_alive.p;
+        mp.top = (uint32_t*)ctx->d_memo_top.p;
+        mp.cap_mask = (uint32_t)(pow2 - 1);
+        mp.fill = (unsigned int*)ctx->d_memo_misc.p;
+        mp.overflow = (int*)ctx->d_memo_misc.p + 1;
+        KTimer kt(ctx, SST_K_PHASE_A);
+        k_memo_phase_a<<<(unsigned)((ctx->n_memo + 63) / 64), 64, 0, ctx->stream>>>(tv, meta, pk, (const uint32_t*)ctx->d_memo_peaks.p,
+                                                                                   ctx->n_memo, mp);
+        kt.stop(1);
+        CK(cudaGetLastError());
+        int misc[2] = {0, 0};
+        CK(cudaMemcpyAsync(misc, ctx->d_memo_misc.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        if (misc[1]) return fail(ctx, SST_ERR_MEMO_FULL, "first-visit map with %llu slots is too small (%d used)", (unsigned long long)pow2, misc[0]);
+    }
+
+    unsigned long long comps = 0;
+    const unsigned rgrid = (unsigned)((roots + 127) / 128);
+    if (roots) {
+        KTimer kt(ctx, SST_K_ENUM_COUNT);
+        k_enumerate<false><<<rgrid, 128, 0, ctx->stream>>>(tv, meta, pk, d_rootv, d_rootpeak, (int64_t)roots, d_cnt, nullptr, rec_width, mp);
+        kt.stop(1);
+        CK(cudaGetLastError());
+    }
+    if ((rc = scan_u64(ctx, d_cnt, (int64_t)roots, d_compoff))) return rc;
+    CK(cudaMemcpyAsync(&comps, d_compoff + roots, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    size_t free_b = 0, total_b = 0;
+    CK(cudaMemGetInfo(&free_b, &total_b));
+    const unsigned long long need = comps * (unsigned long long)rec_width;
+    if (need > ctx->d_recs.cap && need > (unsigned long long)free_b + ctx->d_recs.cap)
+        return fail(ctx, SST_ERR_NOMEM, "%llu compositions x %d bytes do not fit in device memory (%zu bytes free)", comps, rec_width, free_b);
+    if ((rc = reserve(ctx, ctx->d_recs, (size_t)need + 8))) return rc;
+    if (roots && comps) {
+        KTimer kt(ctx, SST_K_ENUM_FILL);
+        k_enumerate<true><<<rgrid, 128, 0, ctx->stream>>>(tv, meta, pk, d_rootv, d_rootpeak, (int64_t)roots, d_compoff,
+                                                          (uint8_t*)ctx->d_recs.p, rec_width, mp);
+        kt.stop(1);
+        CK(cudaGetLastError());
+    }
+    {
+        KTimer kt(ctx, SST_K_PEAK_OFFSETS);
+        k_peak_offsets<<<(unsigned)((P + 1 + 127) / 128), 128, 0, ctx->stream>>>(d_rootoff, d_compoff, P, d_peakoff);
+        kt.stop(1);
+        CK(cudaGetLastError());
+    }
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->n_roots = roots;
+    ctx->n_comps = comps;
+    ctx->rec_width = rec_width;
+    ctx->have_result = true;
+    if (n_roots) *n_roots = roots;
+    if (n_comps) *n_comps = comps;
+    return SST_OK;
+}
+
+int sst_explain(sst_ctx* ctx, const sst_table* t, const int64_t* target, const int64_t* thr, const int32_t* max_mods,
+                const uint8_t* mode, int64_t P, const int32_t* ind, const uint8_t* is_mod, int rec_width,
+                uint64_t memo_capacity, uint64_t* n_roots, uint64_t* n_comps) {
+    int rc = sst_explain_stage(ctx, t, target, thr, max_mods, mode, P, ind, is_mod);
+    if (rc) return rc;
+    return sst_explain_run(ctx, t, rec_width, memo_capacity, n_roots, n_comps);
+}
+
+int sst_explain_fetch(sst_ctx* ctx, uint8_t* status, uint64_t* peak_off, uint8_t* recs) {
+    CK(cudaSetDevice(ctx->device));
+    if (!ctx->have_result) return fail(ctx, SST_ERR_STATE, "no enumeration result to fetch");
+    if (status && ctx->P) CK(cudaMemcpyAsync(status, ctx->d_status.p, (size_t)ctx->P, cudaMemcpyDeviceToHost, ctx->stream));
+    if (peak_off) CK(cudaMemcpyAsync(peak_off, ctx->d_peakoff.p, (size_t)(ctx->P + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    if (recs && ctx->n_comps)
+        CK(cudaMemcpyAsync(recs, ctx->d_recs.p, (size_t)ctx->n_comps * ctx->rec_width, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return SST_OK;
+}
+
+}  // extern "C"

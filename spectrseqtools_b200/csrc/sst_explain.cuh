@@ -1,0 +1,452 @@
+// K2a validity probe, K2b enumerator (+ first-visit budget pass), K3 integer window filter.
+//
+// Replaces is_valid_mass (reference mass_explanation.py:45-89) and explain_mass_with_table
+// (:92-203, inner backtrack :118-188).  Everything works on integer masses; the float -> integer
+// conversion stays on the host so it matches CPython bit for bit.
+//
+// Enumeration model.  The reference walks (mass m, row r): UP to (m, r-1) if bit0, LEFT to (m-w_r, r) if
+// bit1.  Because bit0(i,m) = OR_{r<i} bit1(r,m) (plus mass 0), the children of "mass m, rows <= rmax" are
+// exactly {(m - w_r, r) : r <= rmax, bit1(r, m)}: one 16-byte load of the mass-major mask H[m] replaces
+// the ~100 dependent UP reads per nucleotide.  A composition is emitted when the remainder hits 0.
+//
+// Budget modes (per peak):
+//   FREE   budgets cannot bind (host-checked): enabled edges = table bits.
+//   EXACT  with_memo=False: every path carries its own budgets (global `all`, per-row `ind`).
+//   MEMO   with_memo=True with binding budgets: the reference's memo is keyed (m, r) WITHOUT budgets, so
+//          each node is expanded once with the budgets of its first arrival in DFS order (UP before
+//          LEFT, window ascending).  Phase A replays that order sequentially per peak, one mass at a
+//          time (rows visited at a mass always form a contiguous range [r0(m), top(m)]), and records per
+//          mass the LEFT edges that were enabled AND lead to at least one solution.  Phase B is the same
+//          parallel path enumeration as FREE, reading those masks from a hash map instead of H.
+#pragma once
+#include "sst_common.cuh"
+
+namespace sst {
+
+enum : int { MODE_FREE = 0, MODE_EXACT = 1, MODE_MEMO = 2 };
+enum : int { ST_ZERO_IN_WINDOW = 1, ST_OUT_OF_TABLE = 2 };
+constexpr int kBudgetInf = 1 << 30;
+
+struct TableView {
+    const uint64_t* tbl;  // R x C, row-major (reference layout)
+    const uint4* H;       // C*32 row masks
+    const int32_t* weights;
+    int R;
+    int64_t C;
+};
+
+struct RowMeta {  // per-call budget metadata, device arrays of length R
+    const int32_t* ind;      // IND[r] = round(max_len * rate_r) (host, Python round)
+    const uint8_t* is_mod;   // 1 if the row is a modification
+};
+
+struct PeakBatch {
+    const int64_t* target;
+    const int64_t* thr;
+    const int32_t* max_mods;  // kBudgetInf for "unbounded"
+    const uint8_t* mode;
+    int64_t P;
+};
+
+// ---------------- first-visit memo map (MEMO mode) ----------------
+struct MemoMap {
+    unsigned long long* keys;  // 0 = empty, else ((peak+1) << 32) | mass
+    uint4* alive;              // enabled-and-productive LEFT edges of the visited rows
+    uint32_t* top;             // highest visited row at this mass
+    uint32_t cap_mask;         // capacity - 1 (power of two)
+    unsigned int* fill;        // occupied slots
+    int* overflow;             // set when the map is too small
+};
+
+__device__ __forceinline__ uint64_t mix64(uint64_t k) {
+    k ^= k >> 33; k *= 0xff51afd7ed558ccdULL; k ^= k >> 33; k *= 0xc4ceb9fe1a85ec53ULL; k ^= k >> 33;
+    return k;
+}
+__device__ __forceinline__ unsigned long long memo_key(int64_t peak, uint32_t m) {
+    return ((unsigned long long)(peak + 1) << 32) | m;
+}
+__device__ inline int memo_find(const MemoMap& mp, unsigned long long key) {
+    uint32_t h = (uint32_t)mix64(key) & mp.cap_mask;
+    for (uint32_t probes = 0; probes <= mp.cap_mask; probes++) {
+        unsigned long long k = mp.keys[h];
+        if (k == key) return (int)h;
+        if (k == 0ULL) return -1;
+        h = (h + 1) & mp.cap_mask;
+    }
+    return -1;
+}
+__device__ inline int memo_find_or_insert(const MemoMap& mp, unsigned long long key) {
+    uint32_t h = (uint32_t)mix64(key) & mp.cap_mask;
+    for (uint32_t probes = 0; probes < 4096; probes++) {
+        unsigned long long k = mp.keys[h];
+        if (k == key) return (int)h;
+        if (k == 0ULL) {
+            unsigned long long old = atomicCAS(mp.keys + h, 0ULL, key);
+            if (old == 0ULL) {
+                if (atomicAdd(mp.fill, 1u) > (mp.cap_mask >> 1) + (mp.cap_mask >> 2)) *mp.overflow = 1;
+                return (int)h;  // fresh slot: alive = 0, top = 0 (buffers are zeroed by the host)
+            }
+            if (old == key) return (int)h;
+        }
+        h = (h + 1) & mp.cap_mask;
+    }
+    *mp.overflow = 1;
+    return -1;
+}
+
+// ---------------- K2a: validity ----------------
+// out[p] = 0 not valid, 1 valid, 2 out-of-table value met before any hit (-> NotImplementedError)
+__global__ void k_is_valid(TableView tv, const int64_t* __restrict__ target, const int64_t* __restrict__ thr,
+                           int64_t P, uint8_t* __restrict__ out) {
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= P) return;
+    const int64_t limit = tv.C * 32;
+    const uint64_t* last = tv.tbl + (int64_t)(tv.R - 1) * tv.C;
+    const int64_t lo = target[p] - thr[p], hi = target[p] + thr[p];
+    int64_t a = lo < 1 ? 1 : lo;
+    const int64_t b = hi < limit - 1 ? hi : limit - 1;
+    uint8_t res = 0;
+    bool hit = false;
+    if (a <= b) {
+        for (int64_t wd = a >> 5; wd <= (b >> 5) && !hit; wd++) {
+            uint64_t x = __ldg(last + wd);
+            x = (x | (x >> 1)) & kBit0Mask;
+            if (wd == (a >> 5)) x &= (1ULL << (2 * (31 - (int)(a & 31)) + 1)) - 1ULL;
+            if (wd == (b >> 5)) x &= ~0ULL << (2 * (31 - (int)(b & 31)));
+            if (x) hit = true;
+        }
+    }
+    if (hit) res = 1;
+    else if (hi >= limit && hi >= 1 && lo <= hi) res = 2;
+    out[p] = res;
+}
+
+// ---------------- K3 + root discovery: integer window over the last row ----------------
+template <bool FILL>
+__global__ void k_window_roots(TableView tv, PeakBatch pk, uint8_t* __restrict__ status,
+                               unsigned long long* __restrict__ nroots_or_off, uint32_t* __restrict__ root_v,
+                               uint32_t* __restrict__ root_peak) {
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= pk.P) return;
+    const int64_t limit = tv.C * 32;
+    const uint64_t* last = tv.tbl + (int64_t)(tv.R - 1) * tv.C;
+    const int64_t lo = pk.target[p] - pk.thr[p], hi = pk.target[p] + pk.thr[p];
+    if (!FILL) {
+        uint8_t st = 0;
+        if (lo <= 0 && 0 <= hi) st |= ST_ZERO_IN_WINDOW;
+        if (lo <= hi && hi >= limit) st |= ST_OUT_OF_TABLE;
+        status[p] = st;
+    }
+    const int64_t a = lo < 1 ? 1 : lo;
+    const int64_t b = hi < limit - 1 ? hi : limit - 1;
+    unsigned long long n = 0;
+    unsigned long long off = FILL ? nroots_or_off[p] : 0ULL;
+    if (a <= b) {
+        for (int64_t wd = a >> 5; wd <= (b >> 5); wd++) {
+            uint64_t x = __ldg(last + wd);
+            x = (x | (x >> 1)) & kBit0Mask;
+            if (wd == (a >> 5)) x &= (1ULL << (2 * (31 - (int)(a & 31)) + 1)) - 1ULL;
+            if (wd == (b >> 5)) x &= ~0ULL << (2 * (31 - (int)(b & 31)));
+            if (FILL) {
+                while (x) {  // ascending mass = descending bit position
+                    const int pos = 63 - __clzll((long long)x);
+                    x &= ~(1ULL << pos);
+                    root_v[off] = (uint32_t)(wd * 32 + (31 - (pos >> 1)));
+                    root_peak[off] = (uint32_t)p;
+                    off++;
+                }
+            } else {
+                n += __popcll(x);
+            }
+        }
+    }
+    if (!FILL) nroots_or_off[p] = n;
+}
+
+// ---------------- MEMO phase A: sequential first-visit replay, one thread per peak ----------------
+__global__ void __launch_bounds__(64)
+k_memo_phase_a(TableView tv, RowMeta meta, PeakBatch pk, const uint32_t* __restrict__ memo_peaks, int n_memo,
+               MemoMap mp) {
+    __shared__ int32_t s_w[kMaxRows];
+    __shared__ int32_t s_ind[kMaxRows];
+    __shared__ uint8_t s_mod[kMaxRows];
+    for (int i = threadIdx.x; i < kMaxRows; i += blockDim.x) {
+        s_w[i] = i < tv.R ? tv.weights[i] : 0;
+        s_ind[i] = i < tv.R ? meta.ind[i] : 0;
+        s_mod[i] = i < tv.R ? meta.is_mod[i] : 0;
+    }
+    __syncthreads();
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_memo) return;
+    const int64_t p = memo_peaks[i];
+    const int64_t limit = tv.C * 32;
+    const uint64_t* last = tv.tbl + (int64_t)(tv.R - 1) * tv.C;
+    const int64_t lo = pk.target[p] - pk.thr[p], hi = pk.target[p] + pk.thr[p];
+    const int64_t a = lo < 1 ? 1 : lo;
+    const int64_t b = hi < limit - 1 ? hi : limit - 1;
+    const int top_row = tv.R - 1;
+
+    // explicit recursion stack (one frame per mass on the current path)
+    uint32_t f_m[kMaxDepth + 1];
+    int f_slot[kMaxDepth + 1];
+    uint8_t f_rin[kMaxDepth + 1], f_cur[kMaxDepth + 1];
+    int f_all[kMaxDepth + 1], f_ind[kMaxDepth + 1];
+    Mask128 f_pend[kMaxDepth + 1], f_new[kMaxDepth + 1];
+    int sp = 0;
+
+    // arrival at (m, r_in) with budgets; either answers from the map (returns false, sets alive) or
+    // opens a frame for the rows (top(m), r_in] that this arrival visits for the first time
+    auto arrive = [&](uint32_t m, int r_in, int all, int ind, bool& alive) -> bool {
+        alive = false;
+        const int slot = memo_find_or_insert(mp, memo_key(p, m));
+        if (slot < 0 || sp > kMaxDepth) {
+            *mp.overflow = 1;
+            return false;
+        }
+        const int top = (int)mp.top[slot];
+        if (top >= r_in) {
+            Mask128 A = mk(mp.alive[slot]);
+            mask_keep_le(A, r_in);
+            alive = !mask_empty(A);
+            return false;
+        }
+        Mask128 pend = mk(ld_nc_u4(tv.H + m));
+        mask_keep_le(pend, r_in);
+        mask_keep_gt(pend, top);
+        f_m[sp] = m; f_slot[sp] = slot; f_rin[sp] = (uint8_t)r_in; f_all[sp] = all; f_ind[sp] = ind;
+        f_pend[sp] = pend;
+        f_new[sp].w[0] = f_new[sp].w[1] = f_new[sp].w[2] = f_new[sp].w[3] = 0u;
+        sp++;
+        return true;
+    };
+
+    for (int64_t v = a; v <= b; v++) {
+        if (cell_bits(__ldg(last + (v >> 5)), v) == 0u) continue;
+        bool alive;
+        if (!arrive((uint32_t)v, top_row, pk.max_mods[p], s_ind[top_row], alive)) continue;
+        while (sp > 0) {
+            const int d = sp - 1;
+            if (mask_empty(f_pend[d])) {  // all new rows of this mass expanded: publish and return
+                const int slot = f_slot[d];
+                uint4 A = mp.alive[slot];
+                A.x |= f_new[d].w[0]; A.y |= f_new[d].w[1]; A.z |= f_new[d].w[2]; A.w |= f_new[d].w[3];
+                mp.alive[slot] = A;
+                mp.top[slot] = f_rin[d];
+                Mask128 t = mk(A);
+                mask_keep_le(t, f_rin[d]);
+                const bool ok = !mask_empty(t);
+                sp--;
+                if (sp > 0 && ok) mask_set(f_new[sp - 1], f_cur[sp - 1]);
+                continue;
+            }
+            const int r = mask_pop_lowest(f_pend[d]);  // LEFT edges fire in ascending row order (UP first)
+            f_cur[d] = (uint8_t)r;
+            const int ind_here = (r == f_rin[d]) ? f_ind[d] : s_ind[r];
+            const int mod = s_mod[r];
+            if (mod && !(f_all[d] > 0 && ind_here > 0)) continue;
+            const uint32_t m2 = f_m[d] - (uint32_t)s_w[r];
+            if (m2 == 0u) {
+                mask_set(f_new[d], r);
+                continue;
+            }
+            bool child_alive;
+            if (!arrive(m2, r, f_all[d] - mod, ind_here - mod, child_alive)) {
+                if (child_alive) mask_set(f_new[d], r);
+            }
+        }
+    }
+}
+
+// ---------------- K2b: path enumeration, one thread per root ----------------
+// COUNT pass writes the number of compositions under each root; after an exclusive scan the FILL pass
+// writes fixed-width records (W bytes, row indices ascending, 0-padded) at the scanned offsets, so the
+// output is grouped by peak, ordered by window value, deterministic, and needs no atomics.
+template <bool FILL>
+__global__ void __launch_bounds__(128)
+k_enumerate(TableView tv, RowMeta meta, PeakBatch pk, const uint32_t* __restrict__ root_v,
+            const uint32_t* __restrict__ root_peak, int64_t n_roots, unsigned long long* __restrict__ cnt_or_off,
+            uint8_t* __restrict__ recs, int W, MemoMap mp) {
+    __shared__ int32_t s_w[kMaxRows];
+    __shared__ int32_t s_ind[kMaxRows];
+    __shared__ uint8_t s_mod[kMaxRows];
+    for (int i = threadIdx.x; i < kMaxRows; i += blockDim.x) {
+        s_w[i] = i < tv.R ? tv.weights[i] : 0;
+        s_ind[i] = i < tv.R ? meta.ind[i] : 0;
+        s_mod[i] = i < tv.R ? meta.is_mod[i] : 0;
+    }
+    __syncthreads();
+    const int64_t root = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (root >= n_roots) return;
+    const uint32_t v = root_v[root];
+    const int64_t p = root_peak[root];
+    const int mode = pk.mode[p];
+
+    uint32_t l_m[kMaxDepth];
+    Mask128 l_mask[kMaxDepth];
+    uint8_t l_path[kMaxDepth];
+    int l_all[kMaxDepth], l_ind[kMaxDepth];
+
+    auto children = [&](uint32_t m, int rmax) -> Mask128 {
+        Mask128 c;
+        if (mode == MODE_MEMO) {
+            const int slot = memo_find(mp, memo_key(p, m));
+            if (slot >= 0) c = mk(mp.alive[slot]);
+            else c.w[0] = c.w[1] = c.w[2] = c.w[3] = 0u;
+        } else {
+            c = mk(ld_nc_u4(tv.H + m));
+        }
+        mask_keep_le(c, rmax);
+        return c;
+    };
+
+    unsigned long long count = 0;
+    unsigned long long out = FILL ? cnt_or_off[root] : 0ULL;
+    uint64_t packed = 0;  // W == 8 fast path: rows so far, ascending from byte 0
+    int d = 0;
+    l_m[0] = v;
+    l_mask[0] = children(v, tv.R - 1);
+    l_all[0] = pk.max_mods[p];
+    l_ind[0] = s_ind[tv.R - 1];
+    int rin = tv.R - 1;  // row by which the current level was entered (root: last row)
+    l_path[0] = 0;
+
+    for (;;) {
+        if (mask_empty(l_mask[d])) {
+            if (d == 0) break;
+            d--;
+            packed >>= 8;
+            rin = d == 0 ? tv.R - 1 : l_path[d - 1];
+            continue;
+        }
+        const int r = mask_pop_lowest(l_mask[d]);
+        int child_all = 0, child_ind = 0;
+        if (mode == MODE_EXACT) {
+            const int ind_here = (r == rin) ? l_ind[d] : s_ind[r];
+            const int mod = s_mod[r];
+            if (mod && !(l_all[d] > 0 && ind_here > 0)) continue;
+            child_all = l_all[d] - mod;
+            child_ind = ind_here - mod;
+        }
+        const uint32_t m2 = l_m[d] - (uint32_t)s_w[r];
+        if (m2 == 0u) {
+            if (FILL) {
+                uint8_t* rec = recs + out * (unsigned long long)W;
+                if (W == 8) {
+                    *reinterpret_cast<uint64_t*>(rec) = (packed << 8) | (uint64_t)r;
+                } else {
+                    l_path[d] = (uint8_t)r;
+                    for (int q = 0; q < W; q += 8) {
+                        uint64_t word = 0;
+#pragma unroll
+                        for (int i = 0; i < 8; i++) {
+                            const int idx = q + i;
+                            if (idx <= d) word |= (uint64_t)l_path[d - idx] << (8 * i);
+                        }
+                        *reinterpret_cast<uint64_t*>(rec + q) = word;
+                    }
+                }
+                out++;
+            }
+            count++;
+            continue;
+        }
+        if (d + 1 >= kMaxDepth) continue;  // cannot happen: host checks the depth bound before launch
+        l_path[d] = (uint8_t)r;
+        packed = (packed << 8) | (uint64_t)r;
+        d++;
+        rin = r;
+        l_m[d] = m2;
+        l_mask[d] = children(m2, r);
+        l_all[d] = child_all;
+        l_ind[d] = child_ind;
+    }
+    if (!FILL) cnt_or_off[root] = count;
+}
+
+// per-peak composition offsets: peak_off[p] = comp_off[root_off[p]], peak_off[P] = total
+__global__ void k_peak_offsets(const unsigned long long* __restrict__ root_off, const unsigned long long* __restrict__ comp_off,
+                               int64_t P, unsigned long long* __restrict__ peak_off) {
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p > P) return;
+    peak_off[p] = comp_off[root_off[p]];
+}
+
+// ---------------- exclusive scan of uint64 (three small kernels; out has n+1 entries) ----------------
+constexpr int kScanThreads = 256;
+constexpr int kScanItems = 8;
+constexpr int kScanBlock = kScanThreads * kScanItems;
+
+__device__ __forceinline__ unsigned long long block_exclusive_scan(unsigned long long x, unsigned long long* total) {
+    __shared__ unsigned long long s_warp[kScanThreads / 32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    unsigned long long incl = x;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        unsigned long long y = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+        if (lane >= o) incl += y;
+    }
+    if (lane == 31) s_warp[w] = incl;
+    __syncthreads();
+    if (w == 0) {
+        unsigned long long s = lane < kScanThreads / 32 ? s_warp[lane] : 0ULL;
+#pragma unroll
+        for (int o = 1; o < kScanThreads / 32; o <<= 1) {
+            unsigned long long y = __shfl_up_sync(0xFFFFFFFFu, s, o);
+            if (lane >= o) s += y;
+        }
+        if (lane < kScanThreads / 32) s_warp[lane] = s;
+    }
+    __syncthreads();
+    const unsigned long long before = w ? s_warp[w - 1] : 0ULL;
+    *total = s_warp[kScanThreads / 32 - 1];
+    __syncthreads();
+    return before + incl - x;
+}
+
+__global__ void __launch_bounds__(kScanThreads)
+k_scan_partials(const unsigned long long* __restrict__ in, int64_t n, unsigned long long* __restrict__ block_sums) {
+    const int64_t base = (int64_t)blockIdx.x * kScanBlock + (int64_t)threadIdx.x * kScanItems;
+    unsigned long long s = 0;
+#pragma unroll
+    for (int i = 0; i < kScanItems; i++)
+        if (base + i < n) s += in[base + i];
+    unsigned long long total;
+    block_exclusive_scan(s, &total);
+    if (threadIdx.x == 0) block_sums[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(kScanThreads)
+k_scan_block_sums(unsigned long long* __restrict__ block_sums, int64_t n_blocks) {
+    unsigned long long carry = 0;
+    for (int64_t base = 0; base < n_blocks; base += kScanThreads) {
+        const int64_t i = base + threadIdx.x;
+        const unsigned long long x = i < n_blocks ? block_sums[i] : 0ULL;
+        unsigned long long total;
+        const unsigned long long ex = block_exclusive_scan(x, &total);
+        if (i < n_blocks) block_sums[i] = carry + ex;
+        carry += total;
+    }
+}
+
+__global__ void __launch_bounds__(kScanThreads)
+k_scan_final(const unsigned long long* __restrict__ in, int64_t n, const unsigned long long* __restrict__ block_sums,
+             unsigned long long* __restrict__ out) {
+    const int64_t base = (int64_t)blockIdx.x * kScanBlock + (int64_t)threadIdx.x * kScanItems;
+    unsigned long long vals[kScanItems];
+    unsigned long long s = 0;
+#pragma unroll
+    for (int i = 0; i < kScanItems; i++) {
+        vals[i] = base + i < n ? in[base + i] : 0ULL;
+        s += vals[i];
+    }
+    unsigned long long total;
+    unsigned long long run = block_sums[blockIdx.x] + block_exclusive_scan(s, &total);
+#pragma unroll
+    for (int i = 0; i < kScanItems; i++) {
+        if (base + i < n) out[base + i] = run;
+        run += vals[i];
+        if (base + i == n - 1) out[n] = run;
+    }
+}
+
+}  // namespace sst

@@ -1,0 +1,276 @@
+"""Mass explanation on the B200 behind the reference's ``spectrseqtools.mass_explanation`` names.
+
+Scalar entry points keep the reference's signatures and result structures
+(``is_valid_mass`` mass_explanation.py:45-89, ``explain_mass_with_table`` :92-203,
+``explain_mass_with_recursion`` :206-284, ``convert_nucleotide_masses_to_names`` :287-320,
+``MassExplanations`` :12-14, ``MASS_NAMES`` :17-27, ``IS_MOD`` :29-42) so that prediction.py,
+skeleton_building.py and linear_program.py can consume them unchanged.  ``explain_masses`` and
+``are_valid_masses`` are the batched forms the GPU is built for: many (mass, threshold) pairs per call,
+results as CSR arrays, Python sets only on demand.
+
+Host work here is limited to what must match CPython bit for bit (float -> integer conversions, banker's
+rounding of budgets) and to shaping results.  All table reads, window scans and enumeration run in
+libsst_b200.so; without it (or without a B200) every call raises ``_cabi.DeviceUnavailable``.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+from itertools import chain, combinations_with_replacement, product
+from typing import Iterable, List, Optional, Sequence, Set, Tuple
+
+import numpy as np
+
+from . import _cabi
+from .mass_table import DynamicProgrammingTable
+from .masses import _INT_MASS_IS_MOD, _INT_MASS_NAMES
+
+
+@dataclass
+class MassExplanations:
+    explanations: Set[Tuple[str]]
+
+
+# integer mass -> representative nucleosides / modification flag, for the GLOBAL alphabet
+MASS_NAMES = {m: list(names) for m, names in _INT_MASS_NAMES.items()}
+IS_MOD = dict(_INT_MASS_IS_MOD)
+
+
+# ---------------------------------------------------------------- host-side integer conversions
+
+def _integerise(mass: float, threshold: Optional[float], dp_table) -> Tuple[int, int]:
+    """(target, threshold) in table units, the way mass_explanation.py:51-58 / :107-114 compute them."""
+    target = int(round(mass / dp_table.precision, 0))
+    if threshold is None:
+        threshold = dp_table.tolerance * mass
+    return target, int(np.ceil(threshold / dp_table.precision))
+
+
+def _budget_int(x) -> int:
+    """Budgets are only tested with ``> 0`` and decremented by one: ceil() keeps that behaviour for floats."""
+    if x is None:
+        return _cabi.BUDGET_INF
+    if isinstance(x, float) and (math.isinf(x) or math.isnan(x)):
+        return _cabi.BUDGET_INF if x > 0 or math.isnan(x) else 0
+    v = math.ceil(x)
+    return max(0, min(int(v), _cabi.BUDGET_INF))
+
+
+def _row_metadata(dp_table) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
+    """weights, is_mod, IND[r] = round(max_len * rate_r) (Python round, mass_explanation.py:158-161,200)."""
+    weights = np.array([m.mass for m in dp_table.masses], dtype=np.int64)
+    is_mod = np.array([1 if m.is_modification else 0 for m in dp_table.masses], dtype=np.uint8)
+    ind = np.array([_budget_int(round(dp_table.seq.max_len * m.modification_rate)) for m in dp_table.masses], dtype=np.int32)
+    return weights, is_mod, ind
+
+
+def _modes(weights, is_mod, ind, max_mods: np.ndarray, hi: np.ndarray, with_memo: bool) -> np.ndarray:
+    """Per-peak budget mode.  FREE when no composition inside the window can exhaust a budget."""
+    mod_rows = np.nonzero(is_mod[1:])[0] + 1
+    slow = _cabi.MODE_MEMO if with_memo else _cabi.MODE_EXACT
+    if len(mod_rows) == 0:
+        return np.zeros(len(hi), dtype=np.uint8)
+    w_mod = weights[mod_rows]
+    hi_pos = np.maximum(hi, 0)
+    most_mods = hi_pos // int(w_mod.min())  # most modified nucleotides any composition <= hi can hold
+    free = max_mods >= most_mods
+    # per-row: IND[r] >= hi // w_r for every modified row
+    need = hi_pos[:, None] // w_mod[None, :]
+    free &= (ind[mod_rows][None, :] >= need).all(axis=1)
+    return np.where(free, _cabi.MODE_FREE, slow).astype(np.uint8)
+
+
+# ---------------------------------------------------------------- batched API
+
+class ExplanationBatch:
+    """Result of ``explain_masses``: compositions of all peaks as fixed-width row-index records.
+
+    ``offsets[p] : offsets[p+1]`` are the records of peak p; each record holds table-row indices in
+    ascending order, 0-padded.  ``status`` carries the per-peak flags (zero in window / out of table).
+    """
+
+    def __init__(self, status, offsets, records, weights, names_by_row):
+        self.status, self.offsets, self.records = status, offsets, records
+        self.weights = weights
+        self._names_by_row = names_by_row
+
+    def __len__(self):
+        return len(self.status)
+
+    @property
+    def n_compositions(self) -> int:
+        return int(self.offsets[-1])
+
+    def counts(self) -> np.ndarray:
+        return np.diff(self.offsets)
+
+    def out_of_table(self, p: int) -> bool:
+        return bool(self.status[p] & _cabi.STATUS_OUT_OF_TABLE)
+
+    def has_solution(self, p: int) -> bool:
+        """False = the reference would return ``MassExplanations(None)``."""
+        return bool(self.status[p] & _cabi.STATUS_ZERO_IN_WINDOW) or self.offsets[p + 1] > self.offsets[p]
+
+    def rows(self, p: int) -> np.ndarray:
+        return self.records[self.offsets[p]:self.offsets[p + 1]]
+
+    def solutions(self, p: int) -> List[List[int]]:
+        """Integer-weight lists in ascending order, like the reference's ``solutions`` (:191-201)."""
+        recs = self.rows(p)
+        w = self.weights
+        out = [[int(w[r]) for r in rec if r] for rec in recs]
+        if self.status[p] & _cabi.STATUS_ZERO_IN_WINDOW:
+            out.append([])
+        return out
+
+    def explanations(self, p: int) -> MassExplanations:
+        if self.out_of_table(p):
+            raise _cabi.TableTooSmall("A value of the mass window is not in the DP table. Extend its size if you want to compute larger masses.")
+        return convert_nucleotide_masses_to_names(self.solutions(p))
+
+    def canonical(self, p: int) -> List[Tuple[int, ...]]:
+        """Sorted tuples of row indices (device-side canonical form for parity checks)."""
+        return sorted(tuple(int(r) for r in rec if r) for rec in self.rows(p))
+
+
+def _as_array(x, n, dtype=np.float64):
+    if x is None:
+        return None
+    a = np.asarray(x, dtype=dtype)
+    if a.ndim == 0:
+        a = np.full(n, a, dtype=dtype)
+    return a
+
+
+def explain_masses(masses: Sequence[float], dp_table: DynamicProgrammingTable, max_modifications=np.inf,
+                   thresholds=None, with_memo: bool = True, compression_rate: Optional[int] = None,
+                   fetch_records: bool = True) -> ExplanationBatch:
+    """Batched ``explain_mass_with_table``: one device pass for all masses.
+
+    ``max_modifications`` and ``thresholds`` may be scalars or per-mass sequences (``thresholds`` None =
+    relative ``dp_table.tolerance * mass``).
+    """
+    if compression_rate is not None and compression_rate != dp_table.compression_per_cell:
+        raise ValueError("compression_rate must match the table's compression_per_cell")
+    masses = [float(m) for m in masses]
+    P = len(masses)
+    thr_in = [None] * P if thresholds is None else ([thresholds] * P if np.ndim(thresholds) == 0 else list(thresholds))
+    mm_in = [max_modifications] * P if np.ndim(max_modifications) == 0 else list(max_modifications)
+    target = np.empty(P, dtype=np.int64)
+    thr = np.empty(P, dtype=np.int64)
+    for p in range(P):  # scalar Python arithmetic on purpose: must equal the reference's float ops
+        target[p], thr[p] = _integerise(masses[p], thr_in[p], dp_table)
+    max_mods = np.array([_budget_int(x) for x in mm_in], dtype=np.int32)
+    return _explain_integer(dp_table, target, thr, max_mods, with_memo, fetch_records)
+
+
+def _explain_integer(dp_table, target, thr, max_mods, with_memo=True, fetch_records=True) -> ExplanationBatch:
+    dev = dp_table.device_table()
+    ctx = dev.ctx
+    weights, is_mod, ind = _row_metadata(dp_table)
+    hi = target + thr
+    mode = _modes(weights, is_mod, ind, max_mods.astype(np.int64), hi, with_memo)
+    w_min = int(weights[1]) if len(weights) > 1 else 1
+    deepest = int(min(max(int(hi.max()) if len(hi) else 0, 0), dev.limit - 1) // w_min)
+    rec_width = 8 * max(1, -(-deepest // 8))
+    ctx.explain_stage(dev, target, thr, max_mods, mode, ind, is_mod)
+    cap = 0
+    while True:
+        try:
+            ctx.explain_run(dev, rec_width, cap)
+            break
+        except _cabi.MemoFull:
+            cap = (cap or (1 << 20)) * 4
+            if cap > (1 << 30):
+                raise
+    status, off, recs = ctx.explain_fetch(want_records=fetch_records)
+    names_by_row = [m.names for m in dp_table.masses]
+    return ExplanationBatch(status, off, recs, weights, names_by_row)
+
+
+def are_valid_masses(masses: Sequence[float], dp_table: DynamicProgrammingTable, thresholds=None) -> np.ndarray:
+    """Batched ``is_valid_mass`` -> uint8 array of _cabi.VALID_* codes (2 = out of table)."""
+    masses = [float(m) for m in masses]
+    P = len(masses)
+    thr_in = [None] * P if thresholds is None else ([thresholds] * P if np.ndim(thresholds) == 0 else list(thresholds))
+    target = np.empty(P, dtype=np.int64)
+    thr = np.empty(P, dtype=np.int64)
+    for p in range(P):
+        target[p], thr[p] = _integerise(masses[p], thr_in[p], dp_table)
+    dev = dp_table.device_table()
+    return dev.ctx.is_valid(dev, target, thr)
+
+
+# ---------------------------------------------------------------- reference-shaped scalar API
+
+def is_valid_mass(mass: float, dp_table: DynamicProgrammingTable, threshold: float = None) -> bool:
+    code = int(are_valid_masses([mass], dp_table, None if threshold is None else [threshold])[0])
+    if code == _cabi.VALID_OUT_OF_TABLE:
+        raise _cabi.TableTooSmall("A value of the mass window is not in the DP table. Extend its size if you want to compute larger masses.")
+    return code == _cabi.VALID_YES
+
+
+def explain_mass_with_table(mass: float, dp_table: DynamicProgrammingTable, max_modifications=np.inf,
+                            compression_rate=None, threshold=None, with_memo=True) -> MassExplanations:
+    """Return all possible combinations of nucleosides that could sum up to the given mass."""
+    batch = explain_masses([mass], dp_table, max_modifications=max_modifications,
+                           thresholds=None if threshold is None else [threshold], with_memo=with_memo,
+                           compression_rate=compression_rate)
+    return batch.explanations(0)
+
+
+def convert_nucleotide_masses_to_names(solutions: List[List[int]]) -> MassExplanations:
+    """Integer-weight lists -> set of name tuples (reference :287-320).
+
+    ``None`` when there is no solution at all; the empty solution contributes nothing; a weight shared by
+    several representatives expands into every multiset of their names.
+    """
+    if len(solutions) == 0:
+        return MassExplanations(None)
+    named = set()
+    for sol in solutions:
+        if len(sol) == 0:
+            continue
+        # one pool per run of equal weights; multiplicity = occurrences in the whole solution (as upstream)
+        runs = [(w, sol.count(w)) for i, w in enumerate(sol) if i == 0 or sol[i - 1] != w]
+        pools = [list(combinations_with_replacement(MASS_NAMES[w], k)) for w, k in runs]
+        named.update(tuple(chain.from_iterable(pick)) for pick in product(*pools))
+    return MassExplanations(named)
+
+
+def explain_mass_with_recursion(mass: float, dp_table: DynamicProgrammingTable, max_modifications=np.inf,
+                                threshold=None) -> MassExplanations:
+    """Table-free enumeration (reference :206-284).  A separate host algorithm the reference keeps for
+    cross-checking; it never touches the table and is not a GPU target."""
+    rows = dp_table.masses
+    weights = [r.mass for r in rows]
+    target, thr = _integerise(mass, threshold, dp_table)
+    max_len = dp_table.seq.max_len
+    cache = {}
+
+    def walk(remaining, start, used_all, used_ind):
+        if used_all > max_modifications or used_ind > round(max_len * rows[start].modification_rate):
+            return []
+        key = (remaining, start)
+        if key in cache:
+            return cache[key]
+        if abs(remaining) <= thr or remaining == 0:
+            return [[]]
+        if remaining < 0:
+            return []
+        found = []
+        for i in range(start, len(weights)):
+            w = weights[i]
+            mod = IS_MOD[w]
+            tails = walk(remaining - w, i, used_all + 1 if mod else used_all,
+                         0 if i != start else (used_ind + 1 if mod else used_ind))
+            found.extend([w] + t for t in tails)
+        cache[key] = found
+        return found
+
+    return convert_nucleotide_masses_to_names(walk(target, 1, 0, 0))
+
+
+def _sequence_length_bound_device(dp_table, direction: str) -> int:
+    raise NotImplementedError(
+        "compute_sequence_length_bound has no device kernel yet (SURVEY §8f N1); refusing to fall back to the CPU")
