@@ -66,6 +66,9 @@ int sst_timer_stop(sst_ctx* ctx, float* ms);
 /* device time of each kernel family accumulated since the last sst_stats_reset, and launches made */
 int sst_stats_reset(sst_ctx* ctx);
 int sst_kernel_ms(sst_ctx* ctx, float* ms /* [SST_K_COUNT_] */, uint64_t* launches /* [SST_K_COUNT_] */);
+/* blow-up guard: sst_explain fails with SST_ERR_NOMEM when one window value has more than `cap`
+ * compositions (default 2^26; the reference would simply never return on such inputs) */
+int sst_set_per_root_cap(sst_ctx* ctx, uint64_t cap);
 /* write `bytes` of device scratch (L2 flush between timed iterations) */
 int sst_flush_l2(sst_ctx* ctx, size_t bytes);
 
@@ -88,6 +91,10 @@ void sst_table_destroy(sst_ctx* ctx, sst_table* t);
 /* ---- validity: replaces is_valid_mass (mass_explanation.py:45-89) for P (target, threshold) pairs ---- */
 int sst_is_valid(sst_ctx* ctx, const sst_table* t, const int64_t* target, const int64_t* thr, int64_t P,
                  uint8_t* out /* P, SST_VALID_* */);
+/* the same in three steps (stage = H2D, run = kernel, fetch = D2H) for kernel-only timing */
+int sst_valid_stage(sst_ctx* ctx, const int64_t* target, const int64_t* thr, int64_t P);
+int sst_valid_run(sst_ctx* ctx, const sst_table* t);
+int sst_valid_fetch(sst_ctx* ctx, uint8_t* out);
 
 /* ---- enumeration: replaces explain_mass_with_table (mass_explanation.py:92-203) for P peaks ----
  * max_mods[p]: global modification budget (SST_BUDGET_INF = unbounded); mode[p]: SST_MODE_*;

@@ -30,9 +30,10 @@ KERNEL_SLOTS = ["build", "transpose", "is_valid", "window_count", "window_fill",
 
 EXPORTS = [
     "sst_ctx_create", "sst_ctx_destroy", "sst_last_error", "sst_device_info", "sst_host_alloc", "sst_host_free",
-    "sst_timer_start", "sst_timer_stop", "sst_stats_reset", "sst_kernel_ms", "sst_flush_l2",
+    "sst_timer_start", "sst_timer_stop", "sst_stats_reset", "sst_kernel_ms", "sst_flush_l2", "sst_set_per_root_cap",
     "sst_table_build", "sst_table_upload", "sst_table_rebuild", "sst_table_info", "sst_table_download",
-    "sst_table_download_masks", "sst_table_destroy", "sst_is_valid", "sst_explain", "sst_explain_stage",
+    "sst_table_download_masks", "sst_table_destroy", "sst_is_valid", "sst_valid_stage", "sst_valid_run",
+    "sst_valid_fetch", "sst_explain", "sst_explain_stage",
     "sst_explain_run", "sst_explain_fetch",
 ]
 
@@ -73,6 +74,7 @@ def load() -> C.CDLL:
             "sst_stats_reset": (C.c_int, [vp]),
             "sst_kernel_ms": (C.c_int, [vp, fp, u64p]),
             "sst_flush_l2": (C.c_int, [vp, C.c_size_t]),
+            "sst_set_per_root_cap": (C.c_int, [vp, C.c_uint64]),
             "sst_table_build": (C.c_int, [vp, i64p, C.c_int, C.c_int64, C.c_int, C.c_uint64, C.c_int, C.POINTER(vp)]),
             "sst_table_upload": (C.c_int, [vp, u64p, i64p, C.c_int, C.c_int64, C.POINTER(vp)]),
             "sst_table_rebuild": (C.c_int, [vp, vp]),
@@ -81,6 +83,9 @@ def load() -> C.CDLL:
             "sst_table_download_masks": (C.c_int, [vp, vp, C.c_int64, C.c_int64, u32p]),
             "sst_table_destroy": (None, [vp, vp]),
             "sst_is_valid": (C.c_int, [vp, vp, i64p, i64p, C.c_int64, u8p]),
+            "sst_valid_stage": (C.c_int, [vp, i64p, i64p, C.c_int64]),
+            "sst_valid_run": (C.c_int, [vp, vp]),
+            "sst_valid_fetch": (C.c_int, [vp, u8p]),
             "sst_explain": (C.c_int, [vp, vp, i64p, i64p, i32p, u8p, C.c_int64, i32p, u8p, C.c_int, C.c_uint64, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
             "sst_explain_stage": (C.c_int, [vp, vp, i64p, i64p, i32p, u8p, C.c_int64, i32p, u8p]),
             "sst_explain_run": (C.c_int, [vp, vp, C.c_int, C.c_uint64, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
@@ -165,6 +170,9 @@ class Context:
         self._check(self._lib.sst_kernel_ms(self._h, _p(ms), _p(n)))
         return {k: (float(ms[i]), int(n[i])) for i, k in enumerate(KERNEL_SLOTS)}
 
+    def set_per_root_cap(self, cap: int):
+        self._check(self._lib.sst_set_per_root_cap(self._h, C.c_uint64(cap)))
+
     def flush_l2(self, nbytes: int = 256 << 20):
         self._check(self._lib.sst_flush_l2(self._h, int(nbytes)))
 
@@ -193,6 +201,19 @@ class Context:
         t, h = _arr(target, np.int64), _arr(thr, np.int64)
         out = np.empty(len(t), dtype=np.uint8)
         self._check(self._lib.sst_is_valid(self._h, table._h, _p(t), _p(h), len(t), _p(out)))
+        return out
+
+    def valid_stage(self, target, thr):
+        t, h = _arr(target, np.int64), _arr(thr, np.int64)
+        self._check(self._lib.sst_valid_stage(self._h, _p(t), _p(h), len(t)))
+        self._staged_VP = len(t)
+
+    def valid_run(self, table: "DeviceTable"):
+        self._check(self._lib.sst_valid_run(self._h, table._h))
+
+    def valid_fetch(self) -> np.ndarray:
+        out = np.empty(self._staged_VP, dtype=np.uint8)
+        self._check(self._lib.sst_valid_fetch(self._h, _p(out)))
         return out
 
     def explain_stage(self, table: "DeviceTable", target, thr, max_mods, mode, ind, is_mod):

@@ -17,6 +17,8 @@ using namespace sst;
 
 namespace {
 
+constexpr int kMaxPending = 32;
+
 struct DevBuf {  // grow-only device scratch
     void* p = nullptr;
     size_t cap = 0;
@@ -47,7 +49,10 @@ struct sst_ctx {
     cudaDeviceProp prop{};
     char err[512] = {0};
     cudaEvent_t ev_a = nullptr, ev_b = nullptr;    // user stopwatch
-    cudaEvent_t kev[2 * 16] = {nullptr};            // per-launch brackets
+    cudaEvent_t kev[2 * 32] = {nullptr};            // pooled per-launch brackets
+    int pending_slot[32] = {0};
+    int n_pending = 0;
+    cudaEvent_t tev[2] = {nullptr, nullptr};        // table build stopwatch
     float k_ms[SST_K_COUNT_] = {0};
     uint64_t k_launches[SST_K_COUNT_] = {0};
     bool time_kernels = true;
@@ -61,9 +66,13 @@ struct sst_ctx {
     // results
     DevBuf d_status, d_nroots, d_rootoff, d_rootv, d_rootpeak, d_cnt, d_compoff, d_peakoff, d_recs, d_blocksums;
     DevBuf d_memo_keys, d_memo_alive, d_memo_top, d_memo_misc, d_flush;
+    DevBuf d_vtarget, d_vthr, d_vout;  // staged validity probes
+    int64_t VP = 0;
+    int* h_misc = nullptr;             // pinned: run summary read back with one copy
     uint64_t n_roots = 0, n_comps = 0;
     int rec_width = 0;
     bool have_result = false;
+    uint64_t per_root_cap = (uint64_t)1 << 26;
 };
 
 namespace {
@@ -103,38 +112,48 @@ int reserve(sst_ctx* ctx, DevBuf& b, size_t bytes) {
     return SST_OK;
 }
 
-struct KTimer {  // brackets one kernel family with events on the context stream
+struct KTimer {  // brackets one kernel family with a pair of pooled events; times are read in flush_timers
     sst_ctx* ctx;
-    int slot;
-    KTimer(sst_ctx* c, int s) : ctx(c), slot(s) {
-        if (ctx->time_kernels) cudaEventRecord(ctx->kev[0], ctx->stream);
+    int slot, idx;
+    KTimer(sst_ctx* c, int s) : ctx(c), slot(s), idx(-1) {
+        if (ctx->time_kernels && ctx->n_pending < kMaxPending) {
+            idx = ctx->n_pending++;
+            ctx->pending_slot[idx] = slot;
+            cudaEventRecord(ctx->kev[2 * idx], ctx->stream);
+        }
     }
     void stop(uint64_t launches = 1) {
         ctx->k_launches[slot] += launches;
-        if (ctx->time_kernels) {
-            cudaEventRecord(ctx->kev[1], ctx->stream);
-            cudaEventSynchronize(ctx->kev[1]);
-            float ms = 0.f;
-            cudaEventElapsedTime(&ms, ctx->kev[0], ctx->kev[1]);
-            ctx->k_ms[slot] += ms;
-        }
+        if (idx >= 0) cudaEventRecord(ctx->kev[2 * idx + 1], ctx->stream);
     }
 };
 
-// exclusive scan of n uint64 -> out[n+1]
-int scan_u64(sst_ctx* ctx, const unsigned long long* in, int64_t n, unsigned long long* out) {
-    if (n == 0) {
+// call after the stream has been synchronised
+void flush_timers(sst_ctx* ctx) {
+    for (int i = 0; i < ctx->n_pending; i++) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, ctx->kev[2 * i], ctx->kev[2 * i + 1]) == cudaSuccess) ctx->k_ms[ctx->pending_slot[i]] += ms;
+    }
+    ctx->n_pending = 0;
+    cudaGetLastError();
+}
+
+// exclusive scan of n uint64 -> out[n+1].  n_bound sizes the grid; if n_dev is given the kernels read the
+// real n (<= n_bound) from device memory, so no host round trip is needed between dependent passes.
+int scan_u64(sst_ctx* ctx, const unsigned long long* in, int64_t n_bound, const unsigned long long* n_dev,
+             unsigned long long* out) {
+    if (n_bound == 0) {
         CK(cudaMemsetAsync(out, 0, sizeof(unsigned long long), ctx->stream));
         return SST_OK;
     }
-    const int64_t n_blocks = (n + kScanBlock - 1) / kScanBlock;
+    const int64_t n_blocks = (n_bound + kScanBlock - 1) / kScanBlock;
     int rc = reserve(ctx, ctx->d_blocksums, (size_t)n_blocks * 8);
     if (rc) return rc;
     auto* bs = (unsigned long long*)ctx->d_blocksums.p;
     KTimer kt(ctx, SST_K_SCAN);
-    k_scan_partials<<<(unsigned)n_blocks, kScanThreads, 0, ctx->stream>>>(in, n, bs);
-    k_scan_block_sums<<<1, kScanThreads, 0, ctx->stream>>>(bs, n_blocks);
-    k_scan_final<<<(unsigned)n_blocks, kScanThreads, 0, ctx->stream>>>(in, n, bs, out);
+    k_scan_partials<<<(unsigned)n_blocks, kScanThreads, 0, ctx->stream>>>(in, n_bound, n_dev, bs);
+    k_scan_block_sums<<<1, kScanThreads, 0, ctx->stream>>>(bs, n_blocks, n_dev);
+    k_scan_final<<<(unsigned)n_blocks, kScanThreads, 0, ctx->stream>>>(in, n_bound, n_dev, bs, out);
     kt.stop(3);
     CK(cudaGetLastError());
     return SST_OK;
@@ -143,7 +162,7 @@ int scan_u64(sst_ctx* ctx, const unsigned long long* in, int64_t n, unsigned lon
 int launch_build(sst_ctx* ctx, sst_table* t) {
     const int NW = kBuildWarps;
     KTimer kt(ctx, SST_K_BUILD);
-    cudaEvent_t e0 = ctx->kev[2], e1 = ctx->kev[3];
+    cudaEvent_t e0 = ctx->tev[0], e1 = ctx->tev[1];
     CK(cudaEventRecord(e0, ctx->stream));
     if (t->step_min >= kTileWords) {
         CK(cudaMemsetAsync(t->d_flags, 0, (size_t)(t->n_tiles + 1) * sizeof(int), ctx->stream));
@@ -177,13 +196,14 @@ int launch_build(sst_ctx* ctx, sst_table* t) {
     kt.stop(1);
     CK(cudaEventSynchronize(e1));
     CK(cudaEventElapsedTime(&t->build_ms, e0, e1));
+    flush_timers(ctx);
     return SST_OK;
 }
 
 int launch_transpose(sst_ctx* ctx, sst_table* t) {
     if (!t->H) return SST_OK;
     KTimer kt(ctx, SST_K_TRANSPOSE);
-    cudaEvent_t e0 = ctx->kev[2], e1 = ctx->kev[3];
+    cudaEvent_t e0 = ctx->tev[0], e1 = ctx->tev[1];
     CK(cudaEventRecord(e0, ctx->stream));
     k_transpose_masks<<<(unsigned)t->n_tiles, 256, 0, ctx->stream>>>(t->tbl, t->R, t->C, t->H);
     CK(cudaGetLastError());
@@ -191,6 +211,7 @@ int launch_transpose(sst_ctx* ctx, sst_table* t) {
     kt.stop(1);
     CK(cudaEventSynchronize(e1));
     CK(cudaEventElapsedTime(&t->transpose_ms, e0, e1));
+    flush_timers(ctx);
     return SST_OK;
 }
 
@@ -275,6 +296,8 @@ int sst_ctx_create(int device, sst_ctx** out) {
     cudaEventCreate(&ctx->ev_a);
     cudaEventCreate(&ctx->ev_b);
     for (auto& e : ctx->kev) cudaEventCreate(&e);
+    for (auto& e : ctx->tev) cudaEventCreate(&e);
+    cudaHostAlloc((void**)&ctx->h_misc, 256, cudaHostAllocDefault);
     *out = ctx;
     return SST_OK;
 }
@@ -287,11 +310,13 @@ void sst_ctx_destroy(sst_ctx* ctx) {
                       &ctx->d_memo_peaks, &ctx->d_status, &ctx->d_nroots, &ctx->d_rootoff, &ctx->d_rootv,
                       &ctx->d_rootpeak, &ctx->d_cnt, &ctx->d_compoff, &ctx->d_peakoff, &ctx->d_recs,
                       &ctx->d_blocksums, &ctx->d_memo_keys, &ctx->d_memo_alive, &ctx->d_memo_top,
-                      &ctx->d_memo_misc, &ctx->d_flush};
+                      &ctx->d_memo_misc, &ctx->d_flush, &ctx->d_vtarget, &ctx->d_vthr, &ctx->d_vout};
+    if (ctx->h_misc) cudaFreeHost(ctx->h_misc);
     for (DevBuf* b : bufs) cudaFree(b->p);
     cudaEventDestroy(ctx->ev_a);
     cudaEventDestroy(ctx->ev_b);
     for (auto& e : ctx->kev) cudaEventDestroy(e);
+    for (auto& e : ctx->tev) cudaEventDestroy(e);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -350,6 +375,11 @@ int sst_kernel_ms(sst_ctx* ctx, float* ms, uint64_t* launches) {
         if (ms) ms[i] = ctx->k_ms[i];
         if (launches) launches[i] = ctx->k_launches[i];
     }
+    return SST_OK;
+}
+
+int sst_set_per_root_cap(sst_ctx* ctx, uint64_t cap) {
+    ctx->per_root_cap = cap ? cap : ((uint64_t)1 << 26);
     return SST_OK;
 }
 
@@ -455,24 +485,49 @@ void sst_table_destroy(sst_ctx* ctx, sst_table* t) {
     free_table(t);
 }
 
-int sst_is_valid(sst_ctx* ctx, const sst_table* t, const int64_t* target, const int64_t* thr, int64_t P, uint8_t* out) {
+int sst_valid_stage(sst_ctx* ctx, const int64_t* target, const int64_t* thr, int64_t P) {
     CK(cudaSetDevice(ctx->device));
-    if (P <= 0) return SST_OK;
+    if (P < 0) return fail(ctx, SST_ERR_BAD_ARG, "negative probe count");
     int rc;
-    if ((rc = reserve(ctx, ctx->d_target, (size_t)P * 8))) return rc;
-    if ((rc = reserve(ctx, ctx->d_thr, (size_t)P * 8))) return rc;
-    if ((rc = reserve(ctx, ctx->d_status, (size_t)P))) return rc;
-    ctx->have_result = false;  // the scratch is shared with the enumerator
-    CK(cudaMemcpyAsync(ctx->d_target.p, target, (size_t)P * 8, cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaMemcpyAsync(ctx->d_thr.p, thr, (size_t)P * 8, cudaMemcpyHostToDevice, ctx->stream));
-    KTimer kt(ctx, SST_K_IS_VALID);
-    k_is_valid<<<(unsigned)((P + 255) / 256), 256, 0, ctx->stream>>>(view_of(t), (const int64_t*)ctx->d_target.p,
-                                                                     (const int64_t*)ctx->d_thr.p, P, (uint8_t*)ctx->d_status.p);
-    kt.stop(1);
-    CK(cudaGetLastError());
-    CK(cudaMemcpyAsync(out, ctx->d_status.p, (size_t)P, cudaMemcpyDeviceToHost, ctx->stream));
+    if ((rc = reserve(ctx, ctx->d_vtarget, (size_t)(P ? P : 1) * 8))) return rc;
+    if ((rc = reserve(ctx, ctx->d_vthr, (size_t)(P ? P : 1) * 8))) return rc;
+    if ((rc = reserve(ctx, ctx->d_vout, (size_t)(P ? P : 1)))) return rc;
+    if (P) {
+        CK(cudaMemcpyAsync(ctx->d_vtarget.p, target, (size_t)P * 8, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(ctx->d_vthr.p, thr, (size_t)P * 8, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    ctx->VP = P;
+    return SST_OK;
+}
+
+int sst_valid_run(sst_ctx* ctx, const sst_table* t) {
+    CK(cudaSetDevice(ctx->device));
+    const int64_t P = ctx->VP;
+    if (P) {
+        KTimer kt(ctx, SST_K_IS_VALID);
+        k_is_valid<<<(unsigned)((P + 255) / 256), 256, 0, ctx->stream>>>(view_of(t), (const int64_t*)ctx->d_vtarget.p,
+                                                                         (const int64_t*)ctx->d_vthr.p, P, (uint8_t*)ctx->d_vout.p);
+        kt.stop(1);
+        CK(cudaGetLastError());
+    }
+    CK(cudaStreamSynchronize(ctx->stream));
+    flush_timers(ctx);
+    return SST_OK;
+}
+
+int sst_valid_fetch(sst_ctx* ctx, uint8_t* out) {
+    CK(cudaSetDevice(ctx->device));
+    if (ctx->VP) CK(cudaMemcpyAsync(out, ctx->d_vout.p, (size_t)ctx->VP, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     return SST_OK;
+}
+
+int sst_is_valid(sst_ctx* ctx, const sst_table* t, const int64_t* target, const int64_t* thr, int64_t P, uint8_t* out) {
+    int rc = sst_valid_stage(ctx, target, thr, P);
+    if (!rc) rc = sst_valid_run(ctx, t);
+    if (!rc) rc = sst_valid_fetch(ctx, out);
+    return rc;
 }
 
 int sst_explain_stage(sst_ctx* ctx, const sst_table* t, const int64_t* target, const int64_t* thr, const int32_t* max_mods,
@@ -535,11 +590,21 @@ int sst_explain_run(sst_ctx* ctx, const sst_table* t, int rec_width, uint64_t me
         if (deepest > kMaxDepth) return fail(ctx, SST_ERR_TOO_DEEP, "a composition may need %lld nucleotides (limit %d)", (long long)deepest, kMaxDepth);
         if (deepest > rec_width) return fail(ctx, SST_ERR_BAD_ARG, "a composition may need %lld nucleotides but rec_width is %d", (long long)deepest, rec_width);
     }
+    // The whole pass is enqueued without host round trips: the number of roots is bounded by the summed
+    // window sizes (known at stage time), later kernels read the real counts from device memory, and the
+    // record buffer keeps its capacity from earlier runs (the fill kernel refuses to overflow it).
+    const int64_t root_bound = ctx->window_total;
     int rc;
     if ((rc = reserve(ctx, ctx->d_status, (size_t)(P ? P : 1)))) return rc;
     if ((rc = reserve(ctx, ctx->d_nroots, (size_t)(P + 1) * 8))) return rc;
     if ((rc = reserve(ctx, ctx->d_rootoff, (size_t)(P + 2) * 8))) return rc;
     if ((rc = reserve(ctx, ctx->d_peakoff, (size_t)(P + 2) * 8))) return rc;
+    if ((rc = reserve(ctx, ctx->d_rootv, (size_t)(root_bound + 1) * 4))) return rc;
+    if ((rc = reserve(ctx, ctx->d_rootpeak, (size_t)(root_bound + 1) * 4))) return rc;
+    if ((rc = reserve(ctx, ctx->d_cnt, (size_t)(root_bound + 1) * 8))) return rc;
+    if ((rc = reserve(ctx, ctx->d_compoff, (size_t)(root_bound + 2) * 8))) return rc;
+    if ((rc = reserve(ctx, ctx->d_memo_misc, 64))) return rc;
+    if (!ctx->d_recs.p && (rc = reserve(ctx, ctx->d_recs, (size_t)64 << 20))) return rc;
     TableView tv = view_of(t);
     RowMeta meta{(const int32_t*)ctx->d_ind.p, (const uint8_t*)ctx->d_ismod.p};
     PeakBatch pk{(const int64_t*)ctx->d_target.p, (const int64_t*)ctx->d_thr.p, (const int32_t*)ctx->d_maxmods.p,
@@ -547,27 +612,23 @@ int sst_explain_run(sst_ctx* ctx, const sst_table* t, int rec_width, uint64_t me
     auto* d_nroots = (unsigned long long*)ctx->d_nroots.p;
     auto* d_rootoff = (unsigned long long*)ctx->d_rootoff.p;
     auto* d_peakoff = (unsigned long long*)ctx->d_peakoff.p;
+    auto* d_rootv = (uint32_t*)ctx->d_rootv.p;
+    auto* d_rootpeak = (uint32_t*)ctx->d_rootpeak.p;
+    auto* d_cnt = (unsigned long long*)ctx->d_cnt.p;
+    auto* d_compoff = (unsigned long long*)ctx->d_compoff.p;
+    int* d_flags = (int*)ctx->d_memo_misc.p;  // [0] memo fill, [1] memo overflow, [8] per-root cap hit, [9] records overflow
     const unsigned pgrid = (unsigned)((P + 127) / 128);
+    CK(cudaMemsetAsync(d_flags, 0, 64, ctx->stream));
 
-    unsigned long long roots = 0;
     if (P) {
         KTimer kt(ctx, SST_K_WINDOW_COUNT);
         k_window_roots<false><<<pgrid, 128, 0, ctx->stream>>>(tv, pk, (uint8_t*)ctx->d_status.p, d_nroots, nullptr, nullptr);
         kt.stop(1);
         CK(cudaGetLastError());
     }
-    if ((rc = scan_u64(ctx, d_nroots, P, d_rootoff))) return rc;
-    CK(cudaMemcpyAsync(&roots, d_rootoff + P, 8, cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
-    if ((rc = reserve(ctx, ctx->d_rootv, (size_t)(roots + 1) * 4))) return rc;
-    if ((rc = reserve(ctx, ctx->d_rootpeak, (size_t)(roots + 1) * 4))) return rc;
-    if ((rc = reserve(ctx, ctx->d_cnt, (size_t)(roots + 1) * 8))) return rc;
-    if ((rc = reserve(ctx, ctx->d_compoff, (size_t)(roots + 2) * 8))) return rc;
-    auto* d_rootv = (uint32_t*)ctx->d_rootv.p;
-    auto* d_rootpeak = (uint32_t*)ctx->d_rootpeak.p;
-    auto* d_cnt = (unsigned long long*)ctx->d_cnt.p;
-    auto* d_compoff = (unsigned long long*)ctx->d_compoff.p;
-    if (roots) {
+    if ((rc = scan_u64(ctx, d_nroots, P, nullptr, d_rootoff))) return rc;
+    const unsigned long long* d_nroots_total = d_rootoff + P;
+    if (P && root_bound) {
         KTimer kt(ctx, SST_K_WINDOW_FILL);
         k_window_roots<true><<<pgrid, 128, 0, ctx->stream>>>(tv, pk, nullptr, d_rootoff, d_rootv, d_rootpeak);
         kt.stop(1);
@@ -583,59 +644,77 @@ int sst_explain_run(sst_ctx* ctx, const sst_table* t, int rec_width, uint64_t me
         if ((rc = reserve(ctx, ctx->d_memo_keys, pow2 * 8))) return rc;
         if ((rc = reserve(ctx, ctx->d_memo_alive, pow2 * 16))) return rc;
         if ((rc = reserve(ctx, ctx->d_memo_top, pow2 * 4))) return rc;
-        if ((rc = reserve(ctx, ctx->d_memo_misc, 64))) return rc;
         CK(cudaMemsetAsync(ctx->d_memo_keys.p, 0, pow2 * 8, ctx->stream));
         CK(cudaMemsetAsync(ctx->d_memo_alive.p, 0, pow2 * 16, ctx->stream));
         CK(cudaMemsetAsync(ctx->d_memo_top.p, 0, pow2 * 4, ctx->stream));
-        CK(cudaMemsetAsync(ctx->d_memo_misc.p, 0, 64, ctx->stream));
         mp.keys = (unsigned long long*)ctx->d_memo_keys.p;
         mp.alive = (uint4*)ctx->d_memo_alive.p;
         mp.top = (uint32_t*)ctx->d_memo_top.p;
         mp.cap_mask = (uint32_t)(pow2 - 1);
-        mp.fill = (unsigned int*)ctx->d_memo_misc.p;
-        mp.overflow = (int*)ctx->d_memo_misc.p + 1;
+        mp.fill = (unsigned int*)d_flags;
+        mp.overflow = d_flags + 1;
         KTimer kt(ctx, SST_K_PHASE_A);
         k_memo_phase_a<<<(unsigned)((ctx->n_memo + 63) / 64), 64, 0, ctx->stream>>>(tv, meta, pk, (const uint32_t*)ctx->d_memo_peaks.p,
                                                                                    ctx->n_memo, mp);
         kt.stop(1);
         CK(cudaGetLastError());
-        int misc[2] = {0, 0};
-        CK(cudaMemcpyAsync(misc, ctx->d_memo_misc.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
-        CK(cudaStreamSynchronize(ctx->stream));
-        if (misc[1]) return fail(ctx, SST_ERR_MEMO_FULL, "first-visit map with %llu slots is too small (%d used)", (unsigned long long)pow2, misc[0]);
     }
 
-    unsigned long long comps = 0;
-    const unsigned rgrid = (unsigned)((roots + 127) / 128);
-    if (roots) {
+    // persistent-style grid: enough CTAs to fill the machine, grid-stride over the real root count
+    int64_t rgrid64 = (root_bound + 127) / 128;
+    const int64_t full = (int64_t)ctx->prop.multiProcessorCount * 16;
+    if (rgrid64 > full) rgrid64 = full;
+    const unsigned rgrid = (unsigned)(rgrid64 < 1 ? 1 : rgrid64);
+    if (root_bound) {
         KTimer kt(ctx, SST_K_ENUM_COUNT);
-        k_enumerate<false><<<rgrid, 128, 0, ctx->stream>>>(tv, meta, pk, d_rootv, d_rootpeak, (int64_t)roots, d_cnt, nullptr, rec_width, mp);
+        k_enumerate<false><<<rgrid, 128, 0, ctx->stream>>>(tv, meta, pk, d_rootv, d_rootpeak, d_nroots_total, d_cnt, nullptr,
+                                                           rec_width, mp, ctx->per_root_cap, 0ULL, d_flags + 8);
         kt.stop(1);
         CK(cudaGetLastError());
     }
-    if ((rc = scan_u64(ctx, d_cnt, (int64_t)roots, d_compoff))) return rc;
-    CK(cudaMemcpyAsync(&comps, d_compoff + roots, 8, cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
-    size_t free_b = 0, total_b = 0;
-    CK(cudaMemGetInfo(&free_b, &total_b));
-    const unsigned long long need = comps * (unsigned long long)rec_width;
-    if (need > ctx->d_recs.cap && need > (unsigned long long)free_b + ctx->d_recs.cap)
-        return fail(ctx, SST_ERR_NOMEM, "%llu compositions x %d bytes do not fit in device memory (%zu bytes free)", comps, rec_width, free_b);
-    if ((rc = reserve(ctx, ctx->d_recs, (size_t)need + 8))) return rc;
-    if (roots && comps) {
+    if ((rc = scan_u64(ctx, d_cnt, root_bound, d_nroots_total, d_compoff))) return rc;
+    auto run_fill = [&]() -> int {
+        if (!root_bound) return SST_OK;
         KTimer kt(ctx, SST_K_ENUM_FILL);
-        k_enumerate<true><<<rgrid, 128, 0, ctx->stream>>>(tv, meta, pk, d_rootv, d_rootpeak, (int64_t)roots, d_compoff,
-                                                          (uint8_t*)ctx->d_recs.p, rec_width, mp);
+        k_enumerate<true><<<rgrid, 128, 0, ctx->stream>>>(tv, meta, pk, d_rootv, d_rootpeak, d_nroots_total, d_compoff,
+                                                          (uint8_t*)ctx->d_recs.p, rec_width, mp, ~0ULL,
+                                                          (unsigned long long)(ctx->d_recs.cap / rec_width), d_flags + 8);
         kt.stop(1);
         CK(cudaGetLastError());
-    }
+        return SST_OK;
+    };
+    if ((rc = run_fill())) return rc;
     {
         KTimer kt(ctx, SST_K_PEAK_OFFSETS);
         k_peak_offsets<<<(unsigned)((P + 1 + 127) / 128), 128, 0, ctx->stream>>>(d_rootoff, d_compoff, P, d_peakoff);
         kt.stop(1);
         CK(cudaGetLastError());
     }
+    // one read-back: flags + the two totals
+    unsigned long long* h64 = (unsigned long long*)(ctx->h_misc + 16);
+    CK(cudaMemcpyAsync(ctx->h_misc, d_flags, 64, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(h64, d_nroots_total, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(h64 + 1, d_peakoff + P, 8, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
+    flush_timers(ctx);
+    const unsigned long long roots = h64[0], comps = h64[1];
+    if (ctx->n_memo && ctx->h_misc[1])
+        return fail(ctx, SST_ERR_MEMO_FULL, "first-visit map is too small (%d slots used)", ctx->h_misc[0]);
+    if (ctx->h_misc[8])
+        return fail(ctx, SST_ERR_NOMEM, "more than %llu compositions under a single window value: combinatorial blow-up (raise the cap with sst_set_per_root_cap)",
+                    (unsigned long long)ctx->per_root_cap);
+    if (ctx->h_misc[9]) {  // records did not fit: grow once and fill again
+        size_t free_b = 0, total_b = 0;
+        CK(cudaMemGetInfo(&free_b, &total_b));
+        const unsigned long long need = comps * (unsigned long long)rec_width;
+        if (need > (unsigned long long)free_b + ctx->d_recs.cap)
+            return fail(ctx, SST_ERR_NOMEM, "%llu compositions x %d bytes do not fit in device memory (%zu bytes free)", comps, rec_width, free_b);
+        if ((rc = reserve(ctx, ctx->d_recs, (size_t)need + (need >> 2) + 8))) return rc;
+        CK(cudaMemsetAsync(d_flags + 9, 0, sizeof(int), ctx->stream));
+        if ((rc = run_fill())) return rc;
+        CK(cudaStreamSynchronize(ctx->stream));
+        flush_timers(ctx);
+    }
     ctx->n_roots = roots;
     ctx->n_comps = comps;
     ctx->rec_width = rec_width;

@@ -264,8 +264,10 @@ k_memo_phase_a(TableView tv, RowMeta meta, PeakBatch pk, const uint32_t* __restr
 template <bool FILL>
 __global__ void __launch_bounds__(128)
 k_enumerate(TableView tv, RowMeta meta, PeakBatch pk, const uint32_t* __restrict__ root_v,
-            const uint32_t* __restrict__ root_peak, int64_t n_roots, unsigned long long* __restrict__ cnt_or_off,
-            uint8_t* __restrict__ recs, int W, MemoMap mp) {
+            const uint32_t* __restrict__ root_peak, const unsigned long long* __restrict__ n_roots_dev,
+            unsigned long long* __restrict__ cnt_or_off, uint8_t* __restrict__ recs, int W, MemoMap mp,
+            unsigned long long per_root_cap, unsigned long long rec_capacity, int* __restrict__ flags) {
+    // flags[0]: a root exceeded per_root_cap (COUNT); flags[1]: records do not fit rec_capacity (FILL)
     __shared__ int32_t s_w[kMaxRows];
     __shared__ int32_t s_ind[kMaxRows];
     __shared__ uint8_t s_mod[kMaxRows];
@@ -275,8 +277,12 @@ k_enumerate(TableView tv, RowMeta meta, PeakBatch pk, const uint32_t* __restrict
         s_mod[i] = i < tv.R ? meta.is_mod[i] : 0;
     }
     __syncthreads();
-    const int64_t root = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (root >= n_roots) return;
+    const int64_t n_roots = (int64_t)*n_roots_dev;
+    if (FILL && cnt_or_off[n_roots] > rec_capacity) {  // cnt_or_off = scanned offsets; [n_roots] = total
+        if (blockIdx.x == 0 && threadIdx.x == 0) flags[1] = 1;
+        return;
+    }
+    for (int64_t root = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; root < n_roots; root += (int64_t)gridDim.x * blockDim.x) {
     const uint32_t v = root_v[root];
     const int64_t p = root_peak[root];
     const int mode = pk.mode[p];
@@ -348,6 +354,10 @@ k_enumerate(TableView tv, RowMeta meta, PeakBatch pk, const uint32_t* __restrict
                 out++;
             }
             count++;
+            if (!FILL && count > per_root_cap) {  // combinatorial blow-up guard (the reference would never return)
+                flags[0] = 1;
+                break;
+            }
             continue;
         }
         if (d + 1 >= kMaxDepth) continue;  // cannot happen: host checks the depth bound before launch
@@ -361,6 +371,7 @@ k_enumerate(TableView tv, RowMeta meta, PeakBatch pk, const uint32_t* __restrict
         l_ind[d] = child_ind;
     }
     if (!FILL) cnt_or_off[root] = count;
+    }  // root loop
 }
 
 // per-peak composition offsets: peak_off[p] = comp_off[root_off[p]], peak_off[P] = total
@@ -404,7 +415,10 @@ __device__ __forceinline__ unsigned long long block_exclusive_scan(unsigned long
 }
 
 __global__ void __launch_bounds__(kScanThreads)
-k_scan_partials(const unsigned long long* __restrict__ in, int64_t n, unsigned long long* __restrict__ block_sums) {
+k_scan_partials(const unsigned long long* __restrict__ in, int64_t n, const unsigned long long* __restrict__ n_dev,
+                unsigned long long* __restrict__ block_sums) {
+    if (n_dev) n = (int64_t)*n_dev;
+    if ((int64_t)blockIdx.x * kScanBlock >= n && blockIdx.x > 0) return;
     const int64_t base = (int64_t)blockIdx.x * kScanBlock + (int64_t)threadIdx.x * kScanItems;
     unsigned long long s = 0;
 #pragma unroll
@@ -416,7 +430,8 @@ k_scan_partials(const unsigned long long* __restrict__ in, int64_t n, unsigned l
 }
 
 __global__ void __launch_bounds__(kScanThreads)
-k_scan_block_sums(unsigned long long* __restrict__ block_sums, int64_t n_blocks) {
+k_scan_block_sums(unsigned long long* __restrict__ block_sums, int64_t n_blocks, const unsigned long long* __restrict__ n_dev) {
+    if (n_dev) n_blocks = ((int64_t)*n_dev + kScanBlock - 1) / kScanBlock;
     unsigned long long carry = 0;
     for (int64_t base = 0; base < n_blocks; base += kScanThreads) {
         const int64_t i = base + threadIdx.x;
@@ -429,8 +444,14 @@ k_scan_block_sums(unsigned long long* __restrict__ block_sums, int64_t n_blocks)
 }
 
 __global__ void __launch_bounds__(kScanThreads)
-k_scan_final(const unsigned long long* __restrict__ in, int64_t n, const unsigned long long* __restrict__ block_sums,
-             unsigned long long* __restrict__ out) {
+k_scan_final(const unsigned long long* __restrict__ in, int64_t n, const unsigned long long* __restrict__ n_dev,
+             const unsigned long long* __restrict__ block_sums, unsigned long long* __restrict__ out) {
+    if (n_dev) n = (int64_t)*n_dev;
+    if (n == 0) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) out[0] = 0ULL;
+        return;
+    }
+    if ((int64_t)blockIdx.x * kScanBlock >= n) return;
     const int64_t base = (int64_t)blockIdx.x * kScanBlock + (int64_t)threadIdx.x * kScanItems;
     unsigned long long vals[kScanItems];
     unsigned long long s = 0;

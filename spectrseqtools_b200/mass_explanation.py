@@ -46,6 +46,24 @@ def _integerise(mass: float, threshold: Optional[float], dp_table) -> Tuple[int,
     return target, int(np.ceil(threshold / dp_table.precision))
 
 
+def _integerise_many(masses: np.ndarray, thresholds, dp_table) -> Tuple[np.ndarray, np.ndarray]:
+    """Vectorised ``_integerise``: IEEE division + round-half-even (np.rint == CPython round(x, 0)) + ceil,
+    element for element the same float operations as the scalar code (checked in tests/test_host.py)."""
+    masses = np.asarray(masses, dtype=np.float64)
+    precision = float(dp_table.precision)
+    target = np.rint(masses / precision).astype(np.int64)
+    rel = float(dp_table.tolerance) * masses
+    if thresholds is None:
+        thr_f = rel
+    else:
+        if np.ndim(thresholds) == 0:
+            thresholds = [thresholds] * len(masses)
+        t = np.array([np.nan if x is None else x for x in thresholds], dtype=np.float64) if not isinstance(thresholds, np.ndarray) else thresholds.astype(np.float64)
+        thr_f = np.where(np.isnan(t), rel, t)
+    thr = np.ceil(thr_f / precision).astype(np.int64)
+    return target, thr
+
+
 def _budget_int(x) -> int:
     """Budgets are only tested with ``> 0`` and decremented by one: ceil() keeps that behaviour for floats."""
     if x is None:
@@ -152,15 +170,13 @@ def explain_masses(masses: Sequence[float], dp_table: DynamicProgrammingTable, m
     """
     if compression_rate is not None and compression_rate != dp_table.compression_per_cell:
         raise ValueError("compression_rate must match the table's compression_per_cell")
-    masses = [float(m) for m in masses]
+    masses = np.asarray(masses, dtype=np.float64).reshape(-1)
     P = len(masses)
-    thr_in = [None] * P if thresholds is None else ([thresholds] * P if np.ndim(thresholds) == 0 else list(thresholds))
-    mm_in = [max_modifications] * P if np.ndim(max_modifications) == 0 else list(max_modifications)
-    target = np.empty(P, dtype=np.int64)
-    thr = np.empty(P, dtype=np.int64)
-    for p in range(P):  # scalar Python arithmetic on purpose: must equal the reference's float ops
-        target[p], thr[p] = _integerise(masses[p], thr_in[p], dp_table)
-    max_mods = np.array([_budget_int(x) for x in mm_in], dtype=np.int32)
+    target, thr = _integerise_many(masses, thresholds, dp_table)
+    if np.ndim(max_modifications) == 0:
+        max_mods = np.full(P, _budget_int(max_modifications), dtype=np.int32)
+    else:
+        max_mods = np.array([_budget_int(x) for x in max_modifications], dtype=np.int32)
     return _explain_integer(dp_table, target, thr, max_mods, with_memo, fetch_records)
 
 
@@ -190,13 +206,8 @@ def _explain_integer(dp_table, target, thr, max_mods, with_memo=True, fetch_reco
 
 def are_valid_masses(masses: Sequence[float], dp_table: DynamicProgrammingTable, thresholds=None) -> np.ndarray:
     """Batched ``is_valid_mass`` -> uint8 array of _cabi.VALID_* codes (2 = out of table)."""
-    masses = [float(m) for m in masses]
-    P = len(masses)
-    thr_in = [None] * P if thresholds is None else ([thresholds] * P if np.ndim(thresholds) == 0 else list(thresholds))
-    target = np.empty(P, dtype=np.int64)
-    thr = np.empty(P, dtype=np.int64)
-    for p in range(P):
-        target[p], thr[p] = _integerise(masses[p], thr_in[p], dp_table)
+    masses = np.asarray(masses, dtype=np.float64).reshape(-1)
+    target, thr = _integerise_many(masses, thresholds, dp_table)
     dev = dp_table.device_table()
     return dev.ctx.is_valid(dev, target, thr)
 

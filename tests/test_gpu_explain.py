@@ -108,8 +108,8 @@ def test_edge_cases():
     assert len(empty) == 0 and empty.n_compositions == 0
     assert len(ME.are_valid_masses([], dp)) == 0
     limit = dp.device_table().limit
-    masses = [0.0, -5.0, 1e-4, 0.305042, 305.042, (limit - 1) * 1e-3, limit * 1e-3, 633.169 * 35]
-    batch = ME.explain_masses(masses, dp, thresholds=[0.0, 0.0, 0.001, 0.0, 0.0, 0.0, 0.0, 0.0])
+    masses = [0.0, -5.0, 1e-4, 0.305042, 305.042, (limit - 1) * 1e-3, limit * 1e-3]
+    batch = ME.explain_masses(masses, dp, thresholds=[0.0, 0.0, 0.001, 0.0, 0.0, 0.0, 0.0])
     assert batch.explanations(0).explanations == set()          # only the empty composition
     assert batch.explanations(1).explanations is None           # negative window
     assert batch.explanations(2).explanations == set()          # 0 inside the window
@@ -119,7 +119,14 @@ def test_edge_cases():
     assert batch.out_of_table(6)
     with pytest.raises(NotImplementedError):
         batch.explanations(6)
-    assert batch.explanations(7).explanations is not None       # 35 x heaviest = max_mass, still in the table
+    assert ME.is_valid_mass(633.169 * 35, dp, 0.0) is True      # 35 x heaviest = max_mass, still in the table
+    ctx = dp.device_table().ctx
+    ctx.set_per_root_cap(1000)                                  # blow-up guard: 8-nt window has far more
+    try:
+        with pytest.raises(MemoryError):
+            ME.explain_masses([8 * 345.048], dp, thresholds=[0.01])
+    finally:
+        ctx.set_per_root_cap(0)
     with pytest.raises(ValueError):
         ME.explain_mass_with_table(305.042, dp, compression_rate=16)
 

@@ -85,6 +85,22 @@ def test_budget_conversion_and_modes():
     assert ME._modes(weights, is_mod, ind, np.array([1] * 6), hi, False).tolist() == [0, 0, 1, 1, 1, 0]
 
 
+def test_vectorised_integerisation_equals_scalar_python():
+    class T:
+        precision = 1e-3
+        tolerance = 10e-6
+
+    rng = np.random.default_rng(3)
+    masses = np.concatenate([rng.uniform(0, 23000, 20000), np.arange(0, 2000) * 1e-3 + 0.0005, [0.0, 329.05314, 1285.16888, -3.2]])
+    thr = np.concatenate([rng.uniform(0, 1.2, 10000), np.full(len(masses) - 10000, np.nan)])
+    t_vec, h_vec = ME._integerise_many(masses, thr, T)
+    for i in range(len(masses)):
+        t, h = ME._integerise(float(masses[i]), None if np.isnan(thr[i]) else float(thr[i]), T)
+        assert (t, h) == (int(t_vec[i]), int(h_vec[i])), (masses[i], thr[i])
+    t2, h2 = ME._integerise_many(masses, [None if np.isnan(v) else float(v) for v in thr], T)
+    assert np.array_equal(t2, t_vec) and np.array_equal(h2, h_vec)
+
+
 def test_convert_names_matches_reference_semantics():
     assert ME.convert_nucleotide_masses_to_names([]).explanations is None
     assert ME.convert_nucleotide_masses_to_names([[]]).explanations == set()
