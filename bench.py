@@ -366,7 +366,7 @@ def main():
     k2b_bytes = 16 * len(e_target) + 8 * (len(e_target) + 1) + 4 * int(batch.n_compositions) + comp_len + 8 * int(win_words)
     vwin_words = ((2 * v_thr + 1 + 31) // 32 + 1).sum()
     k2a_bytes = 17 * len(v_target) + 8 * int(vwin_words)
-    fam = ["window_count", "window_fill", "phase_a", "enum_count", "enum_fill", "scan", "peak_offsets"]
+    fam = ["window_count", "window_fill", "phase_a", "items", "enum_count", "enum_fill", "scan", "peak_offsets"]
     k2b_ms = sum(stats[k][0] for k in fam) / args.steps
     k2a_ms = stats["is_valid"][0] / args.steps
     kernels = {k: {"ms_per_step": v[0] / args.steps, "launches_per_step": v[1] / args.steps} for k, v in stats.items() if v[1]}

@@ -50,7 +50,7 @@ enum { SST_VALID_NO = 0, SST_VALID_YES = 1, SST_VALID_OUT_OF_TABLE = 2 };
 /* kernel slots of sst_kernel_ms */
 enum {
     SST_K_BUILD = 0, SST_K_TRANSPOSE, SST_K_IS_VALID, SST_K_WINDOW_COUNT, SST_K_WINDOW_FILL, SST_K_PHASE_A,
-    SST_K_ENUM_COUNT, SST_K_ENUM_FILL, SST_K_SCAN, SST_K_PEAK_OFFSETS, SST_K_COUNT_
+    SST_K_ENUM_COUNT, SST_K_ENUM_FILL, SST_K_SCAN, SST_K_PEAK_OFFSETS, SST_K_ITEMS, SST_K_COUNT_
 };
 
 /* ---- context ---- */

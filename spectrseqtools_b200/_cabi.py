@@ -26,7 +26,7 @@ STATUS_ZERO_IN_WINDOW, STATUS_OUT_OF_TABLE = 1, 2
 VALID_NO, VALID_YES, VALID_OUT_OF_TABLE = 0, 1, 2
 BUDGET_INF = 1 << 30
 KERNEL_SLOTS = ["build", "transpose", "is_valid", "window_count", "window_fill", "phase_a", "enum_count",
-                "enum_fill", "scan", "peak_offsets"]
+                "enum_fill", "scan", "peak_offsets", "items"]
 
 EXPORTS = [
     "sst_ctx_create", "sst_ctx_destroy", "sst_last_error", "sst_device_info", "sst_host_alloc", "sst_host_free",

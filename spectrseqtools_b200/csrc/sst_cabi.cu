@@ -32,7 +32,7 @@ struct sst_table {
     int32_t* d_weights = nullptr;
     int32_t* d_step = nullptr;
     int32_t* d_shift = nullptr;
-    int* d_flags = nullptr;  // n_tiles + 1 ints; the last one is the ticket
+    int* d_flags = nullptr;  // one completion flag per (tile, row group)
     int R = 0;
     int64_t C = 0;
     int n_tiles = 0;
@@ -65,6 +65,8 @@ struct sst_ctx {
     int64_t max_hi = 0;
     // results
     DevBuf d_status, d_nroots, d_rootoff, d_rootv, d_rootpeak, d_cnt, d_compoff, d_peakoff, d_recs, d_blocksums;
+    DevBuf d_itemoff, d_itemroot, d_itemr, d_icnt;
+    uint64_t item_capacity = 0, n_items = 0;
     DevBuf d_memo_keys, d_memo_alive, d_memo_top, d_memo_misc, d_flush;
     DevBuf d_vtarget, d_vthr, d_vout;  // staged validity probes
     int64_t VP = 0;
@@ -165,22 +167,22 @@ int launch_build(sst_ctx* ctx, sst_table* t) {
     cudaEvent_t e0 = ctx->tev[0], e1 = ctx->tev[1];
     CK(cudaEventRecord(e0, ctx->stream));
     if (t->step_min >= kTileWords) {
-        CK(cudaMemsetAsync(t->d_flags, 0, (size_t)(t->n_tiles + 1) * sizeof(int), ctx->stream));
+        CK(cudaMemsetAsync(t->d_flags, 0, (size_t)t->n_tiles * kBuildWarps * sizeof(int), ctx->stream));
         const int rpw = (t->R - 1 + NW - 1) / NW;
         // tiles further apart than this never wait on each other
         int64_t indep = (t->step_min - (kTileWords - 1)) / kTileWords;
         if (indep < 1) indep = 1;
-        int occ = 1;
         auto launch = [&](auto kern) -> cudaError_t {
+            int occ = 1;
             cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NW * 32, 0);
             if (occ < 1) occ = 1;
-            int64_t grid = (int64_t)ctx->prop.multiProcessorCount * occ;
+            int64_t grid = (int64_t)ctx->prop.multiProcessorCount * occ;  // all CTAs co-resident (cooperative launch)
             if (grid > indep) grid = indep;
             if (grid > t->n_tiles) grid = t->n_tiles;
             if (grid < 1) grid = 1;
-            kern<<<(unsigned)grid, NW * 32, 0, ctx->stream>>>(t->tbl, t->R, t->C, t->d_step, t->d_shift, t->last_mask,
-                                                              t->n_tiles, t->step_min, t->d_flags, t->d_flags + t->n_tiles);
-            return cudaGetLastError();
+            void* args[] = {(void*)&t->tbl, (void*)&t->R, (void*)&t->C, (void*)&t->d_step, (void*)&t->d_shift,
+                            (void*)&t->last_mask, (void*)&t->n_tiles, (void*)&t->d_flags};
+            return cudaLaunchCooperativeKernel((const void*)kern, dim3((unsigned)grid), dim3(NW * 32), args, 0, ctx->stream);
         };
         cudaError_t e;
         if (rpw <= 2) e = launch(k_build_table<2>);
@@ -240,7 +242,7 @@ int alloc_table(sst_ctx* ctx, sst_table* t, const int64_t* weights, int R, int64
     CK(cudaMalloc(&t->d_weights, (size_t)kMaxRows * 4));
     CK(cudaMalloc(&t->d_step, (size_t)kMaxRows * 4));
     CK(cudaMalloc(&t->d_shift, (size_t)kMaxRows * 4));
-    CK(cudaMalloc(&t->d_flags, (size_t)(t->n_tiles + 1) * sizeof(int)));
+    CK(cudaMalloc(&t->d_flags, (size_t)(t->n_tiles + 1) * kBuildWarps * sizeof(int)));
     CK(cudaMemcpyAsync(t->d_weights, w.data(), (size_t)R * 4, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(t->d_step, st.data(), (size_t)R * 4, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(t->d_shift, sh.data(), (size_t)R * 4, cudaMemcpyHostToDevice, ctx->stream));
@@ -310,7 +312,8 @@ void sst_ctx_destroy(sst_ctx* ctx) {
                       &ctx->d_memo_peaks, &ctx->d_status, &ctx->d_nroots, &ctx->d_rootoff, &ctx->d_rootv,
                       &ctx->d_rootpeak, &ctx->d_cnt, &ctx->d_compoff, &ctx->d_peakoff, &ctx->d_recs,
                       &ctx->d_blocksums, &ctx->d_memo_keys, &ctx->d_memo_alive, &ctx->d_memo_top,
-                      &ctx->d_memo_misc, &ctx->d_flush, &ctx->d_vtarget, &ctx->d_vthr, &ctx->d_vout};
+                      &ctx->d_memo_misc, &ctx->d_flush, &ctx->d_vtarget, &ctx->d_vthr, &ctx->d_vout,
+                      &ctx->d_itemoff, &ctx->d_itemroot, &ctx->d_itemr, &ctx->d_icnt};
     if (ctx->h_misc) cudaFreeHost(ctx->h_misc);
     for (DevBuf* b : bufs) cudaFree(b->p);
     cudaEventDestroy(ctx->ev_a);
@@ -592,7 +595,8 @@ int sst_explain_run(sst_ctx* ctx, const sst_table* t, int rec_width, uint64_t me
     }
     // The whole pass is enqueued without host round trips: the number of roots is bounded by the summed
     // window sizes (known at stage time), later kernels read the real counts from device memory, and the
-    // record buffer keeps its capacity from earlier runs (the fill kernel refuses to overflow it).
+    // item / record buffers keep their capacity from earlier runs (the fill kernels refuse to overflow
+    // them; the pass is then repeated once with larger buffers).
     const int64_t root_bound = ctx->window_total;
     int rc;
     if ((rc = reserve(ctx, ctx->d_status, (size_t)(P ? P : 1)))) return rc;
@@ -602,120 +606,158 @@ int sst_explain_run(sst_ctx* ctx, const sst_table* t, int rec_width, uint64_t me
     if ((rc = reserve(ctx, ctx->d_rootv, (size_t)(root_bound + 1) * 4))) return rc;
     if ((rc = reserve(ctx, ctx->d_rootpeak, (size_t)(root_bound + 1) * 4))) return rc;
     if ((rc = reserve(ctx, ctx->d_cnt, (size_t)(root_bound + 1) * 8))) return rc;
-    if ((rc = reserve(ctx, ctx->d_compoff, (size_t)(root_bound + 2) * 8))) return rc;
+    if ((rc = reserve(ctx, ctx->d_itemoff, (size_t)(root_bound + 2) * 8))) return rc;
     if ((rc = reserve(ctx, ctx->d_memo_misc, 64))) return rc;
     if (!ctx->d_recs.p && (rc = reserve(ctx, ctx->d_recs, (size_t)64 << 20))) return rc;
+    if (!ctx->item_capacity) ctx->item_capacity = (uint64_t)1 << 20;
     TableView tv = view_of(t);
     RowMeta meta{(const int32_t*)ctx->d_ind.p, (const uint8_t*)ctx->d_ismod.p};
     PeakBatch pk{(const int64_t*)ctx->d_target.p, (const int64_t*)ctx->d_thr.p, (const int32_t*)ctx->d_maxmods.p,
                  (const uint8_t*)ctx->d_mode.p, P};
-    auto* d_nroots = (unsigned long long*)ctx->d_nroots.p;
-    auto* d_rootoff = (unsigned long long*)ctx->d_rootoff.p;
-    auto* d_peakoff = (unsigned long long*)ctx->d_peakoff.p;
-    auto* d_rootv = (uint32_t*)ctx->d_rootv.p;
-    auto* d_rootpeak = (uint32_t*)ctx->d_rootpeak.p;
-    auto* d_cnt = (unsigned long long*)ctx->d_cnt.p;
-    auto* d_compoff = (unsigned long long*)ctx->d_compoff.p;
-    int* d_flags = (int*)ctx->d_memo_misc.p;  // [0] memo fill, [1] memo overflow, [8] per-root cap hit, [9] records overflow
     const unsigned pgrid = (unsigned)((P + 127) / 128);
-    CK(cudaMemsetAsync(d_flags, 0, 64, ctx->stream));
-
-    if (P) {
-        KTimer kt(ctx, SST_K_WINDOW_COUNT);
-        k_window_roots<false><<<pgrid, 128, 0, ctx->stream>>>(tv, pk, (uint8_t*)ctx->d_status.p, d_nroots, nullptr, nullptr);
-        kt.stop(1);
-        CK(cudaGetLastError());
-    }
-    if ((rc = scan_u64(ctx, d_nroots, P, nullptr, d_rootoff))) return rc;
-    const unsigned long long* d_nroots_total = d_rootoff + P;
-    if (P && root_bound) {
-        KTimer kt(ctx, SST_K_WINDOW_FILL);
-        k_window_roots<true><<<pgrid, 128, 0, ctx->stream>>>(tv, pk, nullptr, d_rootoff, d_rootv, d_rootpeak);
-        kt.stop(1);
-        CK(cudaGetLastError());
-    }
-
-    MemoMap mp{};
-    if (ctx->n_memo) {
-        uint64_t cap = memo_capacity ? memo_capacity : ((uint64_t)1 << 20);
-        uint64_t pow2 = 1024;
-        while (pow2 < cap) pow2 <<= 1;
-        if (pow2 > ((uint64_t)1 << 31)) return fail(ctx, SST_ERR_NOMEM, "memo capacity %llu too large", (unsigned long long)cap);
-        if ((rc = reserve(ctx, ctx->d_memo_keys, pow2 * 8))) return rc;
-        if ((rc = reserve(ctx, ctx->d_memo_alive, pow2 * 16))) return rc;
-        if ((rc = reserve(ctx, ctx->d_memo_top, pow2 * 4))) return rc;
-        CK(cudaMemsetAsync(ctx->d_memo_keys.p, 0, pow2 * 8, ctx->stream));
-        CK(cudaMemsetAsync(ctx->d_memo_alive.p, 0, pow2 * 16, ctx->stream));
-        CK(cudaMemsetAsync(ctx->d_memo_top.p, 0, pow2 * 4, ctx->stream));
-        mp.keys = (unsigned long long*)ctx->d_memo_keys.p;
-        mp.alive = (uint4*)ctx->d_memo_alive.p;
-        mp.top = (uint32_t*)ctx->d_memo_top.p;
-        mp.cap_mask = (uint32_t)(pow2 - 1);
-        mp.fill = (unsigned int*)d_flags;
-        mp.overflow = d_flags + 1;
-        KTimer kt(ctx, SST_K_PHASE_A);
-        k_memo_phase_a<<<(unsigned)((ctx->n_memo + 63) / 64), 64, 0, ctx->stream>>>(tv, meta, pk, (const uint32_t*)ctx->d_memo_peaks.p,
-                                                                                   ctx->n_memo, mp);
-        kt.stop(1);
-        CK(cudaGetLastError());
-    }
-
-    // persistent-style grid: enough CTAs to fill the machine, grid-stride over the real root count
-    int64_t rgrid64 = (root_bound + 127) / 128;
     const int64_t full = (int64_t)ctx->prop.multiProcessorCount * 16;
-    if (rgrid64 > full) rgrid64 = full;
-    const unsigned rgrid = (unsigned)(rgrid64 < 1 ? 1 : rgrid64);
-    if (root_bound) {
-        KTimer kt(ctx, SST_K_ENUM_COUNT);
-        k_enumerate<false><<<rgrid, 128, 0, ctx->stream>>>(tv, meta, pk, d_rootv, d_rootpeak, d_nroots_total, d_cnt, nullptr,
-                                                           rec_width, mp, ctx->per_root_cap, 0ULL, d_flags + 8);
-        kt.stop(1);
-        CK(cudaGetLastError());
-    }
-    if ((rc = scan_u64(ctx, d_cnt, root_bound, d_nroots_total, d_compoff))) return rc;
-    auto run_fill = [&]() -> int {
-        if (!root_bound) return SST_OK;
-        KTimer kt(ctx, SST_K_ENUM_FILL);
-        k_enumerate<true><<<rgrid, 128, 0, ctx->stream>>>(tv, meta, pk, d_rootv, d_rootpeak, d_nroots_total, d_compoff,
-                                                          (uint8_t*)ctx->d_recs.p, rec_width, mp, ~0ULL,
-                                                          (unsigned long long)(ctx->d_recs.cap / rec_width), d_flags + 8);
-        kt.stop(1);
-        CK(cudaGetLastError());
-        return SST_OK;
-    };
-    if ((rc = run_fill())) return rc;
-    {
-        KTimer kt(ctx, SST_K_PEAK_OFFSETS);
-        k_peak_offsets<<<(unsigned)((P + 1 + 127) / 128), 128, 0, ctx->stream>>>(d_rootoff, d_compoff, P, d_peakoff);
-        kt.stop(1);
-        CK(cudaGetLastError());
-    }
-    // one read-back: flags + the two totals
-    unsigned long long* h64 = (unsigned long long*)(ctx->h_misc + 16);
-    CK(cudaMemcpyAsync(ctx->h_misc, d_flags, 64, cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaMemcpyAsync(h64, d_nroots_total, 8, cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaMemcpyAsync(h64 + 1, d_peakoff + P, 8, cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
-    flush_timers(ctx);
-    const unsigned long long roots = h64[0], comps = h64[1];
-    if (ctx->n_memo && ctx->h_misc[1])
-        return fail(ctx, SST_ERR_MEMO_FULL, "first-visit map is too small (%d slots used)", ctx->h_misc[0]);
-    if (ctx->h_misc[8])
-        return fail(ctx, SST_ERR_NOMEM, "more than %llu compositions under a single window value: combinatorial blow-up (raise the cap with sst_set_per_root_cap)",
-                    (unsigned long long)ctx->per_root_cap);
-    if (ctx->h_misc[9]) {  // records did not fit: grow once and fill again
-        size_t free_b = 0, total_b = 0;
-        CK(cudaMemGetInfo(&free_b, &total_b));
-        const unsigned long long need = comps * (unsigned long long)rec_width;
-        if (need > (unsigned long long)free_b + ctx->d_recs.cap)
-            return fail(ctx, SST_ERR_NOMEM, "%llu compositions x %d bytes do not fit in device memory (%zu bytes free)", comps, rec_width, free_b);
-        if ((rc = reserve(ctx, ctx->d_recs, (size_t)need + (need >> 2) + 8))) return rc;
-        CK(cudaMemsetAsync(d_flags + 9, 0, sizeof(int), ctx->stream));
-        if ((rc = run_fill())) return rc;
+
+    unsigned long long roots = 0, items = 0, comps = 0;
+    for (int attempt = 0;; attempt++) {
+        const int64_t item_cap = (int64_t)ctx->item_capacity;
+        if ((rc = reserve(ctx, ctx->d_itemroot, (size_t)(item_cap + 1) * 4))) return rc;
+        if ((rc = reserve(ctx, ctx->d_itemr, (size_t)(item_cap + 1)))) return rc;
+        if ((rc = reserve(ctx, ctx->d_icnt, (size_t)(item_cap + 1) * 8))) return rc;
+        if ((rc = reserve(ctx, ctx->d_compoff, (size_t)(item_cap + 2) * 8))) return rc;
+        auto* d_nroots = (unsigned long long*)ctx->d_nroots.p;
+        auto* d_rootoff = (unsigned long long*)ctx->d_rootoff.p;
+        auto* d_peakoff = (unsigned long long*)ctx->d_peakoff.p;
+        auto* d_rootv = (uint32_t*)ctx->d_rootv.p;
+        auto* d_rootpeak = (uint32_t*)ctx->d_rootpeak.p;
+        auto* d_rcnt = (unsigned long long*)ctx->d_cnt.p;
+        auto* d_itemoff = (unsigned long long*)ctx->d_itemoff.p;
+        auto* d_itemroot = (uint32_t*)ctx->d_itemroot.p;
+        auto* d_itemr = (uint8_t*)ctx->d_itemr.p;
+        auto* d_icnt = (unsigned long long*)ctx->d_icnt.p;
+        auto* d_compoff = (unsigned long long*)ctx->d_compoff.p;
+        int* d_flags = (int*)ctx->d_memo_misc.p;  // [0] memo fill, [1] memo overflow, [8] per-item cap, [9] records overflow, [10] items overflow
+        CK(cudaMemsetAsync(d_flags, 0, 64, ctx->stream));
+
+        if (P) {
+            KTimer kt(ctx, SST_K_WINDOW_COUNT);
+            k_window_roots<false><<<pgrid, 128, 0, ctx->stream>>>(tv, pk, (uint8_t*)ctx->d_status.p, d_nroots, nullptr, nullptr);
+            kt.stop(1);
+            CK(cudaGetLastError());
+        }
+        if ((rc = scan_u64(ctx, d_nroots, P, nullptr, d_rootoff))) return rc;
+        const unsigned long long* d_nroots_total = d_rootoff + P;
+        if (P && root_bound) {
+            KTimer kt(ctx, SST_K_WINDOW_FILL);
+            k_window_roots<true><<<pgrid, 128, 0, ctx->stream>>>(tv, pk, nullptr, d_rootoff, d_rootv, d_rootpeak);
+            kt.stop(1);
+            CK(cudaGetLastError());
+        }
+
+        MemoMap mp{};
+        if (ctx->n_memo) {
+            uint64_t cap = memo_capacity ? memo_capacity : ((uint64_t)1 << 20);
+            uint64_t pow2 = 1024;
+            while (pow2 < cap) pow2 <<= 1;
+            if (pow2 > ((uint64_t)1 << 31)) return fail(ctx, SST_ERR_NOMEM, "memo capacity %llu too large", (unsigned long long)cap);
+            if ((rc = reserve(ctx, ctx->d_memo_keys, pow2 * 8))) return rc;
+            if ((rc = reserve(ctx, ctx->d_memo_alive, pow2 * 16))) return rc;
+            if ((rc = reserve(ctx, ctx->d_memo_top, pow2 * 4))) return rc;
+            CK(cudaMemsetAsync(ctx->d_memo_keys.p, 0, pow2 * 8, ctx->stream));
+            CK(cudaMemsetAsync(ctx->d_memo_alive.p, 0, pow2 * 16, ctx->stream));
+            CK(cudaMemsetAsync(ctx->d_memo_top.p, 0, pow2 * 4, ctx->stream));
+            mp.keys = (unsigned long long*)ctx->d_memo_keys.p;
+            mp.alive = (uint4*)ctx->d_memo_alive.p;
+            mp.top = (uint32_t*)ctx->d_memo_top.p;
+            mp.cap_mask = (uint32_t)(pow2 - 1);
+            mp.fill = (unsigned int*)d_flags;
+            mp.overflow = d_flags + 1;
+            KTimer kt(ctx, SST_K_PHASE_A);
+            k_memo_phase_a<<<(unsigned)((ctx->n_memo + 63) / 64), 64, 0, ctx->stream>>>(tv, meta, pk, (const uint32_t*)ctx->d_memo_peaks.p,
+                                                                                       ctx->n_memo, mp);
+            kt.stop(1);
+            CK(cudaGetLastError());
+        }
+
+        // persistent-style grids: enough CTAs to fill the machine, grid-stride over the real counts
+        int64_t g = (root_bound + 127) / 128;
+        const unsigned rgrid = (unsigned)(g < 1 ? 1 : (g > full ? full : g));
+        g = (item_cap + 127) / 128;
+        const unsigned igrid = (unsigned)(g < 1 ? 1 : (g > full ? full : g));
+        if (root_bound) {
+            KTimer kt(ctx, SST_K_ITEMS);
+            k_root_items<false><<<rgrid, 128, 0, ctx->stream>>>(tv, pk, d_rootv, d_rootpeak, d_nroots_total, d_rcnt, nullptr, nullptr, 0ULL, mp, d_flags + 8);
+            kt.stop(1);
+            CK(cudaGetLastError());
+        }
+        if ((rc = scan_u64(ctx, d_rcnt, root_bound, d_nroots_total, d_itemoff))) return rc;
+        // d_itemoff[n_roots] = number of items; its address depends on n_roots, so copy it to a fixed slot
+        {
+            KTimer kt(ctx, SST_K_ITEMS);
+            k_pick_total<<<1, 1, 0, ctx->stream>>>(d_itemoff, d_nroots_total, d_itemoff + root_bound + 1);
+            if (root_bound)
+                k_root_items<true><<<rgrid, 128, 0, ctx->stream>>>(tv, pk, d_rootv, d_rootpeak, d_nroots_total, d_itemoff, d_itemroot, d_itemr,
+                                                                   (unsigned long long)item_cap, mp, d_flags + 8);
+            kt.stop(2);
+            CK(cudaGetLastError());
+        }
+        const unsigned long long* d_nitems_total = d_itemoff + root_bound + 1;
+        {
+            KTimer kt(ctx, SST_K_ENUM_COUNT);
+            k_enumerate<false><<<igrid, 128, 0, ctx->stream>>>(tv, meta, pk, d_rootv, d_rootpeak, d_itemroot, d_itemr, d_nitems_total, d_icnt,
+                                                               nullptr, rec_width, mp, ctx->per_root_cap, 0ULL, (unsigned long long)item_cap, d_flags + 8);
+            kt.stop(1);
+            CK(cudaGetLastError());
+        }
+        if ((rc = scan_u64(ctx, d_icnt, item_cap, d_nitems_total, d_compoff))) return rc;
+        {
+            KTimer kt(ctx, SST_K_ENUM_FILL);
+            k_enumerate<true><<<igrid, 128, 0, ctx->stream>>>(tv, meta, pk, d_rootv, d_rootpeak, d_itemroot, d_itemr, d_nitems_total, d_compoff,
+                                                              (uint8_t*)ctx->d_recs.p, rec_width, mp, ~0ULL,
+                                                              (unsigned long long)(ctx->d_recs.cap / rec_width), (unsigned long long)item_cap, d_flags + 8);
+            kt.stop(1);
+            CK(cudaGetLastError());
+        }
+        {
+            KTimer kt(ctx, SST_K_PEAK_OFFSETS);
+            k_peak_offsets<<<(unsigned)((P + 1 + 127) / 128), 128, 0, ctx->stream>>>(d_rootoff, d_itemoff, d_compoff, P, (unsigned long long)item_cap, d_peakoff);
+            kt.stop(1);
+            CK(cudaGetLastError());
+        }
+        // one read-back: flags + the three totals
+        unsigned long long* h64 = (unsigned long long*)(ctx->h_misc + 16);
+        CK(cudaMemcpyAsync(ctx->h_misc, d_flags, 64, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(h64, d_nroots_total, 8, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(h64 + 1, d_nitems_total, 8, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(h64 + 2, d_peakoff + P, 8, cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
         flush_timers(ctx);
+        roots = h64[0];
+        items = h64[1];
+        comps = h64[2];
+        if (ctx->n_memo && ctx->h_misc[1])
+            return fail(ctx, SST_ERR_MEMO_FULL, "first-visit map is too small (%d slots used)", ctx->h_misc[0]);
+        if (ctx->h_misc[10]) {  // items did not fit: grow and run the pass again
+            if (attempt >= 2) return fail(ctx, SST_ERR_CUDA, "item buffer kept overflowing (%llu items)", items);
+            ctx->item_capacity = items + (items >> 2) + 1024;
+            continue;
+        }
+        if (ctx->h_misc[8])
+            return fail(ctx, SST_ERR_NOMEM, "more than %llu compositions under one (window value, first row) item: combinatorial blow-up (raise the cap with sst_set_per_root_cap)",
+                        (unsigned long long)ctx->per_root_cap);
+        if (ctx->h_misc[9]) {  // records did not fit: grow and run the pass again
+            if (attempt >= 3) return fail(ctx, SST_ERR_CUDA, "record buffer kept overflowing (%llu compositions)", comps);
+            size_t free_b = 0, total_b = 0;
+            CK(cudaMemGetInfo(&free_b, &total_b));
+            const unsigned long long need = comps * (unsigned long long)rec_width;
+            if (need > (unsigned long long)free_b + ctx->d_recs.cap)
+                return fail(ctx, SST_ERR_NOMEM, "%llu compositions x %d bytes do not fit in device memory (%zu bytes free)", comps, rec_width, free_b);
+            if ((rc = reserve(ctx, ctx->d_recs, (size_t)need + (need >> 2) + 8))) return rc;
+            continue;
+        }
+        break;
     }
     ctx->n_roots = roots;
+    ctx->n_items = items;
     ctx->n_comps = comps;
     ctx->rec_width = rec_width;
     ctx->have_result = true;

@@ -257,17 +257,67 @@ k_memo_phase_a(TableView tv, RowMeta meta, PeakBatch pk, const uint32_t* __restr
     }
 }
 
-// ---------------- K2b: path enumeration, one thread per root ----------------
-// COUNT pass writes the number of compositions under each root; after an exclusive scan the FILL pass
-// writes fixed-width records (W bytes, row indices ascending, 0-padded) at the scanned offsets, so the
-// output is grouped by peak, ordered by window value, deterministic, and needs no atomics.
+// ---------------- K2b: path enumeration ----------------
+// Work items.  A root is one window value v with a non-empty last-row cell; an ITEM is (root, first row
+// r1): the subtree of compositions whose largest row is r1.  Roots are expanded into items by
+// k_root_items (count -> scan -> fill), then k_enumerate walks one item per thread (count -> scan -> fill).
+// Splitting at the first level turns the long serial chain of a heavy root (every mask load of a DFS
+// depends on the previous pop) into many short chains, which is what the latency-bound 1-3 nt
+// production calls need; the output stays grouped by peak, ordered by (window value, first row, DFS
+// order), deterministic, and needs no atomics.
+
+__device__ __forceinline__ Mask128 child_mask(const TableView& tv, const MemoMap& mp, int mode, int64_t p, uint32_t m, int rmax) {
+    Mask128 c;
+    if (mode == MODE_MEMO) {
+        const int slot = memo_find(mp, memo_key(p, m));
+        if (slot >= 0) c = mk(mp.alive[slot]);
+        else c.w[0] = c.w[1] = c.w[2] = c.w[3] = 0u;
+    } else {
+        c = mk(ld_nc_u4(tv.H + m));
+    }
+    mask_keep_le(c, rmax);
+    return c;
+}
+
+template <bool FILL>
+__global__ void __launch_bounds__(128)
+k_root_items(TableView tv, PeakBatch pk, const uint32_t* __restrict__ root_v, const uint32_t* __restrict__ root_peak,
+             const unsigned long long* __restrict__ n_roots_dev, unsigned long long* __restrict__ cnt_or_off,
+             uint32_t* __restrict__ item_root, uint8_t* __restrict__ item_r, unsigned long long item_capacity,
+             MemoMap mp, int* __restrict__ flags) {
+    // flags[2]: items do not fit item_capacity (FILL)
+    const int64_t n_roots = (int64_t)*n_roots_dev;
+    if (FILL && cnt_or_off[n_roots] > item_capacity) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) flags[2] = 1;
+        return;
+    }
+    for (int64_t root = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; root < n_roots; root += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t p = root_peak[root];
+        Mask128 c = child_mask(tv, mp, pk.mode[p], p, root_v[root], tv.R - 1);
+        if (!FILL) {
+            cnt_or_off[root] = (unsigned long long)(__popc(c.w[0]) + __popc(c.w[1]) + __popc(c.w[2]) + __popc(c.w[3]));
+        } else {
+            unsigned long long off = cnt_or_off[root];
+            while (!mask_empty(c)) {
+                item_root[off] = (uint32_t)root;
+                item_r[off] = (uint8_t)mask_pop_lowest(c);
+                off++;
+            }
+        }
+    }
+}
+
+// COUNT pass writes the number of compositions under each item; after an exclusive scan the FILL pass
+// writes fixed-width records (W bytes, row indices ascending, 0-padded) at the scanned offsets.
 template <bool FILL>
 __global__ void __launch_bounds__(128)
 k_enumerate(TableView tv, RowMeta meta, PeakBatch pk, const uint32_t* __restrict__ root_v,
-            const uint32_t* __restrict__ root_peak, const unsigned long long* __restrict__ n_roots_dev,
+            const uint32_t* __restrict__ root_peak, const uint32_t* __restrict__ item_root,
+            const uint8_t* __restrict__ item_r, const unsigned long long* __restrict__ n_items_dev,
             unsigned long long* __restrict__ cnt_or_off, uint8_t* __restrict__ recs, int W, MemoMap mp,
-            unsigned long long per_root_cap, unsigned long long rec_capacity, int* __restrict__ flags) {
-    // flags[0]: a root exceeded per_root_cap (COUNT); flags[1]: records do not fit rec_capacity (FILL)
+            unsigned long long per_item_cap, unsigned long long rec_capacity, unsigned long long item_capacity,
+            int* __restrict__ flags) {
+    // flags[0]: an item exceeded per_item_cap (COUNT); flags[1]: records do not fit rec_capacity (FILL)
     __shared__ int32_t s_w[kMaxRows];
     __shared__ int32_t s_ind[kMaxRows];
     __shared__ uint8_t s_mod[kMaxRows];
@@ -277,76 +327,42 @@ k_enumerate(TableView tv, RowMeta meta, PeakBatch pk, const uint32_t* __restrict
         s_mod[i] = i < tv.R ? meta.is_mod[i] : 0;
     }
     __syncthreads();
-    const int64_t n_roots = (int64_t)*n_roots_dev;
-    if (FILL && cnt_or_off[n_roots] > rec_capacity) {  // cnt_or_off = scanned offsets; [n_roots] = total
+    const int64_t n_items = (int64_t)*n_items_dev;
+    if ((unsigned long long)n_items > item_capacity) return;  // item pass overflowed: the host repeats the run
+    if (FILL && cnt_or_off[n_items] > rec_capacity) {  // cnt_or_off = scanned offsets; [n_items] = total
         if (blockIdx.x == 0 && threadIdx.x == 0) flags[1] = 1;
         return;
     }
-    for (int64_t root = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; root < n_roots; root += (int64_t)gridDim.x * blockDim.x) {
-    const uint32_t v = root_v[root];
-    const int64_t p = root_peak[root];
-    const int mode = pk.mode[p];
+    const int top_row = tv.R - 1;
+    const uint32_t two_wmin = tv.R > 1 ? 2u * (uint32_t)s_w[1] : 0u;  // below this a remainder is ONE nucleotide
 
-    uint32_t l_m[kMaxDepth];
-    Mask128 l_mask[kMaxDepth];
-    uint8_t l_path[kMaxDepth];
-    int l_all[kMaxDepth], l_ind[kMaxDepth];
+    for (int64_t item = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; item < n_items; item += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t root = item_root[item];
+        const int64_t p = root_peak[root];
+        const int mode = pk.mode[p];
 
-    auto children = [&](uint32_t m, int rmax) -> Mask128 {
-        Mask128 c;
-        if (mode == MODE_MEMO) {
-            const int slot = memo_find(mp, memo_key(p, m));
-            if (slot >= 0) c = mk(mp.alive[slot]);
-            else c.w[0] = c.w[1] = c.w[2] = c.w[3] = 0u;
-        } else {
-            c = mk(ld_nc_u4(tv.H + m));
-        }
-        mask_keep_le(c, rmax);
-        return c;
-    };
+        uint32_t l_m[kMaxDepth];
+        Mask128 l_mask[kMaxDepth];
+        uint8_t l_path[kMaxDepth];
+        int l_all[kMaxDepth], l_ind[kMaxDepth];
 
-    unsigned long long count = 0;
-    unsigned long long out = FILL ? cnt_or_off[root] : 0ULL;
-    uint64_t packed = 0;  // W == 8 fast path: rows so far, ascending from byte 0
-    int d = 0;
-    l_m[0] = v;
-    l_mask[0] = children(v, tv.R - 1);
-    l_all[0] = pk.max_mods[p];
-    l_ind[0] = s_ind[tv.R - 1];
-    int rin = tv.R - 1;  // row by which the current level was entered (root: last row)
-    l_path[0] = 0;
+        unsigned long long count = 0;
+        unsigned long long out = FILL ? cnt_or_off[item] : 0ULL;
+        uint64_t packed = 0;  // W == 8 fast path: rows so far, ascending from byte 0
 
-    for (;;) {
-        if (mask_empty(l_mask[d])) {
-            if (d == 0) break;
-            d--;
-            packed >>= 8;
-            rin = d == 0 ? tv.R - 1 : l_path[d - 1];
-            continue;
-        }
-        const int r = mask_pop_lowest(l_mask[d]);
-        int child_all = 0, child_ind = 0;
-        if (mode == MODE_EXACT) {
-            const int ind_here = (r == rin) ? l_ind[d] : s_ind[r];
-            const int mod = s_mod[r];
-            if (mod && !(l_all[d] > 0 && ind_here > 0)) continue;
-            child_all = l_all[d] - mod;
-            child_ind = ind_here - mod;
-        }
-        const uint32_t m2 = l_m[d] - (uint32_t)s_w[r];
-        if (m2 == 0u) {
+        // write the composition l_path[0..n-1] (descending rows) as an ascending, 0-padded record
+        auto emit = [&](int n, uint64_t packed_rec) {
             if (FILL) {
                 uint8_t* rec = recs + out * (unsigned long long)W;
                 if (W == 8) {
-                    *reinterpret_cast<uint64_t*>(rec) = (packed << 8) | (uint64_t)r;
+                    *reinterpret_cast<uint64_t*>(rec) = packed_rec;
                 } else {
-                    l_path[d] = (uint8_t)r;
                     for (int q = 0; q < W; q += 8) {
                         uint64_t word = 0;
 #pragma unroll
                         for (int i = 0; i < 8; i++) {
                             const int idx = q + i;
-                            if (idx <= d) word |= (uint64_t)l_path[d - idx] << (8 * i);
+                            if (idx < n) word |= (uint64_t)l_path[n - 1 - idx] << (8 * i);
                         }
                         *reinterpret_cast<uint64_t*>(rec + q) = word;
                     }
@@ -354,32 +370,91 @@ k_enumerate(TableView tv, RowMeta meta, PeakBatch pk, const uint32_t* __restrict
                 out++;
             }
             count++;
-            if (!FILL && count > per_root_cap) {  // combinatorial blow-up guard (the reference would never return)
+        };
+
+        // level 0 is the root restricted to this item's first row: no mask load needed
+        int d = 0;
+        l_m[0] = root_v[root];
+        l_mask[0].w[0] = l_mask[0].w[1] = l_mask[0].w[2] = l_mask[0].w[3] = 0u;
+        mask_set(l_mask[0], item_r[item]);
+        l_all[0] = pk.max_mods[p];
+        l_ind[0] = s_ind[top_row];
+        int rin = top_row;  // row by which the current level was entered (root: last row)
+
+        for (;;) {
+            if (mask_empty(l_mask[d])) {
+                if (d == 0) break;
+                d--;
+                packed >>= 8;
+                rin = d == 0 ? top_row : l_path[d - 1];
+                continue;
+            }
+            const int r = mask_pop_lowest(l_mask[d]);
+            int child_all = 0, child_ind = 0;
+            if (mode == MODE_EXACT) {
+                const int ind_here = (r == rin) ? l_ind[d] : s_ind[r];
+                const int mod = s_mod[r];
+                if (mod && !(l_all[d] > 0 && ind_here > 0)) continue;
+                child_all = l_all[d] - mod;
+                child_ind = ind_here - mod;
+            }
+            const uint32_t m2 = l_m[d] - (uint32_t)s_w[r];
+            if (d + 2 >= kMaxDepth) continue;  // cannot happen: the host checks the depth bound before launch
+            l_path[d] = (uint8_t)r;
+            if (m2 == 0u) {
+                emit(d + 1, (packed << 8) | (uint64_t)r);
+            } else if (mode != MODE_MEMO && m2 < two_wmin) {
+                // the table bit says m2 is a sum of rows <= r, and it is too light for two: m2 == w_q, q <= r
+                int lo = 1, hi = r;
+                while (lo < hi) {
+                    const int mid = (lo + hi) >> 1;
+                    if ((uint32_t)s_w[mid] < m2) lo = mid + 1;
+                    else hi = mid;
+                }
+                const int q = lo;
+                bool ok = (uint32_t)s_w[q] == m2;
+                if (ok && mode == MODE_EXACT) {
+                    const int ind_q = (q == r) ? child_ind : s_ind[q];
+                    if (s_mod[q] && !(child_all > 0 && ind_q > 0)) ok = false;
+                }
+                if (ok) {
+                    l_path[d + 1] = (uint8_t)q;
+                    emit(d + 2, (((packed << 8) | (uint64_t)r) << 8) | (uint64_t)q);
+                }
+            } else {
+                packed = (packed << 8) | (uint64_t)r;
+                d++;
+                rin = r;
+                l_m[d] = m2;
+                l_mask[d] = child_mask(tv, mp, mode, p, m2, r);
+                l_all[d] = child_all;
+                l_ind[d] = child_ind;
+                continue;
+            }
+            if (!FILL && count > per_item_cap) {  // combinatorial blow-up guard (the reference would never return)
                 flags[0] = 1;
                 break;
             }
-            continue;
         }
-        if (d + 1 >= kMaxDepth) continue;  // cannot happen: host checks the depth bound before launch
-        l_path[d] = (uint8_t)r;
-        packed = (packed << 8) | (uint64_t)r;
-        d++;
-        rin = r;
-        l_m[d] = m2;
-        l_mask[d] = children(m2, r);
-        l_all[d] = child_all;
-        l_ind[d] = child_ind;
+        if (!FILL) cnt_or_off[item] = count;
     }
-    if (!FILL) cnt_or_off[root] = count;
-    }  // root loop
 }
 
-// per-peak composition offsets: peak_off[p] = comp_off[root_off[p]], peak_off[P] = total
-__global__ void k_peak_offsets(const unsigned long long* __restrict__ root_off, const unsigned long long* __restrict__ comp_off,
-                               int64_t P, unsigned long long* __restrict__ peak_off) {
+// copies totals[*index] to *out (a scanned total whose position is only known on the device)
+__global__ void k_pick_total(const unsigned long long* __restrict__ totals, const unsigned long long* __restrict__ index,
+                             unsigned long long* __restrict__ out) {
+    *out = totals[*index];
+}
+
+// per-peak composition offsets: peak_off[p] = comp_off[item_off[root_off[p]]], peak_off[P] = total
+__global__ void k_peak_offsets(const unsigned long long* __restrict__ root_off, const unsigned long long* __restrict__ item_off,
+                               const unsigned long long* __restrict__ comp_off, int64_t P, unsigned long long item_capacity,
+                               unsigned long long* __restrict__ peak_off) {
     const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (p > P) return;
-    peak_off[p] = comp_off[root_off[p]];
+    unsigned long long i = item_off[root_off[p]];
+    if (i > item_capacity) i = item_capacity;  // only after an item overflow; the host repeats the run
+    peak_off[p] = comp_off[i];
 }
 
 // ---------------- exclusive scan of uint64 (three small kernels; out has n+1 entries) ----------------
@@ -417,7 +492,7 @@ __device__ __forceinline__ unsigned long long block_exclusive_scan(unsigned long
 __global__ void __launch_bounds__(kScanThreads)
 k_scan_partials(const unsigned long long* __restrict__ in, int64_t n, const unsigned long long* __restrict__ n_dev,
                 unsigned long long* __restrict__ block_sums) {
-    if (n_dev) n = (int64_t)*n_dev;
+    if (n_dev && (int64_t)*n_dev < n) n = (int64_t)*n_dev;  // n is the allocation bound
     if ((int64_t)blockIdx.x * kScanBlock >= n && blockIdx.x > 0) return;
     const int64_t base = (int64_t)blockIdx.x * kScanBlock + (int64_t)threadIdx.x * kScanItems;
     unsigned long long s = 0;
@@ -431,7 +506,7 @@ k_scan_partials(const unsigned long long* __restrict__ in, int64_t n, const unsi
 
 __global__ void __launch_bounds__(kScanThreads)
 k_scan_block_sums(unsigned long long* __restrict__ block_sums, int64_t n_blocks, const unsigned long long* __restrict__ n_dev) {
-    if (n_dev) n_blocks = ((int64_t)*n_dev + kScanBlock - 1) / kScanBlock;
+    if (n_dev && ((int64_t)*n_dev + kScanBlock - 1) / kScanBlock < n_blocks) n_blocks = ((int64_t)*n_dev + kScanBlock - 1) / kScanBlock;
     unsigned long long carry = 0;
     for (int64_t base = 0; base < n_blocks; base += kScanThreads) {
         const int64_t i = base + threadIdx.x;
@@ -446,7 +521,7 @@ k_scan_block_sums(unsigned long long* __restrict__ block_sums, int64_t n_blocks,
 __global__ void __launch_bounds__(kScanThreads)
 k_scan_final(const unsigned long long* __restrict__ in, int64_t n, const unsigned long long* __restrict__ n_dev,
              const unsigned long long* __restrict__ block_sums, unsigned long long* __restrict__ out) {
-    if (n_dev) n = (int64_t)*n_dev;
+    if (n_dev && (int64_t)*n_dev < n) n = (int64_t)*n_dev;
     if (n == 0) {
         if (blockIdx.x == 0 && threadIdx.x == 0) out[0] = 0ULL;
         return;

@@ -11,8 +11,8 @@
 // Parallel form: per word j, T_i(j) = funnel(x_i(j-step_i-1), x_i(j-step_i)) with x = (word|word>>1)&0x55..
 // is the row's "bit1" contribution at even bit positions; bit0 of row i is reach_0 | OR_{i'<i} T_i'(j), a
 // prefix-OR over rows.  A tile = all rows x 32 consecutive words; tile t only reads words
-// <= 32t+31-step_min, i.e. tiles that are ~step_min/32 behind, so tiles are handed out in ascending
-// order by a ticket and each CTA checks per-tile completion flags before reading (no grid barrier).
+// <= 32t+31-step_min, i.e. tiles that are ~step_min/32 behind, so tiles are taken in ascending order and
+// completion flags are checked before reading (no grid barrier).
 #pragma once
 #include "sst_common.cuh"
 
@@ -24,33 +24,39 @@ constexpr int kTileWords = 32;
 template <int RPW>
 __global__ void __launch_bounds__(kBuildWarps * 32)
 k_build_table(uint64_t* __restrict__ tbl, int R, int64_t C, const int32_t* __restrict__ g_step,
-              const int32_t* __restrict__ g_shift, uint64_t last_mask, int n_tiles, int64_t step_min,
-              int* __restrict__ flags, int* __restrict__ ticket) {
-    __shared__ uint64_t s_tot[kBuildWarps][32];
+              const int32_t* __restrict__ g_shift, uint64_t last_mask, int n_tiles, int* __restrict__ flags) {
+    // flags[t * kBuildWarps + g] = 1 once row group g of tile t is stored.  Row r only ever reads row r
+    // of earlier tiles, so the hand-off is per (tile, row group): each warp polls the <= 2*RPW flags its
+    // own rows need and publishes its own flag; the only CTA-wide barrier is the prefix-OR exchange.
+    // Tiles are assigned round-robin (t = blockIdx + k*gridDim): the launch is cooperative so that all
+    // CTAs are co-resident and a waiting CTA can never starve the one it waits for.
+    __shared__ uint64_t s_tot[2][kBuildWarps][32];
     __shared__ int s_step[kMaxRows];
     __shared__ int s_shift[kMaxRows];
-    __shared__ int s_tile;
     const int lane = threadIdx.x & 31, g = threadIdx.x >> 5;
     for (int i = threadIdx.x; i < R; i += blockDim.x) {
         s_step[i] = g_step[i];
         s_shift[i] = g_shift[i];
     }
-    int checked = 0;  // tiles [0, checked) are known complete (uniform across the CTA)
-    for (;;) {
-        if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1);
-        __syncthreads();
-        const int t = s_tile;
-        if (t >= n_tiles) break;
-        const int64_t j = (int64_t)t * kTileWords + lane;
+    __syncthreads();
+    // which row does this lane poll for?  lanes [0,RPW) the tile of word (j0 - step - 1), lanes [16,16+RPW) of (j0 + 31 - step)
+    const int poll_k = lane & 15;
+    const int poll_r = 1 + g * RPW + poll_k;
+    const bool polls = poll_k < RPW && poll_r < R;
+    int buf = 0;
+    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, buf ^= 1) {
+        const int64_t j0 = (int64_t)t * kTileWords;
+        const int64_t j = j0 + lane;
 
-        // wait for every tile this one reads from
-        const int64_t max_src = (int64_t)t * kTileWords + (kTileWords - 1) - step_min;
-        int need = max_src >= 0 ? (int)(max_src / kTileWords) + 1 : 0;
-        for (int i = checked + threadIdx.x; i < need; i += blockDim.x)
-            while (ld_acquire(flags + i) == 0) {
+        if (polls) {
+            const int64_t src = (lane < 16) ? (j0 - s_step[poll_r] - 1) : (j0 + (kTileWords - 1) - s_step[poll_r]);
+            if (src >= 0) {
+                const int* f = flags + (src / kTileWords) * kBuildWarps + g;
+                while (ld_acquire(f) == 0) {
+                }
             }
-        if (need > checked) checked = need;
-        __syncthreads();
+        }
+        __syncwarp();
 
         // phase 1: gather every row's shifted reach word (independent L2 loads)
         uint64_t a[RPW], b0[RPW];
@@ -79,11 +85,11 @@ k_build_table(uint64_t* __restrict__ tbl, int R, int64_t C, const int32_t* __res
             T[k] = sh2 ? ((xa >> sh2) | (xb << (64 - sh2))) : xa;
             wtot |= T[k];
         }
-        // phase 2: prefix-OR across the row groups
-        s_tot[g][lane] = wtot;
+        // phase 2: prefix-OR across the row groups (double-buffered: one barrier per tile)
+        s_tot[buf][g][lane] = wtot;
         __syncthreads();
         uint64_t carry = (j == 0) ? 0x4000000000000000ULL : 0ULL;  // reach_0 = {0}
-        for (int gg = 0; gg < g; gg++) carry |= s_tot[gg][lane];
+        for (int gg = 0; gg < g; gg++) carry |= s_tot[buf][gg][lane];
         // phase 3: interleave and store
         if (j < C) {
             if (g == 0) {
@@ -102,10 +108,10 @@ k_build_table(uint64_t* __restrict__ tbl, int R, int64_t C, const int32_t* __res
                 }
             }
         }
-        __syncthreads();
-        if (threadIdx.x == 0) {
+        __syncwarp();
+        if (lane == 0) {
             __threadfence();
-            st_release(flags + t, 1);
+            st_release(flags + (int64_t)t * kBuildWarps + g, 1);
         }
     }
 }
