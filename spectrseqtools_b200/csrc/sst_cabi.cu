@@ -162,19 +162,22 @@ int scan_u64(sst_ctx* ctx, const unsigned long long* in, int64_t n_bound, const 
 }
 
 int launch_build(sst_ctx* ctx, sst_table* t) {
-    const int NW = kBuildWarps;
     KTimer kt(ctx, SST_K_BUILD);
     cudaEvent_t e0 = ctx->tev[0], e1 = ctx->tev[1];
     CK(cudaEventRecord(e0, ctx->stream));
     if (t->step_min >= kTileWords) {
-        CK(cudaMemsetAsync(t->d_flags, 0, (size_t)t->n_tiles * kBuildWarps * sizeof(int), ctx->stream));
-        const int rpw = (t->R - 1 + NW - 1) / NW;
+        CK(cudaMemsetAsync(t->d_flags, 0, (size_t)t->n_tiles * kBuildMaxWarps * sizeof(int), ctx->stream));
+        // rows per warp: the smallest of {1,2,4,8} that covers the rows with at most 16 warps
+        int rpw = 1;
+        while ((t->R - 1 + rpw - 1) / rpw > kBuildMaxWarps) rpw *= 2;
+        int nwarps = (t->R - 1 + rpw - 1) / rpw;
+        if (nwarps < 1) nwarps = 1;
         // tiles further apart than this never wait on each other
         int64_t indep = (t->step_min - (kTileWords - 1)) / kTileWords;
         if (indep < 1) indep = 1;
         auto launch = [&](auto kern) -> cudaError_t {
             int occ = 1;
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NW * 32, 0);
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, nwarps * 32, 0);
             if (occ < 1) occ = 1;
             int64_t grid = (int64_t)ctx->prop.multiProcessorCount * occ;  // all CTAs co-resident (cooperative launch)
             if (grid > indep) grid = indep;
@@ -182,13 +185,13 @@ int launch_build(sst_ctx* ctx, sst_table* t) {
             if (grid < 1) grid = 1;
             void* args[] = {(void*)&t->tbl, (void*)&t->R, (void*)&t->C, (void*)&t->d_step, (void*)&t->d_shift,
                             (void*)&t->last_mask, (void*)&t->n_tiles, (void*)&t->d_flags};
-            return cudaLaunchCooperativeKernel((const void*)kern, dim3((unsigned)grid), dim3(NW * 32), args, 0, ctx->stream);
+            return cudaLaunchCooperativeKernel((const void*)kern, dim3((unsigned)grid), dim3(nwarps * 32), args, 0, ctx->stream);
         };
         cudaError_t e;
-        if (rpw <= 2) e = launch(k_build_table<2>);
-        else if (rpw <= 4) e = launch(k_build_table<4>);
-        else if (rpw <= 8) e = launch(k_build_table<8>);
-        else e = launch(k_build_table<16>);
+        if (rpw == 1) e = launch(k_build_table<1>);
+        else if (rpw == 2) e = launch(k_build_table<2>);
+        else if (rpw == 4) e = launch(k_build_table<4>);
+        else e = launch(k_build_table<8>);
         CK(e);
     } else {
         k_build_table_small<<<1, 1024, 0, ctx->stream>>>(t->tbl, t->R, t->C, t->d_step, t->d_shift, t->last_mask);
@@ -223,6 +226,7 @@ int alloc_table(sst_ctx* ctx, sst_table* t, const int64_t* weights, int R, int64
     for (int i = 1; i < R; i++)
         if (weights[i] <= weights[i - 1]) return fail(ctx, SST_ERR_BAD_ARG, "weights must be strictly ascending");
     if (C < 1 || C * 32 >= ((int64_t)1 << 31)) return fail(ctx, SST_ERR_BAD_ARG, "table width %lld words out of range", (long long)C);
+    if ((int64_t)R * C >= ((int64_t)1 << 31)) return fail(ctx, SST_ERR_NOMEM, "table of %d x %lld words exceeds the 2^31-word limit of the build kernel", R, (long long)C);
     t->R = R;
     t->C = C;
     t->n_tiles = (int)((C + kTileWords - 1) / kTileWords);
@@ -242,7 +246,7 @@ int alloc_table(sst_ctx* ctx, sst_table* t, const int64_t* weights, int R, int64
     CK(cudaMalloc(&t->d_weights, (size_t)kMaxRows * 4));
     CK(cudaMalloc(&t->d_step, (size_t)kMaxRows * 4));
     CK(cudaMalloc(&t->d_shift, (size_t)kMaxRows * 4));
-    CK(cudaMalloc(&t->d_flags, (size_t)(t->n_tiles + 1) * kBuildWarps * sizeof(int)));
+    CK(cudaMalloc(&t->d_flags, (size_t)(t->n_tiles + 1) * kBuildMaxWarps * sizeof(int)));
     CK(cudaMemcpyAsync(t->d_weights, w.data(), (size_t)R * 4, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(t->d_step, st.data(), (size_t)R * 4, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(t->d_shift, sh.data(), (size_t)R * 4, cudaMemcpyHostToDevice, ctx->stream));
