@@ -289,20 +289,24 @@ def main():
                                "algorithmic_bytes": table_bytes + mask_bytes},
     }
 
-    # ---- stage the batch (inputs resident in HBM for `value`)
-    v_target, v_thr = ME._integerise_many(wl.valid_mass, wl.valid_thr, dp)
+    # ---- stage the batch (inputs resident in HBM for `value`); host inputs live in pinned memory
+    def pinned_copy(a):
+        out = ctx.pinned_empty(a.shape, a.dtype)
+        out[...] = a
+        return out
+
+    v_mass, v_thrf = pinned_copy(wl.valid_mass), pinned_copy(wl.valid_thr)
+    e_mass, e_thrf = pinned_copy(wl.explain_mass), pinned_copy(wl.explain_thr)
+    v_target, v_thr = ME._integerise_many(wl.valid_mass, wl.valid_thr, dp)      # only for the byte accounting below
     e_target, e_thr = ME._integerise_many(wl.explain_mass, wl.explain_thr, dp)
     weights, is_mod, ind = ME._row_metadata(dp)
     max_mods = np.full(len(e_target), wl.max_modifications, dtype=np.int32)
-    mode = ME._modes(weights, is_mod, ind, max_mods.astype(np.int64), e_target + e_thr, True)
-    deepest = int(min(int((e_target + e_thr).max()), dev.limit - 1) // int(weights[1]))
-    rec_width = 8 * max(1, -(-deepest // 8))
-    ctx.valid_stage(v_target, v_thr)
-    ctx.explain_stage(dev, e_target, e_thr, max_mods, mode, ind, is_mod)
+    ctx.valid_stage_f64(v_mass, v_thrf, dp.precision, dp.tolerance)
+    ctx.explain_stage_f64(dev, e_mass, e_thrf, max_mods, ind, is_mod, dp.precision, dp.tolerance, True)
 
     def step():
         ctx.valid_run(dev)
-        return ctx.explain_run(dev, rec_width)
+        return ctx.explain_run(dev, 0)
 
     sampler = ClockSampler(local_rank)
     sampler.start()
@@ -335,8 +339,8 @@ def main():
 
     # ---- e2e: public API, host buffers in, host arrays out (H2D + kernels + D2H of every result)
     def e2e_step():
-        valid = ME.are_valid_masses(wl.valid_mass, dp, wl.valid_thr)
-        batch = ME.explain_masses(wl.explain_mass, dp, max_modifications=wl.max_modifications, thresholds=wl.explain_thr)
+        valid = ME.are_valid_masses(v_mass, dp, v_thrf)
+        batch = ME.explain_masses(e_mass, dp, max_modifications=wl.max_modifications, thresholds=e_thrf, copy=False)
         return valid, batch
 
     for _ in range(2):
@@ -356,6 +360,7 @@ def main():
         t = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
+    rec_width = ctx._last[2]
     h2d = 16 * len(v_target) + 21 * len(e_target) + 5 * dev.R
     d2h = len(v_target) + len(e_target) + 8 * (len(e_target) + 1) + int(batch.n_compositions) * rec_width
     e2e_value = peaks_all * args.steps / e2e_s
@@ -366,12 +371,12 @@ def main():
     k2b_bytes = 16 * len(e_target) + 8 * (len(e_target) + 1) + 4 * int(batch.n_compositions) + comp_len + 8 * int(win_words)
     vwin_words = ((2 * v_thr + 1 + 31) // 32 + 1).sum()
     k2a_bytes = 17 * len(v_target) + 8 * int(vwin_words)
-    fam = ["window_count", "window_fill", "phase_a", "items", "enum_count", "enum_fill", "scan", "peak_offsets"]
+    fam = ["window", "phase_a", "items", "enumerate", "peak_offsets"]
     k2b_ms = sum(stats[k][0] for k in fam) / args.steps
     k2a_ms = stats["is_valid"][0] / args.steps
     kernels = {k: {"ms_per_step": v[0] / args.steps, "launches_per_step": v[1] / args.steps} for k, v in stats.items() if v[1]}
     dominant = max(fam + ["is_valid"], key=lambda k: stats[k][0])
-    roofline = {"bound": "hbm", "kernel": "K2b enumeration pass (window roots + count + scan + fill)",
+    roofline = {"bound": "hbm", "kernel": "K2b enumeration pass (window roots -> items -> count/scan/fill, 4 launches)",
                 "achieved": k2b_bytes / (k2b_ms * 1e-3) / 1e9 if k2b_ms else None, "peak": hbm_peak, "unit": "GB/s",
                 "frac": (k2b_bytes / (k2b_ms * 1e-3) / 1e9 / hbm_peak) if k2b_ms else None, "traffic": None,
                 "algorithmic_bytes": int(k2b_bytes), "peak_source": peak_src, "dominant_launch": dominant,

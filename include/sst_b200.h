@@ -49,8 +49,8 @@ enum { SST_VALID_NO = 0, SST_VALID_YES = 1, SST_VALID_OUT_OF_TABLE = 2 };
 
 /* kernel slots of sst_kernel_ms */
 enum {
-    SST_K_BUILD = 0, SST_K_TRANSPOSE, SST_K_IS_VALID, SST_K_WINDOW_COUNT, SST_K_WINDOW_FILL, SST_K_PHASE_A,
-    SST_K_ENUM_COUNT, SST_K_ENUM_FILL, SST_K_SCAN, SST_K_PEAK_OFFSETS, SST_K_ITEMS, SST_K_COUNT_
+    SST_K_BUILD = 0, SST_K_TRANSPOSE, SST_K_IS_VALID, SST_K_WINDOW, SST_K_PHASE_A, SST_K_ITEMS, SST_K_ENUMERATE,
+    SST_K_PEAK_OFFSETS, SST_K_COUNT_
 };
 
 /* ---- context ---- */
@@ -93,6 +93,9 @@ int sst_is_valid(sst_ctx* ctx, const sst_table* t, const int64_t* target, const 
                  uint8_t* out /* P, SST_VALID_* */);
 /* the same in three steps (stage = H2D, run = kernel, fetch = D2H) for kernel-only timing */
 int sst_valid_stage(sst_ctx* ctx, const int64_t* target, const int64_t* thr, int64_t P);
+/* float inputs: the device does the reference's float -> integer conversion (mass_explanation.py:51-58) with
+ * the same IEEE operations; thr may be NULL (all relative) and a NaN entry means "threshold None" */
+int sst_valid_stage_f64(sst_ctx* ctx, const double* mass, const double* thr, int64_t P, double precision, double tolerance);
 int sst_valid_run(sst_ctx* ctx, const sst_table* t);
 int sst_valid_fetch(sst_ctx* ctx, uint8_t* out);
 
@@ -108,8 +111,14 @@ int sst_explain(sst_ctx* ctx, const sst_table* t, const int64_t* target, const i
 /* the same in two halves, so that the kernel-only time can be measured with inputs resident in HBM */
 int sst_explain_stage(sst_ctx* ctx, const sst_table* t, const int64_t* target, const int64_t* thr, const int32_t* max_mods,
                       const uint8_t* mode, int64_t P, const int32_t* ind, const uint8_t* is_mod);
+/* float inputs: integerises on the host with the reference's float operations (mass_explanation.py:107-114) and
+ * picks the per-peak budget mode (FREE when no budget can bind, else MEMO if with_memo else EXACT) */
+int sst_explain_stage_f64(sst_ctx* ctx, const sst_table* t, const double* mass, const double* thr, const int32_t* max_mods,
+                          int64_t P, const int32_t* ind, const uint8_t* is_mod, double precision, double tolerance, int with_memo);
+/* rec_width 0 = smallest multiple of 8 that holds the longest possible composition of the staged batch */
 int sst_explain_run(sst_ctx* ctx, const sst_table* t, int rec_width, uint64_t memo_capacity, uint64_t* n_roots,
                     uint64_t* n_comps);
+int sst_explain_rec_width(const sst_ctx* ctx); /* record width of the last run */
 /* status[P]; peak_off[P+1] (compositions of peak p are records peak_off[p] .. peak_off[p+1]);
  * recs[n_comps * rec_width]: row indices in ascending order, 0-padded.  Any pointer may be NULL. */
 int sst_explain_fetch(sst_ctx* ctx, uint8_t* status, uint64_t* peak_off, uint8_t* recs);

@@ -25,15 +25,14 @@ MODE_FREE, MODE_EXACT, MODE_MEMO = 0, 1, 2
 STATUS_ZERO_IN_WINDOW, STATUS_OUT_OF_TABLE = 1, 2
 VALID_NO, VALID_YES, VALID_OUT_OF_TABLE = 0, 1, 2
 BUDGET_INF = 1 << 30
-KERNEL_SLOTS = ["build", "transpose", "is_valid", "window_count", "window_fill", "phase_a", "enum_count",
-                "enum_fill", "scan", "peak_offsets", "items"]
+KERNEL_SLOTS = ["build", "transpose", "is_valid", "window", "phase_a", "items", "enumerate", "peak_offsets"]
 
 EXPORTS = [
     "sst_ctx_create", "sst_ctx_destroy", "sst_last_error", "sst_device_info", "sst_host_alloc", "sst_host_free",
     "sst_timer_start", "sst_timer_stop", "sst_stats_reset", "sst_kernel_ms", "sst_flush_l2", "sst_set_per_root_cap",
     "sst_table_build", "sst_table_upload", "sst_table_rebuild", "sst_table_info", "sst_table_download",
     "sst_table_download_masks", "sst_table_destroy", "sst_is_valid", "sst_valid_stage", "sst_valid_run",
-    "sst_valid_fetch", "sst_explain", "sst_explain_stage",
+    "sst_valid_fetch", "sst_valid_stage_f64", "sst_explain", "sst_explain_stage", "sst_explain_stage_f64", "sst_explain_rec_width",
     "sst_explain_run", "sst_explain_fetch",
 ]
 
@@ -84,6 +83,9 @@ def load() -> C.CDLL:
             "sst_table_destroy": (None, [vp, vp]),
             "sst_is_valid": (C.c_int, [vp, vp, i64p, i64p, C.c_int64, u8p]),
             "sst_valid_stage": (C.c_int, [vp, i64p, i64p, C.c_int64]),
+            "sst_valid_stage_f64": (C.c_int, [vp, fp, fp, C.c_int64, C.c_double, C.c_double]),
+            "sst_explain_stage_f64": (C.c_int, [vp, vp, fp, fp, i32p, C.c_int64, i32p, u8p, C.c_double, C.c_double, C.c_int]),
+            "sst_explain_rec_width": (C.c_int, [vp]),
             "sst_valid_run": (C.c_int, [vp, vp]),
             "sst_valid_fetch": (C.c_int, [vp, u8p]),
             "sst_explain": (C.c_int, [vp, vp, i64p, i64p, i32p, u8p, C.c_int64, i32p, u8p, C.c_int, C.c_uint64, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
@@ -208,6 +210,24 @@ class Context:
         self._check(self._lib.sst_valid_stage(self._h, _p(t), _p(h), len(t)))
         self._staged_VP = len(t)
 
+    def valid_stage_f64(self, mass: np.ndarray, thr: Optional[np.ndarray], precision: float, tolerance: float):
+        m = _arr(mass, np.float64)
+        h = None if thr is None else _arr(thr, np.float64)
+        self._check(self._lib.sst_valid_stage_f64(self._h, _p(m), _p(h), len(m), float(precision), float(tolerance)))
+        self._staged_VP = len(m)
+
+    def explain_stage_f64(self, table: "DeviceTable", mass, thr, max_mods, ind, is_mod, precision, tolerance, with_memo):
+        m = _arr(mass, np.float64)
+        h = None if thr is None else _arr(thr, np.float64)
+        mm, iv, im = _arr(max_mods, np.int32), _arr(ind, np.int32), _arr(is_mod, np.uint8)
+        if len(mm) != len(m) or (h is not None and len(h) != len(m)):
+            raise ValueError("per-peak arrays differ in length")
+        if len(iv) != table.R or len(im) != table.R:
+            raise ValueError("ind / is_mod need one entry per table row")
+        self._check(self._lib.sst_explain_stage_f64(self._h, table._h, _p(m), _p(h), _p(mm), len(m), _p(iv), _p(im),
+                                                    float(precision), float(tolerance), 1 if with_memo else 0))
+        self._staged_P = len(m)
+
     def valid_run(self, table: "DeviceTable"):
         self._check(self._lib.sst_valid_run(self._h, table._h))
 
@@ -227,24 +247,38 @@ class Context:
         self._check(self._lib.sst_explain_stage(self._h, table._h, _p(t), _p(h), _p(mm), _p(mo), len(t), _p(iv), _p(im)))
         self._staged_P = len(t)
 
-    def explain_run(self, table: "DeviceTable", rec_width: int, memo_capacity: int = 0) -> Tuple[int, int]:
+    def explain_run(self, table: "DeviceTable", rec_width: int = 0, memo_capacity: int = 0) -> Tuple[int, int]:
+        """rec_width 0 = automatic (smallest multiple of 8 holding the longest possible composition)."""
         nr, nc = C.c_uint64(), C.c_uint64()
         self._check(self._lib.sst_explain_run(self._h, table._h, int(rec_width), C.c_uint64(memo_capacity), C.byref(nr), C.byref(nc)))
-        self._last = (int(nr.value), int(nc.value), int(rec_width))
+        self._last = (int(nr.value), int(nc.value), int(self._lib.sst_explain_rec_width(self._h)))
         return int(nr.value), int(nc.value)
 
-    def explain_fetch(self, want_records: bool = True, out_recs: Optional[np.ndarray] = None):
+    def _pinned(self, name: str, nbytes: int) -> np.ndarray:
+        """Grow-only page-locked staging buffer (uint8) kept on the context."""
+        bufs = self.__dict__.setdefault("_pinned_bufs", {})
+        buf = bufs.get(name)
+        if buf is None or buf.size < nbytes:
+            bufs[name] = buf = self.pinned_empty(max(nbytes + nbytes // 4, 4096), np.uint8)
+        return buf
+
+    def explain_fetch(self, want_records: bool = True, copy: bool = True):
+        """-> (status uint8[P], offsets int64[P+1], records uint8[n, W] or None).
+
+        Results land in pinned buffers owned by the context; ``copy=False`` hands out views of them
+        (valid until the next fetch on this context)."""
         P = self._staged_P
         _nr, nc, W = self._last
-        status = np.empty(P, dtype=np.uint8)
-        off = np.empty(P + 1, dtype=np.uint64)
+        status = self._pinned("status", P)[:P]
+        off = self._pinned("off", 8 * (P + 1))[: 8 * (P + 1)].view(np.uint64)
         recs = None
         if want_records:
-            recs = out_recs if out_recs is not None else np.empty((nc, W), dtype=np.uint8)
-            if recs.size < nc * W:
-                raise ValueError("record buffer too small")
+            recs = self._pinned("recs", nc * W)[: nc * W].reshape(nc, W)
         self._check(self._lib.sst_explain_fetch(self._h, _p(status), _p(off), _p(recs) if (recs is not None and nc) else None))
-        return status, off.astype(np.int64), recs
+        off = off.view(np.int64)
+        if copy:
+            return status.copy(), off.copy(), None if recs is None else recs.copy()
+        return status, off, recs
 
 
 class MemoFull(RuntimeError):

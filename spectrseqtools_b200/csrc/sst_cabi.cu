@@ -5,6 +5,7 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <cmath>
 #include <new>
 #include <vector>
 
@@ -38,6 +39,7 @@ struct sst_table {
     int n_tiles = 0;
     int64_t step_min = 0;
     int64_t w_min = 0;
+    int64_t w_host[128] = {0};
     uint64_t last_mask = ~0ULL;
     float build_ms = 0.f, transpose_ms = 0.f;
     bool built_here = false;
@@ -65,8 +67,11 @@ struct sst_ctx {
     int64_t max_hi = 0;
     // results
     DevBuf d_status, d_nroots, d_rootoff, d_rootv, d_rootpeak, d_cnt, d_compoff, d_peakoff, d_recs, d_blocksums;
-    DevBuf d_itemoff, d_itemroot, d_itemr, d_icnt;
+    DevBuf d_itemoff, d_itemv, d_itempeak, d_itemr, d_scan, d_vmass, d_vthrf;
     uint64_t item_capacity = 0, n_items = 0;
+    bool valid_f64 = false;
+    double v_precision = 1e-3, v_tolerance = 1e-5;
+    int64_t deepest = 0;  // longest composition any staged window value can have
     DevBuf d_memo_keys, d_memo_alive, d_memo_top, d_memo_misc, d_flush;
     DevBuf d_vtarget, d_vthr, d_vout;  // staged validity probes
     int64_t VP = 0;
@@ -138,27 +143,6 @@ void flush_timers(sst_ctx* ctx) {
     }
     ctx->n_pending = 0;
     cudaGetLastError();
-}
-
-// exclusive scan of n uint64 -> out[n+1].  n_bound sizes the grid; if n_dev is given the kernels read the
-// real n (<= n_bound) from device memory, so no host round trip is needed between dependent passes.
-int scan_u64(sst_ctx* ctx, const unsigned long long* in, int64_t n_bound, const unsigned long long* n_dev,
-             unsigned long long* out) {
-    if (n_bound == 0) {
-        CK(cudaMemsetAsync(out, 0, sizeof(unsigned long long), ctx->stream));
-        return SST_OK;
-    }
-    const int64_t n_blocks = (n_bound + kScanBlock - 1) / kScanBlock;
-    int rc = reserve(ctx, ctx->d_blocksums, (size_t)n_blocks * 8);
-    if (rc) return rc;
-    auto* bs = (unsigned long long*)ctx->d_blocksums.p;
-    KTimer kt(ctx, SST_K_SCAN);
-    k_scan_partials<<<(unsigned)n_blocks, kScanThreads, 0, ctx->stream>>>(in, n_bound, n_dev, bs);
-    k_scan_block_sums<<<1, kScanThreads, 0, ctx->stream>>>(bs, n_blocks, n_dev);
-    k_scan_final<<<(unsigned)n_blocks, kScanThreads, 0, ctx->stream>>>(in, n_bound, n_dev, bs, out);
-    kt.stop(3);
-    CK(cudaGetLastError());
-    return SST_OK;
 }
 
 int launch_build(sst_ctx* ctx, sst_table* t) {
@@ -234,6 +218,7 @@ int alloc_table(sst_ctx* ctx, sst_table* t, const int64_t* weights, int R, int64
     int64_t step_min = C + 1, w_min = 0;
     for (int i = 0; i < R; i++) {
         w[i] = (int32_t)weights[i];
+        t->w_host[i] = weights[i];
         st[i] = (int32_t)(weights[i] / 32);
         sh[i] = (int32_t)(weights[i] % 32);
         if (i >= 1 && st[i] < step_min) step_min = st[i];
@@ -317,7 +302,7 @@ void sst_ctx_destroy(sst_ctx* ctx) {
                       &ctx->d_rootpeak, &ctx->d_cnt, &ctx->d_compoff, &ctx->d_peakoff, &ctx->d_recs,
                       &ctx->d_blocksums, &ctx->d_memo_keys, &ctx->d_memo_alive, &ctx->d_memo_top,
                       &ctx->d_memo_misc, &ctx->d_flush, &ctx->d_vtarget, &ctx->d_vthr, &ctx->d_vout,
-                      &ctx->d_itemoff, &ctx->d_itemroot, &ctx->d_itemr, &ctx->d_icnt};
+                      &ctx->d_itemoff, &ctx->d_itemv, &ctx->d_itempeak, &ctx->d_itemr, &ctx->d_scan, &ctx->d_vmass, &ctx->d_vthrf};
     if (ctx->h_misc) cudaFreeHost(ctx->h_misc);
     for (DevBuf* b : bufs) cudaFree(b->p);
     cudaEventDestroy(ctx->ev_a);
@@ -505,6 +490,27 @@ int sst_valid_stage(sst_ctx* ctx, const int64_t* target, const int64_t* thr, int
         CK(cudaStreamSynchronize(ctx->stream));
     }
     ctx->VP = P;
+    ctx->valid_f64 = false;
+    return SST_OK;
+}
+
+int sst_valid_stage_f64(sst_ctx* ctx, const double* mass, const double* thr, int64_t P, double precision, double tolerance) {
+    CK(cudaSetDevice(ctx->device));
+    if (P < 0) return fail(ctx, SST_ERR_BAD_ARG, "negative probe count");
+    int rc;
+    if ((rc = reserve(ctx, ctx->d_vmass, (size_t)(P ? P : 1) * 8))) return rc;
+    if ((rc = reserve(ctx, ctx->d_vthrf, (size_t)(P ? P : 1) * 8))) return rc;
+    if ((rc = reserve(ctx, ctx->d_vout, (size_t)(P ? P : 1)))) return rc;
+    if (P) {
+        CK(cudaMemcpyAsync(ctx->d_vmass.p, mass, (size_t)P * 8, cudaMemcpyHostToDevice, ctx->stream));
+        if (thr) CK(cudaMemcpyAsync(ctx->d_vthrf.p, thr, (size_t)P * 8, cudaMemcpyHostToDevice, ctx->stream));
+        else CK(cudaMemsetAsync(ctx->d_vthrf.p, 0xFF, (size_t)P * 8, ctx->stream));  // all-ones = NaN = "relative"
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    ctx->VP = P;
+    ctx->valid_f64 = true;
+    ctx->v_precision = precision;
+    ctx->v_tolerance = tolerance;
     return SST_OK;
 }
 
@@ -513,8 +519,12 @@ int sst_valid_run(sst_ctx* ctx, const sst_table* t) {
     const int64_t P = ctx->VP;
     if (P) {
         KTimer kt(ctx, SST_K_IS_VALID);
-        k_is_valid<<<(unsigned)((P + 255) / 256), 256, 0, ctx->stream>>>(view_of(t), (const int64_t*)ctx->d_vtarget.p,
-                                                                         (const int64_t*)ctx->d_vthr.p, P, (uint8_t*)ctx->d_vout.p);
+        if (ctx->valid_f64)
+            k_is_valid_f64<<<(unsigned)((P + 255) / 256), 256, 0, ctx->stream>>>(view_of(t), (const double*)ctx->d_vmass.p, (const double*)ctx->d_vthrf.p,
+                                                                                 ctx->v_precision, ctx->v_tolerance, P, (uint8_t*)ctx->d_vout.p);
+        else
+            k_is_valid<<<(unsigned)((P + 255) / 256), 256, 0, ctx->stream>>>(view_of(t), (const int64_t*)ctx->d_vtarget.p,
+                                                                             (const int64_t*)ctx->d_vthr.p, P, (uint8_t*)ctx->d_vout.p);
         kt.stop(1);
         CK(cudaGetLastError());
     }
@@ -581,7 +591,40 @@ int sst_explain_stage(sst_ctx* ctx, const sst_table* t, const int64_t* target, c
     ctx->R_staged = t->R;
     ctx->window_total = window_total;
     ctx->max_hi = max_hi;
+    {
+        const int64_t cap = t->C * 32 - 1;
+        ctx->deepest = t->w_min > 0 ? (max_hi < cap ? max_hi : cap) / t->w_min : 0;
+    }
     return SST_OK;
+}
+
+int sst_explain_stage_f64(sst_ctx* ctx, const sst_table* t, const double* mass, const double* thr, const int32_t* max_mods,
+                          int64_t P, const int32_t* ind, const uint8_t* is_mod, double precision, double tolerance, int with_memo) {
+    if (P < 0) return fail(ctx, SST_ERR_BAD_ARG, "negative peak count");
+    // same float operations as mass_explanation.py:107-114 (true division, round-half-even, ceil), then the
+    // host-side budget test: FREE when no composition inside the window can exhaust a budget
+    std::vector<int64_t> target((size_t)P), ithr((size_t)P);
+    std::vector<uint8_t> mode((size_t)P);
+    int64_t w_min_mod = 0, hi_limit = INT64_MAX;
+    for (int r = 1; r < t->R; r++)
+        if (is_mod[r]) {
+            const int64_t w = t->w_host[r];
+            if (!w_min_mod || w < w_min_mod) w_min_mod = w;
+            const int64_t lim = ((int64_t)ind[r] + 1) * w;  // ind[r] >= hi / w  <=>  hi < (ind[r]+1) * w
+            if (lim < hi_limit) hi_limit = lim;
+        }
+    const uint8_t slow = with_memo ? SST_MODE_MEMO : SST_MODE_EXACT;
+    for (int64_t p = 0; p < P; p++) {
+        const double m = mass[p];
+        target[p] = (int64_t)nearbyint(m / precision);
+        const double th = (thr && !std::isnan(thr[p])) ? thr[p] : tolerance * m;
+        ithr[p] = (int64_t)std::ceil(th / precision);
+        int64_t hi = target[p] + ithr[p];
+        if (hi < 0) hi = 0;
+        const bool free_ok = !w_min_mod || ((int64_t)max_mods[p] >= hi / w_min_mod && hi < hi_limit);
+        mode[p] = free_ok ? SST_MODE_FREE : slow;
+    }
+    return sst_explain_stage(ctx, t, target.data(), ithr.data(), max_mods, mode.data(), P, ind, is_mod);
 }
 
 int sst_explain_run(sst_ctx* ctx, const sst_table* t, int rec_width, uint64_t memo_capacity, uint64_t* n_roots,
@@ -590,71 +633,64 @@ int sst_explain_run(sst_ctx* ctx, const sst_table* t, int rec_width, uint64_t me
     ctx->have_result = false;
     const int64_t P = ctx->P;
     if (ctx->R_staged != t->R) return fail(ctx, SST_ERR_STATE, "staged batch belongs to a table with %d rows", ctx->R_staged);
+    if (ctx->deepest > kMaxDepth - 2) return fail(ctx, SST_ERR_TOO_DEEP, "a composition may need %lld nucleotides (limit %d)", (long long)ctx->deepest, kMaxDepth - 2);
+    if (rec_width == 0) rec_width = (int)(8 * (ctx->deepest > 8 ? (ctx->deepest + 7) / 8 : 1));
     if (rec_width < 8 || rec_width % 8 || rec_width > kMaxDepth) return fail(ctx, SST_ERR_BAD_ARG, "rec_width %d must be a multiple of 8 in [8, %d]", rec_width, kMaxDepth);
-    if (t->w_min > 0) {  // longest composition any in-table window value can have
-        const int64_t cap = t->C * 32 - 1;
-        const int64_t deepest = (ctx->max_hi < cap ? ctx->max_hi : cap) / t->w_min;
-        if (deepest > kMaxDepth) return fail(ctx, SST_ERR_TOO_DEEP, "a composition may need %lld nucleotides (limit %d)", (long long)deepest, kMaxDepth);
-        if (deepest > rec_width) return fail(ctx, SST_ERR_BAD_ARG, "a composition may need %lld nucleotides but rec_width is %d", (long long)deepest, rec_width);
-    }
-    // The whole pass is enqueued without host round trips: the number of roots is bounded by the summed
-    // window sizes (known at stage time), later kernels read the real counts from device memory, and the
-    // item / record buffers keep their capacity from earlier runs (the fill kernels refuse to overflow
-    // them; the pass is then repeated once with larger buffers).
+    if (ctx->deepest > rec_width) return fail(ctx, SST_ERR_BAD_ARG, "a composition may need %lld nucleotides but rec_width is %d", (long long)ctx->deepest, rec_width);
+    // The whole pass is four launches and no host round trip: every stage is count -> chained scan -> fill in
+    // one kernel, later stages read the real counts from device memory, and the item / record buffers keep
+    // their capacity from earlier runs (a stage that would overflow sets a flag and writes nothing; the pass
+    // is then repeated once with larger buffers).  Roots are bounded by the summed window sizes.
     const int64_t root_bound = ctx->window_total;
     int rc;
     if ((rc = reserve(ctx, ctx->d_status, (size_t)(P ? P : 1)))) return rc;
-    if ((rc = reserve(ctx, ctx->d_nroots, (size_t)(P + 1) * 8))) return rc;
     if ((rc = reserve(ctx, ctx->d_rootoff, (size_t)(P + 2) * 8))) return rc;
     if ((rc = reserve(ctx, ctx->d_peakoff, (size_t)(P + 2) * 8))) return rc;
     if ((rc = reserve(ctx, ctx->d_rootv, (size_t)(root_bound + 1) * 4))) return rc;
     if ((rc = reserve(ctx, ctx->d_rootpeak, (size_t)(root_bound + 1) * 4))) return rc;
-    if ((rc = reserve(ctx, ctx->d_cnt, (size_t)(root_bound + 1) * 8))) return rc;
     if ((rc = reserve(ctx, ctx->d_itemoff, (size_t)(root_bound + 2) * 8))) return rc;
-    if ((rc = reserve(ctx, ctx->d_memo_misc, 64))) return rc;
     if (!ctx->d_recs.p && (rc = reserve(ctx, ctx->d_recs, (size_t)64 << 20))) return rc;
     if (!ctx->item_capacity) ctx->item_capacity = (uint64_t)1 << 20;
     TableView tv = view_of(t);
     RowMeta meta{(const int32_t*)ctx->d_ind.p, (const uint8_t*)ctx->d_ismod.p};
     PeakBatch pk{(const int64_t*)ctx->d_target.p, (const int64_t*)ctx->d_thr.p, (const int32_t*)ctx->d_maxmods.p,
                  (const uint8_t*)ctx->d_mode.p, P};
-    const unsigned pgrid = (unsigned)((P + 127) / 128);
     const int64_t full = (int64_t)ctx->prop.multiProcessorCount * 16;
 
     unsigned long long roots = 0, items = 0, comps = 0;
     for (int attempt = 0;; attempt++) {
         const int64_t item_cap = (int64_t)ctx->item_capacity;
-        if ((rc = reserve(ctx, ctx->d_itemroot, (size_t)(item_cap + 1) * 4))) return rc;
+        if ((rc = reserve(ctx, ctx->d_itemv, (size_t)(item_cap + 1) * 4))) return rc;
+        if ((rc = reserve(ctx, ctx->d_itempeak, (size_t)(item_cap + 1) * 4))) return rc;
         if ((rc = reserve(ctx, ctx->d_itemr, (size_t)(item_cap + 1)))) return rc;
-        if ((rc = reserve(ctx, ctx->d_icnt, (size_t)(item_cap + 1) * 8))) return rc;
         if ((rc = reserve(ctx, ctx->d_compoff, (size_t)(item_cap + 2) * 8))) return rc;
-        auto* d_nroots = (unsigned long long*)ctx->d_nroots.p;
+        // scan scratch: [tickets 16 x u32][totals 8 x u64][flags 16 x int][tile states of the three stages]
+        const int64_t tiles_w = (P + kTile - 1) / kTile + 1, tiles_i = (root_bound + kTile - 1) / kTile + 1,
+                      tiles_e = (item_cap + kTile - 1) / kTile + 1;
+        const size_t scan_bytes = 192 + (size_t)(tiles_w + tiles_i + tiles_e) * 8;
+        if ((rc = reserve(ctx, ctx->d_scan, scan_bytes))) return rc;
+        CK(cudaMemsetAsync(ctx->d_scan.p, 0, scan_bytes, ctx->stream));
+        unsigned int* d_tickets = (unsigned int*)ctx->d_scan.p;
+        unsigned long long* d_totals = (unsigned long long*)((char*)ctx->d_scan.p + 64);
+        int* d_flags = (int*)((char*)ctx->d_scan.p + 128);  // [0] per-item cap, [1] records overflow, [2] items overflow, [4] memo fill, [5] memo overflow
+        unsigned long long* d_state = (unsigned long long*)((char*)ctx->d_scan.p + 192);
+        ScanState ss_w{d_state, d_tickets}, ss_i{d_state + tiles_w, d_tickets + 1}, ss_e{d_state + tiles_w + tiles_i, d_tickets + 2};
         auto* d_rootoff = (unsigned long long*)ctx->d_rootoff.p;
         auto* d_peakoff = (unsigned long long*)ctx->d_peakoff.p;
         auto* d_rootv = (uint32_t*)ctx->d_rootv.p;
         auto* d_rootpeak = (uint32_t*)ctx->d_rootpeak.p;
-        auto* d_rcnt = (unsigned long long*)ctx->d_cnt.p;
         auto* d_itemoff = (unsigned long long*)ctx->d_itemoff.p;
-        auto* d_itemroot = (uint32_t*)ctx->d_itemroot.p;
-        auto* d_itemr = (uint8_t*)ctx->d_itemr.p;
-        auto* d_icnt = (unsigned long long*)ctx->d_icnt.p;
         auto* d_compoff = (unsigned long long*)ctx->d_compoff.p;
-        int* d_flags = (int*)ctx->d_memo_misc.p;  // [0] memo fill, [1] memo overflow, [8] per-item cap, [9] records overflow, [10] items overflow
-        CK(cudaMemsetAsync(d_flags, 0, 64, ctx->stream));
+        ItemList il{(uint32_t*)ctx->d_itemv.p, (uint32_t*)ctx->d_itempeak.p, (uint8_t*)ctx->d_itemr.p, (unsigned long long)item_cap};
 
         if (P) {
-            KTimer kt(ctx, SST_K_WINDOW_COUNT);
-            k_window_roots<false><<<pgrid, 128, 0, ctx->stream>>>(tv, pk, (uint8_t*)ctx->d_status.p, d_nroots, nullptr, nullptr);
+            KTimer kt(ctx, SST_K_WINDOW);
+            k_window_roots<<<(unsigned)((P + kTile - 1) / kTile), kTile, 0, ctx->stream>>>(tv, pk, (uint8_t*)ctx->d_status.p, d_rootoff, d_rootv,
+                                                                                          d_rootpeak, ss_w, d_totals);
             kt.stop(1);
             CK(cudaGetLastError());
-        }
-        if ((rc = scan_u64(ctx, d_nroots, P, nullptr, d_rootoff))) return rc;
-        const unsigned long long* d_nroots_total = d_rootoff + P;
-        if (P && root_bound) {
-            KTimer kt(ctx, SST_K_WINDOW_FILL);
-            k_window_roots<true><<<pgrid, 128, 0, ctx->stream>>>(tv, pk, nullptr, d_rootoff, d_rootv, d_rootpeak);
-            kt.stop(1);
-            CK(cudaGetLastError());
+        } else {
+            CK(cudaMemsetAsync(d_rootoff, 0, 8, ctx->stream));
         }
 
         MemoMap mp{};
@@ -673,8 +709,8 @@ int sst_explain_run(sst_ctx* ctx, const sst_table* t, int rec_width, uint64_t me
             mp.alive = (uint4*)ctx->d_memo_alive.p;
             mp.top = (uint32_t*)ctx->d_memo_top.p;
             mp.cap_mask = (uint32_t)(pow2 - 1);
-            mp.fill = (unsigned int*)d_flags;
-            mp.overflow = d_flags + 1;
+            mp.fill = (unsigned int*)(d_flags + 4);
+            mp.overflow = d_flags + 5;
             KTimer kt(ctx, SST_K_PHASE_A);
             k_memo_phase_a<<<(unsigned)((ctx->n_memo + 63) / 64), 64, 0, ctx->stream>>>(tv, meta, pk, (const uint32_t*)ctx->d_memo_peaks.p,
                                                                                        ctx->n_memo, mp);
@@ -682,42 +718,21 @@ int sst_explain_run(sst_ctx* ctx, const sst_table* t, int rec_width, uint64_t me
             CK(cudaGetLastError());
         }
 
-        // persistent-style grids: enough CTAs to fill the machine, grid-stride over the real counts
-        int64_t g = (root_bound + 127) / 128;
+        // persistent grids: enough CTAs to fill the machine; tiles are taken by ticket up to the real counts
+        int64_t g = (root_bound + kTile - 1) / kTile;
         const unsigned rgrid = (unsigned)(g < 1 ? 1 : (g > full ? full : g));
-        g = (item_cap + 127) / 128;
+        g = (item_cap + kTile - 1) / kTile;
         const unsigned igrid = (unsigned)(g < 1 ? 1 : (g > full ? full : g));
-        if (root_bound) {
+        {
             KTimer kt(ctx, SST_K_ITEMS);
-            k_root_items<false><<<rgrid, 128, 0, ctx->stream>>>(tv, pk, d_rootv, d_rootpeak, d_nroots_total, d_rcnt, nullptr, nullptr, 0ULL, mp, d_flags + 8);
+            k_root_items<<<rgrid, kTile, 0, ctx->stream>>>(tv, pk, d_rootv, d_rootpeak, d_totals, d_itemoff, il, mp, ss_i, d_totals, d_flags);
             kt.stop(1);
             CK(cudaGetLastError());
         }
-        if ((rc = scan_u64(ctx, d_rcnt, root_bound, d_nroots_total, d_itemoff))) return rc;
-        // d_itemoff[n_roots] = number of items; its address depends on n_roots, so copy it to a fixed slot
         {
-            KTimer kt(ctx, SST_K_ITEMS);
-            k_pick_total<<<1, 1, 0, ctx->stream>>>(d_itemoff, d_nroots_total, d_itemoff + root_bound + 1);
-            if (root_bound)
-                k_root_items<true><<<rgrid, 128, 0, ctx->stream>>>(tv, pk, d_rootv, d_rootpeak, d_nroots_total, d_itemoff, d_itemroot, d_itemr,
-                                                                   (unsigned long long)item_cap, mp, d_flags + 8);
-            kt.stop(2);
-            CK(cudaGetLastError());
-        }
-        const unsigned long long* d_nitems_total = d_itemoff + root_bound + 1;
-        {
-            KTimer kt(ctx, SST_K_ENUM_COUNT);
-            k_enumerate<false><<<igrid, 128, 0, ctx->stream>>>(tv, meta, pk, d_rootv, d_rootpeak, d_itemroot, d_itemr, d_nitems_total, d_icnt,
-                                                               nullptr, rec_width, mp, ctx->per_root_cap, 0ULL, (unsigned long long)item_cap, d_flags + 8);
-            kt.stop(1);
-            CK(cudaGetLastError());
-        }
-        if ((rc = scan_u64(ctx, d_icnt, item_cap, d_nitems_total, d_compoff))) return rc;
-        {
-            KTimer kt(ctx, SST_K_ENUM_FILL);
-            k_enumerate<true><<<igrid, 128, 0, ctx->stream>>>(tv, meta, pk, d_rootv, d_rootpeak, d_itemroot, d_itemr, d_nitems_total, d_compoff,
-                                                              (uint8_t*)ctx->d_recs.p, rec_width, mp, ~0ULL,
-                                                              (unsigned long long)(ctx->d_recs.cap / rec_width), (unsigned long long)item_cap, d_flags + 8);
+            KTimer kt(ctx, SST_K_ENUMERATE);
+            k_enumerate<<<igrid, kTile, 0, ctx->stream>>>(tv, meta, pk, il, d_totals, d_compoff, (uint8_t*)ctx->d_recs.p, rec_width, mp,
+                                                          ctx->per_root_cap, (unsigned long long)(ctx->d_recs.cap / rec_width), ss_e, d_totals, d_flags);
             kt.stop(1);
             CK(cudaGetLastError());
         }
@@ -727,28 +742,26 @@ int sst_explain_run(sst_ctx* ctx, const sst_table* t, int rec_width, uint64_t me
             kt.stop(1);
             CK(cudaGetLastError());
         }
-        // one read-back: flags + the three totals
-        unsigned long long* h64 = (unsigned long long*)(ctx->h_misc + 16);
-        CK(cudaMemcpyAsync(ctx->h_misc, d_flags, 64, cudaMemcpyDeviceToHost, ctx->stream));
-        CK(cudaMemcpyAsync(h64, d_nroots_total, 8, cudaMemcpyDeviceToHost, ctx->stream));
-        CK(cudaMemcpyAsync(h64 + 1, d_nitems_total, 8, cudaMemcpyDeviceToHost, ctx->stream));
-        CK(cudaMemcpyAsync(h64 + 2, d_peakoff + P, 8, cudaMemcpyDeviceToHost, ctx->stream));
+        // one read-back: totals + flags
+        CK(cudaMemcpyAsync(ctx->h_misc, (char*)ctx->d_scan.p + 64, 128, cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
         flush_timers(ctx);
-        roots = h64[0];
-        items = h64[1];
-        comps = h64[2];
-        if (ctx->n_memo && ctx->h_misc[1])
-            return fail(ctx, SST_ERR_MEMO_FULL, "first-visit map is too small (%d slots used)", ctx->h_misc[0]);
-        if (ctx->h_misc[10]) {  // items did not fit: grow and run the pass again
+        const unsigned long long* h_tot = (const unsigned long long*)ctx->h_misc;
+        const int* h_flags = ctx->h_misc + 16;
+        roots = h_tot[0];
+        items = h_tot[1];
+        comps = h_tot[2];
+        if (ctx->n_memo && h_flags[5])
+            return fail(ctx, SST_ERR_MEMO_FULL, "first-visit map is too small (%d slots used)", h_flags[4]);
+        if (h_flags[2]) {  // items did not fit: grow and run the pass again
             if (attempt >= 2) return fail(ctx, SST_ERR_CUDA, "item buffer kept overflowing (%llu items)", items);
             ctx->item_capacity = items + (items >> 2) + 1024;
             continue;
         }
-        if (ctx->h_misc[8])
+        if (h_flags[0])
             return fail(ctx, SST_ERR_NOMEM, "more than %llu compositions under one (window value, first row) item: combinatorial blow-up (raise the cap with sst_set_per_root_cap)",
                         (unsigned long long)ctx->per_root_cap);
-        if (ctx->h_misc[9]) {  // records did not fit: grow and run the pass again
+        if (h_flags[1]) {  // records did not fit: grow and run the pass again
             if (attempt >= 3) return fail(ctx, SST_ERR_CUDA, "record buffer kept overflowing (%llu compositions)", comps);
             size_t free_b = 0, total_b = 0;
             CK(cudaMemGetInfo(&free_b, &total_b));
@@ -769,6 +782,8 @@ int sst_explain_run(sst_ctx* ctx, const sst_table* t, int rec_width, uint64_t me
     if (n_comps) *n_comps = comps;
     return SST_OK;
 }
+
+int sst_explain_rec_width(const sst_ctx* ctx) { return ctx->rec_width; }
 
 int sst_explain(sst_ctx* ctx, const sst_table* t, const int64_t* target, const int64_t* thr, const int32_t* max_mods,
                 const uint8_t* mode, int64_t P, const int32_t* ind, const uint8_t* is_mod, int rec_width,

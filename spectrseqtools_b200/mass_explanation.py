@@ -83,18 +83,17 @@ def _row_metadata(dp_table) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
 
 
 def _modes(weights, is_mod, ind, max_mods: np.ndarray, hi: np.ndarray, with_memo: bool) -> np.ndarray:
-    """Per-peak budget mode.  FREE when no composition inside the window can exhaust a budget."""
-    mod_rows = np.nonzero(is_mod[1:])[0] + 1
+    """Per-peak budget mode.  FREE when no composition inside the window can exhaust a budget:
+    max_mods >= hi // min modified weight, and IND[r] >= hi // w_r for every modified row r, i.e.
+    hi < min_r (IND[r] + 1) * w_r.  (Same rule as sst_explain_stage_f64.)"""
+    mod_rows = np.nonzero(np.asarray(is_mod)[1:])[0] + 1
     slow = _cabi.MODE_MEMO if with_memo else _cabi.MODE_EXACT
     if len(mod_rows) == 0:
         return np.zeros(len(hi), dtype=np.uint8)
-    w_mod = weights[mod_rows]
-    hi_pos = np.maximum(hi, 0)
-    most_mods = hi_pos // int(w_mod.min())  # most modified nucleotides any composition <= hi can hold
-    free = max_mods >= most_mods
-    # per-row: IND[r] >= hi // w_r for every modified row
-    need = hi_pos[:, None] // w_mod[None, :]
-    free &= (ind[mod_rows][None, :] >= need).all(axis=1)
+    w_mod = np.asarray(weights, dtype=np.int64)[mod_rows]
+    hi_pos = np.maximum(np.asarray(hi, dtype=np.int64), 0)
+    hi_limit = int(((np.asarray(ind, dtype=np.int64)[mod_rows] + 1) * w_mod).min())
+    free = (np.asarray(max_mods, dtype=np.int64) >= hi_pos // int(w_mod.min())) & (hi_pos < hi_limit)
     return np.where(free, _cabi.MODE_FREE, slow).astype(np.uint8)
 
 
@@ -151,65 +150,80 @@ class ExplanationBatch:
         return sorted(tuple(int(r) for r in rec if r) for rec in self.rows(p))
 
 
-def _as_array(x, n, dtype=np.float64):
-    if x is None:
+def _thr_array(thresholds, n: int) -> Optional[np.ndarray]:
+    """Per-mass absolute thresholds as float64, NaN where the reference would use ``tolerance * mass``."""
+    if thresholds is None:
         return None
-    a = np.asarray(x, dtype=dtype)
-    if a.ndim == 0:
-        a = np.full(n, a, dtype=dtype)
-    return a
+    if isinstance(thresholds, np.ndarray) and thresholds.dtype == np.float64:
+        return thresholds.reshape(-1)
+    if np.ndim(thresholds) == 0:
+        return np.full(n, float(thresholds), dtype=np.float64)
+    return np.array([np.nan if x is None else x for x in thresholds], dtype=np.float64)
 
 
 def explain_masses(masses: Sequence[float], dp_table: DynamicProgrammingTable, max_modifications=np.inf,
                    thresholds=None, with_memo: bool = True, compression_rate: Optional[int] = None,
-                   fetch_records: bool = True) -> ExplanationBatch:
+                   fetch_records: bool = True, copy: bool = True) -> ExplanationBatch:
     """Batched ``explain_mass_with_table``: one device pass for all masses.
 
-    ``max_modifications`` and ``thresholds`` may be scalars or per-mass sequences (``thresholds`` None =
-    relative ``dp_table.tolerance * mass``).
+    ``max_modifications`` and ``thresholds`` may be scalars or per-mass sequences (``thresholds`` None, or a
+    None / NaN entry, = relative ``dp_table.tolerance * mass``).  The float -> integer conversion and the
+    choice of the budget mode happen inside the library (``sst_explain_stage_f64``) with the reference's
+    float operations.  ``copy=False`` returns views of the context's pinned result buffers, valid until
+    the next call on the same device.
     """
     if compression_rate is not None and compression_rate != dp_table.compression_per_cell:
         raise ValueError("compression_rate must match the table's compression_per_cell")
-    masses = np.asarray(masses, dtype=np.float64).reshape(-1)
+    masses = np.ascontiguousarray(masses, dtype=np.float64).reshape(-1)
     P = len(masses)
-    target, thr = _integerise_many(masses, thresholds, dp_table)
+    thr = _thr_array(thresholds, P)
     if np.ndim(max_modifications) == 0:
         max_mods = np.full(P, _budget_int(max_modifications), dtype=np.int32)
     else:
         max_mods = np.array([_budget_int(x) for x in max_modifications], dtype=np.int32)
-    return _explain_integer(dp_table, target, thr, max_mods, with_memo, fetch_records)
-
-
-def _explain_integer(dp_table, target, thr, max_mods, with_memo=True, fetch_records=True) -> ExplanationBatch:
     dev = dp_table.device_table()
     ctx = dev.ctx
     weights, is_mod, ind = _row_metadata(dp_table)
-    hi = target + thr
-    mode = _modes(weights, is_mod, ind, max_mods.astype(np.int64), hi, with_memo)
-    w_min = int(weights[1]) if len(weights) > 1 else 1
-    deepest = int(min(max(int(hi.max()) if len(hi) else 0, 0), dev.limit - 1) // w_min)
-    rec_width = 8 * max(1, -(-deepest // 8))
-    ctx.explain_stage(dev, target, thr, max_mods, mode, ind, is_mod)
+    ctx.explain_stage_f64(dev, masses, thr, max_mods, ind, is_mod, dp_table.precision, dp_table.tolerance, with_memo)
+    return _run_and_fetch(dp_table, dev, weights, fetch_records, copy)
+
+
+def _run_and_fetch(dp_table, dev, weights, fetch_records=True, copy=True) -> ExplanationBatch:
+    ctx = dev.ctx
     cap = 0
     while True:
         try:
-            ctx.explain_run(dev, rec_width, cap)
+            ctx.explain_run(dev, 0, cap)
             break
         except _cabi.MemoFull:
             cap = (cap or (1 << 20)) * 4
             if cap > (1 << 30):
                 raise
-    status, off, recs = ctx.explain_fetch(want_records=fetch_records)
-    names_by_row = [m.names for m in dp_table.masses]
-    return ExplanationBatch(status, off, recs, weights, names_by_row)
+    status, off, recs = ctx.explain_fetch(want_records=fetch_records, copy=copy)
+    return ExplanationBatch(status, off, recs, weights, [m.names for m in dp_table.masses])
+
+
+def _explain_integer(dp_table, target, thr, max_mods, with_memo=True, fetch_records=True) -> ExplanationBatch:
+    """Integer-domain entry (targets / thresholds already in table units); budget modes chosen here."""
+    dev = dp_table.device_table()
+    weights, is_mod, ind = _row_metadata(dp_table)
+    target = np.asarray(target, dtype=np.int64)
+    thr = np.asarray(thr, dtype=np.int64)
+    max_mods = np.asarray(max_mods, dtype=np.int32)
+    mode = _modes(weights, is_mod, ind, max_mods.astype(np.int64), target + thr, with_memo)
+    dev.ctx.explain_stage(dev, target, thr, max_mods, mode, ind, is_mod)
+    return _run_and_fetch(dp_table, dev, weights, fetch_records)
 
 
 def are_valid_masses(masses: Sequence[float], dp_table: DynamicProgrammingTable, thresholds=None) -> np.ndarray:
     """Batched ``is_valid_mass`` -> uint8 array of _cabi.VALID_* codes (2 = out of table)."""
-    masses = np.asarray(masses, dtype=np.float64).reshape(-1)
-    target, thr = _integerise_many(masses, thresholds, dp_table)
+    masses = np.ascontiguousarray(masses, dtype=np.float64).reshape(-1)
+    thr = _thr_array(thresholds, len(masses))
     dev = dp_table.device_table()
-    return dev.ctx.is_valid(dev, target, thr)
+    ctx = dev.ctx
+    ctx.valid_stage_f64(masses, thr, dp_table.precision, dp_table.tolerance)
+    ctx.valid_run(dev)
+    return ctx.valid_fetch()
 
 
 # ---------------------------------------------------------------- reference-shaped scalar API
