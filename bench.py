@@ -234,6 +234,8 @@ def main():
     ap.add_argument("--peaks", type=int, default=100_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--flush", default="write", choices=["write", "none"],
+                    help="L2 between timed steps: write a 256 MiB buffer (default, the contract) or leave it warm (diagnostics)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -318,7 +320,8 @@ def main():
     sampler.active.set()
     total_ms = 0.0
     for _ in range(args.steps):
-        ctx.flush_l2()
+        if args.flush == "write":
+            ctx.flush_l2()
         ctx.timer_start()
         n_roots, n_comps = step()
         total_ms += ctx.timer_stop()
@@ -371,18 +374,21 @@ def main():
     k2b_bytes = 16 * len(e_target) + 8 * (len(e_target) + 1) + 4 * int(batch.n_compositions) + comp_len + 8 * int(win_words)
     vwin_words = ((2 * v_thr + 1 + 31) // 32 + 1).sum()
     k2a_bytes = 17 * len(v_target) + 8 * int(vwin_words)
-    fam = ["window", "phase_a", "items", "enumerate", "peak_offsets"]
+    fam = ["phase_a", "explain_pass"]
     k2b_ms = sum(stats[k][0] for k in fam) / args.steps
     k2a_ms = stats["is_valid"][0] / args.steps
     kernels = {k: {"ms_per_step": v[0] / args.steps, "launches_per_step": v[1] / args.steps} for k, v in stats.items() if v[1]}
     dominant = max(fam + ["is_valid"], key=lambda k: stats[k][0])
-    roofline = {"bound": "hbm", "kernel": "K2b enumeration pass (window roots -> items -> count/scan/fill, 4 launches)",
+    roofline = {"bound": "hbm", "kernel": "K3+K2b enumeration pass (k_explain_pass: window roots -> items -> compositions, one cooperative launch)",
                 "achieved": k2b_bytes / (k2b_ms * 1e-3) / 1e9 if k2b_ms else None, "peak": hbm_peak, "unit": "GB/s",
                 "frac": (k2b_bytes / (k2b_ms * 1e-3) / 1e9 / hbm_peak) if k2b_ms else None, "traffic": None,
                 "algorithmic_bytes": int(k2b_bytes), "peak_source": peak_src, "dominant_launch": dominant,
                 "k2a": {"algorithmic_bytes": int(k2a_bytes), "ms": k2a_ms,
                         "achieved": k2a_bytes / (k2a_ms * 1e-3) / 1e9 if k2a_ms else None}}
     launches = sum(v[1] for v in stats.values())
+    ph = ctx.explain_phase_ns().astype(np.int64)
+    ph = ph[ph > 0]
+    phase_us = [round(float(x) * 1e-3, 2) for x in np.diff(ph)] if len(ph) > 1 else None  # see sst_explain_phase_ns
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -394,7 +400,7 @@ def main():
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "ms_per_step": 1e3 * e2e_s / args.steps},
         "gpu_launches": int(launches),
-        "roofline": roofline, "kernels": kernels, "table_build": table_info,
+        "roofline": roofline, "kernels": kernels, "pass_phase_us": phase_us, "table_build": table_info,
     }
 
     if rank == 0 and not args.no_parity:

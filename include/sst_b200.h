@@ -49,8 +49,8 @@ enum { SST_VALID_NO = 0, SST_VALID_YES = 1, SST_VALID_OUT_OF_TABLE = 2 };
 
 /* kernel slots of sst_kernel_ms */
 enum {
-    SST_K_BUILD = 0, SST_K_TRANSPOSE, SST_K_IS_VALID, SST_K_WINDOW, SST_K_PHASE_A, SST_K_ITEMS, SST_K_ENUMERATE,
-    SST_K_PEAK_OFFSETS, SST_K_COUNT_
+    SST_K_BUILD = 0, SST_K_TRANSPOSE, SST_K_IS_VALID, SST_K_PHASE_A, SST_K_EXPLAIN_PASS, SST_K_CLASSIFY,
+    SST_K_LENGTH_BOUND, SST_K_SPARE, SST_K_COUNT_
 };
 
 /* ---- context ---- */
@@ -66,9 +66,10 @@ int sst_timer_stop(sst_ctx* ctx, float* ms);
 /* device time of each kernel family accumulated since the last sst_stats_reset, and launches made */
 int sst_stats_reset(sst_ctx* ctx);
 int sst_kernel_ms(sst_ctx* ctx, float* ms /* [SST_K_COUNT_] */, uint64_t* launches /* [SST_K_COUNT_] */);
-/* blow-up guard: sst_explain fails with SST_ERR_NOMEM when one window value has more than `cap`
- * compositions (default 2^26; the reference would simply never return on such inputs) */
-int sst_set_per_root_cap(sst_ctx* ctx, uint64_t cap);
+/* blow-up guard: sst_explain fails with SST_ERR_NOMEM when a pass would hold more than `limit` partial
+ * compositions in one level (0 = default: whatever fits in device memory; the reference would simply never
+ * return on such inputs) */
+int sst_set_item_limit(sst_ctx* ctx, uint64_t limit);
 /* write `bytes` of device scratch (L2 flush between timed iterations) */
 int sst_flush_l2(sst_ctx* ctx, size_t bytes);
 
@@ -119,6 +120,10 @@ int sst_explain_stage_f64(sst_ctx* ctx, const sst_table* t, const double* mass, 
 int sst_explain_run(sst_ctx* ctx, const sst_table* t, int rec_width, uint64_t memo_capacity, uint64_t* n_roots,
                     uint64_t* n_comps);
 int sst_explain_rec_width(const sst_ctx* ctx); /* record width of the last run */
+/* device timestamps (ns, %globaltimer; the moment the LAST CTA reached the point) of the last enumeration pass:
+ * [0] start, [1] window values counted, [2] level-0 items written, then per expansion level [counted, written],
+ * the last "counted" being the level that had no open item, then [records written], [end].  Unused slots are 0. */
+int sst_explain_phase_ns(const sst_ctx* ctx, uint64_t* out /* [32] */);
 /* status[P]; peak_off[P+1] (compositions of peak p are records peak_off[p] .. peak_off[p+1]);
  * recs[n_comps * rec_width]: row indices in ascending order, 0-padded.  Any pointer may be NULL. */
 int sst_explain_fetch(sst_ctx* ctx, uint8_t* status, uint64_t* peak_off, uint8_t* recs);

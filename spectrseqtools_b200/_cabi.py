@@ -25,14 +25,14 @@ MODE_FREE, MODE_EXACT, MODE_MEMO = 0, 1, 2
 STATUS_ZERO_IN_WINDOW, STATUS_OUT_OF_TABLE = 1, 2
 VALID_NO, VALID_YES, VALID_OUT_OF_TABLE = 0, 1, 2
 BUDGET_INF = 1 << 30
-KERNEL_SLOTS = ["build", "transpose", "is_valid", "window", "phase_a", "items", "enumerate", "peak_offsets"]
+KERNEL_SLOTS = ["build", "transpose", "is_valid", "phase_a", "explain_pass", "classify", "length_bound", "spare"]
 
 EXPORTS = [
     "sst_ctx_create", "sst_ctx_destroy", "sst_last_error", "sst_device_info", "sst_host_alloc", "sst_host_free",
-    "sst_timer_start", "sst_timer_stop", "sst_stats_reset", "sst_kernel_ms", "sst_flush_l2", "sst_set_per_root_cap",
+    "sst_timer_start", "sst_timer_stop", "sst_stats_reset", "sst_kernel_ms", "sst_flush_l2", "sst_set_item_limit",
     "sst_table_build", "sst_table_upload", "sst_table_rebuild", "sst_table_info", "sst_table_download",
     "sst_table_download_masks", "sst_table_destroy", "sst_is_valid", "sst_valid_stage", "sst_valid_run",
-    "sst_valid_fetch", "sst_valid_stage_f64", "sst_explain", "sst_explain_stage", "sst_explain_stage_f64", "sst_explain_rec_width",
+    "sst_valid_fetch", "sst_valid_stage_f64", "sst_explain", "sst_explain_stage", "sst_explain_stage_f64", "sst_explain_rec_width", "sst_explain_phase_ns",
     "sst_explain_run", "sst_explain_fetch",
 ]
 
@@ -73,7 +73,7 @@ def load() -> C.CDLL:
             "sst_stats_reset": (C.c_int, [vp]),
             "sst_kernel_ms": (C.c_int, [vp, fp, u64p]),
             "sst_flush_l2": (C.c_int, [vp, C.c_size_t]),
-            "sst_set_per_root_cap": (C.c_int, [vp, C.c_uint64]),
+            "sst_set_item_limit": (C.c_int, [vp, C.c_uint64]),
             "sst_table_build": (C.c_int, [vp, i64p, C.c_int, C.c_int64, C.c_int, C.c_uint64, C.c_int, C.POINTER(vp)]),
             "sst_table_upload": (C.c_int, [vp, u64p, i64p, C.c_int, C.c_int64, C.POINTER(vp)]),
             "sst_table_rebuild": (C.c_int, [vp, vp]),
@@ -86,6 +86,7 @@ def load() -> C.CDLL:
             "sst_valid_stage_f64": (C.c_int, [vp, fp, fp, C.c_int64, C.c_double, C.c_double]),
             "sst_explain_stage_f64": (C.c_int, [vp, vp, fp, fp, i32p, C.c_int64, i32p, u8p, C.c_double, C.c_double, C.c_int]),
             "sst_explain_rec_width": (C.c_int, [vp]),
+            "sst_explain_phase_ns": (C.c_int, [vp, u64p]),
             "sst_valid_run": (C.c_int, [vp, vp]),
             "sst_valid_fetch": (C.c_int, [vp, u8p]),
             "sst_explain": (C.c_int, [vp, vp, i64p, i64p, i32p, u8p, C.c_int64, i32p, u8p, C.c_int, C.c_uint64, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
@@ -172,8 +173,9 @@ class Context:
         self._check(self._lib.sst_kernel_ms(self._h, _p(ms), _p(n)))
         return {k: (float(ms[i]), int(n[i])) for i, k in enumerate(KERNEL_SLOTS)}
 
-    def set_per_root_cap(self, cap: int):
-        self._check(self._lib.sst_set_per_root_cap(self._h, C.c_uint64(cap)))
+    def set_item_limit(self, limit: int):
+        """Blow-up guard: most partial compositions one level of a pass may hold (0 = device memory)."""
+        self._check(self._lib.sst_set_item_limit(self._h, C.c_uint64(limit)))
 
     def flush_l2(self, nbytes: int = 256 << 20):
         self._check(self._lib.sst_flush_l2(self._h, int(nbytes)))
@@ -253,6 +255,12 @@ class Context:
         self._check(self._lib.sst_explain_run(self._h, table._h, int(rec_width), C.c_uint64(memo_capacity), C.byref(nr), C.byref(nc)))
         self._last = (int(nr.value), int(nc.value), int(self._lib.sst_explain_rec_width(self._h)))
         return int(nr.value), int(nc.value)
+
+    def explain_phase_ns(self) -> np.ndarray:
+        """Device timestamps of the last enumeration pass (see sst_explain_phase_ns)."""
+        out = np.zeros(32, dtype=np.uint64)
+        self._check(self._lib.sst_explain_phase_ns(self._h, _p(out)))
+        return out
 
     def _pinned(self, name: str, nbytes: int) -> np.ndarray:
         """Grow-only page-locked staging buffer (uint8) kept on the context."""

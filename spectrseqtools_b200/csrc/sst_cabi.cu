@@ -41,6 +41,7 @@ struct sst_table {
     int64_t w_min = 0;
     int64_t w_host[128] = {0};
     uint64_t last_mask = ~0ULL;
+    uint32_t leaf_mul = 0;  // collision-free multiplier of the weight -> row hash (0 = none found)
     float build_ms = 0.f, transpose_ms = 0.f;
     bool built_here = false;
 };
@@ -66,8 +67,11 @@ struct sst_ctx {
     int64_t window_total = 0;  // sum of window sizes (upper bound for the number of roots)
     int64_t max_hi = 0;
     // results
-    DevBuf d_status, d_nroots, d_rootoff, d_rootv, d_rootpeak, d_cnt, d_compoff, d_peakoff, d_recs, d_blocksums;
-    DevBuf d_itemoff, d_itemv, d_itempeak, d_itemr, d_scan, d_vmass, d_vthrf;
+    DevBuf d_status, d_cnt, d_peakoff, d_recs, d_blocksums;
+    DevBuf d_scan, d_vmass, d_vthrf, d_peakcnt;
+    DevBuf d_item_m[2], d_item_peak[2], d_item_meta[2], d_item_all[2], d_item_ind[2], d_item_path[2];
+    bool has_exact = false;
+    int levels = 0;
     uint64_t item_capacity = 0, n_items = 0;
     bool valid_f64 = false;
     double v_precision = 1e-3, v_tolerance = 1e-5;
@@ -79,7 +83,9 @@ struct sst_ctx {
     uint64_t n_roots = 0, n_comps = 0;
     int rec_width = 0;
     bool have_result = false;
-    uint64_t per_root_cap = (uint64_t)1 << 26;
+    uint64_t item_limit = ~0ULL;     // blow-up guard (items per level)
+    int pass_grid_max[3] = {0, 0, 0};  // co-resident CTAs of the k_explain_pass instances on this device
+    uint64_t phase_ns[32] = {0};
 };
 
 namespace {
@@ -204,6 +210,24 @@ int launch_transpose(sst_ctx* ctx, sst_table* t) {
     return SST_OK;
 }
 
+// multiplier m such that (w * m) >> 20 (32-bit arithmetic, 4096 slots) is distinct for all row weights
+uint32_t find_leaf_hash(const int64_t* weights, int R) {
+    uint64_t x = 0x9E3779B97F4A7C15ULL;
+    for (int trial = 0; trial < 20000; trial++) {
+        x ^= x << 13; x ^= x >> 7; x ^= x << 17;  // xorshift64
+        const uint32_t mul = (uint32_t)(x >> 16) | 1u;
+        bool used[kLeafSlots] = {false};
+        bool ok = true;
+        for (int r = 1; r < R && ok; r++) {
+            const uint32_t slot = ((uint32_t)weights[r] * mul) >> 20;
+            ok = !used[slot];
+            used[slot] = true;
+        }
+        if (ok) return mul;
+    }
+    return 0;
+}
+
 int alloc_table(sst_ctx* ctx, sst_table* t, const int64_t* weights, int R, int64_t C, bool with_masks) {
     if (R < 1 || R > kMaxRows) return fail(ctx, SST_ERR_TOO_MANY_ROWS, "table has %d rows; at most %d are supported", R, kMaxRows);
     if (weights[0] != 0) return fail(ctx, SST_ERR_BAD_ARG, "weights[0] must be 0");
@@ -227,6 +251,7 @@ int alloc_table(sst_ctx* ctx, sst_table* t, const int64_t* weights, int R, int64
     if (R == 1) step_min = C + 1;
     t->step_min = step_min;
     t->w_min = w_min;
+    t->leaf_mul = find_leaf_hash(weights, R);
     CK(cudaMalloc(&t->tbl, (size_t)R * (size_t)C * 8));
     CK(cudaMalloc(&t->d_weights, (size_t)kMaxRows * 4));
     CK(cudaMalloc(&t->d_step, (size_t)kMaxRows * 4));
@@ -288,7 +313,7 @@ int sst_ctx_create(int device, sst_ctx** out) {
     cudaEventCreate(&ctx->ev_b);
     for (auto& e : ctx->kev) cudaEventCreate(&e);
     for (auto& e : ctx->tev) cudaEventCreate(&e);
-    cudaHostAlloc((void**)&ctx->h_misc, 256, cudaHostAllocDefault);
+    cudaHostAlloc((void**)&ctx->h_misc, 512, cudaHostAllocDefault);
     *out = ctx;
     return SST_OK;
 }
@@ -298,11 +323,13 @@ void sst_ctx_destroy(sst_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     DevBuf* bufs[] = {&ctx->d_target, &ctx->d_thr, &ctx->d_maxmods, &ctx->d_mode, &ctx->d_ind, &ctx->d_ismod,
-                      &ctx->d_memo_peaks, &ctx->d_status, &ctx->d_nroots, &ctx->d_rootoff, &ctx->d_rootv,
-                      &ctx->d_rootpeak, &ctx->d_cnt, &ctx->d_compoff, &ctx->d_peakoff, &ctx->d_recs,
+                      &ctx->d_memo_peaks, &ctx->d_status, &ctx->d_cnt, &ctx->d_peakoff, &ctx->d_recs,
                       &ctx->d_blocksums, &ctx->d_memo_keys, &ctx->d_memo_alive, &ctx->d_memo_top,
                       &ctx->d_memo_misc, &ctx->d_flush, &ctx->d_vtarget, &ctx->d_vthr, &ctx->d_vout,
-                      &ctx->d_itemoff, &ctx->d_itemv, &ctx->d_itempeak, &ctx->d_itemr, &ctx->d_scan, &ctx->d_vmass, &ctx->d_vthrf};
+                      &ctx->d_scan, &ctx->d_vmass, &ctx->d_vthrf, &ctx->d_peakcnt,
+                      &ctx->d_item_m[0], &ctx->d_item_m[1], &ctx->d_item_peak[0], &ctx->d_item_peak[1],
+                      &ctx->d_item_meta[0], &ctx->d_item_meta[1], &ctx->d_item_all[0], &ctx->d_item_all[1],
+                      &ctx->d_item_ind[0], &ctx->d_item_ind[1], &ctx->d_item_path[0], &ctx->d_item_path[1]};
     if (ctx->h_misc) cudaFreeHost(ctx->h_misc);
     for (DevBuf* b : bufs) cudaFree(b->p);
     cudaEventDestroy(ctx->ev_a);
@@ -370,8 +397,8 @@ int sst_kernel_ms(sst_ctx* ctx, float* ms, uint64_t* launches) {
     return SST_OK;
 }
 
-int sst_set_per_root_cap(sst_ctx* ctx, uint64_t cap) {
-    ctx->per_root_cap = cap ? cap : ((uint64_t)1 << 26);
+int sst_set_item_limit(sst_ctx* ctx, uint64_t limit) {
+    ctx->item_limit = limit ? limit : ~0ULL;
     return SST_OK;
 }
 
@@ -563,9 +590,11 @@ int sst_explain_stage(sst_ctx* ctx, const sst_table* t, const int64_t* target, c
     if ((rc = reserve(ctx, ctx->d_ismod, (size_t)kMaxRows))) return rc;
     std::vector<uint32_t> memo_peaks;
     int64_t window_total = 0, max_hi = 0;
+    bool has_exact = false;
     for (int64_t p = 0; p < P; p++) {
         if (mode[p] == SST_MODE_MEMO) memo_peaks.push_back((uint32_t)p);
-        else if (mode[p] != SST_MODE_FREE && mode[p] != SST_MODE_EXACT) return fail(ctx, SST_ERR_BAD_ARG, "peak %lld: unknown mode %d", (long long)p, (int)mode[p]);
+        else if (mode[p] == SST_MODE_EXACT) has_exact = true;
+        else if (mode[p] != SST_MODE_FREE) return fail(ctx, SST_ERR_BAD_ARG, "peak %lld: unknown mode %d", (long long)p, (int)mode[p]);
         if (thr[p] >= 0) {
             int64_t hi = target[p] + thr[p], lo = target[p] - thr[p];
             if (hi > max_hi) max_hi = hi;
@@ -590,6 +619,7 @@ int sst_explain_stage(sst_ctx* ctx, const sst_table* t, const int64_t* target, c
     ctx->P = P;
     ctx->R_staged = t->R;
     ctx->window_total = window_total;
+    ctx->has_exact = has_exact;
     ctx->max_hi = max_hi;
     {
         const int64_t cap = t->C * 32 - 1;
@@ -633,136 +663,147 @@ int sst_explain_run(sst_ctx* ctx, const sst_table* t, int rec_width, uint64_t me
     ctx->have_result = false;
     const int64_t P = ctx->P;
     if (ctx->R_staged != t->R) return fail(ctx, SST_ERR_STATE, "staged batch belongs to a table with %d rows", ctx->R_staged);
-    if (ctx->deepest > kMaxDepth - 2) return fail(ctx, SST_ERR_TOO_DEEP, "a composition may need %lld nucleotides (limit %d)", (long long)ctx->deepest, kMaxDepth - 2);
+    if (ctx->deepest > kMaxDepth - 3) return fail(ctx, SST_ERR_TOO_DEEP, "a composition may need %lld nucleotides (limit %d)", (long long)ctx->deepest, kMaxDepth - 3);
     if (rec_width == 0) rec_width = (int)(8 * (ctx->deepest > 8 ? (ctx->deepest + 7) / 8 : 1));
     if (rec_width < 8 || rec_width % 8 || rec_width > kMaxDepth) return fail(ctx, SST_ERR_BAD_ARG, "rec_width %d must be a multiple of 8 in [8, %d]", rec_width, kMaxDepth);
     if (ctx->deepest > rec_width) return fail(ctx, SST_ERR_BAD_ARG, "a composition may need %lld nucleotides but rec_width is %d", (long long)ctx->deepest, rec_width);
-    // The whole pass is four launches and no host round trip: every stage is count -> chained scan -> fill in
-    // one kernel, later stages read the real counts from device memory, and the item / record buffers keep
-    // their capacity from earlier runs (a stage that would overflow sets a flag and writes nothing; the pass
-    // is then repeated once with larger buffers).  Roots are bounded by the summed window sizes.
+    // The whole pass is ONE cooperative launch and one small read-back (sst_explain.cuh, k_explain_pass).
+    // Level-0 items are bounded by the summed window sizes (known to the host); the two item buffers and the
+    // record buffer keep their capacity from earlier runs — a level that would overflow sets a flag and the pass
+    // is repeated with larger buffers.
     const int64_t root_bound = ctx->window_total;
+    const int nw = rec_width / 8;
     int rc;
+    auto kern = nw == 1 ? k_explain_pass<1> : nw == 2 ? k_explain_pass<2> : k_explain_pass<0>;
+    int& grid_max = ctx->pass_grid_max[nw == 1 ? 0 : nw == 2 ? 1 : 2];
+    if (!grid_max) {
+        int occ = 0;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kPassThreads, 0));
+        if (occ < 1) return fail(ctx, SST_ERR_CUDA, "k_explain_pass does not fit on an SM");
+        grid_max = occ * ctx->prop.multiProcessorCount;
+    }
     if ((rc = reserve(ctx, ctx->d_status, (size_t)(P ? P : 1)))) return rc;
-    if ((rc = reserve(ctx, ctx->d_rootoff, (size_t)(P + 2) * 8))) return rc;
     if ((rc = reserve(ctx, ctx->d_peakoff, (size_t)(P + 2) * 8))) return rc;
-    if ((rc = reserve(ctx, ctx->d_rootv, (size_t)(root_bound + 1) * 4))) return rc;
-    if ((rc = reserve(ctx, ctx->d_rootpeak, (size_t)(root_bound + 1) * 4))) return rc;
-    if ((rc = reserve(ctx, ctx->d_itemoff, (size_t)(root_bound + 2) * 8))) return rc;
+    if ((rc = reserve(ctx, ctx->d_peakcnt, (size_t)(P + 2) * 8))) return rc;
+    if ((rc = reserve(ctx, ctx->d_blocksums, (size_t)3 * grid_max * 8))) return rc;
+    if ((rc = reserve(ctx, ctx->d_scan, 512))) return rc;
     if (!ctx->d_recs.p && (rc = reserve(ctx, ctx->d_recs, (size_t)64 << 20))) return rc;
     if (!ctx->item_capacity) ctx->item_capacity = (uint64_t)1 << 20;
-    TableView tv = view_of(t);
-    RowMeta meta{(const int32_t*)ctx->d_ind.p, (const uint8_t*)ctx->d_ismod.p};
-    PeakBatch pk{(const int64_t*)ctx->d_target.p, (const int64_t*)ctx->d_thr.p, (const int32_t*)ctx->d_maxmods.p,
-                 (const uint8_t*)ctx->d_mode.p, P};
-    const int64_t full = (int64_t)ctx->prop.multiProcessorCount * 16;
+    if ((int64_t)ctx->item_capacity < root_bound + 1) ctx->item_capacity = (uint64_t)root_bound + 1;
 
+    MemoMap mp{};
     unsigned long long roots = 0, items = 0, comps = 0;
     for (int attempt = 0;; attempt++) {
-        const int64_t item_cap = (int64_t)ctx->item_capacity;
-        if ((rc = reserve(ctx, ctx->d_itemv, (size_t)(item_cap + 1) * 4))) return rc;
-        if ((rc = reserve(ctx, ctx->d_itempeak, (size_t)(item_cap + 1) * 4))) return rc;
-        if ((rc = reserve(ctx, ctx->d_itemr, (size_t)(item_cap + 1)))) return rc;
-        if ((rc = reserve(ctx, ctx->d_compoff, (size_t)(item_cap + 2) * 8))) return rc;
-        // scan scratch: [tickets 16 x u32][totals 8 x u64][flags 16 x int][tile states of the three stages]
-        const int64_t tiles_w = (P + kTile - 1) / kTile + 1, tiles_i = (root_bound + kTile - 1) / kTile + 1,
-                      tiles_e = (item_cap + kTile - 1) / kTile + 1;
-        const size_t scan_bytes = 192 + (size_t)(tiles_w + tiles_i + tiles_e) * 8;
-        if ((rc = reserve(ctx, ctx->d_scan, scan_bytes))) return rc;
-        CK(cudaMemsetAsync(ctx->d_scan.p, 0, scan_bytes, ctx->stream));
-        unsigned int* d_tickets = (unsigned int*)ctx->d_scan.p;
-        unsigned long long* d_totals = (unsigned long long*)((char*)ctx->d_scan.p + 64);
-        int* d_flags = (int*)((char*)ctx->d_scan.p + 128);  // [0] per-item cap, [1] records overflow, [2] items overflow, [4] memo fill, [5] memo overflow
-        unsigned long long* d_state = (unsigned long long*)((char*)ctx->d_scan.p + 192);
-        ScanState ss_w{d_state, d_tickets}, ss_i{d_state + tiles_w, d_tickets + 1}, ss_e{d_state + tiles_w + tiles_i, d_tickets + 2};
-        auto* d_rootoff = (unsigned long long*)ctx->d_rootoff.p;
-        auto* d_peakoff = (unsigned long long*)ctx->d_peakoff.p;
-        auto* d_rootv = (uint32_t*)ctx->d_rootv.p;
-        auto* d_rootpeak = (uint32_t*)ctx->d_rootpeak.p;
-        auto* d_itemoff = (unsigned long long*)ctx->d_itemoff.p;
-        auto* d_compoff = (unsigned long long*)ctx->d_compoff.p;
-        ItemList il{(uint32_t*)ctx->d_itemv.p, (uint32_t*)ctx->d_itempeak.p, (uint8_t*)ctx->d_itemr.p, (unsigned long long)item_cap};
-
-        if (P) {
-            KTimer kt(ctx, SST_K_WINDOW);
-            k_window_roots<<<(unsigned)((P + kTile - 1) / kTile), kTile, 0, ctx->stream>>>(tv, pk, (uint8_t*)ctx->d_status.p, d_rootoff, d_rootv,
-                                                                                          d_rootpeak, ss_w, d_totals);
-            kt.stop(1);
-            CK(cudaGetLastError());
-        } else {
-            CK(cudaMemsetAsync(d_rootoff, 0, 8, ctx->stream));
+        const size_t cap = (size_t)ctx->item_capacity;
+        for (int k = 0; k < 2; k++) {
+            if ((rc = reserve(ctx, ctx->d_item_m[k], cap * 4))) return rc;
+            if ((rc = reserve(ctx, ctx->d_item_peak[k], cap * 4))) return rc;
+            if ((rc = reserve(ctx, ctx->d_item_meta[k], cap * 4))) return rc;
+            if ((rc = reserve(ctx, ctx->d_item_path[k], cap * 8 * (size_t)nw))) return rc;
+            if (ctx->has_exact) {
+                if ((rc = reserve(ctx, ctx->d_item_all[k], cap * 4))) return rc;
+                if ((rc = reserve(ctx, ctx->d_item_ind[k], cap * 4))) return rc;
+            }
         }
+        const size_t most = (size_t)P > cap ? (size_t)P : cap;
+        if ((rc = reserve(ctx, ctx->d_cnt, (most + 1) * 4))) return rc;
+        // [0,64) totals, [64,320) timestamps, [320,384) flags, [384,388) grid-barrier counter
+        CK(cudaMemsetAsync(ctx->d_scan.p, 0, 512, ctx->stream));
+        int* d_flags = (int*)((char*)ctx->d_scan.p + 320);  // [0] item limit, [1] records overflow, [2] items overflow
 
-        MemoMap mp{};
-        if (ctx->n_memo) {
-            uint64_t cap = memo_capacity ? memo_capacity : ((uint64_t)1 << 20);
+        if (ctx->n_memo && attempt == 0) {  // the first-visit map does not depend on the buffer sizes: built once
+            uint64_t mcap = memo_capacity ? memo_capacity : ((uint64_t)1 << 20);
             uint64_t pow2 = 1024;
-            while (pow2 < cap) pow2 <<= 1;
-            if (pow2 > ((uint64_t)1 << 31)) return fail(ctx, SST_ERR_NOMEM, "memo capacity %llu too large", (unsigned long long)cap);
+            while (pow2 < mcap) pow2 <<= 1;
+            if (pow2 > ((uint64_t)1 << 31)) return fail(ctx, SST_ERR_NOMEM, "memo capacity %llu too large", (unsigned long long)mcap);
             if ((rc = reserve(ctx, ctx->d_memo_keys, pow2 * 8))) return rc;
             if ((rc = reserve(ctx, ctx->d_memo_alive, pow2 * 16))) return rc;
             if ((rc = reserve(ctx, ctx->d_memo_top, pow2 * 4))) return rc;
+            if ((rc = reserve(ctx, ctx->d_memo_misc, 64))) return rc;
             CK(cudaMemsetAsync(ctx->d_memo_keys.p, 0, pow2 * 8, ctx->stream));
             CK(cudaMemsetAsync(ctx->d_memo_alive.p, 0, pow2 * 16, ctx->stream));
             CK(cudaMemsetAsync(ctx->d_memo_top.p, 0, pow2 * 4, ctx->stream));
+            CK(cudaMemsetAsync(ctx->d_memo_misc.p, 0, 64, ctx->stream));
             mp.keys = (unsigned long long*)ctx->d_memo_keys.p;
             mp.alive = (uint4*)ctx->d_memo_alive.p;
             mp.top = (uint32_t*)ctx->d_memo_top.p;
             mp.cap_mask = (uint32_t)(pow2 - 1);
-            mp.fill = (unsigned int*)(d_flags + 4);
-            mp.overflow = d_flags + 5;
+            mp.fill = (unsigned int*)ctx->d_memo_misc.p;
+            mp.overflow = (int*)ctx->d_memo_misc.p + 1;
             KTimer kt(ctx, SST_K_PHASE_A);
-            k_memo_phase_a<<<(unsigned)((ctx->n_memo + 63) / 64), 64, 0, ctx->stream>>>(tv, meta, pk, (const uint32_t*)ctx->d_memo_peaks.p,
-                                                                                       ctx->n_memo, mp);
+            k_memo_phase_a<<<(unsigned)((ctx->n_memo + 63) / 64), 64, 0, ctx->stream>>>(
+                view_of(t), RowMeta{(const int32_t*)ctx->d_ind.p, (const uint8_t*)ctx->d_ismod.p},
+                PeakBatch{(const int64_t*)ctx->d_target.p, (const int64_t*)ctx->d_thr.p, (const int32_t*)ctx->d_maxmods.p,
+                          (const uint8_t*)ctx->d_mode.p, P},
+                (const uint32_t*)ctx->d_memo_peaks.p, ctx->n_memo, mp);
             kt.stop(1);
             CK(cudaGetLastError());
         }
 
-        // persistent grids: enough CTAs to fill the machine; tiles are taken by ticket up to the real counts
-        int64_t g = (root_bound + kTile - 1) / kTile;
-        const unsigned rgrid = (unsigned)(g < 1 ? 1 : (g > full ? full : g));
-        g = (item_cap + kTile - 1) / kTile;
-        const unsigned igrid = (unsigned)(g < 1 ? 1 : (g > full ? full : g));
+        PassArgs a{};
+        a.tv = view_of(t);
+        a.meta = RowMeta{(const int32_t*)ctx->d_ind.p, (const uint8_t*)ctx->d_ismod.p};
+        a.pk = PeakBatch{(const int64_t*)ctx->d_target.p, (const int64_t*)ctx->d_thr.p, (const int32_t*)ctx->d_maxmods.p,
+                         (const uint8_t*)ctx->d_mode.p, P};
+        a.mp = mp;
+        a.status = (uint8_t*)ctx->d_status.p;
+        for (int k = 0; k < 2; k++)
+            a.buf[k] = ItemBuf{(uint32_t*)ctx->d_item_m[k].p, (uint32_t*)ctx->d_item_peak[k].p, (uint32_t*)ctx->d_item_meta[k].p,
+                               (int32_t*)ctx->d_item_all[k].p, (int32_t*)ctx->d_item_ind[k].p, (unsigned long long*)ctx->d_item_path[k].p};
+        a.cap = (unsigned long long)cap;
+        a.item_limit = ctx->item_limit;
+        a.cnt = (uint32_t*)ctx->d_cnt.p;
+        a.nw = nw;
+        a.has_budget = ctx->has_exact ? 1 : 0;
+        a.recs = (uint8_t*)ctx->d_recs.p;
+        a.rec_capacity = (unsigned long long)(ctx->d_recs.cap / rec_width);
+        a.peak_cnt = (unsigned long long*)ctx->d_peakcnt.p;
+        a.peak_off = (unsigned long long*)ctx->d_peakoff.p;
+        a.cta_tot = (unsigned long long*)ctx->d_blocksums.p;
+        a.totals = (unsigned long long*)ctx->d_scan.p;
+        a.flags = d_flags;
+        a.barrier = (unsigned int*)((char*)ctx->d_scan.p + 384);
+        a.leaf = LeafHash{t->leaf_mul};
+        // enough CTAs that every thread gets about one entity of the longest list, at most one co-resident wave
+        int64_t want = ((int64_t)most + kPassThreads - 1) / kPassThreads;
+        if (want < 1) want = 1;
+        const unsigned grid = (unsigned)(want < grid_max ? want : grid_max);
         {
-            KTimer kt(ctx, SST_K_ITEMS);
-            k_root_items<<<rgrid, kTile, 0, ctx->stream>>>(tv, pk, d_rootv, d_rootpeak, d_totals, d_itemoff, il, mp, ss_i, d_totals, d_flags);
+            KTimer kt(ctx, SST_K_EXPLAIN_PASS);
+            void* args[] = {(void*)&a};
+            CK(cudaLaunchCooperativeKernel((const void*)kern, dim3(grid), dim3(kPassThreads), args, 0, ctx->stream));
             kt.stop(1);
-            CK(cudaGetLastError());
         }
-        {
-            KTimer kt(ctx, SST_K_ENUMERATE);
-            k_enumerate<<<igrid, kTile, 0, ctx->stream>>>(tv, meta, pk, il, d_totals, d_compoff, (uint8_t*)ctx->d_recs.p, rec_width, mp,
-                                                          ctx->per_root_cap, (unsigned long long)(ctx->d_recs.cap / rec_width), ss_e, d_totals, d_flags);
-            kt.stop(1);
-            CK(cudaGetLastError());
-        }
-        {
-            KTimer kt(ctx, SST_K_PEAK_OFFSETS);
-            k_peak_offsets<<<(unsigned)((P + 1 + 127) / 128), 128, 0, ctx->stream>>>(d_rootoff, d_itemoff, d_compoff, P, (unsigned long long)item_cap, d_peakoff);
-            kt.stop(1);
-            CK(cudaGetLastError());
-        }
-        // one read-back: totals + flags
-        CK(cudaMemcpyAsync(ctx->h_misc, (char*)ctx->d_scan.p + 64, 128, cudaMemcpyDeviceToHost, ctx->stream));
+        // one read-back: totals + timestamps + flags
+        CK(cudaMemcpyAsync(ctx->h_misc, ctx->d_scan.p, 384, cudaMemcpyDeviceToHost, ctx->stream));
+        if (ctx->n_memo && attempt == 0) CK(cudaMemcpyAsync(ctx->h_misc + 100, ctx->d_memo_misc.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
         flush_timers(ctx);
         const unsigned long long* h_tot = (const unsigned long long*)ctx->h_misc;
-        const int* h_flags = ctx->h_misc + 16;
+        const int* h_flags = ctx->h_misc + 80;
         roots = h_tot[0];
         items = h_tot[1];
         comps = h_tot[2];
-        if (ctx->n_memo && h_flags[5])
-            return fail(ctx, SST_ERR_MEMO_FULL, "first-visit map is too small (%d slots used)", h_flags[4]);
-        if (h_flags[2]) {  // items did not fit: grow and run the pass again
-            if (attempt >= 2) return fail(ctx, SST_ERR_CUDA, "item buffer kept overflowing (%llu items)", items);
-            ctx->item_capacity = items + (items >> 2) + 1024;
+        ctx->levels = (int)h_tot[3];
+        for (int i = 0; i < 32; i++) ctx->phase_ns[i] = h_tot[8 + i];
+        if (ctx->n_memo && attempt == 0 && ctx->h_misc[101])
+            return fail(ctx, SST_ERR_MEMO_FULL, "first-visit map is too small (%d slots used)", ctx->h_misc[100]);
+        if (h_flags[0])
+            return fail(ctx, SST_ERR_NOMEM, "more than %llu partial compositions in one level (%llu): combinatorial blow-up (raise the limit with sst_set_item_limit)",
+                        (unsigned long long)ctx->item_limit, items);
+        if (h_flags[2]) {  // a level did not fit: grow (deeper levels are larger still) and run the pass again
+            if (attempt >= 12) return fail(ctx, SST_ERR_CUDA, "item buffers kept overflowing (%llu items)", items);
+            size_t free_b = 0, total_b = 0;
+            CK(cudaMemGetInfo(&free_b, &total_b));
+            const unsigned long long want_items = items * 2 + 1024;
+            const unsigned long long per_item = 2ULL * (12 + 8ULL * nw + (ctx->has_exact ? 8 : 0)) + 4;
+            if ((want_items - cap) * per_item > (unsigned long long)free_b)
+                return fail(ctx, SST_ERR_NOMEM, "%llu partial compositions do not fit in device memory (%zu bytes free)", items, free_b);
+            ctx->item_capacity = want_items;
             continue;
         }
-        if (h_flags[0])
-            return fail(ctx, SST_ERR_NOMEM, "more than %llu compositions under one (window value, first row) item: combinatorial blow-up (raise the cap with sst_set_per_root_cap)",
-                        (unsigned long long)ctx->per_root_cap);
         if (h_flags[1]) {  // records did not fit: grow and run the pass again
-            if (attempt >= 3) return fail(ctx, SST_ERR_CUDA, "record buffer kept overflowing (%llu compositions)", comps);
+            if (attempt >= 14) return fail(ctx, SST_ERR_CUDA, "record buffer kept overflowing (%llu compositions)", comps);
             size_t free_b = 0, total_b = 0;
             CK(cudaMemGetInfo(&free_b, &total_b));
             const unsigned long long need = comps * (unsigned long long)rec_width;
@@ -780,6 +821,11 @@ int sst_explain_run(sst_ctx* ctx, const sst_table* t, int rec_width, uint64_t me
     ctx->have_result = true;
     if (n_roots) *n_roots = roots;
     if (n_comps) *n_comps = comps;
+    return SST_OK;
+}
+
+int sst_explain_phase_ns(const sst_ctx* ctx, uint64_t* out) {
+    for (int i = 0; i < 32; i++) out[i] = ctx->phase_ns[i];
     return SST_OK;
 }
 

@@ -137,160 +137,6 @@ __global__ void k_is_valid_f64(TableView tv, const double* __restrict__ mass, co
     out[p] = valid_code(tv, t, h);
 }
 
-// ---------------- single-pass chained scan (decoupled look-back) ----------------
-// Every stage below is count -> exclusive scan -> fill in ONE launch: a CTA counts its tile, publishes the
-// tile aggregate, looks back over earlier tiles for its exclusive prefix and then writes.  Tile ids come
-// from a ticket so that a tile's predecessors have always started.  Flag and value share one 64-bit word
-// (one atomic store), so no fence is needed.
-constexpr unsigned long long kScanFlagA = 1ULL << 62;  // tile aggregate available
-constexpr unsigned long long kScanFlagP = 1ULL << 63;  // inclusive prefix available
-constexpr unsigned long long kScanValue = (1ULL << 62) - 1ULL;
-constexpr int kTile = 128;
-
-struct ScanState {
-    unsigned long long* state;  // one word per tile, zeroed by the host before the launch
-    unsigned int* ticket;
-};
-
-__device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned long long* p) {
-    unsigned long long v;
-    asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_volatile_u64(unsigned long long* p, unsigned long long v) {
-    asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-
-// exclusive scan of one value per thread across a 128-thread CTA; *total = CTA sum
-__device__ __forceinline__ unsigned long long block_scan128(unsigned long long x, unsigned long long* total) {
-    __shared__ unsigned long long s_warp[kTile / 32];
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    unsigned long long incl = x;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const unsigned long long y = __shfl_up_sync(0xFFFFFFFFu, incl, o);
-        if (lane >= o) incl += y;
-    }
-    if (lane == 31) s_warp[w] = incl;
-    __syncthreads();
-    unsigned long long before = 0, sum = 0;
-#pragma unroll
-    for (int i = 0; i < kTile / 32; i++) {
-        const unsigned long long v = s_warp[i];
-        if (i < w) before += v;
-        sum += v;
-    }
-    *total = sum;
-    __syncthreads();
-    return before + incl - x;
-}
-
-// called by warp 0 of the CTA; returns the sum of the aggregates of tiles [0, tile)
-__device__ __forceinline__ unsigned long long tile_exclusive_prefix(const ScanState& ss, int tile, unsigned long long aggregate) {
-    const int lane = threadIdx.x & 31;
-    if (tile == 0) {
-        if (lane == 0) st_volatile_u64(ss.state, kScanFlagP | aggregate);
-        return 0ULL;
-    }
-    if (lane == 0) st_volatile_u64(ss.state + tile, kScanFlagA | aggregate);
-    unsigned long long excl = 0;
-    for (int base = tile - 1;; base -= 32) {
-        const int idx = base - lane;
-        unsigned long long v;
-        do {
-            v = idx >= 0 ? ld_volatile_u64(ss.state + idx) : kScanFlagP;
-        } while (__any_sync(0xFFFFFFFFu, (v & (kScanFlagA | kScanFlagP)) == 0ULL));
-        const unsigned closed = __ballot_sync(0xFFFFFFFFu, (v & kScanFlagP) != 0ULL);
-        const int first = closed ? __ffs(closed) - 1 : 32;  // nearest predecessor with a full prefix
-        unsigned long long part = lane <= first ? (v & kScanValue) : 0ULL;
-#pragma unroll
-        for (int o = 16; o; o >>= 1) part += __shfl_xor_sync(0xFFFFFFFFu, part, o);
-        excl += part;
-        if (closed) break;
-    }
-    if (lane == 0) st_volatile_u64(ss.state + tile, kScanFlagP | (excl + aggregate));
-    return excl;
-}
-
-// CTA-wide: exclusive offset of this thread's `count` among all tiles; one ticket per call
-__device__ __forceinline__ unsigned long long chained_offset(const ScanState& ss, int tile, unsigned long long count,
-                                                             unsigned long long* tile_total) {
-    __shared__ unsigned long long s_base;
-    unsigned long long total;
-    const unsigned long long excl = block_scan128(count, &total);
-    if (threadIdx.x < 32) {
-        const unsigned long long base = tile_exclusive_prefix(ss, tile, total);
-        if (threadIdx.x == 0) s_base = base;
-    }
-    __syncthreads();
-    const unsigned long long off = s_base + excl;
-    *tile_total = total;
-    __syncthreads();
-    return off;
-}
-
-__device__ __forceinline__ int next_tile(const ScanState& ss) {
-    __shared__ int s_tile;
-    if (threadIdx.x == 0) s_tile = (int)atomicAdd(ss.ticket, 1u);
-    __syncthreads();
-    const int t = s_tile;
-    __syncthreads();
-    return t;
-}
-
-// ---------------- K3 + root discovery: integer window over the last row ----------------
-// One thread per peak: count the reachable window values (roots), get the offset, write them.
-// totals[0] = number of roots.
-__global__ void __launch_bounds__(kTile)
-k_window_roots(TableView tv, PeakBatch pk, uint8_t* __restrict__ status, unsigned long long* __restrict__ root_off,
-               uint32_t* __restrict__ root_v, uint32_t* __restrict__ root_peak, ScanState ss,
-               unsigned long long* __restrict__ totals) {
-    const int tile = next_tile(ss);
-    const int64_t p = (int64_t)tile * kTile + threadIdx.x;
-    const int64_t limit = tv.C * 32;
-    const uint64_t* last = tv.tbl + (int64_t)(tv.R - 1) * tv.C;
-    int64_t a = 1, b = 0;
-    unsigned long long n = 0;
-    if (p < pk.P) {
-        const int64_t lo = pk.target[p] - pk.thr[p], hi = pk.target[p] + pk.thr[p];
-        uint8_t st = 0;
-        if (lo <= 0 && 0 <= hi) st |= ST_ZERO_IN_WINDOW;
-        if (lo <= hi && hi >= limit) st |= ST_OUT_OF_TABLE;
-        status[p] = st;
-        a = lo < 1 ? 1 : lo;
-        b = hi < limit - 1 ? hi : limit - 1;
-        for (int64_t wd = a >> 5; a <= b && wd <= (b >> 5); wd++) {
-            uint64_t x = __ldg(last + wd);
-            x = (x | (x >> 1)) & kBit0Mask;
-            if (wd == (a >> 5)) x &= (1ULL << (2 * (31 - (int)(a & 31)) + 1)) - 1ULL;
-            if (wd == (b >> 5)) x &= ~0ULL << (2 * (31 - (int)(b & 31)));
-            n += __popcll(x);
-        }
-    }
-    unsigned long long tile_total;
-    unsigned long long off = chained_offset(ss, tile, n, &tile_total);
-    if (p < pk.P) {
-        root_off[p] = off;
-        if (p == pk.P - 1) {
-            root_off[pk.P] = off + n;
-            totals[0] = off + n;
-        }
-        for (int64_t wd = a >> 5; a <= b && wd <= (b >> 5); wd++) {
-            uint64_t x = __ldg(last + wd);
-            x = (x | (x >> 1)) & kBit0Mask;
-            if (wd == (a >> 5)) x &= (1ULL << (2 * (31 - (int)(a & 31)) + 1)) - 1ULL;
-            if (wd == (b >> 5)) x &= ~0ULL << (2 * (31 - (int)(b & 31)));
-            while (x) {  // ascending mass = descending bit position
-                const int pos = 63 - __clzll((long long)x);
-                x &= ~(1ULL << pos);
-                root_v[off] = (uint32_t)(wd * 32 + (31 - (pos >> 1)));
-                root_peak[off] = (uint32_t)p;
-                off++;
-            }
-        }
-    }
-}
-
 // ---------------- MEMO phase A: sequential first-visit replay, one thread per peak ----------------
 __global__ void __launch_bounds__(64)
 k_memo_phase_a(TableView tv, RowMeta meta, PeakBatch pk, const uint32_t* __restrict__ memo_peaks, int n_memo,
@@ -385,12 +231,27 @@ k_memo_phase_a(TableView tv, RowMeta meta, PeakBatch pk, const uint32_t* __restr
     }
 }
 
-// ---------------- K2b: path enumeration ----------------
-// Work items.  A root is one window value v with a non-empty last-row cell; an ITEM is (root, first row
-// r1): the subtree of compositions whose largest row is r1.  Splitting at the first level turns the long
-// serial chain of a heavy root (every mask load of a DFS depends on the previous pop) into many short
-// chains, which is what the latency-bound 1-3 nt production calls need.  Output order = (peak, window
-// value, first row, DFS order): grouped by peak, deterministic, no atomics on the data path.
+// ---------------- K3 + K2b: the enumeration pass, ONE cooperative launch ----------------
+// Level-synchronous expansion.  An ITEM is a partial composition: (remainder m, largest row still allowed rmax,
+// rows chosen so far, peak).  Level 0 holds one item per reachable window value (K3, the integer window over the
+// last row).  A level is expanded into the next by giving every OPEN item its children {(m - w_r, r) : r <= rmax,
+// edge r enabled at m} — one 16-byte row-mask load per item, every thread does the same work — while items that
+// need no more loads are carried over unchanged.  In FREE mode (budgets cannot bind) an item stops being open
+// early, because the table bits decide everything near the leaves:
+//     m == 0            DONE   the path is a composition
+//     m <  2*w_min      LEAF   exactly one more nucleotide (the table bit guarantees it exists): 1 composition
+//     m <  3*w_min      POPC   every child is DONE or LEAF: popc(children) compositions
+// so 1-4 nt ladder differences need two or three levels.  When a level has no open item, records are written by
+// ONE THREAD PER COMPOSITION (unranking: j-th child of the item), 8-byte stores that coalesce across the warp.
+//
+// Every level is count -> exclusive scan -> write over a flat list: each CTA owns a contiguous slice, publishes
+// its slice total, all CTAs meet at a grid barrier (cooperative launch: all co-resident) and sum the totals of
+// the CTAs before them.  Critical path = (2 barriers + ~3 dependent memory round trips) per level, independent
+// of the batch size.  Items stay in depth-first order at every level, so the output is grouped by peak and
+// deterministic: (peak, window value, rows descending) — no atomics on the data path except one counter add per
+// item for the per-peak totals.
+constexpr int kPassThreads = 512;
+enum : int { KIND_DONE = 0, KIND_LEAF = 1, KIND_POPC = 2, KIND_OPEN = 3 };
 
 __device__ __forceinline__ Mask128 child_mask(const TableView& tv, const MemoMap& mp, int mode, int64_t p, uint32_t m, int rmax) {
     Mask128 c;
@@ -404,234 +265,713 @@ __device__ __forceinline__ Mask128 child_mask(const TableView& tv, const MemoMap
     mask_keep_le(c, rmax);
     return c;
 }
+__device__ __forceinline__ int mask_popc(const Mask128& m) { return __popc(m.w[0]) + __popc(m.w[1]) + __popc(m.w[2]) + __popc(m.w[3]); }
+// j-th (0-based) set row of a mask with more than j rows
+__device__ __forceinline__ int mask_select(const Mask128& m, int j) {
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const int c = __popc(m.w[k]);
+        if (j < c) return k * 32 + (int)__fns(m.w[k], 0, j + 1);
+        j -= c;
+    }
+    return 0;
+}
 
-struct ItemList {  // structure of arrays, capacity `cap`
-    uint32_t* v;     // window value of the item's root
+// weight -> row in O(1): a collision-free multiplicative hash of the <= 127 row weights, multiplier found by the
+// host (sst_cabi.cu, find_leaf_hash), table rebuilt in shared memory by every CTA.  mul == 0: no multiplier was
+// found (does not happen for <= 127 keys in 4096 slots within the host's trial budget) -> binary search.
+constexpr int kLeafSlots = 4096;
+struct LeafHash {
+    uint32_t mul;
+};
+__device__ __forceinline__ uint32_t leaf_slot(uint32_t m, uint32_t mul) { return (m * mul) >> 20; }
+__device__ __forceinline__ void leaf_table_init(uint8_t* s_leaf, const int32_t* s_w, int R, LeafHash lh) {
+    if (!lh.mul) return;
+    for (int i = threadIdx.x; i < kLeafSlots; i += blockDim.x) s_leaf[i] = 0;
+    __syncthreads();
+    for (int r = 1 + threadIdx.x; r < R; r += blockDim.x) s_leaf[leaf_slot((uint32_t)s_w[r], lh.mul)] = (uint8_t)r;
+}
+// row q <= rmax with w_q == m, or 0
+__device__ __forceinline__ int leaf_row(const uint8_t* s_leaf, const int32_t* s_w, LeafHash lh, uint32_t m, int rmax) {
+    if (lh.mul) {
+        const int q = s_leaf[leaf_slot(m, lh.mul)];
+        return (q && q <= rmax && (uint32_t)s_w[q] == m) ? q : 0;
+    }
+    int lo = 1, hi = rmax;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if ((uint32_t)s_w[mid] < m) lo = mid + 1;
+        else hi = mid;
+    }
+    return (uint32_t)s_w[lo] == m ? lo : 0;
+}
+
+// One level of items, structure of arrays with capacity `cap` each.  `path` is the record under construction:
+// a little-endian number of nw 64-bit words (word k of item i at path[k * cap + i]); appending a row shifts it
+// left by one byte, so byte 0 is always the smallest row and the finished number IS the record.
+struct ItemBuf {
+    uint32_t* m;
     uint32_t* peak;
-    uint8_t* r;      // first (largest) row
-    unsigned long long cap;
+    uint32_t* meta;              // rmax | depth << 8 | cached POPC count << 16 | budget mode << 24 (bit 31: scratch)
+    int32_t* all;                // remaining global modification budget   (only when has_budget)
+    int32_t* ind;                // remaining budget of row rmax            (only when has_budget)
+    unsigned long long* path;
+};
+constexpr int kMaxPathWords = kMaxDepth / 8;
+
+struct PassArgs {
+    TableView tv;
+    RowMeta meta;
+    PeakBatch pk;
+    MemoMap mp;
+    uint8_t* status;                 // [P]
+    ItemBuf buf[2];
+    unsigned long long cap;          // items per buffer
+    unsigned long long item_limit;   // blow-up guard: more items than this in one level -> flags[0]
+    uint32_t* cnt;                   // [max(P, cap)] per-entity counts between count and write (children | final << 16)
+    int nw;                          // path / record words (W = 8 * nw bytes)
+    int has_budget;                  // some peak is in EXACT mode
+    uint8_t* recs;
+    unsigned long long rec_capacity;
+    unsigned long long* peak_cnt;    // [P+1] compositions per peak (zeroed in stage 1)
+    unsigned long long* peak_off;    // [P+1]
+    unsigned long long* cta_tot;     // [3][gridDim.x]
+    unsigned long long* totals;      // [0] roots [1] items of the last level [2] compositions [3] levels, [8..39] timestamps
+    int* flags;                      // [0] item_limit hit, [1] records overflow, [2] items overflow (totals[1] = needed)
+    unsigned int* barrier;           // arrival counter, zeroed by the host before the launch
+    LeafHash leaf;
 };
 
-// roots -> items.  flags[2] is set when the items do not fit.  root_item_off[root] = first item of the
-// root, root_item_off[n_roots] = totals[1] = number of items.
-__global__ void __launch_bounds__(kTile)
-k_root_items(TableView tv, PeakBatch pk, const uint32_t* __restrict__ root_v, const uint32_t* __restrict__ root_peak,
-             const unsigned long long* __restrict__ totals_in, unsigned long long* __restrict__ root_item_off, ItemList items,
-             MemoMap mp, ScanState ss, unsigned long long* __restrict__ totals, int* __restrict__ flags) {
-    const int64_t n_roots = (int64_t)totals_in[0];
-    if (n_roots == 0) {
-        if (blockIdx.x == 0 && threadIdx.x == 0) {
-            root_item_off[0] = 0ULL;
-            totals[1] = 0ULL;
-        }
-        return;
-    }
-    const int n_tiles = (int)((n_roots + kTile - 1) / kTile);
-    for (;;) {
-        const int tile = next_tile(ss);
-        if (tile >= n_tiles) break;
-        const int64_t root = (int64_t)tile * kTile + threadIdx.x;
-        Mask128 c;
-        c.w[0] = c.w[1] = c.w[2] = c.w[3] = 0u;
-        uint32_t v = 0, p = 0;
-        if (root < n_roots) {
-            v = root_v[root];
-            p = root_peak[root];
-            c = child_mask(tv, mp, pk.mode[p], p, v, tv.R - 1);
-        }
-        const unsigned long long n = (unsigned long long)(__popc(c.w[0]) + __popc(c.w[1]) + __popc(c.w[2]) + __popc(c.w[3]));
-        unsigned long long tile_total;
-        unsigned long long off = chained_offset(ss, tile, n, &tile_total);
-        if (root < n_roots) {
-            root_item_off[root] = off;
-            if (root == n_roots - 1) {
-                root_item_off[n_roots] = off + n;
-                totals[1] = off + n;
-            }
-            if (off + n > items.cap) {
-                flags[2] = 1;
-            } else {
-                while (!mask_empty(c)) {
-                    items.v[off] = v;
-                    items.peak[off] = p;
-                    items.r[off] = (uint8_t)mask_pop_lowest(c);
-                    off++;
-                }
-            }
-        }
-    }
+__device__ __forceinline__ unsigned int ld_relaxed_u32(const unsigned int* p) {
+    unsigned int v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
 }
 
-// Per-thread DFS under one item.  FILL=false counts, FILL=true writes W-byte records from record index `out`.
-template <bool FILL>
-__device__ __forceinline__ unsigned long long enumerate_item(const TableView& tv, const MemoMap& mp, const int32_t* s_w,
-                                                             const int32_t* s_ind, const uint8_t* s_mod, int mode, int64_t p,
-                                                             uint32_t v, int r1, int max_mods, uint8_t* __restrict__ recs, int W,
-                                                             unsigned long long out, unsigned long long per_item_cap,
-                                                             int* __restrict__ flags) {
-    uint32_t l_m[kMaxDepth];
-    Mask128 l_mask[kMaxDepth];
-    uint8_t l_path[kMaxDepth];
-    int l_all[kMaxDepth], l_ind[kMaxDepth];
-    const int top_row = tv.R - 1;
-    const uint32_t two_wmin = tv.R > 1 ? 2u * (uint32_t)s_w[1] : 0u;  // below this a remainder is ONE nucleotide
-    unsigned long long count = 0;
-    uint64_t packed = 0;  // W == 8 fast path: rows so far, ascending from byte 0
+// All CTAs of the (cooperative) grid.  `gen` counts the barriers this CTA has passed in this launch.
+// The wait polls with a RELAXED load and fences once at the end: an acquire load per poll costs a CCTL.IVALL
+// each time, i.e. early CTAs would keep wiping the L1 of the CTAs on the same SM that are still working.
+__device__ __forceinline__ void grid_barrier(const PassArgs& a, unsigned int& gen) {
+    __syncthreads();
+    gen++;
+    if (threadIdx.x == 0) {
+        __threadfence();  // the CTA's writes (ordered before this by the barrier above) become visible first
+        atomicAdd(a.barrier, 1u);
+        const unsigned int want = gen * gridDim.x;
+        while ((int)(ld_relaxed_u32(a.barrier) - want) < 0) __nanosleep(20);
+        __threadfence();  // acquire side: one L1 invalidation, after the wait
+    }
+    __syncthreads();
+}
 
-    // write the composition l_path[0..n-1] (descending rows) as an ascending, 0-padded record
-    auto emit = [&](int n, uint64_t packed_rec) {
-        if (FILL) {
-            uint8_t* rec = recs + out * (unsigned long long)W;
-            if (W == 8) {
-                *reinterpret_cast<uint64_t*>(rec) = packed_rec;
-            } else {
-                for (int q = 0; q < W; q += 8) {
-                    uint64_t word = 0;
+// timestamp k (diagnostics): CTA 0's clock when it gets here.  Right after a grid barrier that is everybody's
+// clock; before one it is only CTA 0's own finish time.  (An atomicMax over all CTAs measured ~1.5 us per stamp.)
+__device__ __forceinline__ void stamp(const PassArgs& a, int k) {
+    if (blockIdx.x == 0 && threadIdx.x == 0 && k < 32) a.totals[8 + k] = globaltimer_ns();
+}
+
+// exclusive scan of one value per thread across the CTA; *total = CTA sum.  Two barriers.
+__device__ __forceinline__ unsigned long long block_scan(unsigned long long x, unsigned long long* total) {
+    __shared__ unsigned long long s_warp[kPassThreads / 32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    unsigned long long incl = x;
 #pragma unroll
-                    for (int i = 0; i < 8; i++) {
-                        const int idx = q + i;
-                        if (idx < n) word |= (uint64_t)l_path[n - 1 - idx] << (8 * i);
-                    }
-                    *reinterpret_cast<uint64_t*>(rec + q) = word;
-                }
-            }
-            out++;
-        }
-        count++;
-    };
-
-    // level 0 is the root restricted to this item's first row: no mask load needed
-    int d = 0;
-    l_m[0] = v;
-    l_mask[0].w[0] = l_mask[0].w[1] = l_mask[0].w[2] = l_mask[0].w[3] = 0u;
-    mask_set(l_mask[0], r1);
-    l_all[0] = max_mods;
-    l_ind[0] = s_ind[top_row];
-    int rin = top_row;  // row by which the current level was entered (root: last row)
-
-    for (;;) {
-        if (mask_empty(l_mask[d])) {
-            if (d == 0) break;
-            d--;
-            packed >>= 8;
-            rin = d == 0 ? top_row : l_path[d - 1];
-            continue;
-        }
-        const int r = mask_pop_lowest(l_mask[d]);
-        int child_all = 0, child_ind = 0;
-        if (mode == MODE_EXACT) {
-            const int ind_here = (r == rin) ? l_ind[d] : s_ind[r];
-            const int mod = s_mod[r];
-            if (mod && !(l_all[d] > 0 && ind_here > 0)) continue;
-            child_all = l_all[d] - mod;
-            child_ind = ind_here - mod;
-        }
-        const uint32_t m2 = l_m[d] - (uint32_t)s_w[r];
-        if (d + 2 >= kMaxDepth) continue;  // cannot happen: the host checks the depth bound before launch
-        l_path[d] = (uint8_t)r;
-        if (m2 == 0u) {
-            emit(d + 1, (packed << 8) | (uint64_t)r);
-        } else if (mode != MODE_MEMO && m2 < two_wmin) {
-            // the table bit says m2 is a sum of rows <= r, and it is too light for two: m2 == w_q, q <= r
-            int lo = 1, hi = r;
-            while (lo < hi) {
-                const int mid = (lo + hi) >> 1;
-                if ((uint32_t)s_w[mid] < m2) lo = mid + 1;
-                else hi = mid;
-            }
-            const int q = lo;
-            bool ok = (uint32_t)s_w[q] == m2;
-            if (ok && mode == MODE_EXACT) {
-                const int ind_q = (q == r) ? child_ind : s_ind[q];
-                if (s_mod[q] && !(child_all > 0 && ind_q > 0)) ok = false;
-            }
-            if (ok) {
-                l_path[d + 1] = (uint8_t)q;
-                emit(d + 2, (((packed << 8) | (uint64_t)r) << 8) | (uint64_t)q);
-            }
-        } else {
-            packed = (packed << 8) | (uint64_t)r;
-            d++;
-            rin = r;
-            l_m[d] = m2;
-            l_mask[d] = child_mask(tv, mp, mode, p, m2, r);
-            l_all[d] = child_all;
-            l_ind[d] = child_ind;
-            continue;
-        }
-        if (!FILL && count > per_item_cap) {  // combinatorial blow-up guard (the reference would never return)
-            flags[0] = 1;
-            break;
-        }
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned long long y = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+        if (lane >= o) incl += y;
     }
-    return count;
+    if (lane == 31) s_warp[w] = incl;
+    __syncthreads();
+    unsigned long long before = 0, sum = 0;
+#pragma unroll
+    for (int i = 0; i < kPassThreads / 32; i++) {
+        const unsigned long long v = s_warp[i];
+        if (i < w) before += v;
+        sum += v;
+    }
+    *total = sum;
+    __syncthreads();
+    return before + incl - x;
+}
+// 32-bit flavour for the per-round scans (a round's counts always fit): ~35 instructions per warp, 3 barriers
+__device__ __forceinline__ unsigned int block_scan32(unsigned int x, unsigned int* total) {
+    __shared__ unsigned int s_w32[kPassThreads / 32];
+    __shared__ unsigned int s_tot32;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    unsigned int incl = x;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned int y = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+        if (lane >= o) incl += y;
+    }
+    if (lane == 31) s_w32[w] = incl;
+    __syncthreads();
+    if (w == 0) {
+        const unsigned int v = lane < kPassThreads / 32 ? s_w32[lane] : 0u;
+        unsigned int inc = v;
+#pragma unroll
+        for (int o = 1; o < kPassThreads / 32; o <<= 1) {
+            const unsigned int y = __shfl_up_sync(0xFFFFFFFFu, inc, o);
+            if (lane >= o) inc += y;
+        }
+        if (lane < kPassThreads / 32) s_w32[lane] = inc - v;
+        if (lane == kPassThreads / 32 - 1) s_tot32 = inc;
+    }
+    __syncthreads();
+    const unsigned int r = s_w32[w] + incl - x;
+    *total = s_tot32;
+    __syncthreads();
+    return r;
+}
+__device__ __forceinline__ unsigned long long block_sum(unsigned long long x) {
+    unsigned long long t;
+    block_scan(x, &t);
+    return t;
+}
+// CTA-wide sums of N values per thread with one pair of barriers
+template <int N>
+__device__ __forceinline__ void block_sum_n(unsigned long long (&v)[N]) {
+    __shared__ unsigned long long s_part[kPassThreads / 32][N];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < N; k++) {
+#pragma unroll
+        for (int o = 16; o; o >>= 1) v[k] += __shfl_xor_sync(0xFFFFFFFFu, v[k], o);
+        if (lane == 0) s_part[w][k] = v[k];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < N; k++) {
+        unsigned long long t = 0;
+#pragma unroll
+        for (int i = 0; i < kPassThreads / 32; i++) t += s_part[i][k];
+        v[k] = t;
+    }
+    __syncthreads();
 }
 
-// items -> compositions: count, chained scan, fill, in one launch.  item_comp_off[item] = first record of the
-// item, item_comp_off[n_items] = totals[2] = number of compositions.  flags[0]: blow-up guard hit;
-// flags[1]: records do not fit rec_capacity (nothing is written past it; the host grows and reruns).
-__global__ void __launch_bounds__(kTile)
-k_enumerate(TableView tv, RowMeta meta, PeakBatch pk, ItemList items, const unsigned long long* __restrict__ totals_in,
-            unsigned long long* __restrict__ item_comp_off, uint8_t* __restrict__ recs, int W, MemoMap mp,
-            unsigned long long per_item_cap, unsigned long long rec_capacity, ScanState ss,
-            unsigned long long* __restrict__ totals, int* __restrict__ flags) {
+// after a grid barrier: sum of the slice totals of the CTAs before this one, and of all CTAs
+__device__ __forceinline__ void slice_prefix(const unsigned long long* cta_tot, unsigned long long* base, unsigned long long* all) {
+    unsigned long long v[2] = {0ULL, 0ULL};
+    for (unsigned b = threadIdx.x; b < gridDim.x; b += blockDim.x) {
+        const unsigned long long x = __ldcg(cta_tot + b);
+        v[1] += x;
+        if (b < blockIdx.x) v[0] += x;
+    }
+    block_sum_n<2>(v);
+    *base = v[0];
+    *all = v[1];
+}
+// the same for the three per-level totals at once: [0] children, [1] open items, [2] final compositions
+__device__ __forceinline__ void slice_prefix3(const unsigned long long* cta_tot, unsigned long long (&base)[3], unsigned long long (&all)[3]) {
+    unsigned long long v[6] = {0ULL, 0ULL, 0ULL, 0ULL, 0ULL, 0ULL};
+    for (unsigned b = threadIdx.x; b < gridDim.x; b += blockDim.x) {
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            const unsigned long long x = __ldcg(cta_tot + (size_t)k * gridDim.x + b);
+            v[3 + k] += x;
+            if (b < blockIdx.x) v[k] += x;
+        }
+    }
+    block_sum_n<6>(v);
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        base[k] = v[k];
+        all[k] = v[3 + k];
+    }
+}
+
+// entities of a list of n are dealt to CTAs in contiguous slices of `per` (a multiple of 32)
+__device__ __forceinline__ long long slice_size(long long n) {
+    const long long per = (n + gridDim.x - 1) / gridDim.x;
+    return (per + 31) & ~31LL;
+}
+
+// reachable window values of one peak: calls f(word_index, reach_bits) for every word of the window, in
+// ascending order; the loads go out four at a time (the words are independent, the loop would otherwise pay one
+// DRAM round trip per word)
+template <typename F>
+__device__ __forceinline__ void for_window_words(const uint64_t* __restrict__ last, int64_t a, int64_t b, F f) {
+    if (a > b) return;
+    const int64_t w0 = a >> 5, w1 = b >> 5;
+    for (int64_t wd = w0; wd <= w1; wd += 4) {
+        uint64_t x[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++) x[q] = (wd + q <= w1) ? __ldg(last + wd + q) : 0ULL;
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            if (wd + q > w1) break;
+            uint64_t y = (x[q] | (x[q] >> 1)) & kBit0Mask;
+            if (wd + q == w0) y &= (1ULL << (2 * (31 - (int)(a & 31)) + 1)) - 1ULL;
+            if (wd + q == w1) y &= ~0ULL << (2 * (31 - (int)(b & 31)));
+            f(wd + q, y);
+        }
+    }
+}
+
+struct RowTables {  // per-CTA shared copies
+    const int32_t* w;
+    const int32_t* ind;
+    const uint8_t* mod;
+    const uint8_t* leaf;
+    LeafHash lh;
+    uint32_t wmin;
+};
+
+__device__ __forceinline__ int item_kind(int mode, uint32_t m, uint32_t wmin) {
+    if (m == 0u) return KIND_DONE;
+    if (mode != MODE_FREE) return KIND_OPEN;
+    if (m < 2u * wmin) return KIND_LEAF;
+    if (m < 3u * wmin) return KIND_POPC;
+    return KIND_OPEN;
+}
+
+// enabled LEFT edges of an open item.  EXACT mode filters by the budgets the item carries (reference
+// mass_explanation.py:165-172: a modification row needs all > 0 and ind > 0, where ind is the remaining budget
+// of the row the level was entered by, or IND[r] for any other row).
+__device__ __forceinline__ Mask128 open_children(const PassArgs& a, const RowTables& rt, int mode, uint32_t p, uint32_t m, int rmax,
+                                                 int all, int ind) {
+    Mask128 c = child_mask(a.tv, a.mp, mode, p, m, rmax);
+    if (mode == MODE_EXACT) {
+        Mask128 scan = c;
+        while (!mask_empty(scan)) {
+            const int r = mask_pop_lowest(scan);
+            if (!rt.mod[r]) continue;
+            const int ind_here = (r == rmax) ? ind : rt.ind[r];
+            if (!(all > 0 && ind_here > 0)) c.w[r >> 5] &= ~(1u << (r & 31));
+        }
+    }
+    return c;
+}
+
+// append row r to a path held in registers
+__device__ __forceinline__ void path_append(unsigned long long* pw, int nw, int r) {
+    for (int k = nw - 1; k > 0; k--) pw[k] = (pw[k] << 8) | (pw[k - 1] >> 56);
+    pw[0] = (pw[0] << 8) | (unsigned long long)r;
+}
+
+// NW = path words known at compile time (1 or 2: the path stays in registers), 0 = run-time a.nw (deep
+// compositions of test alphabets; path arrays in local memory)
+template <int NW>
+__global__ void __launch_bounds__(kPassThreads, 2)
+k_explain_pass(const PassArgs a) {
+    constexpr int kPW = NW ? NW : kMaxPathWords;
     __shared__ int32_t s_w[kMaxRows];
     __shared__ int32_t s_ind[kMaxRows];
     __shared__ uint8_t s_mod[kMaxRows];
+    __shared__ uint8_t s_leaf[kLeafSlots];
+    __shared__ int s_nheavy;
+    __shared__ int s_heavy_p[kPassThreads];
+    __shared__ unsigned long long s_heavy_off[kPassThreads];
+    const TableView& tv = a.tv;
     for (int i = threadIdx.x; i < kMaxRows; i += blockDim.x) {
         s_w[i] = i < tv.R ? tv.weights[i] : 0;
-        s_ind[i] = i < tv.R ? meta.ind[i] : 0;
-        s_mod[i] = i < tv.R ? meta.is_mod[i] : 0;
+        s_ind[i] = i < tv.R ? a.meta.ind[i] : 0;
+        s_mod[i] = i < tv.R ? a.meta.is_mod[i] : 0;
     }
+    if (blockIdx.x == 0 && threadIdx.x == 0) a.totals[8] = globaltimer_ns();
     __syncthreads();
-    const int64_t n_items = (int64_t)totals_in[1];
-    if (n_items == 0 || (unsigned long long)n_items > items.cap) {  // nothing to do / item pass overflowed
-        if (blockIdx.x == 0 && threadIdx.x == 0) {
-            item_comp_off[0] = 0ULL;
-            totals[2] = 0ULL;
-        }
-        return;
-    }
-    const int n_tiles = (int)((n_items + kTile - 1) / kTile);
-    for (;;) {
-        const int tile = next_tile(ss);
-        if (tile >= n_tiles) break;
-        const int64_t item = (int64_t)tile * kTile + threadIdx.x;
-        unsigned long long n = 0;
-        uint32_t v = 0;
-        int64_t p = 0;
-        int r1 = 0, mode = MODE_FREE, max_mods = 0;
-        if (item < n_items) {
-            v = items.v[item];
-            p = items.peak[item];
-            r1 = items.r[item];
-            mode = pk.mode[p];
-            max_mods = pk.max_mods[p];
-            n = enumerate_item<false>(tv, mp, s_w, s_ind, s_mod, mode, p, v, r1, max_mods, nullptr, W, 0ULL, per_item_cap, flags);
-        }
-        unsigned long long tile_total;
-        const unsigned long long off = chained_offset(ss, tile, n, &tile_total);
-        if (item < n_items) {
-            item_comp_off[item] = off;
-            if (item == n_items - 1) {
-                item_comp_off[n_items] = off + n;
-                totals[2] = off + n;
-            }
-            if (off + n > rec_capacity) flags[1] = 1;
-            else if (n) enumerate_item<true>(tv, mp, s_w, s_ind, s_mod, mode, p, v, r1, max_mods, recs, W, off, ~0ULL, flags);
-        }
-    }
-}
+    leaf_table_init(s_leaf, s_w, tv.R, a.leaf);
+    __syncthreads();
+    const RowTables rt{s_w, s_ind, s_mod, s_leaf, a.leaf, tv.R > 1 ? (uint32_t)s_w[1] : 0u};
+    const int lane = threadIdx.x & 31;
+    const int nw = NW ? NW : a.nw;
+    unsigned int gen = 0;
+    int ts = 1;  // next timestamp slot
+    const int64_t P = a.pk.P;
+    const int64_t limit = tv.C * 32;
+    const int top_row = tv.R - 1;
+    const uint64_t* last = tv.tbl + (int64_t)top_row * tv.C;
+    unsigned long long base, n_roots = 0, n_items = 0, n_comps = 0;
+    int cur = 0, level = 0;
 
-// per-peak composition offsets: peak_off[p] = item_comp_off[root_item_off[root_off[p]]], peak_off[P] = total
-__global__ void k_peak_offsets(const unsigned long long* __restrict__ root_off, const unsigned long long* __restrict__ root_item_off,
-                               const unsigned long long* __restrict__ item_comp_off, int64_t P, unsigned long long item_capacity,
-                               unsigned long long* __restrict__ peak_off) {
-    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (p > P) return;
-    unsigned long long i = root_item_off[root_off[p]];
-    if (i > item_capacity) i = item_capacity;  // only after an item overflow; the host repeats the run
-    peak_off[p] = item_comp_off[i];
+    // ---- stage 1 (K3): peaks -> level-0 items, one per reachable window value ----
+    {
+        const long long per = slice_size(P), first = (long long)blockIdx.x * per;
+        unsigned long long mine = 0;
+        for (long long li = threadIdx.x; li < per; li += blockDim.x) {
+            const long long p = first + li;
+            if (p >= P) break;
+            const int64_t lo = a.pk.target[p] - a.pk.thr[p], hi = a.pk.target[p] + a.pk.thr[p];
+            uint8_t st = 0;
+            if (lo <= 0 && 0 <= hi) st |= ST_ZERO_IN_WINDOW;
+            if (lo <= hi && hi >= limit) st |= ST_OUT_OF_TABLE;
+            a.status[p] = st;
+            a.peak_cnt[p] = 0ULL;
+            unsigned int n = 0;
+            for_window_words(last, lo < 1 ? 1 : lo, hi < limit - 1 ? hi : limit - 1, [&](int64_t, uint64_t x) { n += __popcll(x); });
+            a.cnt[p] = n;
+            mine += n;
+        }
+        const unsigned long long tot = block_sum(mine);
+        if (threadIdx.x == 0) a.cta_tot[blockIdx.x] = tot;
+        stamp(a, ts++);
+        grid_barrier(a, gen);
+        slice_prefix(a.cta_tot, &base, &n_roots);
+        n_items = n_roots;
+        if (n_roots > a.cap) {  // the same answer in every CTA: the host grows the buffers and runs the pass again
+            if (blockIdx.x == 0 && threadIdx.x == 0) {
+                a.flags[2] = 1;
+                a.totals[0] = n_roots;
+                a.totals[1] = n_roots;
+            }
+            return;
+        }
+        const ItemBuf& out = a.buf[0];
+        const uint32_t meta0 = (uint32_t)top_row;
+        auto put_root = [&](unsigned long long o, uint32_t v, uint32_t p) {
+            out.m[o] = v;
+            out.peak[o] = p;
+            out.meta[o] = meta0 | ((uint32_t)a.pk.mode[p] << 24);
+            for (int k = 0; k < nw; k++) out.path[(unsigned long long)k * a.cap + o] = 0ULL;
+            if (a.has_budget) {
+                out.all[o] = a.pk.max_mods[p];
+                out.ind[o] = s_ind[top_row];
+            }
+        };
+        for (long long l0 = 0; l0 < per; l0 += blockDim.x) {  // uniform trip count: block_scan has barriers
+            const long long p = first + l0 + threadIdx.x;
+            const bool ok = l0 + threadIdx.x < per && p < P;
+            const unsigned int n = ok ? a.cnt[p] : 0u;
+            unsigned int round_tot;
+            unsigned long long off = base + block_scan32(n, &round_tot);
+            base += round_tot;
+            int64_t wa = 1, wb = 0;
+            if (ok) {
+                const int64_t lo = a.pk.target[p] - a.pk.thr[p], hi = a.pk.target[p] + a.pk.thr[p];
+                wa = lo < 1 ? 1 : lo;
+                wb = hi < limit - 1 ? hi : limit - 1;
+            }
+            // A peak with few roots writes them itself.  One with many (a wide 2-3 nt window) goes on a CTA-wide
+            // list that all warps then drain together: lane l takes window word l, l+32, ..., a warp scan places the
+            // roots.  (Heavy peaks cluster; left to their own warps they serialise the whole grid at the barrier.)
+            const bool heavy = ok && n > 6;
+            if (ok && n && !heavy) {
+                for_window_words(last, wa, wb, [&](int64_t wd, uint64_t x) {
+                    while (x) {  // ascending mass = descending bit position
+                        const int pos = 63 - __clzll((long long)x);
+                        x &= ~(1ULL << pos);
+                        put_root(off++, (uint32_t)(wd * 32 + (31 - (pos >> 1))), (uint32_t)p);
+                    }
+                });
+            }
+            if (threadIdx.x == 0) s_nheavy = 0;
+            __syncthreads();
+            if (heavy) {
+                const int q = atomicAdd(&s_nheavy, 1);
+                s_heavy_p[q] = (int)(p - first);
+                s_heavy_off[q] = off;
+            }
+            __syncthreads();
+            const int nheavy = s_nheavy;
+            for (int q = threadIdx.x >> 5; q < nheavy; q += kPassThreads / 32) {
+                const long long hp = first + s_heavy_p[q];
+                unsigned long long run = s_heavy_off[q];
+                const int64_t lo = a.pk.target[hp] - a.pk.thr[hp], hi = a.pk.target[hp] + a.pk.thr[hp];
+                const int64_t sa = lo < 1 ? 1 : lo, sb = hi < limit - 1 ? hi : limit - 1;
+                const int64_t w0 = sa >> 5, w1 = sb >> 5;
+                for (int64_t wbase = w0; wbase <= w1; wbase += 32) {
+                    const int64_t wd = wbase + lane;
+                    uint64_t x = 0;
+                    if (wd <= w1) {
+                        x = __ldg(last + wd);
+                        x = (x | (x >> 1)) & kBit0Mask;
+                        if (wd == w0) x &= (1ULL << (2 * (31 - (int)(sa & 31)) + 1)) - 1ULL;
+                        if (wd == w1) x &= ~0ULL << (2 * (31 - (int)(sb & 31)));
+                    }
+                    const unsigned c = __popcll(x);
+                    unsigned incl = c;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const unsigned y = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+                        if (lane >= o) incl += y;
+                    }
+                    unsigned long long o2 = run + (incl - c);
+                    while (x) {
+                        const int pos = 63 - __clzll((long long)x);
+                        x &= ~(1ULL << pos);
+                        put_root(o2++, (uint32_t)(wd * 32 + (31 - (pos >> 1))), (uint32_t)hp);
+                    }
+                    run += __shfl_sync(0xFFFFFFFFu, incl, 31);
+                }
+            }
+            __syncthreads();
+        }
+        if (blockIdx.x == 0 && threadIdx.x == 0) a.peak_cnt[P] = 0ULL;
+        stamp(a, ts++);
+        grid_barrier(a, gen);
+    }
+
+    // ---- expansion: level -> level + 1 until no item is open ----
+    for (;;) {
+        const ItemBuf& in = a.buf[cur];
+        const long long n = (long long)n_items, per = slice_size(n), first = (long long)blockIdx.x * per;
+        unsigned long long mine_children = 0, mine_open = 0, mine_final = 0;
+        for (long long li = threadIdx.x; li < per; li += blockDim.x) {
+            const long long i = first + li;
+            if (i >= n) break;
+            const uint32_t m = __ldcg(in.m + i);
+            uint32_t meta = __ldcg(in.meta + i);
+            const int rmax = meta & 0xFF;
+            const int mode = (meta >> 24) & 3;
+            const uint32_t p = mode == MODE_MEMO ? __ldcg(in.peak + i) : 0u;  // only the memo key needs the peak
+            const int kind = item_kind(mode, m, rt.wmin);
+            unsigned int c_exp = 1, c_fin = 1;
+            if (kind == KIND_POPC) {
+                c_fin = (meta >> 16) & 0xFF;
+                if (!c_fin) {  // counted once, then carried in the item
+                    c_fin = (unsigned)mask_popc(child_mask(tv, a.mp, mode, p, m, rmax));
+                    in.meta[i] = meta | (c_fin << 16);
+                }
+            } else if (kind == KIND_OPEN) {
+                const int all = a.has_budget ? __ldcg(in.all + i) : 0, ind = a.has_budget ? __ldcg(in.ind + i) : 0;
+                c_exp = (unsigned)mask_popc(open_children(a, rt, mode, p, m, rmax, all, ind));
+                c_fin = 0;
+                mine_open++;
+            }
+            a.cnt[i] = c_exp | (c_fin << 16);
+            mine_children += c_exp;
+            mine_final += c_fin;
+        }
+        unsigned long long tsum[3] = {mine_children, mine_open, mine_final};
+        block_sum_n<3>(tsum);
+        if (threadIdx.x < 3) a.cta_tot[(size_t)threadIdx.x * gridDim.x + blockIdx.x] = tsum[threadIdx.x];
+        stamp(a, ts++);
+        grid_barrier(a, gen);
+        stamp(a, ts++);
+        unsigned long long bases[3], alls[3];
+        slice_prefix3(a.cta_tot, bases, alls);
+        stamp(a, ts++);
+        const unsigned long long n_next = alls[0], n_open = alls[1];
+        if (n_open == 0) {
+            base = bases[2];  // record offset of this CTA's slice
+            n_comps = alls[2];
+            break;
+        }
+        base = bases[0];
+        if (n_next > a.cap || n_next > a.item_limit || level + 1 >= kMaxDepth) {
+            if (blockIdx.x == 0 && threadIdx.x == 0) {
+                a.flags[n_next > a.item_limit || level + 1 >= kMaxDepth ? 0 : 2] = 1;
+                a.totals[0] = n_roots;
+                a.totals[1] = n_next;
+                a.totals[3] = (unsigned long long)level;
+            }
+            return;
+        }
+        const ItemBuf& out = a.buf[cur ^ 1];
+        for (long long l0 = 0; l0 < per; l0 += blockDim.x) {
+            const long long i = first + l0 + threadIdx.x;
+            const bool ok = l0 + threadIdx.x < per && i < n;
+            const unsigned int k = ok ? (a.cnt[i] & 0xFFFFu) : 0u;
+            unsigned int round_tot;
+            const unsigned long long off = base + block_scan32(k, &round_tot);
+            base += round_tot;
+            uint32_t m = 0, p = 0, meta = 0;
+            int all = 0, ind = 0;
+            unsigned long long pw[kPW];
+#pragma unroll
+            for (int q = 0; q < kPW; q++) pw[q] = 0ULL;
+            Mask128 c;
+            c.w[0] = c.w[1] = c.w[2] = c.w[3] = 0u;
+            if (ok && k) {
+                m = __ldcg(in.m + i);
+                p = __ldcg(in.peak + i);
+                meta = __ldcg(in.meta + i) & 0x7FFFFFFFu;
+                const int mode = (meta >> 24) & 3;
+                for (int q = 0; q < nw; q++) pw[q] = __ldcg(in.path + (unsigned long long)q * a.cap + i);
+                if (a.has_budget) {
+                    all = __ldcg(in.all + i);
+                    ind = __ldcg(in.ind + i);
+                }
+                if (item_kind(mode, m, rt.wmin) == KIND_OPEN) {
+                    meta |= 0x80000000u;  // open: its outputs are children, not a copy
+                    c = open_children(a, rt, mode, p, m, meta & 0xFF, all, ind);
+                }
+            }
+            // Output-centric placement: the warp's items produce T consecutive outputs (a copy for a finished item,
+            // one per enabled row for an open one); lane l writes outputs l, l+32, ... — finds the producing lane by a
+            // shuffle search over the per-lane output offsets, pulls that lane's item through shuffles and picks its
+            // j-th row.  Work is per OUTPUT (no serial loop over parents) and every store is coalesced.
+            if (__ballot_sync(0xFFFFFFFFu, meta >> 31) == 0u) {  // no open item in this warp: plain copies
+                if (ok && k) {
+                    out.m[off] = m;
+                    out.peak[off] = p;
+                    out.meta[off] = meta;
+                    for (int q = 0; q < nw; q++) out.path[(unsigned long long)q * a.cap + off] = pw[q];
+                    if (a.has_budget) {
+                        out.all[off] = all;
+                        out.ind[off] = ind;
+                    }
+                }
+                continue;
+            }
+            const unsigned long long off0 = __shfl_sync(0xFFFFFFFFu, off, 0);
+            const unsigned wp = (unsigned)(off - off0);
+            const unsigned T = __shfl_sync(0xFFFFFFFFu, wp + k, 31);
+            for (unsigned o0 = 0; o0 < T; o0 += 32) {
+                const unsigned o = o0 + lane;
+                int src = 0;
+#pragma unroll
+                for (int step = 16; step; step >>= 1) {
+                    const int cand = src + step;
+                    const unsigned v = __shfl_sync(0xFFFFFFFFu, wp, cand & 31);
+                    if (cand < 32 && v <= o) src = cand;
+                }
+                const int j = (int)(o - __shfl_sync(0xFFFFFFFFu, wp, src));
+                const uint32_t sm = __shfl_sync(0xFFFFFFFFu, m, src), sp = __shfl_sync(0xFFFFFFFFu, p, src);
+                const uint32_t smeta = __shfl_sync(0xFFFFFFFFu, meta, src);
+                Mask128 sc;
+#pragma unroll
+                for (int q = 0; q < 4; q++) sc.w[q] = __shfl_sync(0xFFFFFFFFu, c.w[q], src);
+                unsigned long long cw[kPW];
+                for (int q = 0; q < nw; q++) cw[q] = __shfl_sync(0xFFFFFFFFu, pw[q], src);
+                int sall = 0, sind = 0;
+                if (a.has_budget) {
+                    sall = __shfl_sync(0xFFFFFFFFu, all, src);
+                    sind = __shfl_sync(0xFFFFFFFFu, ind, src);
+                }
+                if (o < T) {
+                    const unsigned long long o2 = off0 + o;
+                    uint32_t om = sm, ometa = smeta;
+                    if (smeta & 0x80000000u) {
+                        const int r = mask_select(sc, j);
+                        const int srmax = smeta & 0xFF, sdepth = (smeta >> 8) & 0xFF;
+                        om = sm - (uint32_t)s_w[r];
+                        ometa = (uint32_t)r | ((uint32_t)(sdepth + 1) << 8) | (smeta & 0x03000000u);
+                        path_append(cw, nw, r);
+                        if (a.has_budget) {
+                            const int mod = s_mod[r];
+                            sind = ((r == srmax) ? sind : s_ind[r]) - mod;
+                            sall -= mod;
+                        }
+                    }
+                    out.m[o2] = om;
+                    out.peak[o2] = sp;
+                    out.meta[o2] = ometa;
+                    for (int q = 0; q < nw; q++) out.path[(unsigned long long)q * a.cap + o2] = cw[q];
+                    if (a.has_budget) {
+                        out.all[o2] = sall;
+                        out.ind[o2] = sind;
+                    }
+                }
+            }
+        }
+        stamp(a, ts++);
+        grid_barrier(a, gen);
+        cur ^= 1;
+        n_items = n_next;
+        level++;
+    }
+
+    // ---- records: the list in buf[cur] is final; one thread per composition ----
+    const bool fits = n_comps <= a.rec_capacity;
+    {
+        const ItemBuf& in = a.buf[cur];
+        const long long n = (long long)n_items, per = slice_size(n), first = (long long)blockIdx.x * per;
+        // per-peak totals (items of a peak are contiguous; one add per item)
+        for (long long li = threadIdx.x; li < per; li += blockDim.x) {
+            const long long i = first + li;
+            if (i >= n) break;
+            const unsigned int c = a.cnt[i] >> 16;
+            if (c) atomicAdd(a.peak_cnt + __ldcg(in.peak + i), (unsigned long long)c);
+        }
+        if (fits) {
+            unsigned long long* recs64 = reinterpret_cast<unsigned long long*>(a.recs);
+            for (long long l0 = 0; l0 < per; l0 += blockDim.x) {
+                const long long i = first + l0 + threadIdx.x;
+                const bool ok = l0 + threadIdx.x < per && i < n;
+                const unsigned int c = ok ? (a.cnt[i] >> 16) : 0u;
+                unsigned int round_tot;
+                const unsigned long long roff = base + block_scan32(c, &round_tot);
+                base += round_tot;
+                uint32_t m = 0, meta = 0;
+                unsigned long long pw[kPW];
+#pragma unroll
+                for (int q = 0; q < kPW; q++) pw[q] = 0ULL;
+                int kind = KIND_DONE;
+                Mask128 cm;
+                cm.w[0] = cm.w[1] = cm.w[2] = cm.w[3] = 0u;
+                if (c) {
+                    m = __ldcg(in.m + i);
+                    meta = __ldcg(in.meta + i);
+                    for (int q = 0; q < nw; q++) pw[q] = __ldcg(in.path + (unsigned long long)q * a.cap + i);
+                    kind = item_kind((meta >> 24) & 3, m, rt.wmin);
+                    if (kind == KIND_POPC) cm = child_mask(tv, a.mp, MODE_FREE, 0, m, meta & 0xFF);
+                }
+                // the j-th record of an item: its path, plus (LEAF) the one row that closes it, or (POPC) the j-th
+                // enabled row r2 and, if something is left, the row that closes that
+                auto put = [&](unsigned long long at, uint32_t im, int rmax, int knd, int r2, const unsigned long long* path) {
+                    unsigned long long w[kPW];
+                    for (int q = 0; q < nw; q++) w[q] = path[q];
+                    if (knd == KIND_LEAF) {
+                        path_append(w, nw, leaf_row(s_leaf, s_w, a.leaf, im, rmax));
+                    } else if (knd == KIND_POPC) {
+                        const uint32_t m3 = im - (uint32_t)s_w[r2];
+                        path_append(w, nw, r2);
+                        if (m3) path_append(w, nw, leaf_row(s_leaf, s_w, a.leaf, m3, r2));
+                    }
+                    for (int q = 0; q < nw; q++) recs64[at * (unsigned long long)nw + q] = w[q];
+                };
+                const bool heavy = c > 4;
+                if (c && !heavy) {  // the owner writes its few records itself
+                    Mask128 left = cm;
+                    for (unsigned int j = 0; j < c; j++) put(roff + j, m, meta & 0xFF, kind, kind == KIND_POPC ? mask_pop_lowest(left) : 0, pw);
+                }
+                for (unsigned hm = __ballot_sync(0xFFFFFFFFu, heavy); hm; hm &= hm - 1) {  // many records: the warp shares them
+                    const int src = __ffs(hm) - 1;
+                    const uint32_t sm = __shfl_sync(0xFFFFFFFFu, m, src), smeta = __shfl_sync(0xFFFFFFFFu, meta, src);
+                    const unsigned int sc = __shfl_sync(0xFFFFFFFFu, c, src);
+                    const unsigned long long so = __shfl_sync(0xFFFFFFFFu, roff, src);
+                    Mask128 scm;
+#pragma unroll
+                    for (int q = 0; q < 4; q++) scm.w[q] = __shfl_sync(0xFFFFFFFFu, cm.w[q], src);
+                    unsigned long long spw[kPW];
+                    for (int q = 0; q < nw; q++) spw[q] = __shfl_sync(0xFFFFFFFFu, pw[q], src);
+                    for (unsigned int j = lane; j < sc; j += 32) put(so + j, sm, smeta & 0xFF, KIND_POPC, mask_select(scm, (int)j), spw);
+                }
+            }
+        }
+        if (blockIdx.x == 0 && threadIdx.x == 0) {
+            if (!fits) a.flags[1] = 1;
+            a.totals[0] = n_roots;
+            a.totals[1] = n_items;
+            a.totals[2] = n_comps;
+            a.totals[3] = (unsigned long long)level;
+        }
+        stamp(a, ts++);
+        grid_barrier(a, gen);
+    }
+
+    // ---- per-peak record offsets: exclusive scan of the per-peak totals ----
+    {
+        const long long per = slice_size(P + 1), first = (long long)blockIdx.x * per;
+        unsigned long long mine = 0;
+        for (long long li = threadIdx.x; li < per; li += blockDim.x) {
+            const long long p = first + li;
+            if (p > P) break;
+            mine += __ldcg(a.peak_cnt + p);
+        }
+        const unsigned long long tot = block_sum(mine);
+        if (threadIdx.x == 0) a.cta_tot[blockIdx.x] = tot;
+        grid_barrier(a, gen);
+        unsigned long long all_comps;
+        slice_prefix(a.cta_tot, &base, &all_comps);
+        for (long long l0 = 0; l0 < per; l0 += blockDim.x) {
+            const long long p = first + l0 + threadIdx.x;
+            const bool ok = l0 + threadIdx.x < per && p <= P;
+            const unsigned long long c = ok ? __ldcg(a.peak_cnt + p) : 0ULL;
+            unsigned long long round_tot;
+            const unsigned long long off = base + block_scan(c, &round_tot);
+            base += round_tot;
+            if (ok) a.peak_off[p] = off;
+        }
+    }
+    stamp(a, ts++);
 }
 
 }  // namespace sst

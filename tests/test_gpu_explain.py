@@ -121,12 +121,12 @@ def test_edge_cases():
         batch.explanations(6)
     assert ME.is_valid_mass(633.169 * 35, dp, 0.0) is True      # 35 x heaviest = max_mass, still in the table
     ctx = dp.device_table().ctx
-    ctx.set_per_root_cap(1000)                                  # blow-up guard: 8-nt window has far more
+    ctx.set_item_limit(1000)                                  # blow-up guard: 8-nt window has far more
     try:
         with pytest.raises(MemoryError):
             ME.explain_masses([8 * 345.048], dp, thresholds=[0.01])
     finally:
-        ctx.set_per_root_cap(0)
+        ctx.set_item_limit(0)
     with pytest.raises(ValueError):
         ME.explain_mass_with_table(305.042, dp, compression_rate=16)
 
