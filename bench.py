@@ -133,8 +133,8 @@ def _cpu_chunk(args):
             if _G["use_c"]:
                 tg, th = oracle_py.integerise(float(m), float(t), 1e-3, _G["tol"])
                 oracle_c.is_valid(tab, 32, tg, th)
-            else:
-                oracle_py.is_valid_mass(float(m), tab, 32, 1e-3, _G["tol"], float(t))
+            elif oracle_py.is_valid_mass(float(m), tab, 32, 1e-3, _G["tol"], float(t)):
+                oracle_py.is_singleton(float(m), w, 1e-3, _G["tol"], float(t))  # classify_fragments asks this of every valid copy
         except NotImplementedError:
             pass
     return n
@@ -227,7 +227,7 @@ def workload_config(wl, args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="C4")
@@ -255,6 +255,7 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     from spectrseqtools_b200 import _cabi
+    from spectrseqtools_b200 import fragment_classification as FC
     from spectrseqtools_b200 import mass_explanation as ME
     from spectrseqtools_b200 import mass_table as MT
     from spectrseqtools_b200 import synthetic as S
@@ -297,17 +298,18 @@ def main():
         out[...] = a
         return out
 
-    v_mass, v_thrf = pinned_copy(wl.valid_mass), pinned_copy(wl.valid_thr)
+    observed = pinned_copy(wl.observed)
+    offsets = np.array([w * dp.precision for w in wl.breakage], dtype=np.float64)
     e_mass, e_thrf = pinned_copy(wl.explain_mass), pinned_copy(wl.explain_thr)
     v_target, v_thr = ME._integerise_many(wl.valid_mass, wl.valid_thr, dp)      # only for the byte accounting below
     e_target, e_thr = ME._integerise_many(wl.explain_mass, wl.explain_thr, dp)
     weights, is_mod, ind = ME._row_metadata(dp)
     max_mods = np.full(len(e_target), wl.max_modifications, dtype=np.int32)
-    ctx.valid_stage_f64(v_mass, v_thrf, dp.precision, dp.tolerance)
+    ctx.classify_stage(observed, offsets)   # validity of every (peak x breakage offset): the fused N2 front end
     ctx.explain_stage_f64(dev, e_mass, e_thrf, max_mods, ind, is_mod, dp.precision, dp.tolerance, True)
 
     def step():
-        ctx.valid_run(dev)
+        ctx.classify_run(dev, dp.precision, dp.tolerance)
         return ctx.explain_run(dev, 0)
 
     sampler = ClockSampler(local_rank)
@@ -342,7 +344,7 @@ def main():
 
     # ---- e2e: public API, host buffers in, host arrays out (H2D + kernels + D2H of every result)
     def e2e_step():
-        valid = ME.are_valid_masses(v_mass, dp, v_thrf)
+        valid = FC.classify_observed(observed, dp, wl.breakage, copy=False)
         batch = ME.explain_masses(e_mass, dp, max_modifications=wl.max_modifications, thresholds=e_thrf, copy=False)
         return valid, batch
 
@@ -364,7 +366,7 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
     rec_width = ctx._last[2]
-    h2d = 16 * len(v_target) + 21 * len(e_target) + 5 * dev.R
+    h2d = 8 * len(observed) + 8 * len(offsets) + 20 * len(e_target) + 5 * dev.R
     d2h = len(v_target) + len(e_target) + 8 * (len(e_target) + 1) + int(batch.n_compositions) * rec_width
     e2e_value = peaks_all * args.steps / e2e_s
 
@@ -373,12 +375,12 @@ def main():
     comp_len = int((batch.records > 0).sum()) if batch.records is not None and batch.records.size else 0
     k2b_bytes = 16 * len(e_target) + 8 * (len(e_target) + 1) + 4 * int(batch.n_compositions) + comp_len + 8 * int(win_words)
     vwin_words = ((2 * v_thr + 1 + 31) // 32 + 1).sum()
-    k2a_bytes = 17 * len(v_target) + 8 * int(vwin_words)
+    k2a_bytes = 8 * len(observed) + len(v_target) + 8 * int(vwin_words)
     fam = ["phase_a", "explain_pass"]
     k2b_ms = sum(stats[k][0] for k in fam) / args.steps
-    k2a_ms = stats["is_valid"][0] / args.steps
+    k2a_ms = stats["classify"][0] / args.steps
     kernels = {k: {"ms_per_step": v[0] / args.steps, "launches_per_step": v[1] / args.steps} for k, v in stats.items() if v[1]}
-    dominant = max(fam + ["is_valid"], key=lambda k: stats[k][0])
+    dominant = max(fam + ["classify"], key=lambda k: stats[k][0])
     roofline = {"bound": "hbm", "kernel": "K3+K2b enumeration pass (k_explain_pass: window roots -> items -> compositions, one cooperative launch)",
                 "achieved": k2b_bytes / (k2b_ms * 1e-3) / 1e9 if k2b_ms else None, "peak": hbm_peak, "unit": "GB/s",
                 "frac": (k2b_bytes / (k2b_ms * 1e-3) / 1e9 / hbm_peak) if k2b_ms else None, "traffic": None,
@@ -409,7 +411,7 @@ def main():
         rows = table_rows_for(wl)
         workers = os.cpu_count() or 1
         rate0, _, _, _ = cpu_leg(wl, rows, max(50, min(400, wl.n_peaks)), False, workers)
-        n_sample = int(max(100, min(wl.n_peaks, rate0 * 12.0)))
+        n_sample = int(max(100, min(wl.n_peaks, rate0 * 15.0)))
         rate, comps, dt, n_e = cpu_leg(wl, rows, n_sample, False, workers)
         line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": workers, "kind": "port",
                                 "sample": f"first {n_sample} of {wl.n_peaks} peaks ({n_sample * (len(wl.valid_mass) // wl.n_peaks)} validity + {n_e} explanation calls), {dt:.1f} s wall",
@@ -457,13 +459,15 @@ def parity_gate(dp, wl, batch, valid, dev):
     out["explain_digest"] = h.hexdigest()[:16]
     vi = rng.choice(len(wl.valid_mass), size=min(4000, len(wl.valid_mass)), replace=False)
     vok = True
+    n_off = len(wl.breakage)
+    flags = valid.flags  # [breakage, peak]; wl.valid_* are peak-major
     for p in vi:
         tg, th = oracle_py.integerise(float(wl.valid_mass[p]), float(wl.valid_thr[p]), dp.precision, dp.tolerance)
         try:
             want = 1 if oracle_c.is_valid(tab, 32, tg, th) else 0
         except NotImplementedError:
             want = 2
-        vok &= int(valid[p]) == want
+        vok &= int(flags[p % n_off, p // n_off] & 3) == want
     out["validity_subsample"] = len(vi)
     out["validity_ok"] = bool(vok)
     return out

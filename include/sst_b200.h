@@ -100,6 +100,18 @@ int sst_valid_stage_f64(sst_ctx* ctx, const double* mass, const double* thr, int
 int sst_valid_run(sst_ctx* ctx, const sst_table* t);
 int sst_valid_fetch(sst_ctx* ctx, uint8_t* out);
 
+/* ---- fragment classification: replaces the per-(fragment x breakage) map_elements callbacks of classify_fragments
+ * (fragment_classification.py:39-82): standard-unit mass = observed[f] - offsets[b] (offsets[b] = breakage weight *
+ * precision, multiplied by the caller as the reference does), threshold = tolerance * observed[f], validity probe
+ * (is_valid_mass) and singleton test (is_singleton, :104-119).  out[b * F + f] (breakage-major, the reference's
+ * concat order): bit 1 valid, bit 2 out-of-table value met before any hit, bit 4 singleton. ---- */
+enum { SST_CLASS_VALID = 1, SST_CLASS_OUT_OF_TABLE = 2, SST_CLASS_SINGLETON = 4 };
+int sst_classify(sst_ctx* ctx, const sst_table* t, const double* observed, int64_t F, const double* offsets, int B, double precision,
+                 double tolerance, uint8_t* out /* B*F */);
+int sst_classify_stage(sst_ctx* ctx, const double* observed, int64_t F, const double* offsets, int B);
+int sst_classify_run(sst_ctx* ctx, const sst_table* t, double precision, double tolerance);
+int sst_classify_fetch(sst_ctx* ctx, uint8_t* out /* B*F */);
+
 /* ---- enumeration: replaces explain_mass_with_table (mass_explanation.py:92-203) for P peaks ----
  * max_mods[p]: global modification budget (SST_BUDGET_INF = unbounded); mode[p]: SST_MODE_*;
  * ind[r] = round(max_len * rate_r), is_mod[r]: per-row budget data shared by the batch (length R).

@@ -116,6 +116,35 @@ def is_valid_mass(mass: float, table: np.ndarray, compression: int, precision: f
     return False
 
 
+def is_singleton(mass: float, integer_masses: Sequence[int], precision: float, tolerance: float,
+                 threshold: Optional[float] = None) -> bool:
+    """fragment_classification.py:104-119: some row weight (the leading 0 included) lies inside the window."""
+    target, thr = integerise(mass, threshold, precision, tolerance)
+    for value in range(target - thr, target + thr + 1):
+        if value in integer_masses:
+            return True
+    return False
+
+
+def classify_pairs(observed: Sequence[float], breakage_weights: Sequence[int], table: np.ndarray, integer_masses: Sequence[int],
+                   compression: int, precision: float, tolerance: float) -> np.ndarray:
+    """fragment_classification.py:39-82 as flags[b][f]: bit 1 valid, bit 2 out-of-table before any hit, bit 4
+    singleton.  standard-unit mass = observed - (weight * precision), threshold = tolerance * observed."""
+    out = np.zeros((len(breakage_weights), len(observed)), dtype=np.uint8)
+    for b, bw in enumerate(breakage_weights):
+        for f, x in enumerate(observed):
+            su = x - (bw * precision)
+            thr = tolerance * x
+            try:
+                code = 1 if is_valid_mass(su, table, compression, precision, tolerance, thr) else 0
+            except OutOfTable:
+                code = 2
+            if is_singleton(su, integer_masses, precision, tolerance, thr):
+                code |= 4
+            out[b, f] = code
+    return out
+
+
 def individual_budgets(rows: Sequence[Row], max_len: int) -> List[int]:
     """IND[r] = round(max_len * rate_r), Python banker's rounding (mass_explanation.py:158-161,200)."""
     return [round(max_len * r.modification_rate) for r in rows]

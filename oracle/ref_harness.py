@@ -38,6 +38,7 @@ _WANTED = {
         "explain_mass_with_recursion",
         "convert_nucleotide_masses_to_names",
     ],
+    "fragment_classification.py": ["is_singleton"],
 }
 
 

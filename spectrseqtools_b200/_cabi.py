@@ -24,6 +24,7 @@ SST_ERR_TOO_MANY_ROWS, SST_ERR_TOO_DEEP, SST_ERR_NOMEM, SST_ERR_MEMO_FULL, SST_E
 MODE_FREE, MODE_EXACT, MODE_MEMO = 0, 1, 2
 STATUS_ZERO_IN_WINDOW, STATUS_OUT_OF_TABLE = 1, 2
 VALID_NO, VALID_YES, VALID_OUT_OF_TABLE = 0, 1, 2
+CLASS_VALID, CLASS_OUT_OF_TABLE, CLASS_SINGLETON = 1, 2, 4
 BUDGET_INF = 1 << 30
 KERNEL_SLOTS = ["build", "transpose", "is_valid", "phase_a", "explain_pass", "classify", "length_bound", "spare"]
 
@@ -33,7 +34,7 @@ EXPORTS = [
     "sst_table_build", "sst_table_upload", "sst_table_rebuild", "sst_table_info", "sst_table_download",
     "sst_table_download_masks", "sst_table_destroy", "sst_is_valid", "sst_valid_stage", "sst_valid_run",
     "sst_valid_fetch", "sst_valid_stage_f64", "sst_explain", "sst_explain_stage", "sst_explain_stage_f64", "sst_explain_rec_width", "sst_explain_phase_ns",
-    "sst_explain_run", "sst_explain_fetch",
+    "sst_explain_run", "sst_explain_fetch", "sst_classify", "sst_classify_stage", "sst_classify_run", "sst_classify_fetch",
 ]
 
 
@@ -93,6 +94,10 @@ def load() -> C.CDLL:
             "sst_explain_stage": (C.c_int, [vp, vp, i64p, i64p, i32p, u8p, C.c_int64, i32p, u8p]),
             "sst_explain_run": (C.c_int, [vp, vp, C.c_int, C.c_uint64, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
             "sst_explain_fetch": (C.c_int, [vp, u8p, u64p, u8p]),
+            "sst_classify": (C.c_int, [vp, vp, fp, C.c_int64, fp, C.c_int, C.c_double, C.c_double, u8p]),
+            "sst_classify_stage": (C.c_int, [vp, fp, C.c_int64, fp, C.c_int]),
+            "sst_classify_run": (C.c_int, [vp, vp, C.c_double, C.c_double]),
+            "sst_classify_fetch": (C.c_int, [vp, u8p]),
         }
         for name in EXPORTS:
             fn = getattr(lib, name)  # AttributeError here = ABI drift
@@ -237,6 +242,22 @@ class Context:
         out = np.empty(self._staged_VP, dtype=np.uint8)
         self._check(self._lib.sst_valid_fetch(self._h, _p(out)))
         return out
+
+    def classify_stage(self, observed: np.ndarray, offsets: np.ndarray):
+        o, b = _arr(observed, np.float64), _arr(offsets, np.float64)
+        self._check(self._lib.sst_classify_stage(self._h, _p(o), len(o), _p(b), len(b)))
+        self._staged_C = (len(b), len(o))
+
+    def classify_run(self, table: "DeviceTable", precision: float, tolerance: float):
+        self._check(self._lib.sst_classify_run(self._h, table._h, float(precision), float(tolerance)))
+
+    def classify_fetch(self, copy: bool = True) -> np.ndarray:
+        """-> uint8[B, F] of CLASS_* bits (breakage-major)."""
+        B, F = self._staged_C
+        buf = self._pinned("classify", B * F)[: B * F]
+        self._check(self._lib.sst_classify_fetch(self._h, _p(buf)))
+        out = buf.reshape(B, F)
+        return out.copy() if copy else out
 
     def explain_stage(self, table: "DeviceTable", target, thr, max_mods, mode, ind, is_mod):
         t, h = _arr(target, np.int64), _arr(thr, np.int64)

@@ -78,6 +78,9 @@ struct sst_ctx {
     int64_t deepest = 0;  // longest composition any staged window value can have
     DevBuf d_memo_keys, d_memo_alive, d_memo_top, d_memo_misc, d_flush;
     DevBuf d_vtarget, d_vthr, d_vout;  // staged validity probes
+    DevBuf d_cobs, d_coff, d_cout;     // staged classification batch
+    int64_t CF = 0;
+    int CB = 0;
     int64_t VP = 0;
     int* h_misc = nullptr;             // pinned: run summary read back with one copy
     uint64_t n_roots = 0, n_comps = 0;
@@ -326,7 +329,7 @@ void sst_ctx_destroy(sst_ctx* ctx) {
                       &ctx->d_memo_peaks, &ctx->d_status, &ctx->d_cnt, &ctx->d_peakoff, &ctx->d_recs,
                       &ctx->d_blocksums, &ctx->d_memo_keys, &ctx->d_memo_alive, &ctx->d_memo_top,
                       &ctx->d_memo_misc, &ctx->d_flush, &ctx->d_vtarget, &ctx->d_vthr, &ctx->d_vout,
-                      &ctx->d_scan, &ctx->d_vmass, &ctx->d_vthrf, &ctx->d_peakcnt,
+                      &ctx->d_scan, &ctx->d_vmass, &ctx->d_vthrf, &ctx->d_peakcnt, &ctx->d_cobs, &ctx->d_coff, &ctx->d_cout,
                       &ctx->d_item_m[0], &ctx->d_item_m[1], &ctx->d_item_peak[0], &ctx->d_item_peak[1],
                       &ctx->d_item_meta[0], &ctx->d_item_meta[1], &ctx->d_item_all[0], &ctx->d_item_all[1],
                       &ctx->d_item_ind[0], &ctx->d_item_ind[1], &ctx->d_item_path[0], &ctx->d_item_path[1]};
@@ -574,6 +577,51 @@ int sst_is_valid(sst_ctx* ctx, const sst_table* t, const int64_t* target, const 
     return rc;
 }
 
+int sst_classify_stage(sst_ctx* ctx, const double* observed, int64_t F, const double* offsets, int B) {
+    CK(cudaSetDevice(ctx->device));
+    if (F < 0 || B < 0 || B > 65535) return fail(ctx, SST_ERR_BAD_ARG, "fragment / breakage count out of range");
+    int rc;
+    if ((rc = reserve(ctx, ctx->d_cobs, (size_t)(F ? F : 1) * 8))) return rc;
+    if ((rc = reserve(ctx, ctx->d_coff, (size_t)(B ? B : 1) * 8))) return rc;
+    if ((rc = reserve(ctx, ctx->d_cout, (size_t)(F * B ? F * B : 1)))) return rc;
+    if (F) CK(cudaMemcpyAsync(ctx->d_cobs.p, observed, (size_t)F * 8, cudaMemcpyHostToDevice, ctx->stream));
+    if (B) CK(cudaMemcpyAsync(ctx->d_coff.p, offsets, (size_t)B * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->CF = F;
+    ctx->CB = B;
+    return SST_OK;
+}
+
+int sst_classify_run(sst_ctx* ctx, const sst_table* t, double precision, double tolerance) {
+    CK(cudaSetDevice(ctx->device));
+    if (ctx->CF && ctx->CB) {
+        KTimer kt(ctx, SST_K_CLASSIFY);
+        k_classify<<<dim3((unsigned)((ctx->CF + 255) / 256), (unsigned)ctx->CB), 256, 0, ctx->stream>>>(view_of(t), (const double*)ctx->d_cobs.p, ctx->CF,
+                                                                              (const double*)ctx->d_coff.p, ctx->CB, precision, tolerance,
+                                                                              (uint8_t*)ctx->d_cout.p);
+        kt.stop(1);
+        CK(cudaGetLastError());
+    }
+    CK(cudaStreamSynchronize(ctx->stream));
+    flush_timers(ctx);
+    return SST_OK;
+}
+
+int sst_classify_fetch(sst_ctx* ctx, uint8_t* out) {
+    CK(cudaSetDevice(ctx->device));
+    if (ctx->CF && ctx->CB) CK(cudaMemcpyAsync(out, ctx->d_cout.p, (size_t)ctx->CF * ctx->CB, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return SST_OK;
+}
+
+int sst_classify(sst_ctx* ctx, const sst_table* t, const double* observed, int64_t F, const double* offsets, int B, double precision,
+                 double tolerance, uint8_t* out) {
+    int rc = sst_classify_stage(ctx, observed, F, offsets, B);
+    if (!rc) rc = sst_classify_run(ctx, t, precision, tolerance);
+    if (!rc) rc = sst_classify_fetch(ctx, out);
+    return rc;
+}
+
 int sst_explain_stage(sst_ctx* ctx, const sst_table* t, const int64_t* target, const int64_t* thr, const int32_t* max_mods,
                       const uint8_t* mode, int64_t P, const int32_t* ind, const uint8_t* is_mod) {
     CK(cudaSetDevice(ctx->device));
@@ -630,11 +678,13 @@ int sst_explain_stage(sst_ctx* ctx, const sst_table* t, const int64_t* target, c
 
 int sst_explain_stage_f64(sst_ctx* ctx, const sst_table* t, const double* mass, const double* thr, const int32_t* max_mods,
                           int64_t P, const int32_t* ind, const uint8_t* is_mod, double precision, double tolerance, int with_memo) {
+    CK(cudaSetDevice(ctx->device));
+    ctx->have_result = false;
     if (P < 0) return fail(ctx, SST_ERR_BAD_ARG, "negative peak count");
-    // same float operations as mass_explanation.py:107-114 (true division, round-half-even, ceil), then the
-    // host-side budget test: FREE when no composition inside the window can exhaust a budget
-    std::vector<int64_t> target((size_t)P), ithr((size_t)P);
-    std::vector<uint8_t> mode((size_t)P);
+    if (!t->H) return fail(ctx, SST_ERR_STATE, "table was built without row masks");
+    // Integerisation (the float operations of mass_explanation.py:107-114), the choice of the budget mode and
+    // the batch summary all run on the device (k_stage_f64): the host only derives the two mode thresholds
+    // from the per-row budgets.  FREE when no composition inside the window can exhaust a budget.
     int64_t w_min_mod = 0, hi_limit = INT64_MAX;
     for (int r = 1; r < t->R; r++)
         if (is_mod[r]) {
@@ -643,18 +693,47 @@ int sst_explain_stage_f64(sst_ctx* ctx, const sst_table* t, const double* mass, 
             const int64_t lim = ((int64_t)ind[r] + 1) * w;  // ind[r] >= hi / w  <=>  hi < (ind[r]+1) * w
             if (lim < hi_limit) hi_limit = lim;
         }
-    const uint8_t slow = with_memo ? SST_MODE_MEMO : SST_MODE_EXACT;
-    for (int64_t p = 0; p < P; p++) {
-        const double m = mass[p];
-        target[p] = (int64_t)nearbyint(m / precision);
-        const double th = (thr && !std::isnan(thr[p])) ? thr[p] : tolerance * m;
-        ithr[p] = (int64_t)std::ceil(th / precision);
-        int64_t hi = target[p] + ithr[p];
-        if (hi < 0) hi = 0;
-        const bool free_ok = !w_min_mod || ((int64_t)max_mods[p] >= hi / w_min_mod && hi < hi_limit);
-        mode[p] = free_ok ? SST_MODE_FREE : slow;
+    int rc;
+    const size_t p8 = (size_t)(P ? P : 1) * 8;
+    if ((rc = reserve(ctx, ctx->d_target, p8))) return rc;
+    if ((rc = reserve(ctx, ctx->d_thr, p8))) return rc;
+    if ((rc = reserve(ctx, ctx->d_maxmods, p8 / 2))) return rc;
+    if ((rc = reserve(ctx, ctx->d_mode, p8 / 8))) return rc;
+    if ((rc = reserve(ctx, ctx->d_ind, (size_t)kMaxRows * 4))) return rc;
+    if ((rc = reserve(ctx, ctx->d_ismod, (size_t)kMaxRows))) return rc;
+    if ((rc = reserve(ctx, ctx->d_vmass, p8))) return rc;
+    if ((rc = reserve(ctx, ctx->d_vthrf, p8))) return rc;
+    if ((rc = reserve(ctx, ctx->d_memo_peaks, p8 / 2))) return rc;
+    if ((rc = reserve(ctx, ctx->d_scan, 512))) return rc;
+    CK(cudaMemsetAsync(ctx->d_scan.p, 0, 32, ctx->stream));
+    if (P) {
+        CK(cudaMemcpyAsync(ctx->d_vmass.p, mass, (size_t)P * 8, cudaMemcpyHostToDevice, ctx->stream));
+        if (thr) CK(cudaMemcpyAsync(ctx->d_vthrf.p, thr, (size_t)P * 8, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(ctx->d_maxmods.p, max_mods, (size_t)P * 4, cudaMemcpyHostToDevice, ctx->stream));
     }
-    return sst_explain_stage(ctx, t, target.data(), ithr.data(), max_mods, mode.data(), P, ind, is_mod);
+    CK(cudaMemcpyAsync(ctx->d_ind.p, ind, (size_t)t->R * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->d_ismod.p, is_mod, (size_t)t->R, cudaMemcpyHostToDevice, ctx->stream));
+    if (P) {
+        k_stage_f64<<<(unsigned)((P + 255) / 256), 256, 0, ctx->stream>>>(
+            (const double*)ctx->d_vmass.p, thr ? (const double*)ctx->d_vthrf.p : nullptr, (const int32_t*)ctx->d_maxmods.p, P, precision,
+            tolerance, w_min_mod, hi_limit, with_memo ? SST_MODE_MEMO : SST_MODE_EXACT, t->C * 32, (int64_t*)ctx->d_target.p,
+            (int64_t*)ctx->d_thr.p, (uint8_t*)ctx->d_mode.p, (uint32_t*)ctx->d_memo_peaks.p, (unsigned long long*)ctx->d_scan.p);
+        CK(cudaGetLastError());
+    }
+    CK(cudaMemcpyAsync(ctx->h_misc, ctx->d_scan.p, 32, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    const unsigned long long* h = (const unsigned long long*)ctx->h_misc;
+    ctx->P = P;
+    ctx->R_staged = t->R;
+    ctx->window_total = (int64_t)h[0];
+    ctx->max_hi = (int64_t)h[1];
+    ctx->n_memo = (int)h[2];
+    ctx->has_exact = h[3] != 0;
+    {
+        const int64_t cap = t->C * 32 - 1;
+        ctx->deepest = t->w_min > 0 ? (ctx->max_hi < cap ? ctx->max_hi : cap) / t->w_min : 0;
+    }
+    return SST_OK;
 }
 
 int sst_explain_run(sst_ctx* ctx, const sst_table* t, int rec_width, uint64_t memo_capacity, uint64_t* n_roots,

@@ -137,6 +137,84 @@ __global__ void k_is_valid_f64(TableView tv, const double* __restrict__ mass, co
     out[p] = valid_code(tv, t, h);
 }
 
+// ---------------- staging of a float batch: integerise + budget mode + batch summary on the device ----------------
+// Same float operations as mass_explanation.py:107-114 (integerise above).  Mode: FREE when no composition inside
+// the window can exhaust a budget (max_mods >= hi / w_min_mod and hi < hi_limit, both from the host), else `slow`.
+// summary: [0] summed window sizes (upper bound for level-0 items), [1] largest window end, [2] MEMO peaks (their
+// indices are appended to memo_peaks), [3] EXACT peaks.
+__global__ void __launch_bounds__(256)
+k_stage_f64(const double* __restrict__ mass, const double* __restrict__ thr, const int32_t* __restrict__ max_mods, int64_t P,
+            double precision, double tolerance, int64_t w_min_mod, int64_t hi_limit, int slow, int64_t limit,
+            int64_t* __restrict__ target, int64_t* __restrict__ ithr, uint8_t* __restrict__ mode, uint32_t* __restrict__ memo_peaks,
+            unsigned long long* __restrict__ summary) {
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long win = 0, hi_u = 0;
+    if (p < P) {
+        int64_t t, h;
+        integerise(mass[p], thr ? thr[p] : nan(""), precision, tolerance, t, h);
+        target[p] = t;
+        ithr[p] = h;
+        int64_t hi = t + h;
+        const int64_t lo = t - h;
+        if (h >= 0) {
+            const int64_t a = lo < 1 ? 1 : lo, b = hi < limit - 1 ? hi : limit - 1;
+            if (b >= a) win = (unsigned long long)(b - a + 1);
+            if (hi > 0) hi_u = (unsigned long long)hi;
+        }
+        if (hi < 0) hi = 0;
+        const bool free_ok = !w_min_mod || ((int64_t)max_mods[p] >= hi / w_min_mod && hi < hi_limit);
+        const int md = free_ok ? MODE_FREE : slow;
+        mode[p] = (uint8_t)md;
+        if (md == MODE_MEMO) memo_peaks[atomicAdd(summary + 2, 1ULL)] = (uint32_t)p;
+        if (md == MODE_EXACT) atomicAdd(summary + 3, 1ULL);
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        win += __shfl_xor_sync(0xFFFFFFFFu, win, o);
+        const unsigned long long y = __shfl_xor_sync(0xFFFFFFFFu, hi_u, o);
+        hi_u = y > hi_u ? y : hi_u;
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (win) atomicAdd(summary, win);
+        if (hi_u) atomicMax(summary + 1, hi_u);
+    }
+}
+
+// ---------------- N2: fused fragment classification ----------------
+// One thread per (breakage offset b = blockIdx.y, fragment f), breakage-major like the reference's concat
+// (fragment_classification.py:39-49): standard-unit mass = observed - offset_b (offset_b = breakage weight * precision,
+// multiplied on the host exactly as the reference does), threshold = tolerance * observed, then the validity probe
+// (:52-67 -> is_valid_mass) and the singleton test (:104-119: some row weight, 0 included, inside the window).
+// out bits: 1 valid, 2 out-of-table value met before any hit (the reference raises), 4 singleton.
+__global__ void __launch_bounds__(256)
+k_classify(TableView tv, const double* __restrict__ observed, int64_t F, const double* __restrict__ offsets, int B,
+           double precision, double tolerance, uint8_t* __restrict__ out) {
+    __shared__ int32_t s_w[kMaxRows];
+    __shared__ double s_off[64];
+    for (int i = threadIdx.x; i < kMaxRows; i += blockDim.x) s_w[i] = i < tv.R ? tv.weights[i] : 0x7FFFFFFF;
+    for (int i = threadIdx.x; i < B && i < 64; i += blockDim.x) s_off[i] = offsets[i];
+    __syncthreads();
+    const int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int b = blockIdx.y;  // one breakage offset per grid row: F*B independent probes in flight
+    if (f >= F) return;
+    const double obs = observed[f];
+    const double thr = __dmul_rn(tolerance, obs);
+    const double su = __dsub_rn(obs, b < 64 ? s_off[b] : offsets[b]);
+    int64_t t, h;
+    integerise(su, thr, precision, tolerance, t, h);
+    uint8_t code = valid_code(tv, t, h);  // 0 / 1 / 2
+    // singleton: smallest row weight >= lo is <= hi
+    const int64_t lo = t - h, hi = t + h;
+    int a = 0, z = tv.R;  // first index with w >= lo
+    while (a < z) {
+        const int mid = (a + z) >> 1;
+        if ((int64_t)s_w[mid] < lo) a = mid + 1;
+        else z = mid;
+    }
+    if (a < tv.R && (int64_t)s_w[a] <= hi) code |= 4;
+    out[(int64_t)b * F + f] = code;
+}
+
 // ---------------- MEMO phase A: sequential first-visit replay, one thread per peak ----------------
 __global__ void __launch_bounds__(64)
 k_memo_phase_a(TableView tv, RowMeta meta, PeakBatch pk, const uint32_t* __restrict__ memo_peaks, int n_memo,

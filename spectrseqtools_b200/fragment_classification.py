@@ -1,0 +1,132 @@
+"""Fragment classification on the B200 behind the reference's ``spectrseqtools.fragment_classification`` names
+(SURVEY §8f row N2).
+
+The reference copies every fragment once per breakage offset, calls ``is_valid_mass`` and ``is_singleton`` from
+Python for each copy (``map_elements``, fragment_classification.py:39-82) and filters.  Here the whole
+(fragment x breakage) grid is one kernel launch (``sst_classify``): the host ships F observed masses and B
+offsets instead of F*B (mass, threshold) pairs, and gets one flag byte per pair back.
+
+``classify_observed`` is the batched array form; ``classify_fragments`` keeps the reference's signature and
+column semantics on top of it.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+
+from . import _cabi
+from .mass_table import DynamicProgrammingTable
+
+MAX_VARIANCE = 1
+
+
+class ClassifiedMasses:
+    """Result of ``classify_observed``: one flag byte per (breakage, fragment), breakage-major."""
+
+    def __init__(self, observed: np.ndarray, breakage_weights: List[int], labels: List[str], precision: float,
+                 flags: np.ndarray):
+        self.observed = observed
+        self.breakage_weights = breakage_weights
+        self.labels = labels          # first label of every weight, like the reference's pl.lit(breakages[0])
+        self.precision = precision
+        self.flags = flags            # uint8[B, F]
+
+    @property
+    def valid(self) -> np.ndarray:
+        return (self.flags & _cabi.CLASS_VALID) != 0
+
+    @property
+    def out_of_table(self) -> np.ndarray:
+        return (self.flags & _cabi.CLASS_OUT_OF_TABLE) != 0
+
+    @property
+    def singleton(self) -> np.ndarray:
+        return (self.flags & _cabi.CLASS_SINGLETON) != 0
+
+    @property
+    def standard_unit_mass(self) -> np.ndarray:
+        """observed - breakage_weight * precision, float64[B, F] (the same two IEEE operations as upstream)."""
+        off = np.array([w * self.precision for w in self.breakage_weights], dtype=np.float64)
+        return self.observed[None, :] - off[:, None]
+
+
+def classify_observed(observed: Sequence[float], dp_table: DynamicProgrammingTable, breakage_dict: Dict[int, List[str]],
+                      copy: bool = True) -> ClassifiedMasses:
+    """Validity + singleton flags of every observed mass under every breakage offset: one device pass."""
+    observed = np.ascontiguousarray(observed, dtype=np.float64).reshape(-1)
+    weights = list(breakage_dict.keys())
+    offsets = np.array([w * dp_table.precision for w in weights], dtype=np.float64)  # int * float, as upstream
+    dev = dp_table.device_table()
+    ctx = dev.ctx
+    ctx.classify_stage(observed, offsets)
+    ctx.classify_run(dev, dp_table.precision, dp_table.tolerance)
+    flags = ctx.classify_fetch(copy=copy)
+    return ClassifiedMasses(observed, weights, [breakage_dict[w][0] for w in weights], dp_table.precision, flags)
+
+
+def is_singleton(mass, integer_masses, dp_table, threshold=None) -> bool:
+    """Reference fragment_classification.py:104-119 (host scalar; the batched form is a bit of ``classify_observed``)."""
+    target = int(round(mass / dp_table.precision, 0))
+    if threshold is None:
+        threshold = dp_table.tolerance * mass
+    threshold = int(np.ceil(threshold / dp_table.precision))
+    masses = set(integer_masses)
+    return any(v in masses for v in range(target - threshold, target + threshold + 1))
+
+
+def _column(frame, name: str) -> list:
+    return list(frame.get_column(name).to_list())
+
+
+def classify_fragments(fragment_masses, dp_table: DynamicProgrammingTable, breakage_dict: dict, output_file_path=None,
+                       intensity_cutoff=0.5e6, mass_cutoff=50000):
+    """Reference signature and semantics (fragment_classification.py:17-101): every (fragment, breakage) copy whose
+    standard-unit mass is explainable, with ``standard_unit_mass``, ``breakage`` and ``is_singleton`` columns, sorted
+    by standard-unit mass, filtered by intensity, observed mass and the sequence mass.  Returns a frame of the
+    same kind the alphabet lives in (polars when installed, the stand-in otherwise)."""
+    from .masses import _pl as pl
+
+    cols = {c: _column(fragment_masses, c) for c in fragment_masses.columns}
+    n = len(next(iter(cols.values()))) if cols else 0
+    if "intensity" not in cols:
+        cols["intensity"] = [intensity_cutoff * 1.1] * n
+    if "neutral_mass" in cols:
+        cols = {("observed_mass" if k == "neutral_mass" else k): v for k, v in cols.items()}
+    observed = np.array(cols["observed_mass"], dtype=np.float64)
+    res = classify_observed(observed, dp_table, breakage_dict)
+    if res.out_of_table.any():
+        raise _cabi.TableTooSmall("A value of the mass window is not in the DP table. Extend its size if you want to compute larger masses.")
+    su = res.standard_unit_mass
+    b_idx, f_idx = np.nonzero(res.valid)  # breakage-major, fragments ascending: the reference's concat + filter order
+    su_sel = su[b_idx, f_idx]
+    intensity = np.array(cols["intensity"], dtype=np.float64)[f_idx]
+    keep = (intensity > intensity_cutoff) & (observed[f_idx] < mass_cutoff)
+    seq_mass = dp_table.seq.su_mass
+    labels = np.array(res.labels, dtype=object)[b_idx]
+    complete = np.array(["START" in s and "END" in s for s in labels], dtype=bool)
+    keep &= su_sel < seq_mass + MAX_VARIANCE
+    keep &= (su_sel > seq_mass - MAX_VARIANCE) | ~complete
+    order = np.argsort(su_sel, kind="stable")
+    order = order[keep[order]]
+    out = {"fragment_index": [int(f_idx[i]) for i in order]}
+    for c, v in cols.items():
+        out[c] = [v[int(f_idx[i])] for i in order]
+    out["standard_unit_mass"] = [float(su_sel[i]) for i in order]
+    out["breakage"] = [str(labels[i]) for i in order]
+    out["is_singleton"] = [bool(res.singleton[b_idx[i], f_idx[i]]) for i in order]
+    frame = pl.DataFrame(out)
+    if output_file_path is not None and hasattr(frame, "write_csv"):
+        frame.write_csv(output_file_path, separator="\t")
+    return frame
+
+
+def filter_by_sequence_mass(mass_cutoff: float, fragments):
+    """Reference fragment_classification.py:122-139 on a frame with ``standard_unit_mass`` and ``breakage``."""
+    from .masses import _pl as pl
+
+    su = np.array(_column(fragments, "standard_unit_mass"), dtype=np.float64)
+    labels = _column(fragments, "breakage")
+    complete = np.array(["START" in s and "END" in s for s in labels], dtype=bool)
+    keep = (su < mass_cutoff + MAX_VARIANCE) & ((su > mass_cutoff - MAX_VARIANCE) | ~complete)
+    return pl.DataFrame({c: [v for v, k in zip(_column(fragments, c), keep) if k] for c in fragments.columns})

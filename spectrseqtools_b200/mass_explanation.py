@@ -75,10 +75,22 @@ def _budget_int(x) -> int:
 
 
 def _row_metadata(dp_table) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
-    """weights, is_mod, IND[r] = round(max_len * rate_r) (Python round, mass_explanation.py:158-161,200)."""
-    weights = np.array([m.mass for m in dp_table.masses], dtype=np.int64)
-    is_mod = np.array([1 if m.is_modification else 0 for m in dp_table.masses], dtype=np.uint8)
-    ind = np.array([_budget_int(round(dp_table.seq.max_len * m.modification_rate)) for m in dp_table.masses], dtype=np.int32)
+    """weights, is_mod, IND[r] = round(max_len * rate_r) (Python round, mass_explanation.py:158-161,200).
+
+    Cached on the table object; the key holds everything the arrays depend on (callers mutate rates and
+    ``seq.max_len`` between calls, and alphabet reduction swaps the row list)."""
+    rows = dp_table.masses
+    key = (id(rows), len(rows), dp_table.seq.max_len, tuple(m.modification_rate for m in rows))
+    hit = getattr(dp_table, "_row_meta", None)
+    if hit is not None and hit[0] == key:
+        return hit[1]
+    weights = np.array([m.mass for m in rows], dtype=np.int64)
+    is_mod = np.array([1 if m.is_modification else 0 for m in rows], dtype=np.uint8)
+    ind = np.array([_budget_int(round(dp_table.seq.max_len * m.modification_rate)) for m in rows], dtype=np.int32)
+    try:
+        dp_table._row_meta = (key, (weights, is_mod, ind))
+    except AttributeError:  # duck-typed tables without a __dict__
+        pass
     return weights, is_mod, ind
 
 

@@ -39,6 +39,8 @@ class Workload:
     explain_thr: np.ndarray
     explain_nt: np.ndarray     # true number of nucleotides of each difference (for reporting)
     max_modifications: int
+    observed: Optional[np.ndarray] = None   # float64 observed peak masses, n_peaks (valid_* = observed x breakage)
+    breakage: Optional[dict] = None         # breakage weight (integer mDa, ascending) -> labels
 
 
 def alphabet_frame(names: Optional[List[str]]):
@@ -96,7 +98,7 @@ def make_workload(config: str, n_peaks: int = 100_000, seed_offset: int = 0) -> 
         off5_alt = label_of["START_a/w"] * 1e-3
         off3_alt = label_of["a/w_END"] * 1e-3
 
-    v_mass, v_thr, e_mass, e_thr, e_nt = [], [], [], [], []
+    v_mass, v_thr, e_mass, e_thr, e_nt, all_obs = [], [], [], [], [], []
     peaks = 0
     longest = 0
     while peaks < n_peaks:
@@ -115,6 +117,7 @@ def make_workload(config: str, n_peaks: int = 100_000, seed_offset: int = 0) -> 
             if full_dict and rng.random() < 0.5:
                 off = (off5_alt if ladder == 0 else off3_alt)
             obs = (su + off) * (1 + rng.uniform(-ppm / 2, ppm / 2, size=L))
+            all_obs.append(obs)
             # validity: every peak against every breakage offset
             cand = obs[:, None] - offsets[None, :] * 1e-3
             v_mass.append(cand.ravel())
@@ -141,11 +144,13 @@ def make_workload(config: str, n_peaks: int = 100_000, seed_offset: int = 0) -> 
     wl = Workload(name=config, config_id=cid, ppm=ppm, alphabet=reps, max_len=max_len, max_seq_length=msl,
                   n_peaks=peaks, valid_mass=cat(v_mass, np.float64), valid_thr=cat(v_thr, np.float64),
                   explain_mass=cat(e_mass, np.float64), explain_thr=cat(e_thr, np.float64),
-                  explain_nt=cat(e_nt, np.int64), max_modifications=round(0.5 * max_len))
+                  explain_nt=cat(e_nt, np.int64), max_modifications=round(0.5 * max_len),
+                  observed=cat(all_obs, np.float64), breakage={int(k): breakage[int(k)] for k in offsets})
     # trim to exactly n_peaks peaks (validity arrays are peak-major)
     if peaks > n_peaks:
         wl.valid_mass = wl.valid_mass[: n_peaks * n_off]
         wl.valid_thr = wl.valid_thr[: n_peaks * n_off]
+        wl.observed = wl.observed[:n_peaks]
         wl.n_peaks = n_peaks
     return wl
 
@@ -158,4 +163,5 @@ def shard(wl: Workload, rank: int, world: int) -> Workload:
     return Workload(name=wl.name, config_id=wl.config_id, ppm=wl.ppm, alphabet=wl.alphabet, max_len=wl.max_len,
                     max_seq_length=wl.max_seq_length, n_peaks=len(vm), valid_mass=vm.ravel(), valid_thr=vt.ravel(),
                     explain_mass=wl.explain_mass[rank::world], explain_thr=wl.explain_thr[rank::world],
-                    explain_nt=wl.explain_nt[rank::world], max_modifications=wl.max_modifications)
+                    explain_nt=wl.explain_nt[rank::world], max_modifications=wl.max_modifications,
+                    observed=None if wl.observed is None else wl.observed[rank::world], breakage=wl.breakage)
