@@ -211,24 +211,42 @@ k_build_table_small(uint64_t* __restrict__ tbl, int R, int64_t C, const int32_t*
 
 // ---------------- K1t: mass-major row masks ----------------
 // H[v] bit r = bit1(r, v) of the final (masked) table, r in 1..R-1.  One CTA per 32-word tile:
-// coalesced row reads -> 32-bit "bit1" columns in shared memory -> 32x32 bit transposes by warp shuffles
-// -> one 16-byte store per mass.
+// coalesced row reads -> one 32-bit "bit1" word per (row, table word) in shared memory -> 32x32 bit transposes by
+// warp shuffles -> one 16-byte store per mass.
+//
+// The kernel is bound by the (half-rate) integer ALU pipe, so the packing step matters: instead of compressing
+// the 16 odd bits of each 32-bit half (10 operations per half), the two halves of a table word are INTERLEAVED —
+// P = (hi & 0xAAAAAAAA) | ((lo & 0xAAAAAAAA) >> 1), one shift and one LOP3 — and the permutation this leaves in
+// the bit order is undone for free in the store address: bit b of P is mass 15 - b/2 of the word if b is odd,
+// 31 - b/2 if it is even.
 
-__device__ __forceinline__ uint32_t compress_odd_bits(uint32_t v) {  // 16 odd bits -> low 16 bits
-    v = (v >> 1) & 0x55555555u;
-    v = (v | (v >> 1)) & 0x33333333u;
-    v = (v | (v >> 2)) & 0x0F0F0F0Fu;
-    v = (v | (v >> 4)) & 0x00FF00FFu;
-    v = (v | (v >> 8)) & 0x0000FFFFu;
-    return v;
-}
-
-__device__ __forceinline__ uint32_t warp_transpose32(uint32_t x, int lane) {
+// 32x32 bit transpose across a warp (lane = row).  Stage s swaps the off-diagonal s x s blocks: a lane with bit s
+// set takes (partner >> s) into the positions whose bit s is clear, a lane without it takes (partner << s) into
+// the others.  On exactly those positions a shift equals a ROTATE, so each stage is one shuffle, one funnel shift
+// by a per-lane amount and one bit-select LOP3 — amounts and masks are computed once per thread.
+struct TransposePlan {
+    uint32_t rot[5];   // rotate-left amount of stage k (s = 16 >> k)
+    uint32_t keep[5];  // bits this lane keeps from its own word in stage k
+};
+__device__ __forceinline__ TransposePlan transpose_plan(int lane) {
+    TransposePlan p;
 #pragma unroll
-    for (int s = 16; s >= 1; s >>= 1) {
+    for (int k = 0; k < 5; k++) {
+        const int s = 16 >> k;
         const uint32_t m = s == 16 ? 0x0000FFFFu : s == 8 ? 0x00FF00FFu : s == 4 ? 0x0F0F0F0Fu : s == 2 ? 0x33333333u : 0x55555555u;
-        const uint32_t y = __shfl_xor_sync(0xFFFFFFFFu, x, s);
-        x = (lane & s) ? ((x & ~m) | ((y >> s) & m)) : ((x & m) | ((y << s) & ~m));
+        p.rot[k] = (lane & s) ? 32 - s : s;
+        uint32_t keep = (lane & s) ? ~m : m;
+        asm volatile("mov.b32 %0, %0;" : "+r"(keep));  // keep it a register: ptxas otherwise rebuilds it as m ^ flag, 3 LOP3 per stage
+        p.keep[k] = keep;
+    }
+    return p;
+}
+__device__ __forceinline__ uint32_t warp_transpose32(uint32_t x, const TransposePlan& p) {
+#pragma unroll
+    for (int k = 0; k < 5; k++) {
+        const uint32_t y = __shfl_xor_sync(0xFFFFFFFFu, x, 16 >> k);
+        const uint32_t yr = __funnelshift_l(y, y, p.rot[k]);
+        asm("lop3.b32 %0, %1, %2, %3, 0xE4;" : "=r"(x) : "r"(x), "r"(yr), "r"(p.keep[k]));  // keep ? x : yr
     }
     return x;
 }
@@ -238,26 +256,34 @@ k_transpose_masks(const uint64_t* __restrict__ tbl, int R, int64_t C, uint4* __r
     __shared__ uint32_t s_c[kMaxRows][33];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int64_t j0 = (int64_t)blockIdx.x * 32;
-    for (int r = w; r < kMaxRows; r += 8) {
-        uint32_t c = 0;
+    {
         const int64_t j = j0 + lane;
-        if (r >= 1 && r < R && j < C) {
-            const uint64_t word = __ldcs(tbl + (int64_t)r * C + j);
-            c = (compress_odd_bits((uint32_t)(word >> 32)) << 16) | compress_odd_bits((uint32_t)word);
+        const bool col_ok = j < C;
+        const uint64_t* src = tbl + (int64_t)w * C + j;
+        const int64_t stride = 8 * C;
+#pragma unroll 4
+        for (int r = w; r < kMaxRows; r += 8, src += stride) {
+            uint32_t c = 0;
+            if (col_ok && r >= 1 && r < R) {
+                const uint64_t word = __ldcs(src);
+                c = ((uint32_t)(word >> 32) & 0xAAAAAAAAu) | (((uint32_t)word & 0xAAAAAAAAu) >> 1);
+            }
+            s_c[r][lane] = c;
         }
-        s_c[r][lane] = c;
     }
     __syncthreads();
+    const int mass_in_word = (lane & 1) ? 15 - (lane >> 1) : 31 - (lane >> 1);  // which mass bit `lane` of P is
+    const TransposePlan plan = transpose_plan(lane);
+#pragma unroll
     for (int l = w; l < 32; l += 8) {
         const int64_t j = j0 + l;
-        if (j >= C) break;
         uint4 d;
-        d.x = warp_transpose32(s_c[lane][l], lane);
-        d.y = warp_transpose32(s_c[32 + lane][l], lane);
-        d.z = warp_transpose32(s_c[64 + lane][l], lane);
-        d.w = warp_transpose32(s_c[96 + lane][l], lane);
-        // lane q now holds the rows of the mass whose compacted bit index is q, i.e. mass 31-q of word j
-        H[j * 32 + (31 - lane)] = d;
+        d.x = warp_transpose32(s_c[lane][l], plan);
+        d.y = warp_transpose32(s_c[32 + lane][l], plan);
+        d.z = warp_transpose32(s_c[64 + lane][l], plan);
+        d.w = warp_transpose32(s_c[96 + lane][l], plan);
+        // lane q now holds, for bit q of the packed words, the rows that have it set
+        if (j < C) H[j * 32 + mass_in_word] = d;
     }
 }
 
