@@ -36,7 +36,8 @@ enum {
     SST_ERR_TOO_DEEP = 6,      /* a composition could exceed 96 nucleotides */
     SST_ERR_NOMEM = 7,         /* result or scratch does not fit in device memory -> MemoryError */
     SST_ERR_MEMO_FULL = 8,     /* first-visit map too small: call again with a larger memo_capacity */
-    SST_ERR_STATE = 9          /* fetch without a preceding run */
+    SST_ERR_STATE = 9,         /* fetch without a preceding run */
+    SST_ERR_OUT_OF_TABLE = 10  /* a probed mass lies beyond the table -> NotImplementedError */
 };
 
 /* per-peak budget modes for sst_explain (see DESIGN.md "Budget semantics") */
@@ -111,6 +112,14 @@ int sst_classify(sst_ctx* ctx, const sst_table* t, const double* observed, int64
 int sst_classify_stage(sst_ctx* ctx, const double* observed, int64_t F, const double* offsets, int B);
 int sst_classify_run(sst_ctx* ctx, const sst_table* t, double precision, double tolerance);
 int sst_classify_fetch(sst_ctx* ctx, uint8_t* out /* B*F */);
+
+/* ---- sequence-length bounds: replaces compute_sequence_length_bound (mass_table.py:343-487), both directions in one
+ * walk.  target / thr in table units (round(su_mass / precision), ceil(tolerance * obs_mass / precision)),
+ * max_mods = round(modification_rate * max_len), ind / is_mod as for sst_explain.  First-visit memo semantics make
+ * the walk sequential (one device thread); memo_capacity: slots of its map (0 = default, SST_ERR_MEMO_FULL = retry
+ * with more).  SST_ERR_OUT_OF_TABLE when a window value lies beyond the table. ---- */
+int sst_length_bounds(sst_ctx* ctx, const sst_table* t, int64_t target, int64_t thr, int32_t max_mods, int32_t max_len,
+                      const int32_t* ind, const uint8_t* is_mod, uint64_t memo_capacity, int64_t* lower, int64_t* upper);
 
 /* ---- enumeration: replaces explain_mass_with_table (mass_explanation.py:92-203) for P peaks ----
  * max_mods[p]: global modification budget (SST_BUDGET_INF = unbounded); mode[p]: SST_MODE_*;

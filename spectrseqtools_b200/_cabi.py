@@ -21,6 +21,7 @@ LIB_PATH = _HERE / "libsst_b200.so"
 # error codes (include/sst_b200.h)
 SST_OK, SST_ERR_CUDA, SST_ERR_NO_DEVICE, SST_ERR_BAD_ARG, SST_ERR_COMPRESSION = 0, 1, 2, 3, 4
 SST_ERR_TOO_MANY_ROWS, SST_ERR_TOO_DEEP, SST_ERR_NOMEM, SST_ERR_MEMO_FULL, SST_ERR_STATE = 5, 6, 7, 8, 9
+SST_ERR_OUT_OF_TABLE = 10
 MODE_FREE, MODE_EXACT, MODE_MEMO = 0, 1, 2
 STATUS_ZERO_IN_WINDOW, STATUS_OUT_OF_TABLE = 1, 2
 VALID_NO, VALID_YES, VALID_OUT_OF_TABLE = 0, 1, 2
@@ -34,7 +35,7 @@ EXPORTS = [
     "sst_table_build", "sst_table_upload", "sst_table_rebuild", "sst_table_info", "sst_table_download",
     "sst_table_download_masks", "sst_table_destroy", "sst_is_valid", "sst_valid_stage", "sst_valid_run",
     "sst_valid_fetch", "sst_valid_stage_f64", "sst_explain", "sst_explain_stage", "sst_explain_stage_f64", "sst_explain_rec_width", "sst_explain_phase_ns",
-    "sst_explain_run", "sst_explain_fetch", "sst_classify", "sst_classify_stage", "sst_classify_run", "sst_classify_fetch",
+    "sst_explain_run", "sst_explain_fetch", "sst_classify", "sst_classify_stage", "sst_classify_run", "sst_classify_fetch", "sst_length_bounds",
 ]
 
 
@@ -98,6 +99,8 @@ def load() -> C.CDLL:
             "sst_classify_stage": (C.c_int, [vp, fp, C.c_int64, fp, C.c_int]),
             "sst_classify_run": (C.c_int, [vp, vp, C.c_double, C.c_double]),
             "sst_classify_fetch": (C.c_int, [vp, u8p]),
+            "sst_length_bounds": (C.c_int, [vp, vp, C.c_int64, C.c_int64, C.c_int32, C.c_int32, i32p, u8p, C.c_uint64,
+                                            C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
         }
         for name in EXPORTS:
             fn = getattr(lib, name)  # AttributeError here = ABI drift
@@ -141,6 +144,8 @@ class Context:
             raise MemoryError(msg)
         if rc == SST_ERR_MEMO_FULL:
             raise MemoFull(msg)
+        if rc == SST_ERR_OUT_OF_TABLE:
+            raise TableTooSmall(msg)
         raise RuntimeError(f"libsst_b200 rc={rc}: {msg}")
 
     def device_info(self) -> dict:
@@ -258,6 +263,15 @@ class Context:
         self._check(self._lib.sst_classify_fetch(self._h, _p(buf)))
         out = buf.reshape(B, F)
         return out.copy() if copy else out
+
+    def length_bounds(self, table: "DeviceTable", target: int, thr: int, max_mods: int, max_len: int, ind, is_mod,
+                      memo_capacity: int = 0) -> Tuple[int, int]:
+        """(lower, upper) bound on the number of nucleotides explaining the window (sst_length_bounds)."""
+        iv, im = _arr(ind, np.int32), _arr(is_mod, np.uint8)
+        lo, up = C.c_int64(), C.c_int64()
+        self._check(self._lib.sst_length_bounds(self._h, table._h, int(target), int(thr), int(max_mods), int(max_len), _p(iv), _p(im),
+                                                C.c_uint64(memo_capacity), C.byref(lo), C.byref(up)))
+        return int(lo.value), int(up.value)
 
     def explain_stage(self, table: "DeviceTable", target, thr, max_mods, mode, ind, is_mod):
         t, h = _arr(target, np.int64), _arr(thr, np.int64)

@@ -79,6 +79,7 @@ struct sst_ctx {
     DevBuf d_memo_keys, d_memo_alive, d_memo_top, d_memo_misc, d_flush;
     DevBuf d_vtarget, d_vthr, d_vout;  // staged validity probes
     DevBuf d_cobs, d_coff, d_cout;     // staged classification batch
+    DevBuf d_bkeys, d_btop, d_blower, d_bupper, d_bout;  // sequence-length bounds
     int64_t CF = 0;
     int CB = 0;
     int64_t VP = 0;
@@ -329,7 +330,7 @@ void sst_ctx_destroy(sst_ctx* ctx) {
                       &ctx->d_memo_peaks, &ctx->d_status, &ctx->d_cnt, &ctx->d_peakoff, &ctx->d_recs,
                       &ctx->d_blocksums, &ctx->d_memo_keys, &ctx->d_memo_alive, &ctx->d_memo_top,
                       &ctx->d_memo_misc, &ctx->d_flush, &ctx->d_vtarget, &ctx->d_vthr, &ctx->d_vout,
-                      &ctx->d_scan, &ctx->d_vmass, &ctx->d_vthrf, &ctx->d_peakcnt, &ctx->d_cobs, &ctx->d_coff, &ctx->d_cout,
+                      &ctx->d_scan, &ctx->d_vmass, &ctx->d_vthrf, &ctx->d_peakcnt, &ctx->d_cobs, &ctx->d_coff, &ctx->d_cout, &ctx->d_bkeys, &ctx->d_btop, &ctx->d_blower, &ctx->d_bupper, &ctx->d_bout,
                       &ctx->d_item_m[0], &ctx->d_item_m[1], &ctx->d_item_peak[0], &ctx->d_item_peak[1],
                       &ctx->d_item_meta[0], &ctx->d_item_meta[1], &ctx->d_item_all[0], &ctx->d_item_all[1],
                       &ctx->d_item_ind[0], &ctx->d_item_ind[1], &ctx->d_item_path[0], &ctx->d_item_path[1]};
@@ -620,6 +621,52 @@ int sst_classify(sst_ctx* ctx, const sst_table* t, const double* observed, int64
     if (!rc) rc = sst_classify_run(ctx, t, precision, tolerance);
     if (!rc) rc = sst_classify_fetch(ctx, out);
     return rc;
+}
+
+int sst_length_bounds(sst_ctx* ctx, const sst_table* t, int64_t target, int64_t thr, int32_t max_mods, int32_t max_len,
+                      const int32_t* ind, const uint8_t* is_mod, uint64_t memo_capacity, int64_t* lower, int64_t* upper) {
+    CK(cudaSetDevice(ctx->device));
+    if (!t->H) return fail(ctx, SST_ERR_STATE, "table was built without row masks");
+    if (max_len < 0 || max_len > 120) return fail(ctx, SST_ERR_TOO_DEEP, "max_len %d outside [0, 120]", (int)max_len);
+    if (t->w_min > 0 && (target + thr) / t->w_min > kMaxDepth)
+        return fail(ctx, SST_ERR_TOO_DEEP, "a composition may need %lld nucleotides (limit %d)", (long long)((target + thr) / t->w_min), kMaxDepth);
+    uint64_t cap = memo_capacity ? memo_capacity : ((uint64_t)1 << 16);
+    uint64_t pow2 = 1024;
+    while (pow2 < cap) pow2 <<= 1;
+    if (pow2 > ((uint64_t)1 << 26)) return fail(ctx, SST_ERR_NOMEM, "memo capacity %llu too large", (unsigned long long)cap);
+    int rc;
+    if ((rc = reserve(ctx, ctx->d_bkeys, pow2 * 4))) return rc;
+    if ((rc = reserve(ctx, ctx->d_btop, pow2))) return rc;
+    if ((rc = reserve(ctx, ctx->d_blower, pow2 * kMaxRows))) return rc;
+    if ((rc = reserve(ctx, ctx->d_bupper, pow2 * kMaxRows))) return rc;
+    if ((rc = reserve(ctx, ctx->d_bout, 64))) return rc;
+    if ((rc = reserve(ctx, ctx->d_ind, (size_t)kMaxRows * 4))) return rc;
+    if ((rc = reserve(ctx, ctx->d_ismod, (size_t)kMaxRows))) return rc;
+    CK(cudaMemsetAsync(ctx->d_bkeys.p, 0, pow2 * 4, ctx->stream));
+    CK(cudaMemsetAsync(ctx->d_btop.p, 0, pow2, ctx->stream));
+    CK(cudaMemsetAsync(ctx->d_bout.p, 0, 64, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->d_ind.p, ind, (size_t)t->R * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->d_ismod.p, is_mod, (size_t)t->R, cudaMemcpyHostToDevice, ctx->stream));
+    ctx->have_result = false;  // d_ind / d_ismod of a staged enumeration batch are gone: it has to be staged again
+    ctx->R_staged = -1;
+    BoundMap mp{(uint32_t*)ctx->d_bkeys.p, (uint8_t*)ctx->d_btop.p, (int8_t*)ctx->d_blower.p, (int8_t*)ctx->d_bupper.p,
+                (uint32_t)(pow2 - 1), (int*)((char*)ctx->d_bout.p + 32)};
+    {
+        KTimer kt(ctx, SST_K_LENGTH_BOUND);
+        k_length_bounds<<<1, 32, 0, ctx->stream>>>(view_of(t), RowMeta{(const int32_t*)ctx->d_ind.p, (const uint8_t*)ctx->d_ismod.p}, target, thr,
+                                                 max_mods, max_len, mp, (int64_t*)ctx->d_bout.p);
+        kt.stop(1);
+        CK(cudaGetLastError());
+    }
+    CK(cudaMemcpyAsync(ctx->h_misc, ctx->d_bout.p, 64, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    flush_timers(ctx);
+    const int64_t* h = (const int64_t*)ctx->h_misc;
+    if (ctx->h_misc[8]) return fail(ctx, SST_ERR_MEMO_FULL, "memo of the length-bound walk is too small (%llu slots)", (unsigned long long)pow2);
+    if (h[2]) return fail(ctx, SST_ERR_OUT_OF_TABLE, "a value of the mass window is not in the DP table");
+    if (lower) *lower = h[0];
+    if (upper) *upper = h[1];
+    return SST_OK;
 }
 
 int sst_explain_stage(sst_ctx* ctx, const sst_table* t, const int64_t* target, const int64_t* thr, const int32_t* max_mods,

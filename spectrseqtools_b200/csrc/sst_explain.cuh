@@ -309,6 +309,181 @@ k_memo_phase_a(TableView tv, RowMeta meta, PeakBatch pk, const uint32_t* __restr
     }
 }
 
+// ---------------- N1: sequence-length bounds (compute_sequence_length_bound, reference mass_table.py:343-487) ----------------
+// Smallest / largest number of nucleotides over all explanations of the window, with the reference's memo
+// semantics: the memo is keyed (mass, row) WITHOUT the budgets, so every node keeps the value of its FIRST visit
+// in DFS order (UP before LEFT, window ascending), and a dead end reached through LEFT contributes default + 1
+// (for the upper bound that is 0, not -1).  First-visit order makes this inherently sequential: ONE thread walks
+// the same mass-at-a-time replay as k_memo_phase_a — rows visited at a mass always form a prefix [1, top(m)], and
+// node (m, r) is the running min / max over the enabled LEFT candidates of rows <= r — and computes both bounds in
+// the same walk (the traversal does not depend on the direction).
+struct BoundMap {
+    uint32_t* keys;   // 0 = empty, else the mass
+    uint8_t* top;     // highest visited row
+    int8_t* lower;    // [cap][kMaxRows] value of node (m, r) for r <= top, "lower" direction
+    int8_t* upper;    // the same for "upper"
+    uint32_t cap_mask;
+    int* overflow;
+};
+
+__device__ inline int bound_slot(const BoundMap& mp, uint32_t m, unsigned int* fill) {
+    uint32_t h = (uint32_t)mix64(m) & mp.cap_mask;
+    for (uint32_t probes = 0; probes < 4096; probes++) {
+        const uint32_t k = mp.keys[h];
+        if (k == m) return (int)h;
+        if (k == 0u) {
+            mp.keys[h] = m;  // single writer
+            if (++(*fill) > (mp.cap_mask >> 1) + (mp.cap_mask >> 2)) *mp.overflow = 1;
+            return (int)h;
+        }
+        h = (h + 1) & mp.cap_mask;
+    }
+    *mp.overflow = 1;
+    return -1;
+}
+
+// out[0] = lower bound, out[1] = upper bound, out[2] = 1 if a window value lies beyond the table (the reference raises)
+__global__ void __launch_bounds__(32)
+k_length_bounds(TableView tv, RowMeta meta, int64_t target, int64_t thr, int max_mods, int max_len, BoundMap mp, int64_t* __restrict__ out) {
+    __shared__ int32_t s_w[kMaxRows];
+    __shared__ int32_t s_ind[kMaxRows];
+    __shared__ uint8_t s_mod[kMaxRows];
+    for (int i = threadIdx.x; i < kMaxRows; i += blockDim.x) {
+        s_w[i] = i < tv.R ? tv.weights[i] : 0;
+        s_ind[i] = i < tv.R ? meta.ind[i] : 0;
+        s_mod[i] = i < tv.R ? meta.is_mod[i] : 0;
+    }
+    __syncthreads();
+    if (threadIdx.x != 0) return;
+    const int64_t limit = tv.C * 32;
+    const int top_row = tv.R - 1;
+    const int dl = max_len + 1, du = -1;  // defaults (mass_table.py:365-372)
+    const int64_t lo = target - thr, hi = target + thr;
+    if (hi >= limit && hi >= 1 && lo <= hi) {
+        out[2] = 1;
+        return;
+    }
+    unsigned int fill = 0;
+
+    // one frame per mass on the current path
+    uint32_t f_m[kMaxDepth + 2];
+    int f_slot[kMaxDepth + 2];
+    uint8_t f_rin[kMaxDepth + 2], f_cur[kMaxDepth + 2], f_fill[kMaxDepth + 2];
+    int f_all[kMaxDepth + 2], f_ind[kMaxDepth + 2];
+    int8_t f_lo[kMaxDepth + 2], f_up[kMaxDepth + 2];  // running min / max
+    Mask128 f_pend[kMaxDepth + 2];
+    int sp = 0;
+    int ret_lo = 0, ret_up = 0;  // value of the node an arrival / a finished frame stands for
+
+    // arrival at node (m, r_in), m > 0: answered from the map (returns false, sets ret_*) or opens a frame
+    auto arrive = [&](uint32_t m, int r_in, int all, int ind) -> bool {
+        const int slot = bound_slot(mp, m, &fill);
+        if (slot < 0 || sp > kMaxDepth) {
+            *mp.overflow = 1;
+            ret_lo = dl;
+            ret_up = du;
+            return false;
+        }
+        const int top = mp.top[slot];
+        if (top >= r_in) {
+            ret_lo = mp.lower[(size_t)slot * kMaxRows + r_in];
+            ret_up = mp.upper[(size_t)slot * kMaxRows + r_in];
+            return false;
+        }
+        Mask128 pend = mk(ld_nc_u4(tv.H + m));
+        mask_keep_le(pend, r_in);
+        mask_keep_gt(pend, top);
+        f_m[sp] = m; f_slot[sp] = slot; f_rin[sp] = (uint8_t)r_in; f_all[sp] = all; f_ind[sp] = ind;
+        f_pend[sp] = pend;
+        f_fill[sp] = (uint8_t)(top + 1);
+        f_lo[sp] = (int8_t)(top > 0 ? mp.lower[(size_t)slot * kMaxRows + top] : dl);
+        f_up[sp] = (int8_t)(top > 0 ? mp.upper[(size_t)slot * kMaxRows + top] : du);
+        sp++;
+        return true;
+    };
+
+    int best_lo = 0, best_up = 0;
+    bool first = true;
+    for (int64_t v = lo; v <= hi; v++) {
+        int b_lo, b_up;
+        if (v < 0) {
+            b_lo = dl; b_up = du;
+        } else if (v == 0) {
+            b_lo = 0; b_up = 0;
+        } else {
+            if (arrive((uint32_t)v, top_row, max_mods, s_ind[top_row])) {
+                while (sp > 0) {
+                    const int d = sp - 1;
+                    const size_t base = (size_t)f_slot[d] * kMaxRows;
+                    if (mask_empty(f_pend[d])) {  // every new row of this mass is done: publish, return to the parent
+                        for (int r = f_fill[d]; r <= f_rin[d]; r++) {
+                            mp.lower[base + r] = f_lo[d];
+                            mp.upper[base + r] = f_up[d];
+                        }
+                        mp.top[f_slot[d]] = f_rin[d];
+                        ret_lo = f_lo[d];
+                        ret_up = f_up[d];
+                        sp--;
+                        if (sp > 0) {  // the parent's LEFT candidate through row f_cur: child + 1
+                            const int pd = sp - 1;
+                            const int cl = ret_lo + 1, cu = ret_up + 1;
+                            if (cl < f_lo[pd]) f_lo[pd] = (int8_t)cl;
+                            if (cu > f_up[pd]) f_up[pd] = (int8_t)cu;
+                            const size_t pb = (size_t)f_slot[pd] * kMaxRows;
+                            mp.lower[pb + f_cur[pd]] = f_lo[pd];
+                            mp.upper[pb + f_cur[pd]] = f_up[pd];
+                        }
+                        continue;
+                    }
+                    const int r = mask_pop_lowest(f_pend[d]);  // LEFT edges fire in ascending row order (UP first)
+                    for (int q = f_fill[d]; q < r; q++) {      // rows without an edge inherit the running value
+                        mp.lower[base + q] = f_lo[d];
+                        mp.upper[base + q] = f_up[d];
+                    }
+                    f_fill[d] = (uint8_t)(r + 1);
+                    f_cur[d] = (uint8_t)r;
+                    const int ind_here = (r == f_rin[d]) ? f_ind[d] : s_ind[r];
+                    const int mod = s_mod[r];
+                    if (mod && !(f_all[d] > 0 && ind_here > 0)) {  // budget-blocked: no candidate from this row
+                        mp.lower[base + r] = f_lo[d];
+                        mp.upper[base + r] = f_up[d];
+                        continue;
+                    }
+                    const uint32_t m2 = f_m[d] - (uint32_t)s_w[r];
+                    bool opened = false;
+                    if (m2 == 0u) {
+                        ret_lo = 0;
+                        ret_up = 0;
+                    } else {
+                        opened = arrive(m2, r, f_all[d] - mod, ind_here - mod);
+                    }
+                    if (!opened) {
+                        const int cl = ret_lo + 1, cu = ret_up + 1;
+                        if (cl < f_lo[d]) f_lo[d] = (int8_t)cl;
+                        if (cu > f_up[d]) f_up[d] = (int8_t)cu;
+                        mp.lower[base + r] = f_lo[d];
+                        mp.upper[base + r] = f_up[d];
+                    }
+                }
+            }
+            b_lo = ret_lo;
+            b_up = ret_up;
+            // a window value whose last-row cell is empty never enters the memo upstream and yields the default;
+            // here its mask is empty, the frame closes at once with the defaults: the same value
+        }
+        if (first) {
+            best_lo = b_lo; best_up = b_up; first = false;
+        } else {
+            if (b_lo < best_lo) best_lo = b_lo;
+            if (b_up > best_up) best_up = b_up;
+        }
+    }
+    if (best_lo == dl) best_lo = 1;       // mass_table.py:477-479
+    if (best_up == du) best_up = max_len;  // :481-483
+    out[0] = best_lo;
+    out[1] = best_up;
+}
+
 // ---------------- K3 + K2b: the enumeration pass, ONE cooperative launch ----------------
 // Level-synchronous expansion.  An ITEM is a partial composition: (remainder m, largest row still allowed rmax,
 // rows chosen so far, peak).  Level 0 holds one item per reachable window value (K3, the integer window over the

@@ -306,8 +306,3 @@ def explain_mass_with_recursion(mass: float, dp_table: DynamicProgrammingTable, 
         return found
 
     return convert_nucleotide_masses_to_names(walk(target, 1, 0, 0))
-
-
-def _sequence_length_bound_device(dp_table, direction: str) -> int:
-    raise NotImplementedError(
-        "compute_sequence_length_bound has no device kernel yet (SURVEY §8f N1); refusing to fall back to the CPU")

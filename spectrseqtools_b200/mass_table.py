@@ -259,14 +259,36 @@ class DynamicProgrammingTable:
                 f"precision={self.precision}, tolerance={self.tolerance}, seq={self.seq})")
 
 
-def compute_sequence_length_bound(dp_table: DynamicProgrammingTable, dir: str) -> int:
-    """Lower/upper bound on the number of nucleotides explaining ``seq.su_mass`` (mass_table.py:343-487).
+def compute_sequence_length_bounds(dp_table: DynamicProgrammingTable) -> Tuple[int, int]:
+    """(lower, upper) in one device walk (``sst_length_bounds``; the traversal does not depend on the direction)."""
+    from .mass_explanation import _budget_int, _row_metadata
 
-    NOT on the device yet: it needs the same first-visit memo semantics with min/max
-    instead of lists.  Raises until the kernel exists rather than silently computing on the CPU.
-    """
+    max_modifications = round(dp_table.seq.modification_rate * dp_table.seq.max_len)
+    target = int(round(dp_table.seq.su_mass / dp_table.precision, 0))
+    threshold = int(np.ceil(dp_table.tolerance * dp_table.seq.obs_mass / dp_table.precision))
+    dev = dp_table.device_table()
+    _weights, is_mod, ind = _row_metadata(dp_table)
+    cap = 0
+    while True:
+        try:
+            return dev.ctx.length_bounds(dev, target, threshold, _budget_int(max_modifications), dp_table.seq.max_len, ind, is_mod, cap)
+        except _cabi.MemoFull:
+            cap = (cap or (1 << 16)) * 4
+            if cap > (1 << 26):
+                raise
+
+
+def compute_sequence_length_bound(dp_table: DynamicProgrammingTable, dir: str) -> int:
+    """Lower / upper bound on the number of nucleotides of any sequence explaining ``seq.su_mass`` (reference
+    mass_table.py:343-487, including its first-visit memo semantics).  Runs on the device; both directions come
+    out of the same walk, so the pair is kept for the second call a caller usually makes right away."""
     if dir not in ("lower", "upper"):
         raise NotImplementedError(f"Support for '{dir}' is currently not given.")
-    from .mass_explanation import _sequence_length_bound_device
-
-    return _sequence_length_bound_device(dp_table, dir)
+    rows = dp_table.masses
+    key = (id(dp_table.device_table()), dp_table.seq.su_mass, dp_table.seq.obs_mass, dp_table.seq.max_len,
+           dp_table.seq.modification_rate, dp_table.tolerance, tuple(m.modification_rate for m in rows))
+    hit = getattr(dp_table, "_bounds_cache", None)
+    if hit is None or hit[0] != key:
+        hit = (key, compute_sequence_length_bounds(dp_table))
+        dp_table._bounds_cache = hit
+    return hit[1][0 if dir == "lower" else 1]
