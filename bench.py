@@ -309,7 +309,7 @@ def main():
     ctx.explain_stage_f64(dev, e_mass, e_thrf, max_mods, ind, is_mod, dp.precision, dp.tolerance, True)
 
     def step():
-        ctx.classify_run(dev, dp.precision, dp.tolerance)
+        ctx.classify_launch(dev, dp.precision, dp.tolerance)  # queued; explain_run's synchronisation completes both
         return ctx.explain_run(dev, 0)
 
     sampler = ClockSampler(local_rank)

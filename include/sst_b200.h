@@ -111,6 +111,8 @@ int sst_classify(sst_ctx* ctx, const sst_table* t, const double* observed, int64
                  double tolerance, uint8_t* out /* B*F */);
 int sst_classify_stage(sst_ctx* ctx, const double* observed, int64_t F, const double* offsets, int B);
 int sst_classify_run(sst_ctx* ctx, const sst_table* t, double precision, double tolerance);
+/* the same without waiting: the kernel is queued on the context's stream, the next synchronous call completes it */
+int sst_classify_launch(sst_ctx* ctx, const sst_table* t, double precision, double tolerance);
 int sst_classify_fetch(sst_ctx* ctx, uint8_t* out /* B*F */);
 
 /* ---- sequence-length bounds: replaces compute_sequence_length_bound (mass_table.py:343-487), both directions in one

@@ -35,7 +35,7 @@ EXPORTS = [
     "sst_table_build", "sst_table_upload", "sst_table_rebuild", "sst_table_info", "sst_table_download",
     "sst_table_download_masks", "sst_table_destroy", "sst_is_valid", "sst_valid_stage", "sst_valid_run",
     "sst_valid_fetch", "sst_valid_stage_f64", "sst_explain", "sst_explain_stage", "sst_explain_stage_f64", "sst_explain_rec_width", "sst_explain_phase_ns",
-    "sst_explain_run", "sst_explain_fetch", "sst_classify", "sst_classify_stage", "sst_classify_run", "sst_classify_fetch", "sst_length_bounds",
+    "sst_explain_run", "sst_explain_fetch", "sst_classify", "sst_classify_stage", "sst_classify_run", "sst_classify_fetch", "sst_classify_launch", "sst_length_bounds",
 ]
 
 
@@ -99,6 +99,7 @@ def load() -> C.CDLL:
             "sst_classify_stage": (C.c_int, [vp, fp, C.c_int64, fp, C.c_int]),
             "sst_classify_run": (C.c_int, [vp, vp, C.c_double, C.c_double]),
             "sst_classify_fetch": (C.c_int, [vp, u8p]),
+            "sst_classify_launch": (C.c_int, [vp, vp, C.c_double, C.c_double]),
             "sst_length_bounds": (C.c_int, [vp, vp, C.c_int64, C.c_int64, C.c_int32, C.c_int32, i32p, u8p, C.c_uint64,
                                             C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
         }
@@ -255,6 +256,10 @@ class Context:
 
     def classify_run(self, table: "DeviceTable", precision: float, tolerance: float):
         self._check(self._lib.sst_classify_run(self._h, table._h, float(precision), float(tolerance)))
+
+    def classify_launch(self, table: "DeviceTable", precision: float, tolerance: float):
+        """Queue the classification kernel without waiting (the next synchronous call on the context completes it)."""
+        self._check(self._lib.sst_classify_launch(self._h, table._h, float(precision), float(tolerance)))
 
     def classify_fetch(self, copy: bool = True) -> np.ndarray:
         """-> uint8[B, F] of CLASS_* bits (breakage-major)."""

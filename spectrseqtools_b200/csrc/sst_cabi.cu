@@ -68,7 +68,7 @@ struct sst_ctx {
     int64_t max_hi = 0;
     // results
     DevBuf d_status, d_cnt, d_peakoff, d_recs, d_blocksums;
-    DevBuf d_scan, d_vmass, d_vthrf, d_peakcnt;
+    DevBuf d_scan, d_vmass, d_vthrf, d_peakcnt, d_chunk_exp, d_chunk_fin;
     DevBuf d_item_m[2], d_item_peak[2], d_item_meta[2], d_item_all[2], d_item_ind[2], d_item_path[2];
     bool has_exact = false;
     int levels = 0;
@@ -330,7 +330,7 @@ void sst_ctx_destroy(sst_ctx* ctx) {
                       &ctx->d_memo_peaks, &ctx->d_status, &ctx->d_cnt, &ctx->d_peakoff, &ctx->d_recs,
                       &ctx->d_blocksums, &ctx->d_memo_keys, &ctx->d_memo_alive, &ctx->d_memo_top,
                       &ctx->d_memo_misc, &ctx->d_flush, &ctx->d_vtarget, &ctx->d_vthr, &ctx->d_vout,
-                      &ctx->d_scan, &ctx->d_vmass, &ctx->d_vthrf, &ctx->d_peakcnt, &ctx->d_cobs, &ctx->d_coff, &ctx->d_cout, &ctx->d_bkeys, &ctx->d_btop, &ctx->d_blower, &ctx->d_bupper, &ctx->d_bout,
+                      &ctx->d_scan, &ctx->d_vmass, &ctx->d_vthrf, &ctx->d_peakcnt, &ctx->d_chunk_exp, &ctx->d_chunk_fin, &ctx->d_cobs, &ctx->d_coff, &ctx->d_cout, &ctx->d_bkeys, &ctx->d_btop, &ctx->d_blower, &ctx->d_bupper, &ctx->d_bout,
                       &ctx->d_item_m[0], &ctx->d_item_m[1], &ctx->d_item_peak[0], &ctx->d_item_peak[1],
                       &ctx->d_item_meta[0], &ctx->d_item_meta[1], &ctx->d_item_all[0], &ctx->d_item_all[1],
                       &ctx->d_item_ind[0], &ctx->d_item_ind[1], &ctx->d_item_path[0], &ctx->d_item_path[1]};
@@ -593,7 +593,7 @@ int sst_classify_stage(sst_ctx* ctx, const double* observed, int64_t F, const do
     return SST_OK;
 }
 
-int sst_classify_run(sst_ctx* ctx, const sst_table* t, double precision, double tolerance) {
+int sst_classify_launch(sst_ctx* ctx, const sst_table* t, double precision, double tolerance) {
     CK(cudaSetDevice(ctx->device));
     if (ctx->CF && ctx->CB) {
         KTimer kt(ctx, SST_K_CLASSIFY);
@@ -603,6 +603,12 @@ int sst_classify_run(sst_ctx* ctx, const sst_table* t, double precision, double 
         kt.stop(1);
         CK(cudaGetLastError());
     }
+    return SST_OK;
+}
+
+int sst_classify_run(sst_ctx* ctx, const sst_table* t, double precision, double tolerance) {
+    int rc = sst_classify_launch(ctx, t, precision, tolerance);
+    if (rc) return rc;
     CK(cudaStreamSynchronize(ctx->stream));
     flush_timers(ctx);
     return SST_OK;
@@ -807,6 +813,7 @@ int sst_explain_run(sst_ctx* ctx, const sst_table* t, int rec_width, uint64_t me
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kPassThreads, 0));
         if (occ < 1) return fail(ctx, SST_ERR_CUDA, "k_explain_pass does not fit on an SM");
         grid_max = occ * ctx->prop.multiProcessorCount;
+        if (grid_max > kPassThreads) grid_max = kPassThreads;  // the slice totals are scanned by one CTA (balanced_range)
     }
     if ((rc = reserve(ctx, ctx->d_status, (size_t)(P ? P : 1)))) return rc;
     if ((rc = reserve(ctx, ctx->d_peakoff, (size_t)(P + 2) * 8))) return rc;
@@ -833,6 +840,9 @@ int sst_explain_run(sst_ctx* ctx, const sst_table* t, int rec_width, uint64_t me
         }
         const size_t most = (size_t)P > cap ? (size_t)P : cap;
         if ((rc = reserve(ctx, ctx->d_cnt, (most + 1) * 4))) return rc;
+        const size_t n_chunks = most / 32 + (size_t)grid_max + 64;
+        if ((rc = reserve(ctx, ctx->d_chunk_exp, n_chunks * 4))) return rc;
+        if ((rc = reserve(ctx, ctx->d_chunk_fin, n_chunks * 4))) return rc;
         // [0,64) totals, [64,320) timestamps, [320,384) flags, [384,388) grid-barrier counter
         CK(cudaMemsetAsync(ctx->d_scan.p, 0, 512, ctx->stream));
         int* d_flags = (int*)((char*)ctx->d_scan.p + 320);  // [0] item limit, [1] records overflow, [2] items overflow
@@ -879,6 +889,8 @@ int sst_explain_run(sst_ctx* ctx, const sst_table* t, int rec_width, uint64_t me
         a.cap = (unsigned long long)cap;
         a.item_limit = ctx->item_limit;
         a.cnt = (uint32_t*)ctx->d_cnt.p;
+        a.chunk_exp = (uint32_t*)ctx->d_chunk_exp.p;
+        a.chunk_fin = (uint32_t*)ctx->d_chunk_fin.p;
         a.nw = nw;
         a.has_budget = ctx->has_exact ? 1 : 0;
         a.recs = (uint8_t*)ctx->d_recs.p;

@@ -582,6 +582,8 @@ struct PassArgs {
     unsigned long long cap;          // items per buffer
     unsigned long long item_limit;   // blow-up guard: more items than this in one level -> flags[0]
     uint32_t* cnt;                   // [max(P, cap)] per-entity counts between count and write (children | final << 16)
+    uint32_t* chunk_exp;             // [max(P, cap) / 32 + grid + 1] children (stage 1: roots) of every 32-entity chunk
+    uint32_t* chunk_fin;             // the same for the final compositions
     int nw;                          // path / record words (W = 8 * nw bytes)
     int has_budget;                  // some peak is in EXACT mode
     uint8_t* recs;
@@ -681,15 +683,15 @@ __device__ __forceinline__ unsigned int block_scan32(unsigned int x, unsigned in
     __syncthreads();
     return r;
 }
-__device__ __forceinline__ unsigned long long block_sum(unsigned long long x) {
-    unsigned long long t;
-    block_scan(x, &t);
-    return t;
-}
-// CTA-wide sums of N values per thread with one pair of barriers
+template <int N>
+__device__ __forceinline__ void block_sum_n(unsigned long long (&v)[N]);
+__device__ __forceinline__ unsigned long long block_sum(unsigned long long x);
+// CTA-wide sums of N values per thread: warp shuffles, then warp 0 folds the per-warp partials (three barriers, a
+// handful of shared-memory accesses per thread — every thread re-adding all partials cost ~2.5 us per call)
 template <int N>
 __device__ __forceinline__ void block_sum_n(unsigned long long (&v)[N]) {
     __shared__ unsigned long long s_part[kPassThreads / 32][N];
+    __shared__ unsigned long long s_res[N];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
 #pragma unroll
     for (int k = 0; k < N; k++) {
@@ -698,14 +700,25 @@ __device__ __forceinline__ void block_sum_n(unsigned long long (&v)[N]) {
         if (lane == 0) s_part[w][k] = v[k];
     }
     __syncthreads();
+    if (w == 0) {
 #pragma unroll
-    for (int k = 0; k < N; k++) {
-        unsigned long long t = 0;
+        for (int k = 0; k < N; k++) {
+            unsigned long long t = lane < kPassThreads / 32 ? s_part[lane][k] : 0ULL;
 #pragma unroll
-        for (int i = 0; i < kPassThreads / 32; i++) t += s_part[i][k];
-        v[k] = t;
+            for (int o = 16; o; o >>= 1) t += __shfl_xor_sync(0xFFFFFFFFu, t, o);
+            if (lane == 0) s_res[k] = t;
+        }
     }
     __syncthreads();
+#pragma unroll
+    for (int k = 0; k < N; k++) v[k] = s_res[k];
+    __syncthreads();
+}
+
+__device__ __forceinline__ unsigned long long block_sum(unsigned long long x) {
+    unsigned long long v[1] = {x};
+    block_sum_n<1>(v);
+    return v[0];
 }
 
 // after a grid barrier: sum of the slice totals of the CTAs before this one, and of all CTAs
@@ -737,6 +750,93 @@ __device__ __forceinline__ void slice_prefix3(const unsigned long long* cta_tot,
         base[k] = v[k];
         all[k] = v[3 + k];
     }
+}
+
+// ---- output-balanced work split ----
+// The count phases deal ENTITIES evenly (one load each); the write phases cost per OUTPUT, and outputs cluster
+// (a wide 3-nt window is thousands of consecutive open items).  So the write phases re-split the list by outputs:
+// every 32-entity chunk publishes its output total in the count phase, and after the grid barrier CTA b takes the
+// chunks whose first output falls in [T*b/G, T*(b+1)/G).  Finding the two boundary chunks is a two-level search:
+// slice totals (G values, scanned in shared memory), then the chunk totals of one slice.
+struct ChunkRange {
+    long long cb, ce;          // this CTA's chunks
+    unsigned long long base;   // output offset of chunk cb
+    unsigned long long total;  // outputs of the whole list
+};
+
+// number of chunks whose exclusive output prefix is < t, and that prefix at the boundary.  One WARP does it
+// (lane-parallel over the chunks of one slice), so both boundaries of a CTA are found at the same time.
+__device__ __forceinline__ void chunk_boundary_warp(const unsigned long long* s_spre, const uint32_t* __restrict__ chunk_tot, long long cps,
+                                                    long long nchunks, unsigned long long t, long long* F, unsigned long long* excl) {
+    const int lane = threadIdx.x & 31;
+    if (t == 0ULL) {
+        *F = 0;
+        *excl = 0ULL;
+        return;
+    }
+    int lo = 0, hi = (int)gridDim.x;  // last slice with s_spre[s] < t  (s_spre[0] = 0 < t)
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (s_spre[mid] < t) lo = mid;
+        else hi = mid;
+    }
+    const long long s = lo;
+    unsigned long long run = s_spre[s];
+    long long flagged = 0;
+    for (long long i0 = 0; i0 < cps; i0 += 32) {
+        const long long i = i0 + lane, c = s * cps + i;
+        const bool in = i < cps && c < nchunks;
+        const unsigned int x = in ? __ldcg(chunk_tot + c) : 0u;
+        unsigned int incl = x;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned int y = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+            if (lane >= o) incl += y;
+        }
+        const bool f = in && run + (incl - x) < t;
+        const unsigned int fm = __ballot_sync(0xFFFFFFFFu, f);  // a prefix of the lanes: the prefix sums are monotone
+        const int nf = __popc(fm);
+        flagged += nf;
+        const unsigned int upto = nf ? __shfl_sync(0xFFFFFFFFu, incl, nf - 1) : 0u;
+        if (nf < 32 || i0 + 32 >= cps) {
+            run += upto;
+            break;
+        }
+        run += upto;
+    }
+    *F = s * cps + flagged;
+    *excl = run;
+}
+
+__device__ __forceinline__ ChunkRange balanced_range(const unsigned long long* __restrict__ cta_tot, const uint32_t* __restrict__ chunk_tot,
+                                                     long long n, long long per, unsigned long long* s_spre) {
+    __shared__ long long s_F[2];
+    __shared__ unsigned long long s_E[2];
+    const int G = (int)gridDim.x;  // <= kPassThreads (host)
+    unsigned long long tot;
+    const unsigned long long x = (int)threadIdx.x < G ? __ldcg(cta_tot + threadIdx.x) : 0ULL;
+    const unsigned long long ex = block_scan(x, &tot);
+    if ((int)threadIdx.x < G) s_spre[threadIdx.x] = ex;
+    if (threadIdx.x == 0) s_spre[G] = tot;
+    __syncthreads();
+    const long long cps = per / 32, nchunks = (n + 31) / 32;
+    const int w = threadIdx.x >> 5;
+    if (w < 2) {  // warp 0: where this CTA starts, warp 1: where it ends
+        long long F;
+        unsigned long long E;
+        chunk_boundary_warp(s_spre, chunk_tot, cps, nchunks, tot * (blockIdx.x + w) / G, &F, &E);  // tot < 2^44, G < 2^10
+        if ((threadIdx.x & 31) == 0) {
+            s_F[w] = F;
+            s_E[w] = E;
+        }
+    }
+    __syncthreads();
+    ChunkRange r;
+    r.total = tot;
+    r.cb = s_F[0];
+    r.base = s_E[0];
+    r.ce = (int)blockIdx.x == G - 1 ? nchunks : s_F[1];  // trailing chunks without outputs go to the last CTA
+    return r;
 }
 
 // entities of a list of n are dealt to CTAs in contiguous slices of `per` (a multiple of 32)
@@ -819,6 +919,9 @@ k_explain_pass(const PassArgs a) {
     __shared__ uint8_t s_mod[kMaxRows];
     __shared__ uint8_t s_leaf[kLeafSlots];
     __shared__ int s_nheavy;
+    __shared__ unsigned long long s_spre[kPassThreads + 1];
+    __shared__ unsigned int s_cbase[kPassThreads];
+    __shared__ unsigned int s_ttot;
     __shared__ int s_heavy_p[kPassThreads];
     __shared__ unsigned long long s_heavy_off[kPassThreads];
     const TableView& tv = a.tv;
@@ -965,31 +1068,44 @@ k_explain_pass(const PassArgs a) {
         const ItemBuf& in = a.buf[cur];
         const long long n = (long long)n_items, per = slice_size(n), first = (long long)blockIdx.x * per;
         unsigned long long mine_children = 0, mine_open = 0, mine_final = 0;
-        for (long long li = threadIdx.x; li < per; li += blockDim.x) {
+        for (long long li = threadIdx.x; li < per; li += blockDim.x) {  // whole warps enter together: per % 32 == 0
             const long long i = first + li;
-            if (i >= n) break;
-            const uint32_t m = __ldcg(in.m + i);
-            uint32_t meta = __ldcg(in.meta + i);
-            const int rmax = meta & 0xFF;
-            const int mode = (meta >> 24) & 3;
-            const uint32_t p = mode == MODE_MEMO ? __ldcg(in.peak + i) : 0u;  // only the memo key needs the peak
-            const int kind = item_kind(mode, m, rt.wmin);
-            unsigned int c_exp = 1, c_fin = 1;
-            if (kind == KIND_POPC) {
-                c_fin = (meta >> 16) & 0xFF;
-                if (!c_fin) {  // counted once, then carried in the item
-                    c_fin = (unsigned)mask_popc(child_mask(tv, a.mp, mode, p, m, rmax));
-                    in.meta[i] = meta | (c_fin << 16);
+            unsigned int c_exp = 0, c_fin = 0;
+            if (i < n) {
+                const uint32_t m = __ldcg(in.m + i);
+                uint32_t meta = __ldcg(in.meta + i);
+                const int rmax = meta & 0xFF;
+                const int mode = (meta >> 24) & 3;
+                const uint32_t p = mode == MODE_MEMO ? __ldcg(in.peak + i) : 0u;  // only the memo key needs the peak
+                const int kind = item_kind(mode, m, rt.wmin);
+                c_exp = 1;
+                c_fin = 1;
+                if (kind == KIND_POPC) {
+                    c_fin = (meta >> 16) & 0xFF;
+                    if (!c_fin) {  // counted once, then carried in the item
+                        c_fin = (unsigned)mask_popc(child_mask(tv, a.mp, mode, p, m, rmax));
+                        in.meta[i] = meta | (c_fin << 16);
+                    }
+                } else if (kind == KIND_OPEN) {
+                    const int all = a.has_budget ? __ldcg(in.all + i) : 0, ind = a.has_budget ? __ldcg(in.ind + i) : 0;
+                    c_exp = (unsigned)mask_popc(open_children(a, rt, mode, p, m, rmax, all, ind));
+                    c_fin = 0;
+                    mine_open++;
                 }
-            } else if (kind == KIND_OPEN) {
-                const int all = a.has_budget ? __ldcg(in.all + i) : 0, ind = a.has_budget ? __ldcg(in.ind + i) : 0;
-                c_exp = (unsigned)mask_popc(open_children(a, rt, mode, p, m, rmax, all, ind));
-                c_fin = 0;
-                mine_open++;
+                a.cnt[i] = c_exp | (c_fin << 16);
+                mine_children += c_exp;
+                mine_final += c_fin;
             }
-            a.cnt[i] = c_exp | (c_fin << 16);
-            mine_children += c_exp;
-            mine_final += c_fin;
+            unsigned int we = c_exp, wf = c_fin;  // the chunk's totals, for the output-balanced split of the write phase
+#pragma unroll
+            for (int o = 16; o; o >>= 1) {
+                we += __shfl_xor_sync(0xFFFFFFFFu, we, o);
+                wf += __shfl_xor_sync(0xFFFFFFFFu, wf, o);
+            }
+            if (lane == 0) {
+                a.chunk_exp[i >> 5] = we;
+                a.chunk_fin[i >> 5] = wf;
+            }
         }
         unsigned long long tsum[3] = {mine_children, mine_open, mine_final};
         block_sum_n<3>(tsum);
@@ -1017,13 +1133,29 @@ k_explain_pass(const PassArgs a) {
             return;
         }
         const ItemBuf& out = a.buf[cur ^ 1];
-        for (long long l0 = 0; l0 < per; l0 += blockDim.x) {
-            const long long i = first + l0 + threadIdx.x;
-            const bool ok = l0 + threadIdx.x < per && i < n;
+        const ChunkRange cr = balanced_range(a.cta_tot, a.chunk_exp, n, per, s_spre);
+        unsigned long long tile_run = 0;
+        for (long long tile0 = cr.cb; tile0 < cr.ce; tile0 += blockDim.x) {  // up to blockDim chunks per tile, one warp per chunk
+            {
+                const long long c = tile0 + threadIdx.x;
+                const unsigned int x = c < cr.ce ? __ldcg(a.chunk_exp + c) : 0u;
+                unsigned int ttot;
+                s_cbase[threadIdx.x] = block_scan32(x, &ttot);
+                if (threadIdx.x == 0) s_ttot = ttot;
+            }
+            __syncthreads();
+            const unsigned long long tile_base = cr.base + tile_run;
+          for (long long wq = threadIdx.x >> 5; tile0 + wq < cr.ce && wq < (long long)blockDim.x; wq += kPassThreads / 32) {
+            const long long i = (tile0 + wq) * 32 + lane;
+            const bool ok = i < n;
             const unsigned int k = ok ? (a.cnt[i] & 0xFFFFu) : 0u;
-            unsigned int round_tot;
-            const unsigned long long off = base + block_scan32(k, &round_tot);
-            base += round_tot;
+            unsigned int kin = k;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned int y = __shfl_up_sync(0xFFFFFFFFu, kin, o);
+                if (lane >= o) kin += y;
+            }
+            const unsigned long long off = tile_base + s_cbase[wq] + (kin - k);
             uint32_t m = 0, p = 0, meta = 0;
             int all = 0, ind = 0;
             unsigned long long pw[kPW];
@@ -1113,6 +1245,9 @@ k_explain_pass(const PassArgs a) {
                     }
                 }
             }
+          }
+            tile_run += s_ttot;
+            __syncthreads();
         }
         stamp(a, ts++);
         grid_barrier(a, gen);
@@ -1135,13 +1270,29 @@ k_explain_pass(const PassArgs a) {
         }
         if (fits) {
             unsigned long long* recs64 = reinterpret_cast<unsigned long long*>(a.recs);
-            for (long long l0 = 0; l0 < per; l0 += blockDim.x) {
-                const long long i = first + l0 + threadIdx.x;
-                const bool ok = l0 + threadIdx.x < per && i < n;
+            const ChunkRange cr = balanced_range(a.cta_tot + 2 * gridDim.x, a.chunk_fin, n, per, s_spre);
+            unsigned long long tile_run = 0;
+            for (long long tile0 = cr.cb; tile0 < cr.ce; tile0 += blockDim.x) {
+                {
+                    const long long c = tile0 + threadIdx.x;
+                    const unsigned int x = c < cr.ce ? __ldcg(a.chunk_fin + c) : 0u;
+                    unsigned int ttot;
+                    s_cbase[threadIdx.x] = block_scan32(x, &ttot);
+                    if (threadIdx.x == 0) s_ttot = ttot;
+                }
+                __syncthreads();
+                const unsigned long long tile_base = cr.base + tile_run;
+              for (long long wq = threadIdx.x >> 5; tile0 + wq < cr.ce && wq < (long long)blockDim.x; wq += kPassThreads / 32) {
+                const long long i = (tile0 + wq) * 32 + lane;
+                const bool ok = i < n;
                 const unsigned int c = ok ? (a.cnt[i] >> 16) : 0u;
-                unsigned int round_tot;
-                const unsigned long long roff = base + block_scan32(c, &round_tot);
-                base += round_tot;
+                unsigned int cin = c;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const unsigned int y = __shfl_up_sync(0xFFFFFFFFu, cin, o);
+                    if (lane >= o) cin += y;
+                }
+                const unsigned long long roff = tile_base + s_cbase[wq] + (cin - c);
                 uint32_t m = 0, meta = 0;
                 unsigned long long pw[kPW];
 #pragma unroll
@@ -1187,6 +1338,9 @@ k_explain_pass(const PassArgs a) {
                     for (int q = 0; q < nw; q++) spw[q] = __shfl_sync(0xFFFFFFFFu, pw[q], src);
                     for (unsigned int j = lane; j < sc; j += 32) put(so + j, sm, smeta & 0xFF, KIND_POPC, mask_select(scm, (int)j), spw);
                 }
+              }
+                tile_run += s_ttot;
+                __syncthreads();
             }
         }
         if (blockIdx.x == 0 && threadIdx.x == 0) {
