@@ -1261,12 +1261,16 @@ k_explain_pass(const PassArgs a) {
     {
         const ItemBuf& in = a.buf[cur];
         const long long n = (long long)n_items, per = slice_size(n), first = (long long)blockIdx.x * per;
-        // per-peak totals (items of a peak are contiguous; one add per item)
-        for (long long li = threadIdx.x; li < per; li += blockDim.x) {
+        // per-peak totals.  Items of a peak are contiguous, so a warp usually holds one or two peaks: lanes with the
+        // same peak fold their counts first (a blow-up peak would otherwise put 10^5 adds on one address)
+        for (long long li = threadIdx.x; li < per; li += blockDim.x) {  // whole warps: per % 32 == 0
             const long long i = first + li;
-            if (i >= n) break;
-            const unsigned int c = a.cnt[i] >> 16;
-            if (c) atomicAdd(a.peak_cnt + __ldcg(in.peak + i), (unsigned long long)c);
+            const bool ok = i < n;
+            const unsigned int c = ok ? (a.cnt[i] >> 16) : 0u;
+            const uint32_t p = ok ? __ldcg(in.peak + i) : 0xFFFFFFFFu;
+            const unsigned int grp = __match_any_sync(0xFFFFFFFFu, p);
+            const unsigned int sum = __reduce_add_sync(grp, c);
+            if (ok && sum && lane == __ffs(grp) - 1) atomicAdd(a.peak_cnt + p, (unsigned long long)sum);
         }
         if (fits) {
             unsigned long long* recs64 = reinterpret_cast<unsigned long long*>(a.recs);

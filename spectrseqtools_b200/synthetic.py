@@ -69,6 +69,7 @@ def _rows(names: Optional[List[str]]):
 
 def make_workload(config: str, n_peaks: int = 100_000, seed_offset: int = 0) -> Workload:
     config = config.upper()
+    miss_p, max_gap = 0.2, 3
     if config == "C2":
         cid, lens, names, ppm, msl, full_dict = 2, (20, 20), ["A", "C", "G", "U"] + C2_MODS, 5e-6, 35, False
     elif config == "C3":
@@ -77,6 +78,7 @@ def make_workload(config: str, n_peaks: int = 100_000, seed_offset: int = 0) -> 
         cid, lens, names, ppm, msl, full_dict = 4, (10, 40), None, 10e-6, 35, True
     elif config == "C5":
         cid, lens, names, ppm, msl, full_dict = 5, (80, 80), None, 20e-6, 42, False
+        miss_p, max_gap = 0.55, 5  # sparse ladders: 1-5 nt gaps, the combinatorial blow-up case
     else:
         raise ValueError(f"unknown workload {config!r} (C2, C3, C4, C5)")
     rng = np.random.default_rng(20260118 + cid + seed_offset)
@@ -123,7 +125,7 @@ def make_workload(config: str, n_peaks: int = 100_000, seed_offset: int = 0) -> 
             v_mass.append(cand.ravel())
             v_thr.append(np.repeat(ppm * obs, len(offsets)))
             # explanation: adjacent kept rungs
-            kept = np.nonzero(rng.random(L) >= 0.2)[0]
+            kept = np.nonzero(rng.random(L) >= miss_p)[0]
             su_obs = obs - off
             if len(kept) and kept[0] == 0:
                 e_mass.append(np.array([su_obs[0]]))
@@ -131,7 +133,7 @@ def make_workload(config: str, n_peaks: int = 100_000, seed_offset: int = 0) -> 
                 e_nt.append(np.array([1]))
             if len(kept) > 1:
                 gap = np.diff(kept)
-                ok = gap <= 3
+                ok = gap <= max_gap
                 a, b = kept[:-1][ok], kept[1:][ok]
                 e_mass.append(su_obs[b] - su_obs[a])
                 e_thr.append(ppm * (obs[a] + obs[b]))
