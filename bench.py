@@ -45,7 +45,7 @@ def peaks_file():
 class ClockSampler(threading.Thread):
     """Samples SM clock + throttle reasons through NVML while the timed region runs."""
 
-    def __init__(self, index: int, period: float = 0.02):
+    def __init__(self, index: int, period: float = 0.004):
         super().__init__(daemon=True)
         self.index, self.period = index, period
         self.samples, self.reasons = [], set()
@@ -234,6 +234,8 @@ def main():
     ap.add_argument("--peaks", type=int, default=100_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--large-factor", type=int, default=16,
+                    help="also time the same step on the batch tiled this many times (throughput regime; 0 = skip)")
     ap.add_argument("--flush", default="write", choices=["write", "none"],
                     help="L2 between timed steps: write a 256 MiB buffer (default, the contract) or leave it warm (diagnostics)")
     args = ap.parse_args()
@@ -392,6 +394,36 @@ def main():
     ph = ph[ph > 0]
     phase_us = [round(float(x) * 1e-3, 2) for x in np.diff(ph)] if len(ph) > 1 else None  # see sst_explain_phase_ns
 
+    # ---- the same step on a batch `large_factor` times larger (rank 0): where the latency of the ~19 dependent
+    # phases of the pass is amortised and bytes per second mean something
+    large = None
+    if rank == 0 and args.large_factor > 1:
+        f = args.large_factor
+        big_obs = pinned_copy(np.tile(wl.observed, f))
+        big_mass, big_thr = pinned_copy(np.tile(wl.explain_mass, f)), pinned_copy(np.tile(wl.explain_thr, f))
+        big_mm = np.full(len(big_mass), wl.max_modifications, dtype=np.int32)
+        ctx.classify_stage(big_obs, offsets)
+        ctx.explain_stage_f64(dev, big_mass, big_thr, big_mm, ind, is_mod, dp.precision, dp.tolerance, True)
+        for _ in range(3):
+            _r, big_comps = step()
+        ctx.stats_reset()
+        big_ms, big_steps = 0.0, 10
+        for _ in range(big_steps):
+            if args.flush == "write":
+                ctx.flush_l2()
+            ctx.timer_start()
+            _r, big_comps = step()
+            big_ms += ctx.timer_stop()
+        bstats = ctx.kernel_stats()
+        pass_ms = bstats["explain_pass"][0] / big_steps
+        cls_ms = bstats["classify"][0] / big_steps
+        large = {"factor": f, "peaks": wl.n_peaks * f, "ms_per_step": big_ms / big_steps,
+                 "peaks_per_sec": wl.n_peaks * f * big_steps / (big_ms * 1e-3),
+                 "compositions_per_sec": big_comps * big_steps / (big_ms * 1e-3),
+                 "explain_pass_ms": pass_ms, "classify_ms": cls_ms,
+                 "explain_pass_gbs": k2b_bytes * f / (pass_ms * 1e-3) / 1e9, "explain_pass_frac": k2b_bytes * f / (pass_ms * 1e-3) / 1e9 / hbm_peak,
+                 "classify_gbs": k2a_bytes * f / (cls_ms * 1e-3) / 1e9, "classify_frac": k2a_bytes * f / (cls_ms * 1e-3) / 1e9 / hbm_peak}
+
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -402,7 +434,7 @@ def main():
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "ms_per_step": 1e3 * e2e_s / args.steps},
         "gpu_launches": int(launches),
-        "roofline": roofline, "kernels": kernels, "pass_phase_us": phase_us, "table_build": table_info,
+        "roofline": roofline, "kernels": kernels, "pass_phase_us": phase_us, "large_batch": large, "table_build": table_info,
     }
 
     if rank == 0 and not args.no_parity:
