@@ -68,7 +68,7 @@ struct sst_ctx {
     int64_t max_hi = 0;
     // results
     DevBuf d_status, d_cnt, d_peakoff, d_recs, d_blocksums;
-    DevBuf d_scan, d_vmass, d_vthrf, d_peakcnt, d_chunk_exp, d_chunk_fin;
+    DevBuf d_scan, d_vmass, d_vthrf, d_chunk_k, d_chunk_r, d_tmprecs, d_tmppeak, d_lvlcnt, d_lvlA, d_ctalvl;
     DevBuf d_item_m[2], d_item_peak[2], d_item_meta[2], d_item_all[2], d_item_ind[2], d_item_path[2];
     bool has_exact = false;
     int levels = 0;
@@ -330,7 +330,7 @@ void sst_ctx_destroy(sst_ctx* ctx) {
                       &ctx->d_memo_peaks, &ctx->d_status, &ctx->d_cnt, &ctx->d_peakoff, &ctx->d_recs,
                       &ctx->d_blocksums, &ctx->d_memo_keys, &ctx->d_memo_alive, &ctx->d_memo_top,
                       &ctx->d_memo_misc, &ctx->d_flush, &ctx->d_vtarget, &ctx->d_vthr, &ctx->d_vout,
-                      &ctx->d_scan, &ctx->d_vmass, &ctx->d_vthrf, &ctx->d_peakcnt, &ctx->d_chunk_exp, &ctx->d_chunk_fin, &ctx->d_cobs, &ctx->d_coff, &ctx->d_cout, &ctx->d_bkeys, &ctx->d_btop, &ctx->d_blower, &ctx->d_bupper, &ctx->d_bout,
+                      &ctx->d_scan, &ctx->d_vmass, &ctx->d_vthrf, &ctx->d_chunk_k, &ctx->d_chunk_r, &ctx->d_tmprecs, &ctx->d_tmppeak, &ctx->d_lvlcnt, &ctx->d_lvlA, &ctx->d_ctalvl, &ctx->d_cobs, &ctx->d_coff, &ctx->d_cout, &ctx->d_bkeys, &ctx->d_btop, &ctx->d_blower, &ctx->d_bupper, &ctx->d_bout,
                       &ctx->d_item_m[0], &ctx->d_item_m[1], &ctx->d_item_peak[0], &ctx->d_item_peak[1],
                       &ctx->d_item_meta[0], &ctx->d_item_meta[1], &ctx->d_item_all[0], &ctx->d_item_all[1],
                       &ctx->d_item_ind[0], &ctx->d_item_ind[1], &ctx->d_item_path[0], &ctx->d_item_path[1]};
@@ -817,8 +817,12 @@ int sst_explain_run(sst_ctx* ctx, const sst_table* t, int rec_width, uint64_t me
     }
     if ((rc = reserve(ctx, ctx->d_status, (size_t)(P ? P : 1)))) return rc;
     if ((rc = reserve(ctx, ctx->d_peakoff, (size_t)(P + 2) * 8))) return rc;
-    if ((rc = reserve(ctx, ctx->d_peakcnt, (size_t)(P + 2) * 8))) return rc;
     if ((rc = reserve(ctx, ctx->d_blocksums, (size_t)3 * grid_max * 8))) return rc;
+    int lvl_cap = (int)ctx->deepest + 3;
+    if (lvl_cap > kMaxLevels) lvl_cap = kMaxLevels;
+    if ((rc = reserve(ctx, ctx->d_lvlcnt, (size_t)lvl_cap * (size_t)(P + 1) * 4))) return rc;
+    if ((rc = reserve(ctx, ctx->d_lvlA, (size_t)lvl_cap * (size_t)(P + 1) * 8))) return rc;
+    if ((rc = reserve(ctx, ctx->d_ctalvl, (size_t)lvl_cap * (size_t)grid_max * 8))) return rc;
     if ((rc = reserve(ctx, ctx->d_scan, 512))) return rc;
     if (!ctx->d_recs.p && (rc = reserve(ctx, ctx->d_recs, (size_t)64 << 20))) return rc;
     if (!ctx->item_capacity) ctx->item_capacity = (uint64_t)1 << 20;
@@ -841,8 +845,11 @@ int sst_explain_run(sst_ctx* ctx, const sst_table* t, int rec_width, uint64_t me
         const size_t most = (size_t)P > cap ? (size_t)P : cap;
         if ((rc = reserve(ctx, ctx->d_cnt, (most + 1) * 4))) return rc;
         const size_t n_chunks = most / 32 + (size_t)grid_max + 64;
-        if ((rc = reserve(ctx, ctx->d_chunk_exp, n_chunks * 4))) return rc;
-        if ((rc = reserve(ctx, ctx->d_chunk_fin, n_chunks * 4))) return rc;
+        if ((rc = reserve(ctx, ctx->d_chunk_k, n_chunks * 4))) return rc;
+        if ((rc = reserve(ctx, ctx->d_chunk_r, n_chunks * 4))) return rc;
+        // the level-ordered record buffer mirrors the result buffer
+        if ((rc = reserve(ctx, ctx->d_tmprecs, ctx->d_recs.cap))) return rc;
+        if ((rc = reserve(ctx, ctx->d_tmppeak, (ctx->d_recs.cap / rec_width + 1) * 4))) return rc;
         // [0,64) totals, [64,320) timestamps, [320,384) flags, [384,388) grid-barrier counter
         CK(cudaMemsetAsync(ctx->d_scan.p, 0, 512, ctx->stream));
         int* d_flags = (int*)((char*)ctx->d_scan.p + 320);  // [0] item limit, [1] records overflow, [2] items overflow
@@ -889,13 +896,18 @@ int sst_explain_run(sst_ctx* ctx, const sst_table* t, int rec_width, uint64_t me
         a.cap = (unsigned long long)cap;
         a.item_limit = ctx->item_limit;
         a.cnt = (uint32_t*)ctx->d_cnt.p;
-        a.chunk_exp = (uint32_t*)ctx->d_chunk_exp.p;
-        a.chunk_fin = (uint32_t*)ctx->d_chunk_fin.p;
+        a.chunk_k = (uint32_t*)ctx->d_chunk_k.p;
+        a.chunk_r = (uint32_t*)ctx->d_chunk_r.p;
+        a.tmp_recs = (unsigned long long*)ctx->d_tmprecs.p;
+        a.tmp_peak = (uint32_t*)ctx->d_tmppeak.p;
+        a.lvl_cnt = (uint32_t*)ctx->d_lvlcnt.p;
+        a.lvl_A = (unsigned long long*)ctx->d_lvlA.p;
+        a.lvl_cap = lvl_cap;
+        a.cta_lvl = (unsigned long long*)ctx->d_ctalvl.p;
         a.nw = nw;
         a.has_budget = ctx->has_exact ? 1 : 0;
         a.recs = (uint8_t*)ctx->d_recs.p;
         a.rec_capacity = (unsigned long long)(ctx->d_recs.cap / rec_width);
-        a.peak_cnt = (unsigned long long*)ctx->d_peakcnt.p;
         a.peak_off = (unsigned long long*)ctx->d_peakoff.p;
         a.cta_tot = (unsigned long long*)ctx->d_blocksums.p;
         a.totals = (unsigned long long*)ctx->d_scan.p;

@@ -572,27 +572,34 @@ struct ItemBuf {
 };
 constexpr int kMaxPathWords = kMaxDepth / 8;
 
+constexpr int kMaxLevels = kMaxDepth + 2;
+
 struct PassArgs {
     TableView tv;
     RowMeta meta;
     PeakBatch pk;
     MemoMap mp;
     uint8_t* status;                 // [P]
-    ItemBuf buf[2];
-    unsigned long long cap;          // items per buffer
-    unsigned long long item_limit;   // blow-up guard: more items than this in one level -> flags[0]
-    uint32_t* cnt;                   // [max(P, cap)] per-entity counts between count and write (children | final << 16)
-    uint32_t* chunk_exp;             // [max(P, cap) / 32 + grid + 1] children (stage 1: roots) of every 32-entity chunk
-    uint32_t* chunk_fin;             // the same for the final compositions
+    ItemBuf buf[2];                  // the frontier, ping-pong
+    unsigned long long cap;          // nodes per frontier buffer
+    unsigned long long item_limit;   // blow-up guard: more nodes than this in one level -> flags[0]
+    uint32_t* cnt;                   // [max(P, cap)] per-entity counts between count and write (children | records << 16)
+    uint32_t* chunk_k;               // [max(P, cap) / 32 + grid + 64] children (stage 1: roots) of every 32-entity chunk
+    uint32_t* chunk_r;               // the same for the records
     int nw;                          // path / record words (W = 8 * nw bytes)
     int has_budget;                  // some peak is in EXACT mode
-    uint8_t* recs;
+    unsigned long long* tmp_recs;    // [rec_capacity][nw] records in level order
+    uint32_t* tmp_peak;              // [rec_capacity] their peaks
+    uint8_t* recs;                   // [rec_capacity][W] records in peak order (the result)
     unsigned long long rec_capacity;
-    unsigned long long* peak_cnt;    // [P+1] compositions per peak (zeroed in stage 1)
+    uint32_t* lvl_cnt;               // [lvl_cap][P+1] records of every peak that were finished at every level
+    unsigned long long* lvl_A;       // [lvl_cap][P+1] final position of a level-l record of peak p, minus its index in the level
+    int lvl_cap;
+    unsigned long long* cta_lvl;     // [lvl_cap][gridDim.x] per-level record totals of every CTA's slice of the peaks
     unsigned long long* peak_off;    // [P+1]
-    unsigned long long* cta_tot;     // [3][gridDim.x]
-    unsigned long long* totals;      // [0] roots [1] items of the last level [2] compositions [3] levels, [8..39] timestamps
-    int* flags;                      // [0] item_limit hit, [1] records overflow, [2] items overflow (totals[1] = needed)
+    unsigned long long* cta_tot;     // [2][gridDim.x] children / records of every CTA's slice of the nodes
+    unsigned long long* totals;      // [0] roots [1] widest level [2] compositions [3] levels, [8..39] timestamps
+    int* flags;                      // [0] item_limit / level limit hit, [1] records overflow (totals[2] = needed), [2] nodes overflow (totals[1] = needed)
     unsigned int* barrier;           // arrival counter, zeroed by the host before the launch
     LeafHash leaf;
 };
@@ -753,89 +760,106 @@ __device__ __forceinline__ void slice_prefix3(const unsigned long long* cta_tot,
 }
 
 // ---- output-balanced work split ----
-// The count phases deal ENTITIES evenly (one load each); the write phases cost per OUTPUT, and outputs cluster
-// (a wide 3-nt window is thousands of consecutive open items).  So the write phases re-split the list by outputs:
-// every 32-entity chunk publishes its output total in the count phase, and after the grid barrier CTA b takes the
-// chunks whose first output falls in [T*b/G, T*(b+1)/G).  Finding the two boundary chunks is a two-level search:
-// slice totals (G values, scanned in shared memory), then the chunk totals of one slice.
+// The count phases deal NODES evenly (one load each); the write phases cost per OUTPUT (a child or a record), and
+// outputs cluster (a wide 3-nt window is thousands of consecutive open nodes).  So the write phases re-split the
+// list by outputs: every 32-node chunk publishes its children and record totals in the count phase, and after
+// the grid barrier CTA b takes the chunks whose first output falls in [T*b/G, T*(b+1)/G), T = all outputs.  Finding
+// the two boundary chunks is a two-level search: slice totals (G values, scanned in shared memory), then the chunk
+// totals of one slice.
 struct ChunkRange {
-    long long cb, ce;          // this CTA's chunks
-    unsigned long long base;   // output offset of chunk cb
-    unsigned long long total;  // outputs of the whole list
+    long long cb, ce;             // this CTA's chunks
+    unsigned long long kbase;     // children before chunk cb
+    unsigned long long rbase;     // records before chunk cb
+    unsigned long long ktotal, rtotal;
 };
 
-// number of chunks whose exclusive output prefix is < t, and that prefix at the boundary.  One WARP does it
-// (lane-parallel over the chunks of one slice), so both boundaries of a CTA are found at the same time.
-__device__ __forceinline__ void chunk_boundary_warp(const unsigned long long* s_spre, const uint32_t* __restrict__ chunk_tot, long long cps,
-                                                    long long nchunks, unsigned long long t, long long* F, unsigned long long* excl) {
+// number of chunks whose exclusive output prefix is < t, and the children / records before that boundary.  One
+// WARP does it (lane-parallel over the chunks of one slice), so both boundaries of a CTA are found at once.
+__device__ __forceinline__ void chunk_boundary_warp(const unsigned long long* s_pk, const unsigned long long* s_pr,
+                                                    const uint32_t* __restrict__ chunk_k, const uint32_t* __restrict__ chunk_r, long long cps,
+                                                    long long nchunks, unsigned long long t, long long* F, unsigned long long* kb,
+                                                    unsigned long long* rb) {
     const int lane = threadIdx.x & 31;
     if (t == 0ULL) {
         *F = 0;
-        *excl = 0ULL;
+        *kb = 0ULL;
+        *rb = 0ULL;
         return;
     }
-    int lo = 0, hi = (int)gridDim.x;  // last slice with s_spre[s] < t  (s_spre[0] = 0 < t)
+    int lo = 0, hi = (int)gridDim.x;  // last slice that starts before t (slice 0 starts at 0 < t)
     while (hi - lo > 1) {
         const int mid = (lo + hi) >> 1;
-        if (s_spre[mid] < t) lo = mid;
+        if (s_pk[mid] + s_pr[mid] < t) lo = mid;
         else hi = mid;
     }
     const long long s = lo;
-    unsigned long long run = s_spre[s];
+    unsigned long long runk = s_pk[s], runr = s_pr[s];
     long long flagged = 0;
     for (long long i0 = 0; i0 < cps; i0 += 32) {
         const long long i = i0 + lane, c = s * cps + i;
         const bool in = i < cps && c < nchunks;
-        const unsigned int x = in ? __ldcg(chunk_tot + c) : 0u;
-        unsigned int incl = x;
+        const unsigned int xk = in ? __ldcg(chunk_k + c) : 0u, xr = in ? __ldcg(chunk_r + c) : 0u;
+        unsigned int ik = xk, ir = xr;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
-            const unsigned int y = __shfl_up_sync(0xFFFFFFFFu, incl, o);
-            if (lane >= o) incl += y;
+            const unsigned int yk = __shfl_up_sync(0xFFFFFFFFu, ik, o), yr = __shfl_up_sync(0xFFFFFFFFu, ir, o);
+            if (lane >= o) {
+                ik += yk;
+                ir += yr;
+            }
         }
-        const bool f = in && run + (incl - x) < t;
-        const unsigned int fm = __ballot_sync(0xFFFFFFFFu, f);  // a prefix of the lanes: the prefix sums are monotone
-        const int nf = __popc(fm);
+        const bool f = in && runk + runr + (ik - xk) + (ir - xr) < t;
+        const int nf = __popc(__ballot_sync(0xFFFFFFFFu, f));  // a prefix of the lanes: the prefix sums are monotone
         flagged += nf;
-        const unsigned int upto = nf ? __shfl_sync(0xFFFFFFFFu, incl, nf - 1) : 0u;
-        if (nf < 32 || i0 + 32 >= cps) {
-            run += upto;
-            break;
-        }
-        run += upto;
+        runk += nf ? __shfl_sync(0xFFFFFFFFu, ik, nf - 1) : 0u;
+        runr += nf ? __shfl_sync(0xFFFFFFFFu, ir, nf - 1) : 0u;
+        if (nf < 32) break;
     }
     *F = s * cps + flagged;
-    *excl = run;
+    *kb = runk;
+    *rb = runr;
 }
 
-__device__ __forceinline__ ChunkRange balanced_range(const unsigned long long* __restrict__ cta_tot, const uint32_t* __restrict__ chunk_tot,
-                                                     long long n, long long per, unsigned long long* s_spre) {
+__device__ __forceinline__ ChunkRange balanced_range(const unsigned long long* __restrict__ cta_tot, const uint32_t* __restrict__ chunk_k,
+                                                     const uint32_t* __restrict__ chunk_r, long long n, long long per,
+                                                     unsigned long long* s_pk, unsigned long long* s_pr) {
     __shared__ long long s_F[2];
-    __shared__ unsigned long long s_E[2];
+    __shared__ unsigned long long s_K[2], s_R[2];
     const int G = (int)gridDim.x;  // <= kPassThreads (host)
-    unsigned long long tot;
-    const unsigned long long x = (int)threadIdx.x < G ? __ldcg(cta_tot + threadIdx.x) : 0ULL;
-    const unsigned long long ex = block_scan(x, &tot);
-    if ((int)threadIdx.x < G) s_spre[threadIdx.x] = ex;
-    if (threadIdx.x == 0) s_spre[G] = tot;
+    unsigned long long ktot, rtot;
+    const unsigned long long xk = (int)threadIdx.x < G ? __ldcg(cta_tot + threadIdx.x) : 0ULL;
+    const unsigned long long xr = (int)threadIdx.x < G ? __ldcg(cta_tot + G + threadIdx.x) : 0ULL;
+    const unsigned long long ek = block_scan(xk, &ktot), er = block_scan(xr, &rtot);
+    if ((int)threadIdx.x < G) {
+        s_pk[threadIdx.x] = ek;
+        s_pr[threadIdx.x] = er;
+    }
+    if (threadIdx.x == 0) {
+        s_pk[G] = ktot;
+        s_pr[G] = rtot;
+    }
     __syncthreads();
     const long long cps = per / 32, nchunks = (n + 31) / 32;
     const int w = threadIdx.x >> 5;
     if (w < 2) {  // warp 0: where this CTA starts, warp 1: where it ends
         long long F;
-        unsigned long long E;
-        chunk_boundary_warp(s_spre, chunk_tot, cps, nchunks, tot * (blockIdx.x + w) / G, &F, &E);  // tot < 2^44, G < 2^10
+        unsigned long long kb, rb;
+        chunk_boundary_warp(s_pk, s_pr, chunk_k, chunk_r, cps, nchunks, (ktot + rtot) * (blockIdx.x + w) / G, &F, &kb, &rb);
         if ((threadIdx.x & 31) == 0) {
             s_F[w] = F;
-            s_E[w] = E;
+            s_K[w] = kb;
+            s_R[w] = rb;
         }
     }
     __syncthreads();
     ChunkRange r;
-    r.total = tot;
+    r.ktotal = ktot;
+    r.rtotal = rtot;
     r.cb = s_F[0];
-    r.base = s_E[0];
+    r.kbase = s_K[0];
+    r.rbase = s_R[0];
     r.ce = (int)blockIdx.x == G - 1 ? nchunks : s_F[1];  // trailing chunks without outputs go to the last CTA
+    __syncthreads();
     return r;
 }
 
@@ -919,9 +943,10 @@ k_explain_pass(const PassArgs a) {
     __shared__ uint8_t s_mod[kMaxRows];
     __shared__ uint8_t s_leaf[kLeafSlots];
     __shared__ int s_nheavy;
-    __shared__ unsigned long long s_spre[kPassThreads + 1];
-    __shared__ unsigned int s_cbase[kPassThreads];
-    __shared__ unsigned int s_ttot;
+    __shared__ unsigned long long s_pk[kPassThreads + 1], s_pr[kPassThreads + 1];
+    __shared__ unsigned int s_cbase_k[kPassThreads], s_cbase_r[kPassThreads];
+    __shared__ unsigned int s_ttot_k, s_ttot_r;
+    __shared__ unsigned long long s_lbase[kMaxLevels + 1], s_lrun[kMaxLevels];
     __shared__ int s_heavy_p[kPassThreads];
     __shared__ unsigned long long s_heavy_off[kPassThreads];
     const TableView& tv = a.tv;
@@ -944,6 +969,7 @@ k_explain_pass(const PassArgs a) {
     const int top_row = tv.R - 1;
     const uint64_t* last = tv.tbl + (int64_t)top_row * tv.C;
     unsigned long long base, n_roots = 0, n_items = 0, n_comps = 0;
+    (void)n_comps;
     int cur = 0, level = 0;
 
     // ---- stage 1 (K3): peaks -> level-0 items, one per reachable window value ----
@@ -958,7 +984,6 @@ k_explain_pass(const PassArgs a) {
             if (lo <= 0 && 0 <= hi) st |= ST_ZERO_IN_WINDOW;
             if (lo <= hi && hi >= limit) st |= ST_OUT_OF_TABLE;
             a.status[p] = st;
-            a.peak_cnt[p] = 0ULL;
             unsigned int n = 0;
             for_window_words(last, lo < 1 ? 1 : lo, hi < limit - 1 ? hi : limit - 1, [&](int64_t, uint64_t x) { n += __popcll(x); });
             a.cnt[p] = n;
@@ -1058,328 +1083,315 @@ k_explain_pass(const PassArgs a) {
             }
             __syncthreads();
         }
-        if (blockIdx.x == 0 && threadIdx.x == 0) a.peak_cnt[P] = 0ULL;
         stamp(a, ts++);
         grid_barrier(a, gen);
     }
 
-    // ---- expansion: level -> level + 1 until no item is open ----
+    // ---- levels: every node of the frontier either FINISHES (its records go to the level-ordered buffer) or is
+    //      EXPANDED (its children are the next frontier).  Nothing is carried along. ----
+    unsigned long long rec_run = 0;  // records of the levels before this one
+    bool dry = false;                // the record buffers are too small: keep counting, write no records
+    unsigned long long widest = n_roots;
     for (;;) {
         const ItemBuf& in = a.buf[cur];
         const long long n = (long long)n_items, per = slice_size(n), first = (long long)blockIdx.x * per;
-        unsigned long long mine_children = 0, mine_open = 0, mine_final = 0;
+        if (level >= a.lvl_cap || level >= kMaxLevels) {  // cannot happen: the host sizes lvl_cap from the depth bound
+            if (blockIdx.x == 0 && threadIdx.x == 0) a.flags[0] = 1;
+            return;
+        }
+        if (threadIdx.x == 0) s_lbase[level] = rec_run;
+        // this level's per-peak record counters start at zero (they are added to after the barrier)
+        {
+            uint32_t* lc = a.lvl_cnt + (size_t)level * (size_t)(P + 1);
+            for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q <= P; q += (long long)gridDim.x * blockDim.x) lc[q] = 0u;
+        }
+        // count: one row-mask load per node that needs one
+        unsigned long long mine_k = 0, mine_r = 0;
         for (long long li = threadIdx.x; li < per; li += blockDim.x) {  // whole warps enter together: per % 32 == 0
             const long long i = first + li;
-            unsigned int c_exp = 0, c_fin = 0;
+            unsigned int k = 0, r = 0;
             if (i < n) {
                 const uint32_t m = __ldcg(in.m + i);
-                uint32_t meta = __ldcg(in.meta + i);
+                const uint32_t meta = __ldcg(in.meta + i);
                 const int rmax = meta & 0xFF;
                 const int mode = (meta >> 24) & 3;
                 const uint32_t p = mode == MODE_MEMO ? __ldcg(in.peak + i) : 0u;  // only the memo key needs the peak
                 const int kind = item_kind(mode, m, rt.wmin);
-                c_exp = 1;
-                c_fin = 1;
-                if (kind == KIND_POPC) {
-                    c_fin = (meta >> 16) & 0xFF;
-                    if (!c_fin) {  // counted once, then carried in the item
-                        c_fin = (unsigned)mask_popc(child_mask(tv, a.mp, mode, p, m, rmax));
-                        in.meta[i] = meta | (c_fin << 16);
-                    }
-                } else if (kind == KIND_OPEN) {
+                if (kind == KIND_DONE || kind == KIND_LEAF) {
+                    r = 1;
+                } else if (kind == KIND_POPC) {
+                    r = (unsigned)mask_popc(child_mask(tv, a.mp, mode, p, m, rmax));
+                } else {
                     const int all = a.has_budget ? __ldcg(in.all + i) : 0, ind = a.has_budget ? __ldcg(in.ind + i) : 0;
-                    c_exp = (unsigned)mask_popc(open_children(a, rt, mode, p, m, rmax, all, ind));
-                    c_fin = 0;
-                    mine_open++;
+                    k = (unsigned)mask_popc(open_children(a, rt, mode, p, m, rmax, all, ind));
                 }
-                a.cnt[i] = c_exp | (c_fin << 16);
-                mine_children += c_exp;
-                mine_final += c_fin;
+                a.cnt[i] = k | (r << 16);
+                mine_k += k;
+                mine_r += r;
             }
-            unsigned int we = c_exp, wf = c_fin;  // the chunk's totals, for the output-balanced split of the write phase
+            unsigned int wk = k, wr = r;  // the chunk's totals, for the output-balanced split of the write phase
 #pragma unroll
             for (int o = 16; o; o >>= 1) {
-                we += __shfl_xor_sync(0xFFFFFFFFu, we, o);
-                wf += __shfl_xor_sync(0xFFFFFFFFu, wf, o);
+                wk += __shfl_xor_sync(0xFFFFFFFFu, wk, o);
+                wr += __shfl_xor_sync(0xFFFFFFFFu, wr, o);
             }
             if (lane == 0) {
-                a.chunk_exp[i >> 5] = we;
-                a.chunk_fin[i >> 5] = wf;
+                a.chunk_k[i >> 5] = wk;
+                a.chunk_r[i >> 5] = wr;
             }
         }
-        unsigned long long tsum[3] = {mine_children, mine_open, mine_final};
-        block_sum_n<3>(tsum);
-        if (threadIdx.x < 3) a.cta_tot[(size_t)threadIdx.x * gridDim.x + blockIdx.x] = tsum[threadIdx.x];
+        unsigned long long tsum[2] = {mine_k, mine_r};
+        block_sum_n<2>(tsum);
+        if (threadIdx.x < 2) a.cta_tot[(size_t)threadIdx.x * gridDim.x + blockIdx.x] = tsum[threadIdx.x];
         stamp(a, ts++);
         grid_barrier(a, gen);
         stamp(a, ts++);
-        unsigned long long bases[3], alls[3];
-        slice_prefix3(a.cta_tot, bases, alls);
-        stamp(a, ts++);
-        const unsigned long long n_next = alls[0], n_open = alls[1];
-        if (n_open == 0) {
-            base = bases[2];  // record offset of this CTA's slice
-            n_comps = alls[2];
-            break;
-        }
-        base = bases[0];
-        if (n_next > a.cap || n_next > a.item_limit || level + 1 >= kMaxDepth) {
+        const ChunkRange cr = balanced_range(a.cta_tot, a.chunk_k, a.chunk_r, n, per, s_pk, s_pr);
+        const unsigned long long n_next = cr.ktotal, n_rec = cr.rtotal;
+        if (n_next > a.cap || n_next > a.item_limit) {  // the same answer in every CTA
             if (blockIdx.x == 0 && threadIdx.x == 0) {
-                a.flags[n_next > a.item_limit || level + 1 >= kMaxDepth ? 0 : 2] = 1;
+                a.flags[n_next > a.item_limit ? 0 : 2] = 1;
                 a.totals[0] = n_roots;
                 a.totals[1] = n_next;
                 a.totals[3] = (unsigned long long)level;
             }
             return;
         }
+        if (rec_run + n_rec > a.rec_capacity) dry = true;
+        if (n_next > widest) widest = n_next;
         const ItemBuf& out = a.buf[cur ^ 1];
-        const ChunkRange cr = balanced_range(a.cta_tot, a.chunk_exp, n, per, s_spre);
-        unsigned long long tile_run = 0;
+        uint32_t* lc = a.lvl_cnt + (size_t)level * (size_t)(P + 1);
+        unsigned long long tile_k = 0, tile_r = 0;
         for (long long tile0 = cr.cb; tile0 < cr.ce; tile0 += blockDim.x) {  // up to blockDim chunks per tile, one warp per chunk
             {
                 const long long c = tile0 + threadIdx.x;
-                const unsigned int x = c < cr.ce ? __ldcg(a.chunk_exp + c) : 0u;
-                unsigned int ttot;
-                s_cbase[threadIdx.x] = block_scan32(x, &ttot);
-                if (threadIdx.x == 0) s_ttot = ttot;
+                const unsigned int xk = c < cr.ce ? __ldcg(a.chunk_k + c) : 0u, xr = c < cr.ce ? __ldcg(a.chunk_r + c) : 0u;
+                unsigned int tk, tr;
+                s_cbase_k[threadIdx.x] = block_scan32(xk, &tk);
+                s_cbase_r[threadIdx.x] = block_scan32(xr, &tr);
+                if (threadIdx.x == 0) {
+                    s_ttot_k = tk;
+                    s_ttot_r = tr;
+                }
             }
             __syncthreads();
-            const unsigned long long tile_base = cr.base + tile_run;
-          for (long long wq = threadIdx.x >> 5; tile0 + wq < cr.ce && wq < (long long)blockDim.x; wq += kPassThreads / 32) {
-            const long long i = (tile0 + wq) * 32 + lane;
-            const bool ok = i < n;
-            const unsigned int k = ok ? (a.cnt[i] & 0xFFFFu) : 0u;
-            unsigned int kin = k;
+            for (long long wq = threadIdx.x >> 5; tile0 + wq < cr.ce && wq < (long long)blockDim.x; wq += kPassThreads / 32) {
+                const long long i = (tile0 + wq) * 32 + lane;
+                const bool ok = i < n;
+                const unsigned int packed = ok ? a.cnt[i] : 0u;
+                const unsigned int k = packed & 0xFFFFu, r = packed >> 16;
+                unsigned int kin = k, rin = r;
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const unsigned int y = __shfl_up_sync(0xFFFFFFFFu, kin, o);
-                if (lane >= o) kin += y;
-            }
-            const unsigned long long off = tile_base + s_cbase[wq] + (kin - k);
-            uint32_t m = 0, p = 0, meta = 0;
-            int all = 0, ind = 0;
-            unsigned long long pw[kPW];
-#pragma unroll
-            for (int q = 0; q < kPW; q++) pw[q] = 0ULL;
-            Mask128 c;
-            c.w[0] = c.w[1] = c.w[2] = c.w[3] = 0u;
-            if (ok && k) {
-                m = __ldcg(in.m + i);
-                p = __ldcg(in.peak + i);
-                meta = __ldcg(in.meta + i) & 0x7FFFFFFFu;
-                const int mode = (meta >> 24) & 3;
-                for (int q = 0; q < nw; q++) pw[q] = __ldcg(in.path + (unsigned long long)q * a.cap + i);
-                if (a.has_budget) {
-                    all = __ldcg(in.all + i);
-                    ind = __ldcg(in.ind + i);
-                }
-                if (item_kind(mode, m, rt.wmin) == KIND_OPEN) {
-                    meta |= 0x80000000u;  // open: its outputs are children, not a copy
-                    c = open_children(a, rt, mode, p, m, meta & 0xFF, all, ind);
-                }
-            }
-            // Output-centric placement: the warp's items produce T consecutive outputs (a copy for a finished item,
-            // one per enabled row for an open one); lane l writes outputs l, l+32, ... — finds the producing lane by a
-            // shuffle search over the per-lane output offsets, pulls that lane's item through shuffles and picks its
-            // j-th row.  Work is per OUTPUT (no serial loop over parents) and every store is coalesced.
-            if (__ballot_sync(0xFFFFFFFFu, meta >> 31) == 0u) {  // no open item in this warp: plain copies
-                if (ok && k) {
-                    out.m[off] = m;
-                    out.peak[off] = p;
-                    out.meta[off] = meta;
-                    for (int q = 0; q < nw; q++) out.path[(unsigned long long)q * a.cap + off] = pw[q];
-                    if (a.has_budget) {
-                        out.all[off] = all;
-                        out.ind[off] = ind;
+                for (int o = 1; o < 32; o <<= 1) {
+                    const unsigned int yk = __shfl_up_sync(0xFFFFFFFFu, kin, o), yr = __shfl_up_sync(0xFFFFFFFFu, rin, o);
+                    if (lane >= o) {
+                        kin += yk;
+                        rin += yr;
                     }
                 }
-                continue;
-            }
-            const unsigned long long off0 = __shfl_sync(0xFFFFFFFFu, off, 0);
-            const unsigned wp = (unsigned)(off - off0);
-            const unsigned T = __shfl_sync(0xFFFFFFFFu, wp + k, 31);
-            for (unsigned o0 = 0; o0 < T; o0 += 32) {
-                const unsigned o = o0 + lane;
-                int src = 0;
+                const unsigned long long off = cr.kbase + tile_k + s_cbase_k[wq] + (kin - k);            // first child
+                const unsigned long long roff = rec_run + cr.rbase + tile_r + s_cbase_r[wq] + (rin - r);  // first record
+                uint32_t m = 0, p = 0xFFFFFFFFu, meta = 0;
+                int all = 0, ind = 0, kind = KIND_DONE;
+                unsigned long long pw[kPW];
 #pragma unroll
-                for (int step = 16; step; step >>= 1) {
-                    const int cand = src + step;
-                    const unsigned v = __shfl_sync(0xFFFFFFFFu, wp, cand & 31);
-                    if (cand < 32 && v <= o) src = cand;
+                for (int q = 0; q < kPW; q++) pw[q] = 0ULL;
+                Mask128 c;
+                c.w[0] = c.w[1] = c.w[2] = c.w[3] = 0u;
+                if (ok && (k | r)) {
+                    m = __ldcg(in.m + i);
+                    p = __ldcg(in.peak + i);
+                    meta = __ldcg(in.meta + i) & 0x7FFFFFFFu;
+                    const int mode = (meta >> 24) & 3;
+                    for (int q = 0; q < nw; q++) pw[q] = __ldcg(in.path + (unsigned long long)q * a.cap + i);
+                    if (a.has_budget) {
+                        all = __ldcg(in.all + i);
+                        ind = __ldcg(in.ind + i);
+                    }
+                    kind = item_kind(mode, m, rt.wmin);
+                    if (kind == KIND_OPEN) c = open_children(a, rt, mode, p, m, meta & 0xFF, all, ind);
+                    else if (kind == KIND_POPC) c = child_mask(tv, a.mp, MODE_FREE, 0, m, meta & 0xFF);
                 }
-                const int j = (int)(o - __shfl_sync(0xFFFFFFFFu, wp, src));
-                const uint32_t sm = __shfl_sync(0xFFFFFFFFu, m, src), sp = __shfl_sync(0xFFFFFFFFu, p, src);
-                const uint32_t smeta = __shfl_sync(0xFFFFFFFFu, meta, src);
-                Mask128 sc;
+
+                // ---- records of the nodes that finish here ----
+                {
+                    // per-peak totals of this level: lanes with the same peak fold their counts first
+                    const unsigned int grp = __match_any_sync(0xFFFFFFFFu, p);
+                    const unsigned int sum = __reduce_add_sync(grp, r);
+                    if (sum && lane == __ffs(grp) - 1) atomicAdd(lc + p, sum);
+                }
+                if (!dry) {
+                    // the j-th record of a node: its path, plus (LEAF) the one row that closes it, or (POPC) the j-th
+                    // enabled row r2 and, if something is left, the row that closes that
+                    auto put = [&](unsigned long long at, uint32_t im, int rmax, int knd, int r2, const unsigned long long* path, uint32_t pk) {
+                        unsigned long long w[kPW];
+                        for (int q = 0; q < nw; q++) w[q] = path[q];
+                        if (knd == KIND_LEAF) {
+                            path_append(w, nw, leaf_row(s_leaf, s_w, a.leaf, im, rmax));
+                        } else if (knd == KIND_POPC) {
+                            const uint32_t m3 = im - (uint32_t)s_w[r2];
+                            path_append(w, nw, r2);
+                            if (m3) path_append(w, nw, leaf_row(s_leaf, s_w, a.leaf, m3, r2));
+                        }
+                        for (int q = 0; q < nw; q++) a.tmp_recs[at * (unsigned long long)nw + q] = w[q];
+                        a.tmp_peak[at] = pk;
+                    };
+                    const bool heavy = r > 4;
+                    if (r && !heavy) {  // the owner writes its few records itself
+                        Mask128 left = c;
+                        for (unsigned int j = 0; j < r; j++) put(roff + j, m, meta & 0xFF, kind, kind == KIND_POPC ? mask_pop_lowest(left) : 0, pw, p);
+                    }
+                    for (unsigned hm = __ballot_sync(0xFFFFFFFFu, heavy); hm; hm &= hm - 1) {  // many records: the warp shares them
+                        const int src = __ffs(hm) - 1;
+                        const uint32_t sm = __shfl_sync(0xFFFFFFFFu, m, src), smeta = __shfl_sync(0xFFFFFFFFu, meta, src);
+                        const uint32_t sp = __shfl_sync(0xFFFFFFFFu, p, src);
+                        const unsigned int sr = __shfl_sync(0xFFFFFFFFu, r, src);
+                        const unsigned long long so = __shfl_sync(0xFFFFFFFFu, roff, src);
+                        Mask128 scm;
 #pragma unroll
-                for (int q = 0; q < 4; q++) sc.w[q] = __shfl_sync(0xFFFFFFFFu, c.w[q], src);
-                unsigned long long cw[kPW];
-                for (int q = 0; q < nw; q++) cw[q] = __shfl_sync(0xFFFFFFFFu, pw[q], src);
-                int sall = 0, sind = 0;
-                if (a.has_budget) {
-                    sall = __shfl_sync(0xFFFFFFFFu, all, src);
-                    sind = __shfl_sync(0xFFFFFFFFu, ind, src);
+                        for (int q = 0; q < 4; q++) scm.w[q] = __shfl_sync(0xFFFFFFFFu, c.w[q], src);
+                        unsigned long long spw[kPW];
+                        for (int q = 0; q < nw; q++) spw[q] = __shfl_sync(0xFFFFFFFFu, pw[q], src);
+                        for (unsigned int j = lane; j < sr; j += 32) put(so + j, sm, smeta & 0xFF, KIND_POPC, mask_select(scm, (int)j), spw, sp);
+                    }
                 }
-                if (o < T) {
-                    const unsigned long long o2 = off0 + o;
-                    uint32_t om = sm, ometa = smeta;
-                    if (smeta & 0x80000000u) {
-                        const int r = mask_select(sc, j);
+
+                // ---- children of the nodes that are expanded ----
+                // Output-centric placement: the warp's open nodes produce T consecutive children; lane l writes children
+                // l, l+32, ... — finds the parent lane by a shuffle search over the per-lane child offsets, pulls the
+                // parent through shuffles and picks its j-th enabled row.  Work is per CHILD and every store coalesces.
+                const unsigned long long off0 = __shfl_sync(0xFFFFFFFFu, off, 0);
+                const unsigned wp = (unsigned)(off - off0);
+                const unsigned T = __shfl_sync(0xFFFFFFFFu, wp + k, 31);
+                for (unsigned o0 = 0; o0 < T; o0 += 32) {
+                    const unsigned o = o0 + lane;
+                    int src = 0;
+#pragma unroll
+                    for (int step = 16; step; step >>= 1) {
+                        const int cand = src + step;
+                        const unsigned v = __shfl_sync(0xFFFFFFFFu, wp, cand & 31);
+                        if (cand < 32 && v <= o) src = cand;
+                    }
+                    const int j = (int)(o - __shfl_sync(0xFFFFFFFFu, wp, src));
+                    const uint32_t sm = __shfl_sync(0xFFFFFFFFu, m, src), sp = __shfl_sync(0xFFFFFFFFu, p, src);
+                    const uint32_t smeta = __shfl_sync(0xFFFFFFFFu, meta, src);
+                    Mask128 sc;
+#pragma unroll
+                    for (int q = 0; q < 4; q++) sc.w[q] = __shfl_sync(0xFFFFFFFFu, c.w[q], src);
+                    unsigned long long cw[kPW];
+                    for (int q = 0; q < nw; q++) cw[q] = __shfl_sync(0xFFFFFFFFu, pw[q], src);
+                    int sall = 0, sind = 0;
+                    if (a.has_budget) {
+                        sall = __shfl_sync(0xFFFFFFFFu, all, src);
+                        sind = __shfl_sync(0xFFFFFFFFu, ind, src);
+                    }
+                    if (o < T) {
+                        const unsigned long long o2 = off0 + o;
+                        const int rr = mask_select(sc, j);
                         const int srmax = smeta & 0xFF, sdepth = (smeta >> 8) & 0xFF;
-                        om = sm - (uint32_t)s_w[r];
-                        ometa = (uint32_t)r | ((uint32_t)(sdepth + 1) << 8) | (smeta & 0x03000000u);
-                        path_append(cw, nw, r);
+                        path_append(cw, nw, rr);
+                        out.m[o2] = sm - (uint32_t)s_w[rr];
+                        out.peak[o2] = sp;
+                        out.meta[o2] = (uint32_t)rr | ((uint32_t)(sdepth + 1) << 8) | (smeta & 0x03000000u);
+                        for (int q = 0; q < nw; q++) out.path[(unsigned long long)q * a.cap + o2] = cw[q];
                         if (a.has_budget) {
-                            const int mod = s_mod[r];
-                            sind = ((r == srmax) ? sind : s_ind[r]) - mod;
-                            sall -= mod;
+                            const int mod = s_mod[rr];
+                            out.all[o2] = sall - mod;
+                            out.ind[o2] = ((rr == srmax) ? sind : s_ind[rr]) - mod;
                         }
                     }
-                    out.m[o2] = om;
-                    out.peak[o2] = sp;
-                    out.meta[o2] = ometa;
-                    for (int q = 0; q < nw; q++) out.path[(unsigned long long)q * a.cap + o2] = cw[q];
-                    if (a.has_budget) {
-                        out.all[o2] = sall;
-                        out.ind[o2] = sind;
-                    }
                 }
             }
-          }
-            tile_run += s_ttot;
+            tile_k += s_ttot_k;
+            tile_r += s_ttot_r;
             __syncthreads();
         }
+        rec_run += n_rec;
+        level++;
         stamp(a, ts++);
         grid_barrier(a, gen);
         cur ^= 1;
         n_items = n_next;
-        level++;
+        if (n_next == 0) break;
     }
-
-    // ---- records: the list in buf[cur] is final; one thread per composition ----
-    const bool fits = n_comps <= a.rec_capacity;
-    {
-        const ItemBuf& in = a.buf[cur];
-        const long long n = (long long)n_items, per = slice_size(n), first = (long long)blockIdx.x * per;
-        // per-peak totals.  Items of a peak are contiguous, so a warp usually holds one or two peaks: lanes with the
-        // same peak fold their counts first (a blow-up peak would otherwise put 10^5 adds on one address)
-        for (long long li = threadIdx.x; li < per; li += blockDim.x) {  // whole warps: per % 32 == 0
-            const long long i = first + li;
-            const bool ok = i < n;
-            const unsigned int c = ok ? (a.cnt[i] >> 16) : 0u;
-            const uint32_t p = ok ? __ldcg(in.peak + i) : 0xFFFFFFFFu;
-            const unsigned int grp = __match_any_sync(0xFFFFFFFFu, p);
-            const unsigned int sum = __reduce_add_sync(grp, c);
-            if (ok && sum && lane == __ffs(grp) - 1) atomicAdd(a.peak_cnt + p, (unsigned long long)sum);
-        }
-        if (fits) {
-            unsigned long long* recs64 = reinterpret_cast<unsigned long long*>(a.recs);
-            const ChunkRange cr = balanced_range(a.cta_tot + 2 * gridDim.x, a.chunk_fin, n, per, s_spre);
-            unsigned long long tile_run = 0;
-            for (long long tile0 = cr.cb; tile0 < cr.ce; tile0 += blockDim.x) {
-                {
-                    const long long c = tile0 + threadIdx.x;
-                    const unsigned int x = c < cr.ce ? __ldcg(a.chunk_fin + c) : 0u;
-                    unsigned int ttot;
-                    s_cbase[threadIdx.x] = block_scan32(x, &ttot);
-                    if (threadIdx.x == 0) s_ttot = ttot;
-                }
-                __syncthreads();
-                const unsigned long long tile_base = cr.base + tile_run;
-              for (long long wq = threadIdx.x >> 5; tile0 + wq < cr.ce && wq < (long long)blockDim.x; wq += kPassThreads / 32) {
-                const long long i = (tile0 + wq) * 32 + lane;
-                const bool ok = i < n;
-                const unsigned int c = ok ? (a.cnt[i] >> 16) : 0u;
-                unsigned int cin = c;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const unsigned int y = __shfl_up_sync(0xFFFFFFFFu, cin, o);
-                    if (lane >= o) cin += y;
-                }
-                const unsigned long long roff = tile_base + s_cbase[wq] + (cin - c);
-                uint32_t m = 0, meta = 0;
-                unsigned long long pw[kPW];
-#pragma unroll
-                for (int q = 0; q < kPW; q++) pw[q] = 0ULL;
-                int kind = KIND_DONE;
-                Mask128 cm;
-                cm.w[0] = cm.w[1] = cm.w[2] = cm.w[3] = 0u;
-                if (c) {
-                    m = __ldcg(in.m + i);
-                    meta = __ldcg(in.meta + i);
-                    for (int q = 0; q < nw; q++) pw[q] = __ldcg(in.path + (unsigned long long)q * a.cap + i);
-                    kind = item_kind((meta >> 24) & 3, m, rt.wmin);
-                    if (kind == KIND_POPC) cm = child_mask(tv, a.mp, MODE_FREE, 0, m, meta & 0xFF);
-                }
-                // the j-th record of an item: its path, plus (LEAF) the one row that closes it, or (POPC) the j-th
-                // enabled row r2 and, if something is left, the row that closes that
-                auto put = [&](unsigned long long at, uint32_t im, int rmax, int knd, int r2, const unsigned long long* path) {
-                    unsigned long long w[kPW];
-                    for (int q = 0; q < nw; q++) w[q] = path[q];
-                    if (knd == KIND_LEAF) {
-                        path_append(w, nw, leaf_row(s_leaf, s_w, a.leaf, im, rmax));
-                    } else if (knd == KIND_POPC) {
-                        const uint32_t m3 = im - (uint32_t)s_w[r2];
-                        path_append(w, nw, r2);
-                        if (m3) path_append(w, nw, leaf_row(s_leaf, s_w, a.leaf, m3, r2));
-                    }
-                    for (int q = 0; q < nw; q++) recs64[at * (unsigned long long)nw + q] = w[q];
-                };
-                const bool heavy = c > 4;
-                if (c && !heavy) {  // the owner writes its few records itself
-                    Mask128 left = cm;
-                    for (unsigned int j = 0; j < c; j++) put(roff + j, m, meta & 0xFF, kind, kind == KIND_POPC ? mask_pop_lowest(left) : 0, pw);
-                }
-                for (unsigned hm = __ballot_sync(0xFFFFFFFFu, heavy); hm; hm &= hm - 1) {  // many records: the warp shares them
-                    const int src = __ffs(hm) - 1;
-                    const uint32_t sm = __shfl_sync(0xFFFFFFFFu, m, src), smeta = __shfl_sync(0xFFFFFFFFu, meta, src);
-                    const unsigned int sc = __shfl_sync(0xFFFFFFFFu, c, src);
-                    const unsigned long long so = __shfl_sync(0xFFFFFFFFu, roff, src);
-                    Mask128 scm;
-#pragma unroll
-                    for (int q = 0; q < 4; q++) scm.w[q] = __shfl_sync(0xFFFFFFFFu, cm.w[q], src);
-                    unsigned long long spw[kPW];
-                    for (int q = 0; q < nw; q++) spw[q] = __shfl_sync(0xFFFFFFFFu, pw[q], src);
-                    for (unsigned int j = lane; j < sc; j += 32) put(so + j, sm, smeta & 0xFF, KIND_POPC, mask_select(scm, (int)j), spw);
-                }
-              }
-                tile_run += s_ttot;
-                __syncthreads();
-            }
-        }
-        if (blockIdx.x == 0 && threadIdx.x == 0) {
-            if (!fits) a.flags[1] = 1;
-            a.totals[0] = n_roots;
-            a.totals[1] = n_items;
-            a.totals[2] = n_comps;
-            a.totals[3] = (unsigned long long)level;
-        }
-        stamp(a, ts++);
-        grid_barrier(a, gen);
+    n_comps = rec_run;
+    if (threadIdx.x == 0) s_lbase[level] = rec_run;
+    const int n_levels = level;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        if (dry) a.flags[1] = 1;
+        a.totals[0] = n_roots;
+        a.totals[1] = widest;
+        a.totals[2] = n_comps;
+        a.totals[3] = (unsigned long long)n_levels;
     }
+    if (dry) return;  // the host enlarges the record buffers and runs the pass again
 
-    // ---- per-peak record offsets: exclusive scan of the per-peak totals ----
-    {
-        const long long per = slice_size(P + 1), first = (long long)blockIdx.x * per;
+    // ---- where the records go: peak_off[p] = records of the peaks before p; a level-l record of peak p that is
+    //      the x-th record of its level goes to A[l][p] + x, A[l][p] = peak_off[p] + (records of p finished at
+    //      earlier levels) - (records of level l that belong to peaks before p) ----
+    const long long pper = slice_size(P + 1), pfirst = (long long)blockIdx.x * pper;
+    for (int l = 0; l < n_levels; l++) {
+        const uint32_t* lc = a.lvl_cnt + (size_t)l * (size_t)(P + 1);
         unsigned long long mine = 0;
-        for (long long li = threadIdx.x; li < per; li += blockDim.x) {
-            const long long p = first + li;
-            if (p > P) break;
-            mine += __ldcg(a.peak_cnt + p);
+        for (long long li = threadIdx.x; li < pper; li += blockDim.x) {
+            const long long q = pfirst + li;
+            if (q <= P) mine += __ldcg(lc + q);
         }
         const unsigned long long tot = block_sum(mine);
-        if (threadIdx.x == 0) a.cta_tot[blockIdx.x] = tot;
-        grid_barrier(a, gen);
-        unsigned long long all_comps;
-        slice_prefix(a.cta_tot, &base, &all_comps);
-        for (long long l0 = 0; l0 < per; l0 += blockDim.x) {
-            const long long p = first + l0 + threadIdx.x;
-            const bool ok = l0 + threadIdx.x < per && p <= P;
-            const unsigned long long c = ok ? __ldcg(a.peak_cnt + p) : 0ULL;
-            unsigned long long round_tot;
-            const unsigned long long off = base + block_scan(c, &round_tot);
-            base += round_tot;
-            if (ok) a.peak_off[p] = off;
+        if (threadIdx.x == 0) a.cta_lvl[(size_t)l * gridDim.x + blockIdx.x] = tot;
+    }
+    stamp(a, ts++);
+    grid_barrier(a, gen);
+    for (int l = 0; l < n_levels; l++) {  // records of level l in the slices before this CTA's
+        unsigned long long mine = 0;
+        for (unsigned b2 = threadIdx.x; b2 < blockIdx.x; b2 += blockDim.x) mine += __ldcg(a.cta_lvl + (size_t)l * gridDim.x + b2);
+        const unsigned long long v = block_sum(mine);
+        if (threadIdx.x == 0) s_lrun[l] = v;
+    }
+    __syncthreads();
+    for (long long l0 = 0; l0 < pper; l0 += blockDim.x) {
+        const long long q = pfirst + l0 + threadIdx.x;
+        const bool ok = l0 + threadIdx.x < pper && q <= P;
+        unsigned long long poff = 0;
+        for (int l = 0; l < n_levels; l++) {  // first pass: start of peak q inside level l
+            const unsigned int x = ok ? __ldcg(a.lvl_cnt + (size_t)l * (size_t)(P + 1) + q) : 0u;
+            unsigned int tot;
+            const unsigned long long before = s_lrun[l];  // read before the scan's barriers: thread 0 advances it after them
+            const unsigned long long start = before + block_scan32(x, &tot);
+            if (ok) a.lvl_A[(size_t)l * (size_t)(P + 1) + q] = start;
+            poff += start;
+            if (threadIdx.x == 0) s_lrun[l] += tot;
+            __syncthreads();
+        }
+        if (ok) {
+            a.peak_off[q] = poff;
+            unsigned long long cum = 0;
+            for (int l = 0; l < n_levels; l++) {  // second pass: the placement table
+                const size_t at = (size_t)l * (size_t)(P + 1) + q;
+                const unsigned long long start = a.lvl_A[at];
+                a.lvl_A[at] = poff + cum - start;
+                cum += __ldcg(a.lvl_cnt + at);
+            }
+        }
+    }
+    if (n_levels == 0)
+        for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q <= P; q += (long long)gridDim.x * blockDim.x) a.peak_off[q] = 0ULL;
+    stamp(a, ts++);
+    grid_barrier(a, gen);
+
+    // ---- permute: level order -> peak order ----
+    {
+        unsigned long long* recs64 = reinterpret_cast<unsigned long long*>(a.recs);
+        const unsigned long long j0 = n_comps * blockIdx.x / gridDim.x, j1 = n_comps * (blockIdx.x + 1) / gridDim.x;
+        int l = 0;
+        for (unsigned long long jb = j0; jb < j1; jb += blockDim.x) {
+            const unsigned long long j = jb + threadIdx.x;
+            if (j < j1) {
+                while (l + 1 < n_levels && j >= s_lbase[l + 1]) l++;
+                const uint32_t p = __ldcg(a.tmp_peak + j);
+                const unsigned long long dst = __ldcg(a.lvl_A + (size_t)l * (size_t)(P + 1) + p) + (j - s_lbase[l]);
+                for (int q = 0; q < nw; q++) recs64[dst * (unsigned long long)nw + q] = __ldcg(a.tmp_recs + j * (unsigned long long)nw + q);
+            }
         }
     }
     stamp(a, ts++);
