@@ -68,7 +68,7 @@ struct sst_ctx {
     int64_t max_hi = 0;
     // results
     DevBuf d_status, d_cnt, d_peakoff, d_recs, d_blocksums;
-    DevBuf d_scan, d_vmass, d_vthrf, d_chunk_k, d_chunk_r, d_tmprecs, d_tmppeak, d_lvlcnt, d_lvlA, d_ctalvl;
+    DevBuf d_scan, d_vmass, d_vthrf, d_chunk_k, d_chunk_r, d_tmprecs, d_tmppeak, d_lvlcnt, d_lvlA, d_ctalvl, d_nodemask;
     DevBuf d_item_m[2], d_item_peak[2], d_item_meta[2], d_item_all[2], d_item_ind[2], d_item_path[2];
     bool has_exact = false;
     int levels = 0;
@@ -330,7 +330,7 @@ void sst_ctx_destroy(sst_ctx* ctx) {
                       &ctx->d_memo_peaks, &ctx->d_status, &ctx->d_cnt, &ctx->d_peakoff, &ctx->d_recs,
                       &ctx->d_blocksums, &ctx->d_memo_keys, &ctx->d_memo_alive, &ctx->d_memo_top,
                       &ctx->d_memo_misc, &ctx->d_flush, &ctx->d_vtarget, &ctx->d_vthr, &ctx->d_vout,
-                      &ctx->d_scan, &ctx->d_vmass, &ctx->d_vthrf, &ctx->d_chunk_k, &ctx->d_chunk_r, &ctx->d_tmprecs, &ctx->d_tmppeak, &ctx->d_lvlcnt, &ctx->d_lvlA, &ctx->d_ctalvl, &ctx->d_cobs, &ctx->d_coff, &ctx->d_cout, &ctx->d_bkeys, &ctx->d_btop, &ctx->d_blower, &ctx->d_bupper, &ctx->d_bout,
+                      &ctx->d_scan, &ctx->d_vmass, &ctx->d_vthrf, &ctx->d_chunk_k, &ctx->d_chunk_r, &ctx->d_tmprecs, &ctx->d_tmppeak, &ctx->d_lvlcnt, &ctx->d_lvlA, &ctx->d_ctalvl, &ctx->d_nodemask, &ctx->d_cobs, &ctx->d_coff, &ctx->d_cout, &ctx->d_bkeys, &ctx->d_btop, &ctx->d_blower, &ctx->d_bupper, &ctx->d_bout,
                       &ctx->d_item_m[0], &ctx->d_item_m[1], &ctx->d_item_peak[0], &ctx->d_item_peak[1],
                       &ctx->d_item_meta[0], &ctx->d_item_meta[1], &ctx->d_item_all[0], &ctx->d_item_all[1],
                       &ctx->d_item_ind[0], &ctx->d_item_ind[1], &ctx->d_item_path[0], &ctx->d_item_path[1]};
@@ -845,6 +845,7 @@ int sst_explain_run(sst_ctx* ctx, const sst_table* t, int rec_width, uint64_t me
         const size_t most = (size_t)P > cap ? (size_t)P : cap;
         if ((rc = reserve(ctx, ctx->d_cnt, (most + 1) * 4))) return rc;
         const size_t n_chunks = most / 32 + (size_t)grid_max + 64;
+        if ((rc = reserve(ctx, ctx->d_nodemask, (cap + 1) * 16))) return rc;
         if ((rc = reserve(ctx, ctx->d_chunk_k, n_chunks * 4))) return rc;
         if ((rc = reserve(ctx, ctx->d_chunk_r, n_chunks * 4))) return rc;
         // the level-ordered record buffer mirrors the result buffer
@@ -896,6 +897,7 @@ int sst_explain_run(sst_ctx* ctx, const sst_table* t, int rec_width, uint64_t me
         a.cap = (unsigned long long)cap;
         a.item_limit = ctx->item_limit;
         a.cnt = (uint32_t*)ctx->d_cnt.p;
+        a.node_mask = (uint4*)ctx->d_nodemask.p;
         a.chunk_k = (uint32_t*)ctx->d_chunk_k.p;
         a.chunk_r = (uint32_t*)ctx->d_chunk_r.p;
         a.tmp_recs = (unsigned long long*)ctx->d_tmprecs.p;

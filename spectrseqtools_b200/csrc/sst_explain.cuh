@@ -586,6 +586,7 @@ struct PassArgs {
     uint32_t* cnt;                   // [max(P, cap)] per-entity counts between count and write (children | records << 16)
     uint32_t* chunk_k;               // [max(P, cap) / 32 + grid + 64] children (stage 1: roots) of every 32-entity chunk
     uint32_t* chunk_r;               // the same for the records
+    uint4* node_mask;                // [cap] enabled rows of every node, kept from the count phase for the write phase
     int nw;                          // path / record words (W = 8 * nw bytes)
     int has_budget;                  // some peak is in EXACT mode
     unsigned long long* tmp_recs;    // [rec_capacity][nw] records in level order
@@ -637,9 +638,11 @@ __device__ __forceinline__ void stamp(const PassArgs& a, int k) {
     if (blockIdx.x == 0 && threadIdx.x == 0 && k < 32) a.totals[8 + k] = globaltimer_ns();
 }
 
-// exclusive scan of one value per thread across the CTA; *total = CTA sum.  Two barriers.
+// exclusive scan of one value per thread across the CTA; *total = CTA sum.  Warp scans, then warp 0 scans the
+// per-warp totals (three barriers, ~50 instructions per warp).
 __device__ __forceinline__ unsigned long long block_scan(unsigned long long x, unsigned long long* total) {
-    __shared__ unsigned long long s_warp[kPassThreads / 32];
+    __shared__ unsigned long long s_w64[kPassThreads / 32];
+    __shared__ unsigned long long s_tot64;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     unsigned long long incl = x;
 #pragma unroll
@@ -647,19 +650,26 @@ __device__ __forceinline__ unsigned long long block_scan(unsigned long long x, u
         const unsigned long long y = __shfl_up_sync(0xFFFFFFFFu, incl, o);
         if (lane >= o) incl += y;
     }
-    if (lane == 31) s_warp[w] = incl;
+    if (lane == 31) s_w64[w] = incl;
     __syncthreads();
-    unsigned long long before = 0, sum = 0;
+    if (w == 0) {
+        const unsigned long long v = lane < kPassThreads / 32 ? s_w64[lane] : 0ULL;
+        unsigned long long inc = v;
 #pragma unroll
-    for (int i = 0; i < kPassThreads / 32; i++) {
-        const unsigned long long v = s_warp[i];
-        if (i < w) before += v;
-        sum += v;
+        for (int o = 1; o < kPassThreads / 32; o <<= 1) {
+            const unsigned long long y = __shfl_up_sync(0xFFFFFFFFu, inc, o);
+            if (lane >= o) inc += y;
+        }
+        if (lane < kPassThreads / 32) s_w64[lane] = inc - v;
+        if (lane == kPassThreads / 32 - 1) s_tot64 = inc;
     }
-    *total = sum;
     __syncthreads();
-    return before + incl - x;
+    const unsigned long long r = s_w64[w] + incl - x;
+    *total = s_tot64;
+    __syncthreads();
+    return r;
 }
+
 // 32-bit flavour for the per-round scans (a round's counts always fit): ~35 instructions per warp, 3 barriers
 __device__ __forceinline__ unsigned int block_scan32(unsigned int x, unsigned int* total) {
     __shared__ unsigned int s_w32[kPassThreads / 32];
@@ -1117,15 +1127,20 @@ k_explain_pass(const PassArgs a) {
                 const int mode = (meta >> 24) & 3;
                 const uint32_t p = mode == MODE_MEMO ? __ldcg(in.peak + i) : 0u;  // only the memo key needs the peak
                 const int kind = item_kind(mode, m, rt.wmin);
+                Mask128 c;
+                c.w[0] = c.w[1] = c.w[2] = c.w[3] = 0u;
                 if (kind == KIND_DONE || kind == KIND_LEAF) {
                     r = 1;
                 } else if (kind == KIND_POPC) {
-                    r = (unsigned)mask_popc(child_mask(tv, a.mp, mode, p, m, rmax));
+                    c = child_mask(tv, a.mp, mode, p, m, rmax);
+                    r = (unsigned)mask_popc(c);
                 } else {
                     const int all = a.has_budget ? __ldcg(in.all + i) : 0, ind = a.has_budget ? __ldcg(in.ind + i) : 0;
-                    k = (unsigned)mask_popc(open_children(a, rt, mode, p, m, rmax, all, ind));
+                    c = open_children(a, rt, mode, p, m, rmax, all, ind);
+                    k = (unsigned)mask_popc(c);
                 }
                 a.cnt[i] = k | (r << 16);
+                a.node_mask[i] = make_uint4(c.w[0], c.w[1], c.w[2], c.w[3]);  // the write phase reads it back coalesced
                 mine_k += k;
                 mine_r += r;
             }
@@ -1178,7 +1193,7 @@ k_explain_pass(const PassArgs a) {
             for (long long wq = threadIdx.x >> 5; tile0 + wq < cr.ce && wq < (long long)blockDim.x; wq += kPassThreads / 32) {
                 const long long i = (tile0 + wq) * 32 + lane;
                 const bool ok = i < n;
-                const unsigned int packed = ok ? a.cnt[i] : 0u;
+                const unsigned int packed = ok ? __ldcg(a.cnt + i) : 0u;
                 const unsigned int k = packed & 0xFFFFu, r = packed >> 16;
                 unsigned int kin = k, rin = r;
 #pragma unroll
@@ -1198,19 +1213,18 @@ k_explain_pass(const PassArgs a) {
                 for (int q = 0; q < kPW; q++) pw[q] = 0ULL;
                 Mask128 c;
                 c.w[0] = c.w[1] = c.w[2] = c.w[3] = 0u;
-                if (ok && (k | r)) {
+                if (ok) {  // everything a node needs comes in one round of coalesced loads (no dependent gather)
                     m = __ldcg(in.m + i);
                     p = __ldcg(in.peak + i);
                     meta = __ldcg(in.meta + i) & 0x7FFFFFFFu;
-                    const int mode = (meta >> 24) & 3;
                     for (int q = 0; q < nw; q++) pw[q] = __ldcg(in.path + (unsigned long long)q * a.cap + i);
                     if (a.has_budget) {
                         all = __ldcg(in.all + i);
                         ind = __ldcg(in.ind + i);
                     }
-                    kind = item_kind(mode, m, rt.wmin);
-                    if (kind == KIND_OPEN) c = open_children(a, rt, mode, p, m, meta & 0xFF, all, ind);
-                    else if (kind == KIND_POPC) c = child_mask(tv, a.mp, MODE_FREE, 0, m, meta & 0xFF);
+                    c = mk(__ldcg(a.node_mask + i));
+                    kind = item_kind((meta >> 24) & 3, m, rt.wmin);
+                    if (!(k | r)) p = 0xFFFFFFFFu;  // a dead end: takes no part in the per-peak totals
                 }
 
                 // ---- records of the nodes that finish here ----
