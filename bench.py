@@ -346,8 +346,9 @@ def main():
 
     # ---- e2e: public API, host buffers in, host arrays out (H2D + kernels + D2H of every result)
     def e2e_step():
-        valid = FC.classify_observed(observed, dp, wl.breakage, copy=False)
+        valid = FC.classify_observed(observed, dp, wl.breakage, copy=False, wait=False)  # side stream: overlaps the enumeration
         batch = ME.explain_masses(e_mass, dp, max_modifications=wl.max_modifications, thresholds=e_thrf, copy=False)
+        valid.wait()
         return valid, batch
 
     for _ in range(2):

@@ -114,6 +114,11 @@ int sst_classify_run(sst_ctx* ctx, const sst_table* t, double precision, double 
 /* the same without waiting: the kernel is queued on the context's stream, the next synchronous call completes it */
 int sst_classify_launch(sst_ctx* ctx, const sst_table* t, double precision, double tolerance);
 int sst_classify_fetch(sst_ctx* ctx, uint8_t* out /* B*F */);
+/* the whole call on the context's side stream without waiting (inputs and `out` should be pinned and must stay valid
+ * until sst_classify_wait returns); an enumeration pass issued in between overlaps it */
+int sst_classify_async(sst_ctx* ctx, const sst_table* t, const double* observed, int64_t F, const double* offsets, int B,
+                       double precision, double tolerance, uint8_t* out /* B*F */);
+int sst_classify_wait(sst_ctx* ctx);
 
 /* ---- sequence-length bounds: replaces compute_sequence_length_bound (mass_table.py:343-487), both directions in one
  * walk.  target / thr in table units (round(su_mass / precision), ceil(tolerance * obs_mass / precision)),

@@ -35,7 +35,7 @@ EXPORTS = [
     "sst_table_build", "sst_table_upload", "sst_table_rebuild", "sst_table_info", "sst_table_download",
     "sst_table_download_masks", "sst_table_destroy", "sst_is_valid", "sst_valid_stage", "sst_valid_run",
     "sst_valid_fetch", "sst_valid_stage_f64", "sst_explain", "sst_explain_stage", "sst_explain_stage_f64", "sst_explain_rec_width", "sst_explain_phase_ns",
-    "sst_explain_run", "sst_explain_fetch", "sst_classify", "sst_classify_stage", "sst_classify_run", "sst_classify_fetch", "sst_classify_launch", "sst_length_bounds",
+    "sst_explain_run", "sst_explain_fetch", "sst_classify", "sst_classify_stage", "sst_classify_run", "sst_classify_fetch", "sst_classify_launch", "sst_classify_async", "sst_classify_wait", "sst_length_bounds",
 ]
 
 
@@ -100,6 +100,8 @@ def load() -> C.CDLL:
             "sst_classify_run": (C.c_int, [vp, vp, C.c_double, C.c_double]),
             "sst_classify_fetch": (C.c_int, [vp, u8p]),
             "sst_classify_launch": (C.c_int, [vp, vp, C.c_double, C.c_double]),
+            "sst_classify_async": (C.c_int, [vp, vp, fp, C.c_int64, fp, C.c_int, C.c_double, C.c_double, u8p]),
+            "sst_classify_wait": (C.c_int, [vp]),
             "sst_length_bounds": (C.c_int, [vp, vp, C.c_int64, C.c_int64, C.c_int32, C.c_int32, i32p, u8p, C.c_uint64,
                                             C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
         }
@@ -260,6 +262,20 @@ class Context:
     def classify_launch(self, table: "DeviceTable", precision: float, tolerance: float):
         """Queue the classification kernel without waiting (the next synchronous call on the context completes it)."""
         self._check(self._lib.sst_classify_launch(self._h, table._h, float(precision), float(tolerance)))
+
+    def classify_async(self, table: "DeviceTable", observed: np.ndarray, offsets: np.ndarray, precision: float, tolerance: float):
+        """Whole classification on the side stream, no waiting; returns the pinned uint8[B, F] buffer the flags will
+        land in — valid after ``classify_wait()`` and until the next classification on this context."""
+        o, b = _arr(observed, np.float64), _arr(offsets, np.float64)
+        self._async_keep = (o, b)  # the copies are asynchronous: keep the host arrays alive
+        B, F = len(b), len(o)
+        buf = self._pinned("classify", B * F)[: B * F]
+        self._check(self._lib.sst_classify_async(self._h, table._h, _p(o), F, _p(b), B, float(precision), float(tolerance), _p(buf)))
+        return buf.reshape(B, F)
+
+    def classify_wait(self):
+        self._check(self._lib.sst_classify_wait(self._h))
+        self._async_keep = None
 
     def classify_fetch(self, copy: bool = True) -> np.ndarray:
         """-> uint8[B, F] of CLASS_* bits (breakage-major)."""

@@ -49,6 +49,7 @@ struct sst_table {
 struct sst_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t stream2 = nullptr;  // side stream: classification that overlaps an enumeration pass
     cudaDeviceProp prop{};
     char err[512] = {0};
     cudaEvent_t ev_a = nullptr, ev_b = nullptr;    // user stopwatch
@@ -313,6 +314,7 @@ int sst_ctx_create(int device, sst_ctx** out) {
         return SST_ERR_NO_DEVICE;
     }
     cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+    cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking);
     cudaEventCreate(&ctx->ev_a);
     cudaEventCreate(&ctx->ev_b);
     for (auto& e : ctx->kev) cudaEventCreate(&e);
@@ -340,6 +342,8 @@ void sst_ctx_destroy(sst_ctx* ctx) {
     cudaEventDestroy(ctx->ev_b);
     for (auto& e : ctx->kev) cudaEventDestroy(e);
     for (auto& e : ctx->tev) cudaEventDestroy(e);
+    cudaStreamSynchronize(ctx->stream2);
+    cudaStreamDestroy(ctx->stream2);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -611,6 +615,38 @@ int sst_classify_run(sst_ctx* ctx, const sst_table* t, double precision, double 
     if (rc) return rc;
     CK(cudaStreamSynchronize(ctx->stream));
     flush_timers(ctx);
+    return SST_OK;
+}
+
+// the whole classification on the context's SIDE stream, without waiting: stage (pinned `observed` / `offsets`
+// recommended), kernel, copy of the flags into `out` (pinned).  sst_classify_wait completes it.  An enumeration pass
+// issued in between runs concurrently on the main stream.
+int sst_classify_async(sst_ctx* ctx, const sst_table* t, const double* observed, int64_t F, const double* offsets, int B,
+                       double precision, double tolerance, uint8_t* out) {
+    CK(cudaSetDevice(ctx->device));
+    if (F < 0 || B < 0 || B > 65535) return fail(ctx, SST_ERR_BAD_ARG, "fragment / breakage count out of range");
+    CK(cudaStreamSynchronize(ctx->stream2));  // an earlier asynchronous classification still owns the buffers
+    int rc;
+    if ((rc = reserve(ctx, ctx->d_cobs, (size_t)(F ? F : 1) * 8))) return rc;
+    if ((rc = reserve(ctx, ctx->d_coff, (size_t)(B ? B : 1) * 8))) return rc;
+    if ((rc = reserve(ctx, ctx->d_cout, (size_t)(F * B ? F * B : 1)))) return rc;
+    ctx->CF = F;
+    ctx->CB = B;
+    if (!F || !B) return SST_OK;
+    CK(cudaMemcpyAsync(ctx->d_cobs.p, observed, (size_t)F * 8, cudaMemcpyHostToDevice, ctx->stream2));
+    CK(cudaMemcpyAsync(ctx->d_coff.p, offsets, (size_t)B * 8, cudaMemcpyHostToDevice, ctx->stream2));
+    k_classify<<<dim3((unsigned)((F + 255) / 256), (unsigned)B), 256, 0, ctx->stream2>>>(view_of(t), (const double*)ctx->d_cobs.p, F,
+                                                                                       (const double*)ctx->d_coff.p, B, precision, tolerance,
+                                                                                       (uint8_t*)ctx->d_cout.p);
+    CK(cudaGetLastError());
+    ctx->k_launches[SST_K_CLASSIFY] += 1;
+    CK(cudaMemcpyAsync(out, ctx->d_cout.p, (size_t)F * B, cudaMemcpyDeviceToHost, ctx->stream2));
+    return SST_OK;
+}
+
+int sst_classify_wait(sst_ctx* ctx) {
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream2));
     return SST_OK;
 }
 

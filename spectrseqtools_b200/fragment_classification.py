@@ -25,12 +25,23 @@ class ClassifiedMasses:
     """Result of ``classify_observed``: one flag byte per (breakage, fragment), breakage-major."""
 
     def __init__(self, observed: np.ndarray, breakage_weights: List[int], labels: List[str], precision: float,
-                 flags: np.ndarray):
+                 flags: np.ndarray, pending=None):
         self.observed = observed
         self.breakage_weights = breakage_weights
         self.labels = labels          # first label of every weight, like the reference's pl.lit(breakages[0])
         self.precision = precision
-        self.flags = flags            # uint8[B, F]
+        self._flags = flags           # uint8[B, F]
+        self._pending = pending       # context of an asynchronous call that has not been waited for yet
+
+    def wait(self) -> "ClassifiedMasses":
+        if self._pending is not None:
+            self._pending.classify_wait()
+            self._pending = None
+        return self
+
+    @property
+    def flags(self) -> np.ndarray:
+        return self.wait()._flags
 
     @property
     def valid(self) -> np.ndarray:
@@ -52,17 +63,25 @@ class ClassifiedMasses:
 
 
 def classify_observed(observed: Sequence[float], dp_table: DynamicProgrammingTable, breakage_dict: Dict[int, List[str]],
-                      copy: bool = True) -> ClassifiedMasses:
-    """Validity + singleton flags of every observed mass under every breakage offset: one device pass."""
+                      copy: bool = True, wait: bool = True) -> ClassifiedMasses:
+    """Validity + singleton flags of every observed mass under every breakage offset: one device pass.
+
+    ``wait=False`` queues the whole call (copies and kernel) on the context's side stream and returns at once; the
+    flags are waited for on first access (``.flags`` / ``.wait()``), so an ``explain_masses`` call issued in between
+    overlaps it.  ``copy=False`` hands out the context's pinned buffer (valid until the next classification)."""
     observed = np.ascontiguousarray(observed, dtype=np.float64).reshape(-1)
     weights = list(breakage_dict.keys())
     offsets = np.array([w * dp_table.precision for w in weights], dtype=np.float64)  # int * float, as upstream
     dev = dp_table.device_table()
     ctx = dev.ctx
+    labels = [breakage_dict[w][0] for w in weights]
+    if not wait:
+        flags = ctx.classify_async(dev, observed, offsets, dp_table.precision, dp_table.tolerance)
+        return ClassifiedMasses(observed, weights, labels, dp_table.precision, flags, pending=ctx)
     ctx.classify_stage(observed, offsets)
     ctx.classify_run(dev, dp_table.precision, dp_table.tolerance)
     flags = ctx.classify_fetch(copy=copy)
-    return ClassifiedMasses(observed, weights, [breakage_dict[w][0] for w in weights], dp_table.precision, flags)
+    return ClassifiedMasses(observed, weights, labels, dp_table.precision, flags)
 
 
 def is_singleton(mass, integer_masses, dp_table, threshold=None) -> bool:

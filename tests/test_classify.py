@@ -40,6 +40,8 @@ def test_device_classification_matches_reference(name):
     breakage = {int(k): v for k, v in c["breakage"].items()}
     res = FC.classify_observed(c["observed"], dp, breakage)
     assert np.array_equal(res.flags, _want(c))
+    lazy = FC.classify_observed(c["observed"], dp, breakage, wait=False)  # side stream, waited for on first access
+    assert np.array_equal(lazy.flags, _want(c))
     assert res.standard_unit_mass.shape == res.flags.shape
     # the same pairs through the plain validity call
     from spectrseqtools_b200 import mass_explanation as ME
