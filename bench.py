@@ -31,6 +31,18 @@ METRIC = "peaks_explained_per_sec"
 UNIT = "peaks/s"
 
 
+def ncu_traffic(kernel: str, wl=None):
+    """DRAM bytes per launch of `kernel` from the committed ncu --set full capture (profiles/traffic.json), or None.
+    Only valid for the workload the capture was taken on (C4, 10^5 peaks)."""
+    if wl is not None and not (wl.name == "C4" and wl.n_peaks == 100_000):
+        return None
+    try:
+        doc = json.loads((ROOT / "profiles" / "traffic.json").read_text())
+        return int(doc["kernels"][kernel]["dram_bytes_per_launch"])
+    except Exception:
+        return None
+
+
 def peaks_file():
     p = ROOT / "MEASURED_PEAKS.json"
     if p.exists():
@@ -286,11 +298,12 @@ def main():
         "rows": dev.R, "words_per_row": dev.C, "bytes": table_bytes,
         "build_ms": min(build_ms), "build_ms_median": statistics.median(build_ms),
         "roofline": {"bound": "hbm", "achieved": table_bytes / (min(build_ms) * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                     "frac": table_bytes / (min(build_ms) * 1e-3) / 1e9 / hbm_peak, "traffic": None,
+                     "frac": table_bytes / (min(build_ms) * 1e-3) / 1e9 / hbm_peak, "traffic": ncu_traffic("k_build_table<8, 0>") if dev.R == 105 and wl.max_seq_length == 35 else None,
                      "algorithmic_bytes": table_bytes, "note": "R*C*8 bytes written once (SURVEY §8d K1)"},
         "row_masks_ms": min(tr_ms),
         "row_masks_roofline": {"bound": "hbm", "achieved": (table_bytes + mask_bytes) / (min(tr_ms) * 1e-3) / 1e9, "peak": hbm_peak,
                                "unit": "GB/s", "frac": (table_bytes + mask_bytes) / (min(tr_ms) * 1e-3) / 1e9 / hbm_peak,
+                               "traffic": ncu_traffic("k_transpose_masks") if dev.R == 105 and wl.max_seq_length == 35 else None,
                                "algorithmic_bytes": table_bytes + mask_bytes},
     }
 
@@ -386,10 +399,12 @@ def main():
     dominant = max(fam + ["classify"], key=lambda k: stats[k][0])
     roofline = {"bound": "hbm", "kernel": "K3+K2b enumeration pass (k_explain_pass: window roots -> items -> compositions, one cooperative launch)",
                 "achieved": k2b_bytes / (k2b_ms * 1e-3) / 1e9 if k2b_ms else None, "peak": hbm_peak, "unit": "GB/s",
-                "frac": (k2b_bytes / (k2b_ms * 1e-3) / 1e9 / hbm_peak) if k2b_ms else None, "traffic": None,
+                "frac": (k2b_bytes / (k2b_ms * 1e-3) / 1e9 / hbm_peak) if k2b_ms else None,
+                "traffic": ncu_traffic("k_explain_pass<1>", wl), "traffic_source": "profiles/traffic.json (ncu --set full, same workload)",
                 "algorithmic_bytes": int(k2b_bytes), "peak_source": peak_src, "dominant_launch": dominant,
-                "k2a": {"algorithmic_bytes": int(k2a_bytes), "ms": k2a_ms,
-                        "achieved": k2a_bytes / (k2a_ms * 1e-3) / 1e9 if k2a_ms else None}}
+                "k2a": {"kernel": "k_classify (validity + singleton of every peak x breakage pair)", "algorithmic_bytes": int(k2a_bytes), "ms": k2a_ms,
+                        "achieved": k2a_bytes / (k2a_ms * 1e-3) / 1e9 if k2a_ms else None,
+                        "frac": (k2a_bytes / (k2a_ms * 1e-3) / 1e9 / hbm_peak) if k2a_ms else None, "traffic": ncu_traffic("k_classify", wl)}}
     launches = sum(v[1] for v in stats.values())
     ph = ctx.explain_phase_ns().astype(np.int64)
     ph = ph[ph > 0]
