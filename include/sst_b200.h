@@ -7,11 +7,14 @@
  * binding, INTEGRATION.md shows the stub a reference maintainer would add.
  *
  * Conventions: plain pointers and sizes only; every function returns an SST_* code (0 = ok) unless
- * noted; sst_last_error(ctx) gives the text of the last failure.  A context owns one CUDA stream on one
- * device and is not thread-safe; tables belong to the context that made them.  Host pointers may be
- * pageable or pinned (sst_host_alloc gives pinned memory); all calls are synchronous on return.
- * Integer masses are in table units (1 mDa for the stock alphabet).  The float -> integer conversions of
- * mass_explanation.py:107-114 stay on the host (Python) so they match CPython bit for bit.
+ * noted; sst_last_error(ctx) gives the text of the last failure.  A context owns a main and a side CUDA
+ * stream on one device and is not thread-safe; tables belong to the context that made them.  Host pointers may
+ * be pageable or pinned (sst_host_alloc gives pinned memory); all calls are synchronous on return except
+ * sst_classify_launch / sst_classify_async.
+ * Integer masses are in table units (1 mDa for the stock alphabet).  The *_f64 entries and sst_classify take
+ * float masses and do the float -> integer conversions of mass_explanation.py:51-58,107-114 on the device with
+ * the same IEEE operations (true division, round-half-even, ceil; no FMA contraction), so they match CPython
+ * bit for bit (tests/test_host.py, tests/test_gpu_explain.py).
  */
 #ifndef SST_B200_H
 #define SST_B200_H

@@ -507,6 +507,7 @@ int sst_table_download_masks(sst_ctx* ctx, const sst_table* t, int64_t first_mas
 void sst_table_destroy(sst_ctx* ctx, sst_table* t) {
     if (ctx) {
         cudaSetDevice(ctx->device);
+        cudaStreamSynchronize(ctx->stream2);
         cudaStreamSynchronize(ctx->stream);
     }
     free_table(t);
@@ -584,6 +585,7 @@ int sst_is_valid(sst_ctx* ctx, const sst_table* t, const int64_t* target, const 
 
 int sst_classify_stage(sst_ctx* ctx, const double* observed, int64_t F, const double* offsets, int B) {
     CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream2));  // an asynchronous classification may still own the buffers
     if (F < 0 || B < 0 || B > 65535) return fail(ctx, SST_ERR_BAD_ARG, "fragment / breakage count out of range");
     int rc;
     if ((rc = reserve(ctx, ctx->d_cobs, (size_t)(F ? F : 1) * 8))) return rc;
@@ -599,6 +601,7 @@ int sst_classify_stage(sst_ctx* ctx, const double* observed, int64_t F, const do
 
 int sst_classify_launch(sst_ctx* ctx, const sst_table* t, double precision, double tolerance) {
     CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream2));
     if (ctx->CF && ctx->CB) {
         KTimer kt(ctx, SST_K_CLASSIFY);
         k_classify<<<dim3((unsigned)((ctx->CF + 255) / 256), (unsigned)ctx->CB), 256, 0, ctx->stream>>>(view_of(t), (const double*)ctx->d_cobs.p, ctx->CF,

@@ -1,8 +1,11 @@
-// K2a validity probe, K2b enumerator (+ first-visit budget pass), K3 integer window filter.
+// K2a validity probe, K3 integer window + K2b enumerator (one cooperative pass, + first-visit budget replay),
+// staging of float batches, N2 fragment classification, N1 sequence-length bounds.
 //
-// Replaces is_valid_mass (reference mass_explanation.py:45-89) and explain_mass_with_table
-// (:92-203, inner backtrack :118-188).  Everything works on integer masses; the float -> integer
-// conversion stays on the host so it matches CPython bit for bit.
+// Replaces is_valid_mass (reference mass_explanation.py:45-89), explain_mass_with_table (:92-203, inner backtrack
+// :118-188), the per-pair callbacks of classify_fragments (fragment_classification.py:39-82) and
+// compute_sequence_length_bound (mass_table.py:343-487).  Kernels work on integer masses; the float -> integer
+// conversions (k_stage_f64, k_is_valid_f64, k_classify) use the same IEEE operations as the reference's Python
+// (division, round-half-even, ceil; no FMA contraction), so they match CPython bit for bit.
 //
 // Enumeration model.  The reference walks (mass m, row r): UP to (m, r-1) if bit0, LEFT to (m-w_r, r) if
 // bit1.  Because bit0(i,m) = OR_{r<i} bit1(r,m) (plus mass 0), the children of "mass m, rows <= rmax" are
@@ -10,14 +13,14 @@
 // the ~100 dependent UP reads per nucleotide.  A composition is emitted when the remainder hits 0.
 //
 // Budget modes (per peak):
-//   FREE   budgets cannot bind (host-checked): enabled edges = table bits.
+//   FREE   budgets cannot bind (closed-form test when the batch is staged): enabled edges = table bits.
 //   EXACT  with_memo=False: every path carries its own budgets (global `all`, per-row `ind`).
 //   MEMO   with_memo=True with binding budgets: the reference's memo is keyed (m, r) WITHOUT budgets, so
 //          each node is expanded once with the budgets of its first arrival in DFS order (UP before
 //          LEFT, window ascending).  Phase A replays that order sequentially per peak, one mass at a
 //          time (rows visited at a mass always form a contiguous range [r0(m), top(m)]), and records per
-//          mass the LEFT edges that were enabled AND lead to at least one solution.  Phase B is the same
-//          parallel path enumeration as FREE, reading those masks from a hash map instead of H.
+//          mass the LEFT edges that were enabled AND lead to at least one solution.  The enumeration pass then
+//          reads those masks from a hash map instead of H.
 #pragma once
 #include "sst_common.cuh"
 
@@ -750,25 +753,6 @@ __device__ __forceinline__ void slice_prefix(const unsigned long long* cta_tot, 
     *base = v[0];
     *all = v[1];
 }
-// the same for the three per-level totals at once: [0] children, [1] open items, [2] final compositions
-__device__ __forceinline__ void slice_prefix3(const unsigned long long* cta_tot, unsigned long long (&base)[3], unsigned long long (&all)[3]) {
-    unsigned long long v[6] = {0ULL, 0ULL, 0ULL, 0ULL, 0ULL, 0ULL};
-    for (unsigned b = threadIdx.x; b < gridDim.x; b += blockDim.x) {
-#pragma unroll
-        for (int k = 0; k < 3; k++) {
-            const unsigned long long x = __ldcg(cta_tot + (size_t)k * gridDim.x + b);
-            v[3 + k] += x;
-            if (b < blockIdx.x) v[k] += x;
-        }
-    }
-    block_sum_n<6>(v);
-#pragma unroll
-    for (int k = 0; k < 3; k++) {
-        base[k] = v[k];
-        all[k] = v[3 + k];
-    }
-}
-
 // ---- output-balanced work split ----
 // The count phases deal NODES evenly (one load each); the write phases cost per OUTPUT (a child or a record), and
 // outputs cluster (a wide 3-nt window is thousands of consecutive open nodes).  So the write phases re-split the
