@@ -1,0 +1,66 @@
+"""GPU: the reference's own unit-test scenario for this path, driven exactly the way upstream drives it.
+
+Same import paths (``spectrseqtools.*`` — this repo's drop-in alias), the same polars idioms for the oligo masses
+(real polars when installed, the stand-in otherwise), the same table construction, budgets and membership assertion
+as the reference's tests/test_explain_masses.py (7 unmodified oligos x 3 tolerances x {recursion, table}).  When the
+reference checkout itself is reachable (the build container) its unmodified test file is additionally run as-is.
+"""
+import pathlib
+import subprocess
+import sys
+
+import pytest
+
+import polars as pl  # conftest installs the stand-in when polars is missing
+from spectrseqtools.mass_explanation import explain_mass_with_recursion, explain_mass_with_table
+from spectrseqtools.mass_table import DynamicProgrammingTable, SequenceInformation
+from spectrseqtools.masses import EXPLANATION_MASSES, PHOSPHATE_LINK_MASS, TOLERANCE
+
+pytestmark = pytest.mark.gpu
+
+OLIGOS = [("A",), ("A", "A"), ("G", "G"), ("C", "C"), ("U", "U"), ("C", "U", "A", "G"), ("C", "C", "U", "A", "G", "G")]
+TOLERANCES = [10e-6, 5e-6, 2e-6]
+RATE = 0.5
+
+
+def oligo_mass(seq) -> float:
+    frame = pl.DataFrame(data=seq, schema=["name"])
+    nucleoside_mass = lambda n: EXPLANATION_MASSES.filter(pl.col("nucleoside") == n).get_column("monoisotopic_mass").to_list()[0]  # noqa: E731
+    frame = frame.with_columns(pl.col("name").map_elements(nucleoside_mass, return_dtype=pl.Float64).alias("mass"))
+    return round(len(seq) * PHOSPHATE_LINK_MASS + frame.select("mass").sum().item(), 5)
+
+
+def table_for(mass: float, tolerance: float) -> DynamicProgrammingTable:
+    lightest = min(pl.Series(EXPLANATION_MASSES.select("tolerated_integer_masses")).to_list())
+    seq = SequenceInformation(max_len=int(mass / TOLERANCE / lightest), su_mass=mass, obs_mass=mass, modification_rate=RATE)
+    return DynamicProgrammingTable(EXPLANATION_MASSES, compression_rate=32, tolerance=tolerance, precision=TOLERANCE, seq=seq)
+
+
+@pytest.mark.parametrize("seq", OLIGOS)
+@pytest.mark.parametrize("tolerance", TOLERANCES)
+def test_oligo_is_among_the_table_explanations(seq, tolerance):
+    mass = oligo_mass(seq)
+    found = explain_mass_with_table(mass, dp_table=table_for(mass, tolerance), compression_rate=32,
+                                    max_modifications=round(RATE * len(seq)), with_memo=True).explanations
+    assert found is not None
+    assert tuple(seq) in [tuple(e) for e in found]
+
+
+@pytest.mark.parametrize("seq", OLIGOS)
+@pytest.mark.parametrize("tolerance", TOLERANCES)
+def test_oligo_is_among_the_recursive_explanations(seq, tolerance):
+    mass = oligo_mass(seq)
+    found = explain_mass_with_recursion(mass, dp_table=table_for(mass, tolerance), max_modifications=round(RATE * len(seq))).explanations
+    assert found is not None
+    assert tuple(seq) in [tuple(e) for e in found]
+
+
+def test_upstream_file_as_is():
+    upstream = pathlib.Path("/root/reference/tests/test_explain_masses.py")
+    if not upstream.is_file():
+        pytest.skip("reference checkout not on this machine (GPU box); the scenario above is its transcription")
+    repo = pathlib.Path(__file__).resolve().parents[1]
+    code = ("import sys; sys.path.insert(0, %r); from spectrseqtools_b200 import _frame; _frame.install_polars_shim(); "
+            "import pytest; sys.exit(pytest.main(['-q', '-x', '-p', 'no:cacheprovider', %r]))" % (str(repo), str(upstream)))
+    done = subprocess.run([sys.executable, "-c", code], cwd="/tmp", capture_output=True, text=True, timeout=1200)
+    assert done.returncode == 0, done.stdout[-2000:] + done.stderr[-2000:]
