@@ -151,9 +151,10 @@ int sst_explain_stage_f64(sst_ctx* ctx, const sst_table* t, const double* mass, 
 int sst_explain_run(sst_ctx* ctx, const sst_table* t, int rec_width, uint64_t memo_capacity, uint64_t* n_roots,
                     uint64_t* n_comps);
 int sst_explain_rec_width(const sst_ctx* ctx); /* record width of the last run */
-/* device timestamps (ns, %globaltimer; the moment the LAST CTA reached the point) of the last enumeration pass:
- * [0] start, [1] window values counted, [2] level-0 items written, then per expansion level [counted, written],
- * the last "counted" being the level that had no open item, then [records written], [end].  Unused slots are 0. */
+/* diagnostics: device timestamps (ns, %globaltimer, CTA 0's clock) at the phase boundaries of the last enumeration
+ * pass, in order: [0] start, [1] window values counted, [2] level-0 nodes written, then for every level
+ * [counted, grid barrier passed, written]; after the last level [per-level peak totals summed], [placement table
+ * written], [records permuted].  Right after a grid barrier that is every CTA's clock.  Unused slots are 0. */
 int sst_explain_phase_ns(const sst_ctx* ctx, uint64_t* out /* [32] */);
 /* status[P]; peak_off[P+1] (compositions of peak p are records peak_off[p] .. peak_off[p+1]);
  * recs[n_comps * rec_width]: row indices in ascending order, 0-padded.  Any pointer may be NULL. */
