@@ -67,6 +67,9 @@ void sst_host_free(sst_ctx* ctx, void* p);
 /* CUDA-event stopwatch on the context's stream (what bench.py times with) */
 int sst_timer_start(sst_ctx* ctx);
 int sst_timer_stop(sst_ctx* ctx, float* ms);
+/* device time from sst_timer_start to the end of the device work of the last sst_explain_run (its result read-back
+ * included, the host's wake-up after it not) */
+int sst_timer_stop_at_run(sst_ctx* ctx, float* ms);
 /* device time of each kernel family accumulated since the last sst_stats_reset, and launches made */
 int sst_stats_reset(sst_ctx* ctx);
 int sst_kernel_ms(sst_ctx* ctx, float* ms /* [SST_K_COUNT_] */, uint64_t* launches /* [SST_K_COUNT_] */);

@@ -31,7 +31,7 @@ KERNEL_SLOTS = ["build", "transpose", "is_valid", "phase_a", "explain_pass", "cl
 
 EXPORTS = [
     "sst_ctx_create", "sst_ctx_destroy", "sst_last_error", "sst_device_info", "sst_host_alloc", "sst_host_free",
-    "sst_timer_start", "sst_timer_stop", "sst_stats_reset", "sst_kernel_ms", "sst_flush_l2", "sst_set_item_limit",
+    "sst_timer_start", "sst_timer_stop", "sst_timer_stop_at_run", "sst_stats_reset", "sst_kernel_ms", "sst_flush_l2", "sst_set_item_limit",
     "sst_table_build", "sst_table_upload", "sst_table_rebuild", "sst_table_info", "sst_table_download",
     "sst_table_download_masks", "sst_table_destroy", "sst_is_valid", "sst_valid_stage", "sst_valid_run",
     "sst_valid_fetch", "sst_valid_stage_f64", "sst_explain", "sst_explain_stage", "sst_explain_stage_f64", "sst_explain_rec_width", "sst_explain_phase_ns",
@@ -72,6 +72,7 @@ def load() -> C.CDLL:
             "sst_host_free": (None, [vp, vp]),
             "sst_timer_start": (C.c_int, [vp]),
             "sst_timer_stop": (C.c_int, [vp, C.POINTER(C.c_float)]),
+            "sst_timer_stop_at_run": (C.c_int, [vp, C.POINTER(C.c_float)]),
             "sst_stats_reset": (C.c_int, [vp]),
             "sst_kernel_ms": (C.c_int, [vp, fp, u64p]),
             "sst_flush_l2": (C.c_int, [vp, C.c_size_t]),
@@ -175,6 +176,12 @@ class Context:
     def timer_stop(self) -> float:
         ms = C.c_float()
         self._check(self._lib.sst_timer_stop(self._h, C.byref(ms)))
+        return float(ms.value)
+
+    def timer_stop_at_run(self) -> float:
+        """Device time from ``timer_start`` to the end of the device work of the last ``explain_run``."""
+        ms = C.c_float()
+        self._check(self._lib.sst_timer_stop_at_run(self._h, C.byref(ms)))
         return float(ms.value)
 
     def stats_reset(self):

@@ -53,6 +53,7 @@ struct sst_ctx {
     cudaDeviceProp prop{};
     char err[512] = {0};
     cudaEvent_t ev_a = nullptr, ev_b = nullptr;    // user stopwatch
+    cudaEvent_t ev_run = nullptr;                  // end of the device work of the last enumeration pass
     cudaEvent_t kev[2 * 32] = {nullptr};            // pooled per-launch brackets
     int pending_slot[32] = {0};
     int n_pending = 0;
@@ -317,6 +318,7 @@ int sst_ctx_create(int device, sst_ctx** out) {
     cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking);
     cudaEventCreate(&ctx->ev_a);
     cudaEventCreate(&ctx->ev_b);
+    cudaEventCreate(&ctx->ev_run);
     for (auto& e : ctx->kev) cudaEventCreate(&e);
     for (auto& e : ctx->tev) cudaEventCreate(&e);
     cudaHostAlloc((void**)&ctx->h_misc, 512, cudaHostAllocDefault);
@@ -340,6 +342,7 @@ void sst_ctx_destroy(sst_ctx* ctx) {
     for (DevBuf* b : bufs) cudaFree(b->p);
     cudaEventDestroy(ctx->ev_a);
     cudaEventDestroy(ctx->ev_b);
+    cudaEventDestroy(ctx->ev_run);
     for (auto& e : ctx->kev) cudaEventDestroy(e);
     for (auto& e : ctx->tev) cudaEventDestroy(e);
     cudaStreamSynchronize(ctx->stream2);
@@ -388,6 +391,12 @@ int sst_timer_stop(sst_ctx* ctx, float* ms) {
     CK(cudaEventRecord(ctx->ev_b, ctx->stream));
     CK(cudaEventSynchronize(ctx->ev_b));
     CK(cudaEventElapsedTime(ms, ctx->ev_a, ctx->ev_b));
+    return SST_OK;
+}
+
+int sst_timer_stop_at_run(sst_ctx* ctx, float* ms) {
+    CK(cudaEventSynchronize(ctx->ev_run));
+    CK(cudaEventElapsedTime(ms, ctx->ev_a, ctx->ev_run));
     return SST_OK;
 }
 
@@ -968,6 +977,7 @@ int sst_explain_run(sst_ctx* ctx, const sst_table* t, int rec_width, uint64_t me
         // one read-back: totals + timestamps + flags
         CK(cudaMemcpyAsync(ctx->h_misc, ctx->d_scan.p, 384, cudaMemcpyDeviceToHost, ctx->stream));
         if (ctx->n_memo && attempt == 0) CK(cudaMemcpyAsync(ctx->h_misc + 100, ctx->d_memo_misc.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaEventRecord(ctx->ev_run, ctx->stream));  // the device is done here; what follows is the host waking up
         CK(cudaStreamSynchronize(ctx->stream));
         flush_timers(ctx);
         const unsigned long long* h_tot = (const unsigned long long*)ctx->h_misc;
