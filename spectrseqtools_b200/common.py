@@ -20,31 +20,42 @@ def parse_nucleosides(sequence: str):
 
 
 class Explanation:
-    def __init__(self, *nucleosides):
-        self.nucleosides = tuple(sorted(nucleosides))
+    """A composition as a name-sorted tuple: iterable, sized, printable as {a,b,c}, equal to another Explanation
+    or to a plain tuple with the same names (what the reference's consumers rely on)."""
+
+    __slots__ = ("nucleosides",)
+
+    def __init__(self, *names: str):
+        self.nucleosides = tuple(sorted(names))
 
     def __iter__(self):
-        yield from self.nucleosides
+        return iter(self.nucleosides)
 
-    def __len__(self):
+    def __len__(self) -> int:
         return len(self.nucleosides)
 
-    def __repr__(self):
-        return f"{{{','.join(self.nucleosides)}}}"
+    def __repr__(self) -> str:
+        return "{" + ",".join(self.nucleosides) + "}"
 
-    def __eq__(self, other):
-        return self.nucleosides == other
+    def __eq__(self, other) -> bool:
+        return self.nucleosides == (other.nucleosides if isinstance(other, Explanation) else other)
 
-    def __hash__(self):
+    def __hash__(self) -> int:
         return hash(self.nucleosides)
 
 
+_ERROR_NORMS = {
+    "l1_norm": lambda m1, m2: m1 + m2,
+    "l2_norm": lambda m1, m2: (m1**2 + m2**2) ** 0.5,
+}
+
+
 def calculate_error_threshold(mass1: float, mass2: float, threshold: float) -> float:
-    if ERROR_METHOD == "l1_norm":
-        return threshold * (mass1 + mass2)
-    if ERROR_METHOD == "l2_norm":
-        return threshold * ((mass1**2 + mass2**2) ** 0.5)
-    raise NotImplementedError("This error method is not implemented.")
+    """Absolute threshold of a mass difference: relative tolerance times the norm of the two observed masses."""
+    norm = _ERROR_NORMS.get(ERROR_METHOD)
+    if norm is None:
+        raise NotImplementedError("This error method is not implemented.")
+    return threshold * norm(mass1, mass2)
 
 
 def _budget(dp_table) -> int:
