@@ -74,6 +74,7 @@ struct sst_ctx {
     DevBuf d_item_m[2], d_item_peak[2], d_item_meta[2], d_item_all[2], d_item_ind[2], d_item_path[2];
     bool has_exact = false;
     int levels = 0;
+    uint64_t widest_level = 0;      // nodes of the widest level of the last run (sizes the next grid)
     uint64_t item_capacity = 0, n_items = 0;
     bool valid_f64 = false;
     double v_precision = 1e-3, v_tolerance = 1e-5;
@@ -964,8 +965,12 @@ int sst_explain_run(sst_ctx* ctx, const sst_table* t, int rec_width, uint64_t me
         a.flags = d_flags;
         a.barrier = (unsigned int*)((char*)ctx->d_scan.p + 384);
         a.leaf = LeafHash{t->leaf_mul};
-        // enough CTAs that every thread gets about one entity of the longest list, at most one co-resident wave
-        int64_t want = ((int64_t)most + kPassThreads - 1) / kPassThreads;
+        // enough CTAs that every thread gets about one entity of the longest list we can foresee (peaks, window
+        // values, the widest level of the previous run), at most one co-resident wave: a single-peak call must not
+        // pay twelve grid barriers of a full-machine grid
+        int64_t foresee = P > root_bound ? P : root_bound;
+        if ((int64_t)ctx->widest_level > foresee) foresee = (int64_t)ctx->widest_level;
+        int64_t want = (foresee + kPassThreads - 1) / kPassThreads;
         if (want < 1) want = 1;
         const unsigned grid = (unsigned)(want < grid_max ? want : grid_max);
         {
@@ -986,6 +991,7 @@ int sst_explain_run(sst_ctx* ctx, const sst_table* t, int rec_width, uint64_t me
         items = h_tot[1];
         comps = h_tot[2];
         ctx->levels = (int)h_tot[3];
+        if (!h_flags[2]) ctx->widest_level = items;
         for (int i = 0; i < 32; i++) ctx->phase_ns[i] = h_tot[8 + i];
         if (ctx->n_memo && attempt == 0 && ctx->h_misc[101])
             return fail(ctx, SST_ERR_MEMO_FULL, "first-visit map is too small (%d slots used)", ctx->h_misc[100]);
