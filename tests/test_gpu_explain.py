@@ -184,3 +184,29 @@ def test_memo_map_grows_on_demand():
         ctx.explain_run(dev, 8, 1024)
     _, n = ctx.explain_run(dev, 8, 1 << 20)
     assert n == 792  # SURVEY Appendix C (first-visit semantics)
+
+
+def test_deep_compositions_use_wide_records():
+    """20-40 nucleotides per composition: records wider than 16 bytes (the run-time path-width instance of the pass),
+    FREE and budgeted modes, against the C oracle."""
+    w = [0, 1201, 1333, 1479]
+    is_mod = [False, False, True, False]
+    rates = [0.0, 1.0, 0.5, 1.0]
+    max_len = 40
+    dp = Hh.small_dp_table(w, is_mod, rates, max_len, 2e-6)
+    tab = OC.build_bit_table(w, max(w) * 35, 32)
+    rows = Hh.oracle_rows(dp)
+    ind = OP.individual_budgets(rows, max_len)
+    rng = np.random.default_rng(21)
+    masses = [float(sum(w[i] for i in rng.integers(1, len(w), size=int(n)))) * 1e-3 for n in rng.integers(18, 34, size=24)]
+    for mm, memo in ((np.inf, True), (6, True), (6, False), (25, False)):
+        batch = ME.explain_masses(masses, dp, max_modifications=mm, thresholds=[0.002] * len(masses), with_memo=memo)
+        assert batch.records.shape[1] >= 24
+        total = 0
+        for p, mass in enumerate(masses):
+            t, h = OP.integerise(mass, 0.002, 1e-3, 2e-6)
+            r, off, _ = OC.explain(tab, 32, w, is_mod, ind, t, h, mm, memo)
+            want = sorted(tuple(int(x) for x in r[off[i]:off[i + 1]]) for i in range(len(off) - 1) if off[i + 1] > off[i])
+            assert batch.canonical(p) == want, (mm, memo, p)
+            total += len(want)
+        assert total > 20
