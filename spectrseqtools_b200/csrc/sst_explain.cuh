@@ -706,6 +706,46 @@ __device__ __forceinline__ unsigned int block_scan32(unsigned int x, unsigned in
 template <int N>
 __device__ __forceinline__ void block_sum_n(unsigned long long (&v)[N]);
 __device__ __forceinline__ unsigned long long block_sum(unsigned long long x);
+
+// four independent 32-bit scans at once (the per-level scans over the peaks share their barriers)
+__device__ __forceinline__ void block_scan32x4(unsigned int (&x)[4], unsigned int (&tot)[4]) {
+    __shared__ unsigned int s_w4[kPassThreads / 32][4];
+    __shared__ unsigned int s_t4[4];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    unsigned int incl[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        incl[k] = x[k];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned int y = __shfl_up_sync(0xFFFFFFFFu, incl[k], o);
+            if (lane >= o) incl[k] += y;
+        }
+        if (lane == 31) s_w4[w][k] = incl[k];
+    }
+    __syncthreads();
+    if (w == 0) {
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const unsigned int v = lane < kPassThreads / 32 ? s_w4[lane][k] : 0u;
+            unsigned int inc = v;
+#pragma unroll
+            for (int o = 1; o < kPassThreads / 32; o <<= 1) {
+                const unsigned int y = __shfl_up_sync(0xFFFFFFFFu, inc, o);
+                if (lane >= o) inc += y;
+            }
+            if (lane < kPassThreads / 32) s_w4[lane][k] = inc - v;
+            if (lane == kPassThreads / 32 - 1) s_t4[k] = inc;
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        x[k] = s_w4[w][k] + incl[k] - x[k];  // exclusive prefix
+        tot[k] = s_t4[k];
+    }
+    __syncthreads();
+}
 // CTA-wide sums of N values per thread: warp shuffles, then warp 0 folds the per-warp partials (three barriers, a
 // handful of shared-memory accesses per thread — every thread re-adding all partials cost ~2.5 us per call)
 template <int N>
@@ -943,6 +983,7 @@ k_explain_pass(const PassArgs a) {
     __shared__ unsigned long long s_lbase[kMaxLevels + 1], s_lrun[kMaxLevels];
     __shared__ int s_heavy_p[kPassThreads];
     __shared__ unsigned long long s_heavy_off[kPassThreads];
+    __shared__ uint32_t s_heavy_wa[kPassThreads], s_heavy_wb[kPassThreads];
     const TableView& tv = a.tv;
     for (int i = threadIdx.x; i < kMaxRows; i += blockDim.x) {
         s_w[i] = i < tv.R ? tv.weights[i] : 0;
@@ -1041,19 +1082,26 @@ k_explain_pass(const PassArgs a) {
                 const int q = atomicAdd(&s_nheavy, 1);
                 s_heavy_p[q] = (int)(p - first);
                 s_heavy_off[q] = off;
+                s_heavy_wa[q] = (uint32_t)wa;  // window bounds (masses fit 32 bits: the table is < 2^31 masses wide)
+                s_heavy_wb[q] = (uint32_t)wb;
             }
             __syncthreads();
             const int nheavy = s_nheavy;
-            for (int q = threadIdx.x >> 5; q < nheavy; q += kPassThreads / 32) {
-                const long long hp = first + s_heavy_p[q];
-                unsigned long long run = s_heavy_off[q];
-                const int64_t lo = a.pk.target[hp] - a.pk.thr[hp], hi = a.pk.target[hp] + a.pk.thr[hp];
-                const int64_t sa = lo < 1 ? 1 : lo, sb = hi < limit - 1 ? hi : limit - 1;
+            // four heavy peaks per warp at a time: an 8-lane group takes one peak, lane s of the group its window
+            // words s, s+8, ..., an 8-wide scan places the roots
+            const int grp = threadIdx.x >> 3, sub = lane & 7;
+            for (int q0 = 0; q0 < nheavy; q0 += kPassThreads / 8) {  // uniform trip count
+                const int q = q0 + grp;
+                const bool live = q < nheavy;
+                const uint32_t hp = live ? (uint32_t)(first + s_heavy_p[q]) : 0u;
+                unsigned long long run = live ? s_heavy_off[q] : 0ULL;
+                const int64_t sa = live ? (int64_t)s_heavy_wa[q] : 1, sb = live ? (int64_t)s_heavy_wb[q] : 0;
                 const int64_t w0 = sa >> 5, w1 = sb >> 5;
-                for (int64_t wbase = w0; wbase <= w1; wbase += 32) {
-                    const int64_t wd = wbase + lane;
+                const int64_t w1_all = __reduce_max_sync(0xFFFFFFFFu, (int)(live ? (w1 - w0) : -1));  // longest window in the warp, in words
+                for (int64_t k0 = 0; k0 <= w1_all; k0 += 8) {
+                    const int64_t wd = w0 + k0 + sub;
                     uint64_t x = 0;
-                    if (wd <= w1) {
+                    if (live && wd <= w1) {
                         x = __ldg(last + wd);
                         x = (x | (x >> 1)) & kBit0Mask;
                         if (wd == w0) x &= (1ULL << (2 * (31 - (int)(sa & 31)) + 1)) - 1ULL;
@@ -1062,17 +1110,17 @@ k_explain_pass(const PassArgs a) {
                     const unsigned c = __popcll(x);
                     unsigned incl = c;
 #pragma unroll
-                    for (int o = 1; o < 32; o <<= 1) {
-                        const unsigned y = __shfl_up_sync(0xFFFFFFFFu, incl, o);
-                        if (lane >= o) incl += y;
+                    for (int o = 1; o < 8; o <<= 1) {
+                        const unsigned y = __shfl_up_sync(0xFFFFFFFFu, incl, o, 8);
+                        if (sub >= o) incl += y;
                     }
                     unsigned long long o2 = run + (incl - c);
                     while (x) {
                         const int pos = 63 - __clzll((long long)x);
                         x &= ~(1ULL << pos);
-                        put_root(o2++, (uint32_t)(wd * 32 + (31 - (pos >> 1))), (uint32_t)hp);
+                        put_root(o2++, (uint32_t)(wd * 32 + (31 - (pos >> 1))), hp);
                     }
-                    run += __shfl_sync(0xFFFFFFFFu, incl, 31);
+                    run += __shfl_sync(0xFFFFFFFFu, incl, 7, 8);
                 }
             }
             __syncthreads();
@@ -1328,44 +1376,62 @@ k_explain_pass(const PassArgs a) {
     //      the x-th record of its level goes to A[l][p] + x, A[l][p] = peak_off[p] + (records of p finished at
     //      earlier levels) - (records of level l that belong to peaks before p) ----
     const long long pper = slice_size(P + 1), pfirst = (long long)blockIdx.x * pper;
-    for (int l = 0; l < n_levels; l++) {
-        const uint32_t* lc = a.lvl_cnt + (size_t)l * (size_t)(P + 1);
-        unsigned long long mine = 0;
+    const size_t pstride = (size_t)(P + 1);
+    for (int l4 = 0; l4 < n_levels; l4 += 4) {  // four levels share one reduction
+        unsigned long long mine[4] = {0ULL, 0ULL, 0ULL, 0ULL};
         for (long long li = threadIdx.x; li < pper; li += blockDim.x) {
             const long long q = pfirst + li;
-            if (q <= P) mine += __ldcg(lc + q);
+            if (q <= P) {
+#pragma unroll
+                for (int k = 0; k < 4; k++)
+                    if (l4 + k < n_levels) mine[k] += __ldcg(a.lvl_cnt + (size_t)(l4 + k) * pstride + q);
+            }
         }
-        const unsigned long long tot = block_sum(mine);
-        if (threadIdx.x == 0) a.cta_lvl[(size_t)l * gridDim.x + blockIdx.x] = tot;
+        block_sum_n<4>(mine);
+        if (threadIdx.x < 4 && l4 + (int)threadIdx.x < n_levels) a.cta_lvl[(size_t)(l4 + threadIdx.x) * gridDim.x + blockIdx.x] = mine[threadIdx.x];
     }
     stamp(a, ts++);
     grid_barrier(a, gen);
-    for (int l = 0; l < n_levels; l++) {  // records of level l in the slices before this CTA's
-        unsigned long long mine = 0;
-        for (unsigned b2 = threadIdx.x; b2 < blockIdx.x; b2 += blockDim.x) mine += __ldcg(a.cta_lvl + (size_t)l * gridDim.x + b2);
-        const unsigned long long v = block_sum(mine);
-        if (threadIdx.x == 0) s_lrun[l] = v;
+    for (int l4 = 0; l4 < n_levels; l4 += 4) {  // records of every level in the slices before this CTA's
+        unsigned long long mine[4] = {0ULL, 0ULL, 0ULL, 0ULL};
+        for (unsigned b2 = threadIdx.x; b2 < blockIdx.x; b2 += blockDim.x) {
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+                if (l4 + k < n_levels) mine[k] += __ldcg(a.cta_lvl + (size_t)(l4 + k) * gridDim.x + b2);
+        }
+        block_sum_n<4>(mine);
+        if (threadIdx.x < 4 && l4 + (int)threadIdx.x < n_levels) s_lrun[l4 + threadIdx.x] = mine[threadIdx.x];
     }
     __syncthreads();
     for (long long l0 = 0; l0 < pper; l0 += blockDim.x) {
         const long long q = pfirst + l0 + threadIdx.x;
         const bool ok = l0 + threadIdx.x < pper && q <= P;
         unsigned long long poff = 0;
-        for (int l = 0; l < n_levels; l++) {  // first pass: start of peak q inside level l
-            const unsigned int x = ok ? __ldcg(a.lvl_cnt + (size_t)l * (size_t)(P + 1) + q) : 0u;
-            unsigned int tot;
-            const unsigned long long before = s_lrun[l];  // read before the scan's barriers: thread 0 advances it after them
-            const unsigned long long start = before + block_scan32(x, &tot);
-            if (ok) a.lvl_A[(size_t)l * (size_t)(P + 1) + q] = start;
-            poff += start;
-            if (threadIdx.x == 0) s_lrun[l] += tot;
+        for (int l4 = 0; l4 < n_levels; l4 += 4) {  // first pass: start of peak q inside every level
+            unsigned int x[4], tot[4];
+            unsigned long long before[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                x[k] = (ok && l4 + k < n_levels) ? __ldcg(a.lvl_cnt + (size_t)(l4 + k) * pstride + q) : 0u;
+                before[k] = l4 + k < n_levels ? s_lrun[l4 + k] : 0ULL;  // read before the scan's barriers: advanced after them
+            }
+            block_scan32x4(x, tot);
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                if (l4 + k < n_levels) {
+                    const unsigned long long start = before[k] + x[k];
+                    if (ok) a.lvl_A[(size_t)(l4 + k) * pstride + q] = start;
+                    poff += start;
+                }
+            }
+            if (threadIdx.x < 4 && l4 + (int)threadIdx.x < n_levels) s_lrun[l4 + threadIdx.x] += tot[threadIdx.x];
             __syncthreads();
         }
         if (ok) {
             a.peak_off[q] = poff;
             unsigned long long cum = 0;
             for (int l = 0; l < n_levels; l++) {  // second pass: the placement table
-                const size_t at = (size_t)l * (size_t)(P + 1) + q;
+                const size_t at = (size_t)l * pstride + q;
                 const unsigned long long start = a.lvl_A[at];
                 a.lvl_A[at] = poff + cum - start;
                 cum += __ldcg(a.lvl_cnt + at);
@@ -1377,19 +1443,31 @@ k_explain_pass(const PassArgs a) {
     stamp(a, ts++);
     grid_barrier(a, gen);
 
-    // ---- permute: level order -> peak order ----
+    // ---- permute: level order -> peak order (four records per thread in flight) ----
     {
         unsigned long long* recs64 = reinterpret_cast<unsigned long long*>(a.recs);
         const unsigned long long j0 = n_comps * blockIdx.x / gridDim.x, j1 = n_comps * (blockIdx.x + 1) / gridDim.x;
-        int l = 0;
-        for (unsigned long long jb = j0; jb < j1; jb += blockDim.x) {
-            const unsigned long long j = jb + threadIdx.x;
-            if (j < j1) {
-                while (l + 1 < n_levels && j >= s_lbase[l + 1]) l++;
-                const uint32_t p = __ldcg(a.tmp_peak + j);
-                const unsigned long long dst = __ldcg(a.lvl_A + (size_t)l * (size_t)(P + 1) + p) + (j - s_lbase[l]);
-                for (int q = 0; q < nw; q++) recs64[dst * (unsigned long long)nw + q] = __ldcg(a.tmp_recs + j * (unsigned long long)nw + q);
+        for (unsigned long long jb = j0; jb < j1; jb += 4ULL * blockDim.x) {
+            unsigned long long j[4], dst[4];
+            uint32_t pk[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                j[u] = jb + (unsigned long long)u * blockDim.x + threadIdx.x;
+                pk[u] = j[u] < j1 ? __ldcg(a.tmp_peak + j[u]) : 0u;
             }
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                dst[u] = 0;
+                if (j[u] < j1) {
+                    int l = 0;
+                    while (l + 1 < n_levels && j[u] >= s_lbase[l + 1]) l++;
+                    dst[u] = __ldcg(a.lvl_A + (size_t)l * pstride + pk[u]) + (j[u] - s_lbase[l]);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++)
+                if (j[u] < j1)
+                    for (int q = 0; q < nw; q++) recs64[dst[u] * (unsigned long long)nw + q] = __ldcg(a.tmp_recs + j[u] * (unsigned long long)nw + q);
         }
     }
     stamp(a, ts++);
