@@ -614,7 +614,7 @@ int sst_classify_launch(sst_ctx* ctx, const sst_table* t, double precision, doub
     CK(cudaStreamSynchronize(ctx->stream2));
     if (ctx->CF && ctx->CB) {
         KTimer kt(ctx, SST_K_CLASSIFY);
-        k_classify<<<dim3((unsigned)((ctx->CF + 255) / 256), (unsigned)ctx->CB), 256, 0, ctx->stream>>>(view_of(t), (const double*)ctx->d_cobs.p, ctx->CF,
+        k_classify<<<dim3((unsigned)((ctx->CF + 255) / 256), (unsigned)((ctx->CB + kClassifyPerThread - 1) / kClassifyPerThread)), 256, 0, ctx->stream>>>(view_of(t), (const double*)ctx->d_cobs.p, ctx->CF,
                                                                               (const double*)ctx->d_coff.p, ctx->CB, precision, tolerance,
                                                                               (uint8_t*)ctx->d_cout.p);
         kt.stop(1);
@@ -648,7 +648,7 @@ int sst_classify_async(sst_ctx* ctx, const sst_table* t, const double* observed,
     if (!F || !B) return SST_OK;
     CK(cudaMemcpyAsync(ctx->d_cobs.p, observed, (size_t)F * 8, cudaMemcpyHostToDevice, ctx->stream2));
     CK(cudaMemcpyAsync(ctx->d_coff.p, offsets, (size_t)B * 8, cudaMemcpyHostToDevice, ctx->stream2));
-    k_classify<<<dim3((unsigned)((F + 255) / 256), (unsigned)B), 256, 0, ctx->stream2>>>(view_of(t), (const double*)ctx->d_cobs.p, F,
+    k_classify<<<dim3((unsigned)((F + 255) / 256), (unsigned)((B + kClassifyPerThread - 1) / kClassifyPerThread)), 256, 0, ctx->stream2>>>(view_of(t), (const double*)ctx->d_cobs.p, F,
                                                                                        (const double*)ctx->d_coff.p, B, precision, tolerance,
                                                                                        (uint8_t*)ctx->d_cout.p);
     CK(cudaGetLastError());

@@ -184,38 +184,46 @@ k_stage_f64(const double* __restrict__ mass, const double* __restrict__ thr, con
 }
 
 // ---------------- N2: fused fragment classification ----------------
-// One thread per (breakage offset b = blockIdx.y, fragment f), breakage-major like the reference's concat
-// (fragment_classification.py:39-49): standard-unit mass = observed - offset_b (offset_b = breakage weight * precision,
-// multiplied on the host exactly as the reference does), threshold = tolerance * observed, then the validity probe
-// (:52-67 -> is_valid_mass) and the singleton test (:104-119: some row weight, 0 included, inside the window).
-// out bits: 1 valid, 2 out-of-table value met before any hit (the reference raises), 4 singleton.
+// One thread per fragment f and group of kClassifyPerThread breakage offsets (blockIdx.y), output breakage-major
+// like the reference's concat (fragment_classification.py:39-49): standard-unit mass = observed - offset_b (offset_b =
+// breakage weight * precision, multiplied on the host exactly as the reference does), threshold = tolerance *
+// observed (integerised once per fragment), then the validity probe (:52-67 -> is_valid_mass) and the singleton test
+// (:104-119: some row weight, 0 included, inside the window).  The probes of a thread are independent: their
+// last-row loads overlap.  out bits: 1 valid, 2 out-of-table value met before any hit (the reference raises), 4 singleton.
+constexpr int kClassifyPerThread = 3;
 __global__ void __launch_bounds__(256)
 k_classify(TableView tv, const double* __restrict__ observed, int64_t F, const double* __restrict__ offsets, int B,
            double precision, double tolerance, uint8_t* __restrict__ out) {
     __shared__ int32_t s_w[kMaxRows];
-    __shared__ double s_off[64];
     for (int i = threadIdx.x; i < kMaxRows; i += blockDim.x) s_w[i] = i < tv.R ? tv.weights[i] : 0x7FFFFFFF;
-    for (int i = threadIdx.x; i < B && i < 64; i += blockDim.x) s_off[i] = offsets[i];
     __syncthreads();
     const int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int b = blockIdx.y;  // one breakage offset per grid row: F*B independent probes in flight
     if (f >= F) return;
     const double obs = observed[f];
-    const double thr = __dmul_rn(tolerance, obs);
-    const double su = __dsub_rn(obs, b < 64 ? s_off[b] : offsets[b]);
-    int64_t t, h;
-    integerise(su, thr, precision, tolerance, t, h);
-    uint8_t code = valid_code(tv, t, h);  // 0 / 1 / 2
-    // singleton: smallest row weight >= lo is <= hi
-    const int64_t lo = t - h, hi = t + h;
-    int a = 0, z = tv.R;  // first index with w >= lo
-    while (a < z) {
-        const int mid = (a + z) >> 1;
-        if ((int64_t)s_w[mid] < lo) a = mid + 1;
-        else z = mid;
+    const int64_t h = (int64_t)ceil(__ddiv_rn(__dmul_rn(tolerance, obs), precision));  // the same for every offset
+    const int b0 = blockIdx.y * kClassifyPerThread;
+    int64_t t[kClassifyPerThread];
+    uint8_t code[kClassifyPerThread];
+#pragma unroll
+    for (int k = 0; k < kClassifyPerThread; k++) {
+        const int b = b0 + k < B ? b0 + k : B - 1;
+        t[k] = (int64_t)rint(__ddiv_rn(__dsub_rn(obs, __ldg(offsets + b)), precision));
     }
-    if (a < tv.R && (int64_t)s_w[a] <= hi) code |= 4;
-    out[(int64_t)b * F + f] = code;
+#pragma unroll
+    for (int k = 0; k < kClassifyPerThread; k++) code[k] = valid_code(tv, t[k], h);  // 0 / 1 / 2
+#pragma unroll
+    for (int k = 0; k < kClassifyPerThread; k++) {
+        // singleton: smallest row weight >= lo is <= hi
+        const int64_t lo = t[k] - h, hi = t[k] + h;
+        int a = 0, z = tv.R;  // first index with w >= lo
+        while (a < z) {
+            const int mid = (a + z) >> 1;
+            if ((int64_t)s_w[mid] < lo) a = mid + 1;
+            else z = mid;
+        }
+        if (a < tv.R && (int64_t)s_w[a] <= hi) code[k] |= 4;
+        if (b0 + k < B) out[(int64_t)(b0 + k) * F + f] = code[k];
+    }
 }
 
 // ---------------- MEMO phase A: sequential first-visit replay, one thread per peak ----------------
