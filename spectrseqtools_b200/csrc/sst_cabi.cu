@@ -30,6 +30,7 @@ struct DevBuf {  // grow-only device scratch
 struct sst_table {
     uint64_t* tbl = nullptr;
     uint4* H = nullptr;
+    uint32_t* d_any = nullptr;  // last-row summary, one bit per table word (k_last_row_summary)
     int32_t* d_weights = nullptr;
     int32_t* d_step = nullptr;
     int32_t* d_shift = nullptr;
@@ -203,14 +204,25 @@ int launch_build(sst_ctx* ctx, sst_table* t) {
 }
 
 int launch_transpose(sst_ctx* ctx, sst_table* t) {
-    if (!t->H) return SST_OK;
+    // every table path (build, upload, rebuild) comes through here: the last-row summary for the classification
+    // probes is derived first and timed with the row masks
+    auto summary = [&]() {
+        k_last_row_summary<<<(unsigned)((t->C + 255) / 256), 256, 0, ctx->stream>>>(t->tbl + (int64_t)(t->R - 1) * t->C, t->C, t->d_any);
+    };
+    if (!t->H) {
+        summary();
+        CK(cudaGetLastError());
+        CK(cudaStreamSynchronize(ctx->stream));
+        return SST_OK;
+    }
     KTimer kt(ctx, SST_K_TRANSPOSE);
     cudaEvent_t e0 = ctx->tev[0], e1 = ctx->tev[1];
     CK(cudaEventRecord(e0, ctx->stream));
+    summary();
     k_transpose_masks<<<(unsigned)t->n_tiles, 256, 0, ctx->stream>>>(t->tbl, t->R, t->C, t->H);
     CK(cudaGetLastError());
     CK(cudaEventRecord(e1, ctx->stream));
-    kt.stop(1);
+    kt.stop(2);
     CK(cudaEventSynchronize(e1));
     CK(cudaEventElapsedTime(&t->transpose_ms, e0, e1));
     flush_timers(ctx);
@@ -264,6 +276,7 @@ int alloc_table(sst_ctx* ctx, sst_table* t, const int64_t* weights, int R, int64
     CK(cudaMalloc(&t->d_step, (size_t)kMaxRows * 4));
     CK(cudaMalloc(&t->d_shift, (size_t)kMaxRows * 4));
     CK(cudaMalloc(&t->d_flags, (size_t)(t->n_tiles + 1) * kBuildMaxWarps * sizeof(int)));
+    CK(cudaMalloc(&t->d_any, (size_t)(C / 32 + 2) * sizeof(uint32_t)));
     CK(cudaMemcpyAsync(t->d_weights, w.data(), (size_t)R * 4, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(t->d_step, st.data(), (size_t)R * 4, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(t->d_shift, sh.data(), (size_t)R * 4, cudaMemcpyHostToDevice, ctx->stream));
@@ -276,6 +289,7 @@ void free_table(sst_table* t) {
     if (!t) return;
     cudaFree(t->tbl);
     cudaFree(t->H);
+    cudaFree(t->d_any);
     cudaFree(t->d_weights);
     cudaFree(t->d_step);
     cudaFree(t->d_shift);
@@ -287,6 +301,7 @@ TableView view_of(const sst_table* t) {
     TableView tv;
     tv.tbl = t->tbl;
     tv.H = t->H;
+    tv.any = t->d_any;
     tv.weights = t->d_weights;
     tv.R = t->R;
     tv.C = t->C;
