@@ -31,6 +31,7 @@ struct sst_table {
     uint64_t* tbl = nullptr;
     uint4* H = nullptr;
     uint32_t* d_any = nullptr;  // last-row summary, one bit per table word (k_last_row_summary)
+    uint8_t* d_wbucket = nullptr;  // first row at or above every multiple of 1024 (classification's singleton test)
     int32_t* d_weights = nullptr;
     int32_t* d_step = nullptr;
     int32_t* d_shift = nullptr;
@@ -277,6 +278,13 @@ int alloc_table(sst_ctx* ctx, sst_table* t, const int64_t* weights, int R, int64
     CK(cudaMalloc(&t->d_shift, (size_t)kMaxRows * 4));
     CK(cudaMalloc(&t->d_flags, (size_t)(t->n_tiles + 1) * kBuildMaxWarps * sizeof(int)));
     CK(cudaMalloc(&t->d_any, (size_t)(C / 32 + 2) * sizeof(uint32_t)));
+    std::vector<uint8_t> wb((size_t)(weights[R - 1] >> kWeightBucketShift) + 2);
+    for (size_t k = 0, r = 0; k < wb.size(); k++) {
+        while (r < (size_t)R && weights[r] < (int64_t)(k << kWeightBucketShift)) r++;
+        wb[k] = (uint8_t)r;  // R <= 128
+    }
+    CK(cudaMalloc(&t->d_wbucket, wb.size()));
+    CK(cudaMemcpyAsync(t->d_wbucket, wb.data(), wb.size(), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(t->d_weights, w.data(), (size_t)R * 4, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(t->d_step, st.data(), (size_t)R * 4, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(t->d_shift, sh.data(), (size_t)R * 4, cudaMemcpyHostToDevice, ctx->stream));
@@ -290,6 +298,7 @@ void free_table(sst_table* t) {
     cudaFree(t->tbl);
     cudaFree(t->H);
     cudaFree(t->d_any);
+    cudaFree(t->d_wbucket);
     cudaFree(t->d_weights);
     cudaFree(t->d_step);
     cudaFree(t->d_shift);
@@ -302,6 +311,7 @@ TableView view_of(const sst_table* t) {
     tv.tbl = t->tbl;
     tv.H = t->H;
     tv.any = t->d_any;
+    tv.wbucket = t->d_wbucket;
     tv.weights = t->d_weights;
     tv.R = t->R;
     tv.C = t->C;

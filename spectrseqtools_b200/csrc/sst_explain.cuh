@@ -34,6 +34,7 @@ struct TableView {
     const uint64_t* tbl;  // R x C, row-major (reference layout)
     const uint4* H;       // C*32 row masks
     const uint32_t* any;  // last-row summary: bit (j & 31) of any[j >> 5] = word j of the last row is non-zero (may be null)
+    const uint8_t* wbucket;  // wbucket[k] = first row whose weight is >= k * 1024, k <= w_top / 1024 (may be null)
     const int32_t* weights;
     int R;
     int64_t C;
@@ -193,50 +194,18 @@ k_stage_f64(const double* __restrict__ mass, const double* __restrict__ thr, con
 // last-row loads overlap.  out bits: 1 valid, 2 out-of-table value met before any hit (the reference raises), 4 singleton.
 constexpr int kClassifyPerThread = 3;
 
-// The kernel is bound by the integer pipe (ncu: ALU 68 % of peak, 137 integer instructions per probe in the first
-// version), so a probe whose window fits 32-bit arithmetic takes a lean path (only "any bit" matters), and the
-// singleton test starts with a range check against the heaviest row — almost every fragment is heavier than any
-// single nucleotide — before it searches.  The interior words of a window are answered by the last-row summary
-// (one bit per word, L1 resident): above a few nucleotides nearly every word has a reachable mass, so most probes
-// never touch the table itself; only when the interior is empty are the two end words loaded and masked.  Anything else (negative or huge masses, NaN) takes the general 64-bit path.
-__device__ __forceinline__ uint8_t classify_probe32(const uint64_t* __restrict__ last, const uint32_t* __restrict__ any, int limit,
-                                                     const int32_t* __restrict__ s_w, int R, int t, int h) {
-    const int lo = t - h, hi = t + h;
-    const int a = lo < 1 ? 1 : lo;
-    const int b = hi < limit - 1 ? hi : limit - 1;
-    bool hit = false;
-    if (a <= b) {
-        const int w0 = a >> 5, w1 = b >> 5;
-        // interior words of the window: one bit each in the summary (86 KB for the full table: L1 resident)
-        if (w1 - w0 >= 2) {
-            const int i0 = w0 + 1, i1 = w1 - 1;
-            for (int q = i0 >> 5; q <= (i1 >> 5) && !hit; q++) {
-                uint32_t m = __ldg(any + q);
-                if (q == (i0 >> 5)) m &= ~0u << (i0 & 31);
-                if (q == (i1 >> 5)) m &= ~0u >> (31 - (i1 & 31));
-                hit = m != 0u;
-            }
-        }
-        if (!hit) {  // the two end words decide, masked to the window
-            const uint64_t mf = ~0ULL >> (2 * (a & 31));         // cells of masses >= a in word w0
-            const uint64_t ml = ~0ULL << (2 * (31 - (b & 31)));  // cells of masses <= b in word w1
-            const uint64_t xf = __ldg(last + w0), xl = __ldg(last + w1);
-            hit = ((w0 == w1) ? (xf & mf & ml) : ((xf & mf) | (xl & ml))) != 0ULL;
-        }
-    }
-    uint8_t code = hit ? 1 : ((hi >= limit && hi >= 1 && lo <= hi) ? 2 : 0);
-    // singleton: some row weight (0 included) inside [lo, hi]
-    if (lo <= __ldg(s_w + R - 1) && hi >= 0 && lo <= hi) {
-        int x = 0, z = R;  // first index with w >= lo
-        while (x < z) {
-            const int mid = (x + z) >> 1;
-            if (__ldg(s_w + mid) < lo) x = mid + 1;
-            else z = mid;
-        }
-        if (x < R && __ldg(s_w + x) <= hi) code |= 4;
-    }
-    return code;
-}
+// The first version (one thread per probe, window words scanned with early exits, a binary search over the row
+// weights per probe) was bound by the integer pipe and by per-lane dependent loads (ncu: ALU 68 % of peak, 137 integer
+// instructions per probe).  Now a thread whose three probes fit 32-bit arithmetic takes a staged path:
+//   * the interior words of a window are answered by the last-row summary (one bit per table word, 86 KB for the
+//     full table: L1 resident) - above a few nucleotides nearly every word holds a reachable mass, so most probes
+//     never touch the table itself;
+//   * only when the interior is empty are the two end words loaded and masked to the window;
+//   * the singleton test (some row weight inside the window) starts from a bucket index of the weights
+//     (first row at or above every multiple of 1024) instead of a binary search;
+//   * every stage is done for the three probes together, so their loads are in flight at the same time.
+// Anything else (negative or huge masses, NaN, tables without the side arrays) takes the general 64-bit path.
+constexpr int kWeightBucketShift = 10;
 
 // last-row summary for the probes above: one bit per table word
 __global__ void __launch_bounds__(256)
@@ -250,35 +219,93 @@ k_last_row_summary(const uint64_t* __restrict__ last, int64_t C, uint32_t* __res
 __global__ void __launch_bounds__(256)
 k_classify(TableView tv, const double* __restrict__ observed, int64_t F, const double* __restrict__ offsets, int B,
            double precision, double tolerance, uint8_t* __restrict__ out) {
+    constexpr int K = kClassifyPerThread;
     const int32_t* __restrict__ s_w = tv.weights;  // <= 512 B, read-only: L1 resident, no per-CTA staging and no barrier
     const int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (f >= F) return;
     const double obs = observed[f];
-    const int64_t h = (int64_t)ceil(__ddiv_rn(__dmul_rn(tolerance, obs), precision));  // the same for every offset
-    const int b0 = blockIdx.y * kClassifyPerThread;
-    const uint64_t* last = tv.tbl + (int64_t)(tv.R - 1) * tv.C;
+    const int64_t h64 = (int64_t)ceil(__ddiv_rn(__dmul_rn(tolerance, obs), precision));  // the same for every offset
+    const int b0 = blockIdx.y * K;
+    const uint64_t* __restrict__ last = tv.tbl + (int64_t)(tv.R - 1) * tv.C;
     const int limit = (int)(tv.C * 32);  // < 2^31 (checked when the table is allocated)
-    const bool small_h = h >= 0 && h < (1 << 24);
+    int64_t t64[K];
+    bool lean = tv.any && tv.wbucket && h64 >= 0 && h64 < (1 << 24);
 #pragma unroll
-    for (int k = 0; k < kClassifyPerThread; k++) {
+    for (int k = 0; k < K; k++) {
         const int b = b0 + k < B ? b0 + k : B - 1;
-        const int64_t t = (int64_t)rint(__ddiv_rn(__dsub_rn(obs, __ldg(offsets + b)), precision));
-        uint8_t code;
-        if (tv.any && small_h && t > -(1LL << 30) && t < (1LL << 30)) {
-            code = classify_probe32(last, tv.any, limit, s_w, tv.R, (int)t, (int)h);
-        } else {
-            code = valid_code(tv, t, h);  // 0 / 1 / 2
-            const int64_t lo = t - h, hi = t + h;
+        t64[k] = (int64_t)rint(__ddiv_rn(__dsub_rn(obs, __ldg(offsets + b)), precision));
+        lean = lean && t64[k] > -(1LL << 30) && t64[k] < (1LL << 30);
+    }
+    uint8_t code[K];
+    if (lean) {
+        const int h = (int)h64;
+        const int w_top = __ldg(s_w + tv.R - 1);
+        int lo[K], hi[K], a[K], e[K];
+        uint32_t inner[K];  // summary bits of the window's interior words
+        int x[K];           // singleton search position
+#pragma unroll
+        for (int k = 0; k < K; k++) {
+            lo[k] = (int)t64[k] - h;
+            hi[k] = (int)t64[k] + h;
+            a[k] = lo[k] < 1 ? 1 : lo[k];
+            e[k] = hi[k] < limit - 1 ? hi[k] : limit - 1;
+            inner[k] = 0u;
+            const int i0 = (a[k] >> 5) + 1, i1 = (e[k] >> 5) - 1;  // interior words (a <= e is implied by i0 <= i1)
+            if (i0 <= i1) {
+                const int q0 = i0 >> 5, q1 = i1 >> 5;
+                uint32_t m0 = __ldg(tv.any + q0) & (~0u << (i0 & 31));
+                if (q1 == q0) {
+                    m0 &= ~0u >> (31 - (i1 & 31));
+                } else {
+                    m0 |= __ldg(tv.any + q1) & (~0u >> (31 - (i1 & 31)));
+                    for (int q = q0 + 1; q < q1; q++) m0 |= __ldg(tv.any + q);  // windows wider than 1024 masses
+                }
+                inner[k] = m0;
+            }
+            // first row at or above the bucket of lo (rows ascend; row 0 has weight 0)
+            const int lo_c = lo[k] < 0 ? 0 : lo[k];
+            x[k] = (lo_c <= w_top) ? (int)__ldg(tv.wbucket + (lo_c >> kWeightBucketShift)) : tv.R;
+        }
+        uint64_t ends[K];
+#pragma unroll
+        for (int k = 0; k < K; k++) {
+            ends[k] = 0ULL;
+            if (!inner[k] && a[k] <= e[k]) {  // the two end words decide, masked to the window
+                const int w0 = a[k] >> 5, w1 = e[k] >> 5;
+                const uint64_t mf = ~0ULL >> (2 * (a[k] & 31));         // cells of masses >= a in word w0
+                const uint64_t ml = ~0ULL << (2 * (31 - (e[k] & 31)));  // cells of masses <= e in word w1
+                const uint64_t xf = __ldg(last + w0), xl = __ldg(last + w1);
+                ends[k] = (w0 == w1) ? (xf & mf & ml) : ((xf & mf) | (xl & ml));
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < K; k++) {
+            const bool hit = inner[k] != 0u || ends[k] != 0ULL;
+            code[k] = hit ? 1 : ((hi[k] >= limit && hi[k] >= 1 && lo[k] <= hi[k]) ? 2 : 0);
+            // singleton: some row weight (0 included) inside [lo, hi]
+            if (hi[k] >= 0 && lo[k] <= hi[k]) {
+                int xx = x[k];
+                while (xx < tv.R && __ldg(s_w + xx) < lo[k]) xx++;
+                if (xx < tv.R && __ldg(s_w + xx) <= hi[k]) code[k] |= 4;
+            }
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < K; k++) {
+            code[k] = valid_code(tv, t64[k], h64);  // 0 / 1 / 2
+            const int64_t lo = t64[k] - h64, hi = t64[k] + h64;
             int x = 0, z = tv.R;  // first index with w >= lo
             while (x < z) {
                 const int mid = (x + z) >> 1;
                 if ((int64_t)__ldg(s_w + mid) < lo) x = mid + 1;
                 else z = mid;
             }
-            if (x < tv.R && (int64_t)__ldg(s_w + x) <= hi) code |= 4;
+            if (x < tv.R && (int64_t)__ldg(s_w + x) <= hi) code[k] |= 4;
         }
-        if (b0 + k < B) out[(int64_t)(b0 + k) * F + f] = code;
     }
+#pragma unroll
+    for (int k = 0; k < K; k++)
+        if (b0 + k < B) out[(int64_t)(b0 + k) * F + f] = code[k];
 }
 
 // ---------------- MEMO phase A: sequential first-visit replay, one thread per peak ----------------
