@@ -101,3 +101,32 @@ def test_classify_fragments_frame_semantics():
                 if observed[f] < 50000 and s < su_total + 1 and (s > su_total - 1 or not complete):
                     want.add((f, labels[b]))
     assert {(fi, br) for fi, br, _ in rows} == want
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("tolerance", [2e-6, 10e-6, 4e-4])
+def test_device_classification_edge_windows(tolerance):
+    """The lean probe path of k_classify against the Python oracle on the windows its shortcuts are made for:
+    one-word windows, windows whose interior spans several words of the last-row summary (> 1024 masses wide at
+    4e-4), standard-unit masses below zero, around single nucleotides (singletons), sparse low masses where the two
+    end words decide, the last words of the table and beyond it (code 2)."""
+    from spectrseqtools_b200 import fragment_classification as FC
+
+    w = [0, 305042, 306026, 329053, 345048]  # A/C/G/U (SURVEY App. A)
+    dp = Hh.small_dp_table(w, [False] * 5, [0.0] + [1.0] * 4, 40, tolerance)
+    table = OC.build_bit_table(w, max(w) * 35, 32)
+    limit = table.shape[1] * 32
+    rng = np.random.default_rng(20260118 + int(tolerance * 1e7))
+    breakage = {0: ["c/y_c/y"], 375183: ["c/y_END"], 537119: ["START_c/y"], 912303: ["START_END"], -79965: ["c/y_a/w"]}
+    observed = np.concatenate([
+        rng.uniform(0.0, 1500.0, 40),                       # few nucleotides: sparse table, negative SU masses
+        np.array(w[1:]) * 1e-3 + rng.uniform(-0.002, 0.002, 4),  # around a single nucleotide
+        np.array(w[1:]) * 1e-3 + 537.119,                    # exactly one nucleotide under START_c/y
+        rng.uniform(1500.0, 9000.0, 30),                    # dense part
+        (limit - rng.integers(1, 4000, 12)) * 1e-3,          # the last words of the table
+        (limit + rng.integers(0, 3000, 8)) * 1e-3,           # beyond it
+    ])
+    res = FC.classify_observed(observed, dp, breakage)
+    want = OP.classify_pairs(list(observed), list(breakage), table, w, 32, 1e-3, tolerance)
+    assert np.array_equal(res.flags, want)
+    assert (want & 4).any() and (want & 2).any() and (want & 1).any() and (want == 0).any()
