@@ -89,6 +89,10 @@ struct sst_ctx {
     int CB = 0;
     int64_t VP = 0;
     int* h_misc = nullptr;             // pinned: run summary read back with one copy
+    unsigned long long* h_run = nullptr;  // pinned + mapped: the enumeration pass writes its summary here itself
+    unsigned long long* h_run_dev = nullptr;
+    unsigned int* d_bar = nullptr;     // two grid-barrier counters (64 words apart) that alternate between launches
+    unsigned run_parity = 0;
     uint64_t n_roots = 0, n_comps = 0;
     int rec_width = 0;
     bool have_result = false;
@@ -348,6 +352,9 @@ int sst_ctx_create(int device, sst_ctx** out) {
     for (auto& e : ctx->kev) cudaEventCreate(&e);
     for (auto& e : ctx->tev) cudaEventCreate(&e);
     cudaHostAlloc((void**)&ctx->h_misc, 512, cudaHostAllocDefault);
+    cudaHostAlloc((void**)&ctx->h_run, 512, cudaHostAllocMapped);
+    if (ctx->h_run) cudaHostGetDevicePointer((void**)&ctx->h_run_dev, ctx->h_run, 0);
+    if (cudaMalloc(&ctx->d_bar, 512) == cudaSuccess) cudaMemset(ctx->d_bar, 0, 512);
     *out = ctx;
     return SST_OK;
 }
@@ -365,6 +372,8 @@ void sst_ctx_destroy(sst_ctx* ctx) {
                       &ctx->d_item_meta[0], &ctx->d_item_meta[1], &ctx->d_item_all[0], &ctx->d_item_all[1],
                       &ctx->d_item_ind[0], &ctx->d_item_ind[1], &ctx->d_item_path[0], &ctx->d_item_path[1]};
     if (ctx->h_misc) cudaFreeHost(ctx->h_misc);
+    if (ctx->h_run) cudaFreeHost(ctx->h_run);
+    cudaFree(ctx->d_bar);
     for (DevBuf* b : bufs) cudaFree(b->p);
     cudaEventDestroy(ctx->ev_a);
     cudaEventDestroy(ctx->ev_b);
@@ -925,9 +934,9 @@ int sst_explain_run(sst_ctx* ctx, const sst_table* t, int rec_width, uint64_t me
         // the level-ordered record buffer mirrors the result buffer
         if ((rc = reserve(ctx, ctx->d_tmprecs, ctx->d_recs.cap))) return rc;
         if ((rc = reserve(ctx, ctx->d_tmppeak, (ctx->d_recs.cap / rec_width + 1) * 4))) return rc;
-        // [0,64) totals, [64,320) timestamps, [320,384) flags, [384,388) grid-barrier counter
-        CK(cudaMemsetAsync(ctx->d_scan.p, 0, 512, ctx->stream));
-        int* d_flags = (int*)((char*)ctx->d_scan.p + 320);  // [0] item limit, [1] records overflow, [2] items overflow
+        // totals, timestamps and flags live in shared memory of CTA 0 during the pass, which stores them to pinned host
+        // memory on its way out (h_run: [0,40) totals and timestamps, then the flags)
+        if (!ctx->h_run_dev || !ctx->d_bar) return fail(ctx, SST_ERR_NOMEM, "run summary buffers are missing");
 
         if (ctx->n_memo && attempt == 0) {  // the first-visit map does not depend on the buffer sizes: built once
             uint64_t mcap = memo_capacity ? memo_capacity : ((uint64_t)1 << 20);
@@ -986,9 +995,10 @@ int sst_explain_run(sst_ctx* ctx, const sst_table* t, int rec_width, uint64_t me
         a.rec_capacity = (unsigned long long)(ctx->d_recs.cap / rec_width);
         a.peak_off = (unsigned long long*)ctx->d_peakoff.p;
         a.cta_tot = (unsigned long long*)ctx->d_blocksums.p;
-        a.totals = (unsigned long long*)ctx->d_scan.p;
-        a.flags = d_flags;
-        a.barrier = (unsigned int*)((char*)ctx->d_scan.p + 384);
+        a.barrier = ctx->d_bar + 64 * (ctx->run_parity & 1);
+        a.barrier_next = ctx->d_bar + 64 * ((ctx->run_parity + 1) & 1);
+        ctx->run_parity++;
+        a.host_out = ctx->h_run_dev;
         a.leaf = LeafHash{t->leaf_mul};
         // enough CTAs that every thread gets about one entity of the longest list we can foresee (peaks, window
         // values, the widest level of the previous run), at most one co-resident wave: a single-peak call must not
@@ -1004,14 +1014,13 @@ int sst_explain_run(sst_ctx* ctx, const sst_table* t, int rec_width, uint64_t me
             CK(cudaLaunchCooperativeKernel((const void*)kern, dim3(grid), dim3(kPassThreads), args, 0, ctx->stream));
             kt.stop(1);
         }
-        // one read-back: totals + timestamps + flags
-        CK(cudaMemcpyAsync(ctx->h_misc, ctx->d_scan.p, 384, cudaMemcpyDeviceToHost, ctx->stream));
+        // totals + timestamps + flags arrive in h_run by the kernel's own stores
         if (ctx->n_memo && attempt == 0) CK(cudaMemcpyAsync(ctx->h_misc + 100, ctx->d_memo_misc.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaEventRecord(ctx->ev_run, ctx->stream));  // the device is done here; what follows is the host waking up
         CK(cudaStreamSynchronize(ctx->stream));
         flush_timers(ctx);
-        const unsigned long long* h_tot = (const unsigned long long*)ctx->h_misc;
-        const int* h_flags = ctx->h_misc + 80;
+        const unsigned long long* h_tot = ctx->h_run;
+        const int* h_flags = reinterpret_cast<const int*>(ctx->h_run + 40);
         roots = h_tot[0];
         items = h_tot[1];
         comps = h_tot[2];

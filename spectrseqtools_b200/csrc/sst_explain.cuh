@@ -692,9 +692,12 @@ struct PassArgs {
     unsigned long long* cta_lvl;     // [lvl_cap][gridDim.x] per-level record totals of every CTA's slice of the peaks
     unsigned long long* peak_off;    // [P+1]
     unsigned long long* cta_tot;     // [2][gridDim.x] children / records of every CTA's slice of the nodes
-    unsigned long long* totals;      // [0] roots [1] widest level [2] compositions [3] levels, [8..39] timestamps
-    int* flags;                      // [0] item_limit / level limit hit, [1] records overflow (totals[2] = needed), [2] nodes overflow (totals[1] = needed)
-    unsigned int* barrier;           // arrival counter, zeroed by the host before the launch
+    // run summary, kept in shared memory by thread 0 of CTA 0 (PassSummary below) and stored to host_out on the way out:
+    //   totals [0] roots [1] widest level [2] compositions [3] levels, [8..39] timestamps
+    //   flags  [0] item_limit / level limit hit, [1] records overflow (totals[2] = needed), [2] nodes overflow (totals[1] = needed)
+    unsigned int* barrier;           // arrival counter of this launch (zero: the previous launch cleared it)
+    unsigned int* barrier_next;      // the next launch's counter: cleared by this one (two counters alternate, no memset per run)
+    unsigned long long* host_out;    // pinned host memory, [0,40) = totals, [40,42) = flags as ints: written once, by CTA 0, on the way out
     LeafHash leaf;
 };
 
@@ -727,8 +730,12 @@ __device__ __forceinline__ void grid_barrier(const PassArgs& a, unsigned int& ge
 
 // timestamp k (diagnostics): CTA 0's clock when it gets here.  Right after a grid barrier that is everybody's
 // clock; before one it is only CTA 0's own finish time.  (An atomicMax over all CTAs measured ~1.5 us per stamp.)
-__device__ __forceinline__ void stamp(const PassArgs& a, int k) {
-    if (blockIdx.x == 0 && threadIdx.x == 0 && k < 32) a.totals[8 + k] = globaltimer_ns();
+struct PassSummary {
+    unsigned long long totals[40];
+    int flags[4];
+};
+__device__ __forceinline__ void stamp(PassSummary& sum, int k) {
+    if (blockIdx.x == 0 && threadIdx.x == 0 && k < 32) sum.totals[8 + k] = globaltimer_ns();
 }
 
 // exclusive scan of one value per thread across the CTA; *total = CTA sum.  Warp scans, then warp 0 scans the
@@ -1080,7 +1087,21 @@ k_explain_pass(const PassArgs a) {
         s_ind[i] = i < tv.R ? a.meta.ind[i] : 0;
         s_mod[i] = i < tv.R ? a.meta.is_mod[i] : 0;
     }
-    if (blockIdx.x == 0 && threadIdx.x == 0) a.totals[8] = globaltimer_ns();
+    __shared__ PassSummary s_sum;  // only thread 0 of CTA 0 touches it
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        for (int k = 0; k < 40; k++) s_sum.totals[k] = 0ULL;
+        for (int k = 0; k < 4; k++) s_sum.flags[k] = 0;
+        *a.barrier_next = 0u;  // nobody uses it during this launch
+        s_sum.totals[8] = globaltimer_ns();
+    }
+    // the run summary goes straight to pinned host memory when the pass ends (no copy operation after the launch)
+    auto publish = [&]() {
+        if (blockIdx.x == 0 && threadIdx.x == 0) {
+            for (int k = 0; k < 40; k++) a.host_out[k] = s_sum.totals[k];
+            int* hf = reinterpret_cast<int*>(a.host_out + 40);
+            for (int k = 0; k < 4; k++) hf[k] = s_sum.flags[k];
+        }
+    };
     __syncthreads();
     leaf_table_init(s_leaf, s_w, tv.R, a.leaf);
     __syncthreads();
@@ -1116,16 +1137,17 @@ k_explain_pass(const PassArgs a) {
         }
         const unsigned long long tot = block_sum(mine);
         if (threadIdx.x == 0) a.cta_tot[blockIdx.x] = tot;
-        stamp(a, ts++);
+        stamp(s_sum, ts++);
         grid_barrier(a, gen);
         slice_prefix(a.cta_tot, &base, &n_roots);
         n_items = n_roots;
         if (n_roots > a.cap) {  // the same answer in every CTA: the host grows the buffers and runs the pass again
             if (blockIdx.x == 0 && threadIdx.x == 0) {
-                a.flags[2] = 1;
-                a.totals[0] = n_roots;
-                a.totals[1] = n_roots;
+                s_sum.flags[2] = 1;
+                s_sum.totals[0] = n_roots;
+                s_sum.totals[1] = n_roots;
             }
+            publish();
             return;
         }
         const ItemBuf& out = a.buf[0];
@@ -1215,7 +1237,7 @@ k_explain_pass(const PassArgs a) {
             }
             __syncthreads();
         }
-        stamp(a, ts++);
+        stamp(s_sum, ts++);
         grid_barrier(a, gen);
     }
 
@@ -1228,7 +1250,8 @@ k_explain_pass(const PassArgs a) {
         const ItemBuf& in = a.buf[cur];
         const long long n = (long long)n_items, per = slice_size(n), first = (long long)blockIdx.x * per;
         if (level >= a.lvl_cap || level >= kMaxLevels) {  // cannot happen: the host sizes lvl_cap from the depth bound
-            if (blockIdx.x == 0 && threadIdx.x == 0) a.flags[0] = 1;
+            if (blockIdx.x == 0 && threadIdx.x == 0) s_sum.flags[0] = 1;
+            publish();
             return;
         }
         if (threadIdx.x == 0) s_lbase[level] = rec_run;
@@ -1280,18 +1303,19 @@ k_explain_pass(const PassArgs a) {
         unsigned long long tsum[2] = {mine_k, mine_r};
         block_sum_n<2>(tsum);
         if (threadIdx.x < 2) a.cta_tot[(size_t)threadIdx.x * gridDim.x + blockIdx.x] = tsum[threadIdx.x];
-        stamp(a, ts++);
+        stamp(s_sum, ts++);
         grid_barrier(a, gen);
-        stamp(a, ts++);
+        stamp(s_sum, ts++);
         const ChunkRange cr = balanced_range(a.cta_tot, a.chunk_k, a.chunk_r, n, per, s_pk, s_pr);
         const unsigned long long n_next = cr.ktotal, n_rec = cr.rtotal;
         if (n_next > a.cap || n_next > a.item_limit) {  // the same answer in every CTA
             if (blockIdx.x == 0 && threadIdx.x == 0) {
-                a.flags[n_next > a.item_limit ? 0 : 2] = 1;
-                a.totals[0] = n_roots;
-                a.totals[1] = n_next;
-                a.totals[3] = (unsigned long long)level;
+                s_sum.flags[n_next > a.item_limit ? 0 : 2] = 1;
+                s_sum.totals[0] = n_roots;
+                s_sum.totals[1] = n_next;
+                s_sum.totals[3] = (unsigned long long)level;
             }
+            publish();
             return;
         }
         if (rec_run + n_rec > a.rec_capacity) dry = true;
@@ -1444,7 +1468,7 @@ k_explain_pass(const PassArgs a) {
         }
         rec_run += n_rec;
         level++;
-        stamp(a, ts++);
+        stamp(s_sum, ts++);
         grid_barrier(a, gen);
         cur ^= 1;
         n_items = n_next;
@@ -1454,13 +1478,16 @@ k_explain_pass(const PassArgs a) {
     if (threadIdx.x == 0) s_lbase[level] = rec_run;
     const int n_levels = level;
     if (blockIdx.x == 0 && threadIdx.x == 0) {
-        if (dry) a.flags[1] = 1;
-        a.totals[0] = n_roots;
-        a.totals[1] = widest;
-        a.totals[2] = n_comps;
-        a.totals[3] = (unsigned long long)n_levels;
+        if (dry) s_sum.flags[1] = 1;
+        s_sum.totals[0] = n_roots;
+        s_sum.totals[1] = widest;
+        s_sum.totals[2] = n_comps;
+        s_sum.totals[3] = (unsigned long long)n_levels;
     }
-    if (dry) return;  // the host enlarges the record buffers and runs the pass again
+    if (dry) {  // the host enlarges the record buffers and runs the pass again
+        publish();
+        return;
+    }
 
     // ---- where the records go: peak_off[p] = records of the peaks before p; a level-l record of peak p that is
     //      the x-th record of its level goes to A[l][p] + x, A[l][p] = peak_off[p] + (records of p finished at
@@ -1480,7 +1507,7 @@ k_explain_pass(const PassArgs a) {
         block_sum_n<4>(mine);
         if (threadIdx.x < 4 && l4 + (int)threadIdx.x < n_levels) a.cta_lvl[(size_t)(l4 + threadIdx.x) * gridDim.x + blockIdx.x] = mine[threadIdx.x];
     }
-    stamp(a, ts++);
+    stamp(s_sum, ts++);
     grid_barrier(a, gen);
     for (int l4 = 0; l4 < n_levels; l4 += 4) {  // records of every level in the slices before this CTA's
         unsigned long long mine[4] = {0ULL, 0ULL, 0ULL, 0ULL};
@@ -1530,7 +1557,7 @@ k_explain_pass(const PassArgs a) {
     }
     if (n_levels == 0)
         for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q <= P; q += (long long)gridDim.x * blockDim.x) a.peak_off[q] = 0ULL;
-    stamp(a, ts++);
+    stamp(s_sum, ts++);
     grid_barrier(a, gen);
 
     // ---- permute: level order -> peak order (four records per thread in flight) ----
@@ -1560,7 +1587,8 @@ k_explain_pass(const PassArgs a) {
                     for (int q = 0; q < nw; q++) recs64[dst[u] * (unsigned long long)nw + q] = __ldcg(a.tmp_recs + j[u] * (unsigned long long)nw + q);
         }
     }
-    stamp(a, ts++);
+    stamp(s_sum, ts++);
+    publish();
 }
 
 }  // namespace sst
