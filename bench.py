@@ -382,7 +382,7 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
     rec_width = ctx._last[2]
-    h2d = 8 * len(observed) + 8 * len(offsets) + 20 * len(e_target) + 5 * dev.R
+    h2d = 8 * len(observed) + 8 * len(offsets) + 16 * len(e_target) + 5 * dev.R  # masses + thresholds; the batch-wide budget is a scalar
     d2h = len(v_target) + len(e_target) + 8 * (len(e_target) + 1) + int(batch.n_compositions) * rec_width
     e2e_value = peaks_all * args.steps / e2e_s
 

@@ -150,6 +150,10 @@ int sst_explain_stage(sst_ctx* ctx, const sst_table* t, const int64_t* target, c
  * picks the per-peak budget mode (FREE when no budget can bind, else MEMO if with_memo else EXACT) */
 int sst_explain_stage_f64(sst_ctx* ctx, const sst_table* t, const double* mass, const double* thr, const int32_t* max_mods,
                           int64_t P, const int32_t* ind, const uint8_t* is_mod, double precision, double tolerance, int with_memo);
+/* the same with one modification budget for the whole batch (what calculate_explanations passes, common.py:47-65:
+ * max_modifications = round(rate * max_len)): no per-peak budget array crosses the bus */
+int sst_explain_stage_f64_uniform(sst_ctx* ctx, const sst_table* t, const double* mass, const double* thr, int32_t max_mods,
+                                  int64_t P, const int32_t* ind, const uint8_t* is_mod, double precision, double tolerance, int with_memo);
 /* rec_width 0 = smallest multiple of 8 that holds the longest possible composition of the staged batch */
 int sst_explain_run(sst_ctx* ctx, const sst_table* t, int rec_width, uint64_t memo_capacity, uint64_t* n_roots,
                     uint64_t* n_comps);

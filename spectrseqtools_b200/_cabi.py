@@ -34,7 +34,7 @@ EXPORTS = [
     "sst_timer_start", "sst_timer_stop", "sst_timer_stop_at_run", "sst_stats_reset", "sst_kernel_ms", "sst_flush_l2", "sst_set_item_limit",
     "sst_table_build", "sst_table_upload", "sst_table_rebuild", "sst_table_info", "sst_table_download",
     "sst_table_download_masks", "sst_table_destroy", "sst_is_valid", "sst_valid_stage", "sst_valid_run",
-    "sst_valid_fetch", "sst_valid_stage_f64", "sst_explain", "sst_explain_stage", "sst_explain_stage_f64", "sst_explain_rec_width", "sst_explain_phase_ns",
+    "sst_valid_fetch", "sst_valid_stage_f64", "sst_explain", "sst_explain_stage", "sst_explain_stage_f64", "sst_explain_stage_f64_uniform", "sst_explain_rec_width", "sst_explain_phase_ns",
     "sst_explain_run", "sst_explain_fetch", "sst_classify", "sst_classify_stage", "sst_classify_run", "sst_classify_fetch", "sst_classify_launch", "sst_classify_async", "sst_classify_wait", "sst_length_bounds",
 ]
 
@@ -88,6 +88,7 @@ def load() -> C.CDLL:
             "sst_valid_stage": (C.c_int, [vp, i64p, i64p, C.c_int64]),
             "sst_valid_stage_f64": (C.c_int, [vp, fp, fp, C.c_int64, C.c_double, C.c_double]),
             "sst_explain_stage_f64": (C.c_int, [vp, vp, fp, fp, i32p, C.c_int64, i32p, u8p, C.c_double, C.c_double, C.c_int]),
+            "sst_explain_stage_f64_uniform": (C.c_int, [vp, vp, fp, fp, C.c_int32, C.c_int64, i32p, u8p, C.c_double, C.c_double, C.c_int]),
             "sst_explain_rec_width": (C.c_int, [vp]),
             "sst_explain_phase_ns": (C.c_int, [vp, u64p]),
             "sst_valid_run": (C.c_int, [vp, vp]),
@@ -239,15 +240,23 @@ class Context:
         self._staged_VP = len(m)
 
     def explain_stage_f64(self, table: "DeviceTable", mass, thr, max_mods, ind, is_mod, precision, tolerance, with_memo):
+        """``max_mods``: one int for the whole batch, or one int32 per peak."""
         m = _arr(mass, np.float64)
         h = None if thr is None else _arr(thr, np.float64)
-        mm, iv, im = _arr(max_mods, np.int32), _arr(ind, np.int32), _arr(is_mod, np.uint8)
-        if len(mm) != len(m) or (h is not None and len(h) != len(m)):
+        iv, im = _arr(ind, np.int32), _arr(is_mod, np.uint8)
+        if h is not None and len(h) != len(m):
             raise ValueError("per-peak arrays differ in length")
         if len(iv) != table.R or len(im) != table.R:
             raise ValueError("ind / is_mod need one entry per table row")
-        self._check(self._lib.sst_explain_stage_f64(self._h, table._h, _p(m), _p(h), _p(mm), len(m), _p(iv), _p(im),
-                                                    float(precision), float(tolerance), 1 if with_memo else 0))
+        if np.ndim(max_mods) == 0:
+            self._check(self._lib.sst_explain_stage_f64_uniform(self._h, table._h, _p(m), _p(h), int(max_mods), len(m), _p(iv), _p(im),
+                                                                float(precision), float(tolerance), 1 if with_memo else 0))
+        else:
+            mm = _arr(max_mods, np.int32)
+            if len(mm) != len(m):
+                raise ValueError("per-peak arrays differ in length")
+            self._check(self._lib.sst_explain_stage_f64(self._h, table._h, _p(m), _p(h), _p(mm), len(m), _p(iv), _p(im),
+                                                        float(precision), float(tolerance), 1 if with_memo else 0))
         self._staged_P = len(m)
 
     def valid_run(self, table: "DeviceTable"):

@@ -812,8 +812,12 @@ int sst_explain_stage(sst_ctx* ctx, const sst_table* t, const int64_t* target, c
     return SST_OK;
 }
 
-int sst_explain_stage_f64(sst_ctx* ctx, const sst_table* t, const double* mass, const double* thr, const int32_t* max_mods,
-                          int64_t P, const int32_t* ind, const uint8_t* is_mod, double precision, double tolerance, int with_memo) {
+}  // extern "C"
+
+namespace {
+// max_mods == nullptr: every peak has the budget `uniform_mods` (the array is filled on the device)
+int stage_f64(sst_ctx* ctx, const sst_table* t, const double* mass, const double* thr, const int32_t* max_mods, int32_t uniform_mods,
+              int64_t P, const int32_t* ind, const uint8_t* is_mod, double precision, double tolerance, int with_memo) {
     CK(cudaSetDevice(ctx->device));
     ctx->have_result = false;
     if (P < 0) return fail(ctx, SST_ERR_BAD_ARG, "negative peak count");
@@ -845,13 +849,14 @@ int sst_explain_stage_f64(sst_ctx* ctx, const sst_table* t, const double* mass, 
     if (P) {
         CK(cudaMemcpyAsync(ctx->d_vmass.p, mass, (size_t)P * 8, cudaMemcpyHostToDevice, ctx->stream));
         if (thr) CK(cudaMemcpyAsync(ctx->d_vthrf.p, thr, (size_t)P * 8, cudaMemcpyHostToDevice, ctx->stream));
-        CK(cudaMemcpyAsync(ctx->d_maxmods.p, max_mods, (size_t)P * 4, cudaMemcpyHostToDevice, ctx->stream));
+        if (max_mods) CK(cudaMemcpyAsync(ctx->d_maxmods.p, max_mods, (size_t)P * 4, cudaMemcpyHostToDevice, ctx->stream));
     }
     CK(cudaMemcpyAsync(ctx->d_ind.p, ind, (size_t)t->R * 4, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(ctx->d_ismod.p, is_mod, (size_t)t->R, cudaMemcpyHostToDevice, ctx->stream));
     if (P) {
         k_stage_f64<<<(unsigned)((P + 255) / 256), 256, 0, ctx->stream>>>(
-            (const double*)ctx->d_vmass.p, thr ? (const double*)ctx->d_vthrf.p : nullptr, (const int32_t*)ctx->d_maxmods.p, P, precision,
+            (const double*)ctx->d_vmass.p, thr ? (const double*)ctx->d_vthrf.p : nullptr, (int32_t*)ctx->d_maxmods.p, uniform_mods,
+            max_mods ? 0 : 1, P, precision,
             tolerance, w_min_mod, hi_limit, with_memo ? SST_MODE_MEMO : SST_MODE_EXACT, t->C * 32, (int64_t*)ctx->d_target.p,
             (int64_t*)ctx->d_thr.p, (uint8_t*)ctx->d_mode.p, (uint32_t*)ctx->d_memo_peaks.p, (unsigned long long*)ctx->d_scan.p);
         CK(cudaGetLastError());
@@ -870,6 +875,20 @@ int sst_explain_stage_f64(sst_ctx* ctx, const sst_table* t, const double* mass, 
         ctx->deepest = t->w_min > 0 ? (ctx->max_hi < cap ? ctx->max_hi : cap) / t->w_min : 0;
     }
     return SST_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int sst_explain_stage_f64(sst_ctx* ctx, const sst_table* t, const double* mass, const double* thr, const int32_t* max_mods,
+                          int64_t P, const int32_t* ind, const uint8_t* is_mod, double precision, double tolerance, int with_memo) {
+    if (!max_mods && P) return fail(ctx, SST_ERR_BAD_ARG, "max_mods is null");
+    return stage_f64(ctx, t, mass, thr, max_mods, 0, P, ind, is_mod, precision, tolerance, with_memo);
+}
+
+int sst_explain_stage_f64_uniform(sst_ctx* ctx, const sst_table* t, const double* mass, const double* thr, int32_t max_mods,
+                                  int64_t P, const int32_t* ind, const uint8_t* is_mod, double precision, double tolerance, int with_memo) {
+    return stage_f64(ctx, t, mass, thr, nullptr, max_mods, P, ind, is_mod, precision, tolerance, with_memo);
 }
 
 int sst_explain_run(sst_ctx* ctx, const sst_table* t, int rec_width, uint64_t memo_capacity, uint64_t* n_roots,

@@ -148,8 +148,8 @@ __global__ void k_is_valid_f64(TableView tv, const double* __restrict__ mass, co
 // summary: [0] summed window sizes (upper bound for level-0 items), [1] largest window end, [2] MEMO peaks (their
 // indices are appended to memo_peaks), [3] EXACT peaks.
 __global__ void __launch_bounds__(256)
-k_stage_f64(const double* __restrict__ mass, const double* __restrict__ thr, const int32_t* __restrict__ max_mods, int64_t P,
-            double precision, double tolerance, int64_t w_min_mod, int64_t hi_limit, int slow, int64_t limit,
+k_stage_f64(const double* __restrict__ mass, const double* __restrict__ thr, int32_t* __restrict__ max_mods, int32_t uniform_mods,
+            int use_uniform, int64_t P, double precision, double tolerance, int64_t w_min_mod, int64_t hi_limit, int slow, int64_t limit,
             int64_t* __restrict__ target, int64_t* __restrict__ ithr, uint8_t* __restrict__ mode, uint32_t* __restrict__ memo_peaks,
             unsigned long long* __restrict__ summary) {
     const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -167,7 +167,9 @@ k_stage_f64(const double* __restrict__ mass, const double* __restrict__ thr, con
             if (hi > 0) hi_u = (unsigned long long)hi;
         }
         if (hi < 0) hi = 0;
-        const bool free_ok = !w_min_mod || ((int64_t)max_mods[p] >= hi / w_min_mod && hi < hi_limit);
+        if (use_uniform) max_mods[p] = uniform_mods;  // one budget for the whole batch: filled here instead of copied in
+        const int64_t mm = use_uniform ? (int64_t)uniform_mods : (int64_t)max_mods[p];
+        const bool free_ok = !w_min_mod || (mm >= hi / w_min_mod && hi < hi_limit);
         const int md = free_ok ? MODE_FREE : slow;
         mode[p] = (uint8_t)md;
         if (md == MODE_MEMO) memo_peaks[atomicAdd(summary + 2, 1ULL)] = (uint32_t)p;

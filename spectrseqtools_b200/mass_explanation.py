@@ -190,7 +190,7 @@ def explain_masses(masses: Sequence[float], dp_table: DynamicProgrammingTable, m
     P = len(masses)
     thr = _thr_array(thresholds, P)
     if np.ndim(max_modifications) == 0:
-        max_mods = np.full(P, _budget_int(max_modifications), dtype=np.int32)
+        max_mods = _budget_int(max_modifications)  # one budget for the batch: filled on the device
     else:
         max_mods = np.array([_budget_int(x) for x in max_modifications], dtype=np.int32)
     dev = dp_table.device_table()
