@@ -1046,7 +1046,10 @@ int sst_explain_run(sst_ctx* ctx, const sst_table* t, int rec_width, uint64_t me
         ctx->levels = (int)h_tot[3];
         if (!h_flags[2]) ctx->widest_level = items;
         for (int i = 0; i < 32; i++) ctx->phase_ns[i] = h_tot[8 + i];
-        if (ctx->n_memo && attempt == 0 && ctx->h_misc[101])
+        // too small = an insertion failed, or the load factor passed 3/4 (the replay still finished, but probing a map
+        // that full is slow: the caller grows it, as before)
+        if (ctx->n_memo && attempt == 0 &&
+            (ctx->h_misc[101] || (unsigned)ctx->h_misc[100] > (mp.cap_mask >> 1) + (mp.cap_mask >> 2)))
             return fail(ctx, SST_ERR_MEMO_FULL, "first-visit map is too small (%d slots used)", ctx->h_misc[100]);
         if (h_flags[0])
             return fail(ctx, SST_ERR_NOMEM, "more than %llu partial compositions in one level (%llu): combinatorial blow-up (raise the limit with sst_set_item_limit)",

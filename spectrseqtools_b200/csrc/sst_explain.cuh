@@ -70,8 +70,18 @@ __device__ __forceinline__ uint64_t mix64(uint64_t k) {
 __device__ __forceinline__ unsigned long long memo_key(int64_t peak, uint32_t m) {
     return ((unsigned long long)(peak + 1) << 32) | m;
 }
+// Home slot of a key: the entries of one peak cluster in a window of kMemoRegion slots that starts at a
+// peak-dependent place, so the map of the peak a thread is replaying stays in L2 (a heavy 3-4 nt window visits
+// ~10^4 masses, one dependent probe at a time: with slots scattered over the whole map every probe was a DRAM
+// round trip).  Longer runs simply probe on past the window.
+constexpr uint32_t kMemoRegion = 1u << 14;
+__device__ __forceinline__ uint32_t memo_home(const MemoMap& mp, unsigned long long key) {
+    const uint32_t base = (uint32_t)mix64(key >> 32);
+    const uint32_t off = (uint32_t)mix64(key & 0xFFFFFFFFULL) & (kMemoRegion - 1);
+    return (base + off) & mp.cap_mask;
+}
 __device__ inline int memo_find(const MemoMap& mp, unsigned long long key) {
-    uint32_t h = (uint32_t)mix64(key) & mp.cap_mask;
+    uint32_t h = memo_home(mp, key);
     for (uint32_t probes = 0; probes <= mp.cap_mask; probes++) {
         unsigned long long k = mp.keys[h];
         if (k == key) return (int)h;
@@ -80,15 +90,18 @@ __device__ inline int memo_find(const MemoMap& mp, unsigned long long key) {
     }
     return -1;
 }
-__device__ inline int memo_find_or_insert(const MemoMap& mp, unsigned long long key) {
-    uint32_t h = (uint32_t)mix64(key) & mp.cap_mask;
+// `inserted` counts the slots this thread has claimed; the caller adds it to mp.fill ONCE when it is done (one
+// atomic per claimed slot on a single counter serialised the whole replay) and the host compares the total with
+// the load-factor limit after the launch.
+__device__ inline int memo_find_or_insert(const MemoMap& mp, unsigned long long key, unsigned int& inserted) {
+    uint32_t h = memo_home(mp, key);
     for (uint32_t probes = 0; probes < 4096; probes++) {
         unsigned long long k = mp.keys[h];
         if (k == key) return (int)h;
         if (k == 0ULL) {
             unsigned long long old = atomicCAS(mp.keys + h, 0ULL, key);
             if (old == 0ULL) {
-                if (atomicAdd(mp.fill, 1u) > (mp.cap_mask >> 1) + (mp.cap_mask >> 2)) *mp.overflow = 1;
+                inserted++;
                 return (int)h;  // fresh slot: alive = 0, top = 0 (buffers are zeroed by the host)
             }
             if (old == key) return (int)h;
@@ -343,9 +356,11 @@ k_memo_phase_a(TableView tv, RowMeta meta, PeakBatch pk, const uint32_t* __restr
 
     // arrival at (m, r_in) with budgets; either answers from the map (returns false, sets alive) or
     // opens a frame for the rows (top(m), r_in] that this arrival visits for the first time
+    unsigned int inserted = 0;
     auto arrive = [&](uint32_t m, int r_in, int all, int ind, bool& alive) -> bool {
         alive = false;
-        const int slot = memo_find_or_insert(mp, memo_key(p, m));
+        const uint4 hm = ld_nc_u4(tv.H + m);  // issued before the hash probe: the two round trips overlap
+        const int slot = memo_find_or_insert(mp, memo_key(p, m), inserted);
         if (slot < 0 || sp > kMaxDepth) {
             *mp.overflow = 1;
             return false;
@@ -357,7 +372,7 @@ k_memo_phase_a(TableView tv, RowMeta meta, PeakBatch pk, const uint32_t* __restr
             alive = !mask_empty(A);
             return false;
         }
-        Mask128 pend = mk(ld_nc_u4(tv.H + m));
+        Mask128 pend = mk(hm);
         mask_keep_le(pend, r_in);
         mask_keep_gt(pend, top);
         f_m[sp] = m; f_slot[sp] = slot; f_rin[sp] = (uint8_t)r_in; f_all[sp] = all; f_ind[sp] = ind;
@@ -402,6 +417,7 @@ k_memo_phase_a(TableView tv, RowMeta meta, PeakBatch pk, const uint32_t* __restr
             }
         }
     }
+    if (inserted) atomicAdd(mp.fill, inserted);
 }
 
 // ---------------- N1: sequence-length bounds (compute_sequence_length_bound, reference mass_table.py:343-487) ----------------
