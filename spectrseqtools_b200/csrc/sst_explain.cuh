@@ -70,18 +70,8 @@ __device__ __forceinline__ uint64_t mix64(uint64_t k) {
 __device__ __forceinline__ unsigned long long memo_key(int64_t peak, uint32_t m) {
     return ((unsigned long long)(peak + 1) << 32) | m;
 }
-// Home slot of a key: the entries of one peak cluster in a window of kMemoRegion slots that starts at a
-// peak-dependent place, so the map of the peak a thread is replaying stays in L2 (a heavy 3-4 nt window visits
-// ~10^4 masses, one dependent probe at a time: with slots scattered over the whole map every probe was a DRAM
-// round trip).  Longer runs simply probe on past the window.
-constexpr uint32_t kMemoRegion = 1u << 14;
-__device__ __forceinline__ uint32_t memo_home(const MemoMap& mp, unsigned long long key) {
-    const uint32_t base = (uint32_t)mix64(key >> 32);
-    const uint32_t off = (uint32_t)mix64(key & 0xFFFFFFFFULL) & (kMemoRegion - 1);
-    return (base + off) & mp.cap_mask;
-}
 __device__ inline int memo_find(const MemoMap& mp, unsigned long long key) {
-    uint32_t h = memo_home(mp, key);
+    uint32_t h = (uint32_t)mix64(key) & mp.cap_mask;
     for (uint32_t probes = 0; probes <= mp.cap_mask; probes++) {
         unsigned long long k = mp.keys[h];
         if (k == key) return (int)h;
@@ -94,7 +84,7 @@ __device__ inline int memo_find(const MemoMap& mp, unsigned long long key) {
 // atomic per claimed slot on a single counter serialised the whole replay) and the host compares the total with
 // the load-factor limit after the launch.
 __device__ inline int memo_find_or_insert(const MemoMap& mp, unsigned long long key, unsigned int& inserted) {
-    uint32_t h = memo_home(mp, key);
+    uint32_t h = (uint32_t)mix64(key) & mp.cap_mask;
     for (uint32_t probes = 0; probes < 4096; probes++) {
         unsigned long long k = mp.keys[h];
         if (k == key) return (int)h;
@@ -359,7 +349,6 @@ k_memo_phase_a(TableView tv, RowMeta meta, PeakBatch pk, const uint32_t* __restr
     unsigned int inserted = 0;
     auto arrive = [&](uint32_t m, int r_in, int all, int ind, bool& alive) -> bool {
         alive = false;
-        const uint4 hm = ld_nc_u4(tv.H + m);  // issued before the hash probe: the two round trips overlap
         const int slot = memo_find_or_insert(mp, memo_key(p, m), inserted);
         if (slot < 0 || sp > kMaxDepth) {
             *mp.overflow = 1;
@@ -372,7 +361,7 @@ k_memo_phase_a(TableView tv, RowMeta meta, PeakBatch pk, const uint32_t* __restr
             alive = !mask_empty(A);
             return false;
         }
-        Mask128 pend = mk(hm);
+        Mask128 pend = mk(ld_nc_u4(tv.H + m));
         mask_keep_le(pend, r_in);
         mask_keep_gt(pend, top);
         f_m[sp] = m; f_slot[sp] = slot; f_rin[sp] = (uint8_t)r_in; f_all[sp] = all; f_ind[sp] = ind;
