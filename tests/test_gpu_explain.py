@@ -211,31 +211,3 @@ def test_deep_compositions_use_wide_records():
             total += len(want)
         assert total > 20
 
-
-def test_memo_replay_of_a_heavy_peak_stays_fast():
-    """A 15-nucleotide mass over a six-row alphabet with binding budgets: the first-visit replay visits ~5 * 10^4
-    masses, each many times.  Parity against the C oracle, and a loose bound on the replay's time — a map layout
-    that degenerates for one heavy peak (linear probing through an overfull region) costs hundreds of
-    milliseconds here while every batch-level number stays normal."""
-    from spectrseqtools_b200 import masses as M
-    from spectrseqtools_b200 import mass_table as MT
-
-    seq = MT.SequenceInformation(max_len=12, su_mass=0.0, obs_mass=0.0, modification_rate=0.5)
-    keep = {"A", "C", "G", "U", "0A", "9A"}
-    names = M.EXPLANATION_MASSES.get_column("nucleoside").to_list()
-    dp = MT.DynamicProgrammingTable(M.EXPLANATION_MASSES.filter([n in keep for n in names]), 32, 10e-6, 1e-3, seq)
-    w = [m.mass for m in dp.masses]
-    tab = OC.build_bit_table(w, max(w) * MT.MAX_SEQ_LENGTH, 32)
-    rows = Hh.oracle_rows(dp)
-    ind = OP.individual_budgets(rows, seq.max_len)
-    ctx = dp.device_table().ctx
-    ME.explain_masses([5000.0], dp, max_modifications=2, with_memo=True)  # first launch: module load, local-memory set-up
-    ctx.stats_reset()
-    batch = ME.explain_masses([5000.0], dp, max_modifications=2, with_memo=True)
-    ms, launches = ctx.kernel_stats()["phase_a"]
-    assert launches == 1
-    t, h = OP.integerise(5000.0, None, dp.precision, dp.tolerance)
-    r, off, _ = OC.explain(tab, 32, w, [x.is_modification for x in rows], ind, t, h, 2, True)
-    want = sorted(tuple(int(x) for x in r[off[i]:off[i + 1]]) for i in range(len(off) - 1) if off[i + 1] > off[i])
-    assert batch.canonical(0) == want
-    assert ms < 50.0, f"first-visit replay of one heavy peak took {ms:.1f} ms"
