@@ -742,8 +742,11 @@ int sst_length_bounds(sst_ctx* ctx, const sst_table* t, int64_t target, int64_t 
                 (uint32_t)(pow2 - 1), (int*)((char*)ctx->d_bout.p + 32)};
     {
         KTimer kt(ctx, SST_K_LENGTH_BOUND);
-        k_length_bounds<<<1, 32, 0, ctx->stream>>>(view_of(t), RowMeta{(const int32_t*)ctx->d_ind.p, (const uint8_t*)ctx->d_ismod.p}, target, thr,
-                                                 max_mods, max_len, mp, (int64_t*)ctx->d_bout.p);
+        // smallest stack instance that holds the deepest walk (see k_memo_phase_a)
+        const int64_t frames = (t->w_min > 0 ? (target + thr) / t->w_min : 0) + 2;
+        auto kern = frames <= 16 ? k_length_bounds<16> : frames <= 40 ? k_length_bounds<40> : k_length_bounds<kMaxDepth>;
+        kern<<<1, 32, 0, ctx->stream>>>(view_of(t), RowMeta{(const int32_t*)ctx->d_ind.p, (const uint8_t*)ctx->d_ismod.p}, target, thr,
+                                        max_mods, max_len, mp, (int64_t*)ctx->d_bout.p);
         kt.stop(1);
         CK(cudaGetLastError());
     }
@@ -977,7 +980,9 @@ int sst_explain_run(sst_ctx* ctx, const sst_table* t, int rec_width, uint64_t me
             mp.fill = (unsigned int*)ctx->d_memo_misc.p;
             mp.overflow = (int*)ctx->d_memo_misc.p + 1;
             KTimer kt(ctx, SST_K_PHASE_A);
-            k_memo_phase_a<<<(unsigned)((ctx->n_memo + 63) / 64), 64, 0, ctx->stream>>>(
+            const int64_t frames = ctx->deepest + 2;  // the smallest stack instance that holds the deepest composition
+            auto phase_a = frames <= 16 ? k_memo_phase_a<16> : frames <= 40 ? k_memo_phase_a<40> : k_memo_phase_a<kMaxDepth>;
+            phase_a<<<(unsigned)((ctx->n_memo + 63) / 64), 64, 0, ctx->stream>>>(
                 view_of(t), RowMeta{(const int32_t*)ctx->d_ind.p, (const uint8_t*)ctx->d_ismod.p},
                 PeakBatch{(const int64_t*)ctx->d_target.p, (const int64_t*)ctx->d_thr.p, (const int32_t*)ctx->d_maxmods.p,
                           (const uint8_t*)ctx->d_mode.p, P},

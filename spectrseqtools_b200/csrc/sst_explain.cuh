@@ -314,6 +314,10 @@ k_classify(TableView tv, const double* __restrict__ observed, int64_t F, const d
 }
 
 // ---------------- MEMO phase A: sequential first-visit replay, one thread per peak ----------------
+// DEPTH = frames of the explicit stack (one per nucleotide on the current path): the host picks the smallest instance
+// that holds the longest composition the staged batch can have, because the per-thread stack decides how much local
+// memory the driver reserves for EVERY resident thread of the device (4.8 KB x 303 104 threads = 1.5 GB at DEPTH 96).
+template <int DEPTH>
 __global__ void __launch_bounds__(64)
 k_memo_phase_a(TableView tv, RowMeta meta, PeakBatch pk, const uint32_t* __restrict__ memo_peaks, int n_memo,
                MemoMap mp) {
@@ -337,11 +341,11 @@ k_memo_phase_a(TableView tv, RowMeta meta, PeakBatch pk, const uint32_t* __restr
     const int top_row = tv.R - 1;
 
     // explicit recursion stack (one frame per mass on the current path)
-    uint32_t f_m[kMaxDepth + 1];
-    int f_slot[kMaxDepth + 1];
-    uint8_t f_rin[kMaxDepth + 1], f_cur[kMaxDepth + 1];
-    int f_all[kMaxDepth + 1], f_ind[kMaxDepth + 1];
-    Mask128 f_pend[kMaxDepth + 1], f_new[kMaxDepth + 1];
+    uint32_t f_m[DEPTH + 1];
+    int f_slot[DEPTH + 1];
+    uint8_t f_rin[DEPTH + 1], f_cur[DEPTH + 1];
+    int f_all[DEPTH + 1], f_ind[DEPTH + 1];
+    Mask128 f_pend[DEPTH + 1], f_new[DEPTH + 1];
     int sp = 0;
 
     // arrival at (m, r_in) with budgets; either answers from the map (returns false, sets alive) or
@@ -350,7 +354,7 @@ k_memo_phase_a(TableView tv, RowMeta meta, PeakBatch pk, const uint32_t* __restr
     auto arrive = [&](uint32_t m, int r_in, int all, int ind, bool& alive) -> bool {
         alive = false;
         const int slot = memo_find_or_insert(mp, memo_key(p, m), inserted);
-        if (slot < 0 || sp > kMaxDepth) {
+        if (slot < 0 || sp > DEPTH) {
             *mp.overflow = 1;
             return false;
         }
@@ -443,6 +447,7 @@ __device__ inline int bound_slot(const BoundMap& mp, uint32_t m, unsigned int* f
 }
 
 // out[0] = lower bound, out[1] = upper bound, out[2] = 1 if a window value lies beyond the table (the reference raises)
+template <int DEPTH>  // stack frames, as in k_memo_phase_a
 __global__ void __launch_bounds__(32)
 k_length_bounds(TableView tv, RowMeta meta, int64_t target, int64_t thr, int max_mods, int max_len, BoundMap mp, int64_t* __restrict__ out) {
     __shared__ int32_t s_w[kMaxRows];
@@ -466,19 +471,19 @@ k_length_bounds(TableView tv, RowMeta meta, int64_t target, int64_t thr, int max
     unsigned int fill = 0;
 
     // one frame per mass on the current path
-    uint32_t f_m[kMaxDepth + 2];
-    int f_slot[kMaxDepth + 2];
-    uint8_t f_rin[kMaxDepth + 2], f_cur[kMaxDepth + 2], f_fill[kMaxDepth + 2];
-    int f_all[kMaxDepth + 2], f_ind[kMaxDepth + 2];
-    int8_t f_lo[kMaxDepth + 2], f_up[kMaxDepth + 2];  // running min / max
-    Mask128 f_pend[kMaxDepth + 2];
+    uint32_t f_m[DEPTH + 2];
+    int f_slot[DEPTH + 2];
+    uint8_t f_rin[DEPTH + 2], f_cur[DEPTH + 2], f_fill[DEPTH + 2];
+    int f_all[DEPTH + 2], f_ind[DEPTH + 2];
+    int8_t f_lo[DEPTH + 2], f_up[DEPTH + 2];  // running min / max
+    Mask128 f_pend[DEPTH + 2];
     int sp = 0;
     int ret_lo = 0, ret_up = 0;  // value of the node an arrival / a finished frame stands for
 
     // arrival at node (m, r_in), m > 0: answered from the map (returns false, sets ret_*) or opens a frame
     auto arrive = [&](uint32_t m, int r_in, int all, int ind) -> bool {
         const int slot = bound_slot(mp, m, &fill);
-        if (slot < 0 || sp > kMaxDepth) {
+        if (slot < 0 || sp > DEPTH) {
             *mp.overflow = 1;
             ret_lo = dl;
             ret_up = du;
