@@ -93,6 +93,26 @@ def gen_small_tables(ref):
             arrays[key] = t
             cases.append(dict(weights=w, max_mass=mm, compression=comp, key=key, sha256=sha(t)))
             made += 1
+    # narrow cells over weights the device build accepts (>= 32): the host re-pack of set_up_bit_table is checked on these
+    rng2 = np.random.default_rng(20260122)
+    for comp in (4, 8, 16):
+        made = 0
+        while made < 5:
+            k = int(rng2.integers(1, 6))
+            w = [0] + sorted({int(x) for x in rng2.integers(32, 260, size=k)})
+            mm = max(w) * int(rng2.integers(2, 12)) + int(rng2.integers(0, 40))
+            if made == 4:
+                mm = (mm // comp + 1) * comp - 1  # (max_mass + 1) a multiple of the compression rate
+            try:
+                t = ref.set_up_bit_table(w, mm, comp)
+            except OverflowError:
+                cases.append(dict(weights=w, max_mass=mm, compression=comp, raises="OverflowError", narrow=True))
+                made += 1
+                continue
+            key = f"t{len(arrays)}"
+            arrays[key] = t
+            cases.append(dict(weights=w, max_mass=mm, compression=comp, key=key, sha256=sha(t), narrow=True))
+            made += 1
     # mask-wipe quirk: (35*w+1) % 32 == 0 for the maximum weight
     for w in ([0, 40, 53], [0, 33, 64 + 21]):
         mm = max(w) * 35
@@ -103,6 +123,27 @@ def gen_small_tables(ref):
     np.savez_compressed(GOLD / "tables_small.npz", **arrays)
     (GOLD / "tables_small.json").write_text(json.dumps(cases, indent=0) + "\n")
     print(f"small tables: {len(cases)} cases")
+
+
+def gen_mass_tables(ref):
+    """Byte-per-mass tables (set_up_mass_table, mass_table.py:292-316) for small alphabets, incl. a width whose
+    (max_mass + 1) is a multiple of 32 (where the PACKED table's last-column mask wipes a whole word, the byte table
+    keeps every cell)."""
+    rng = np.random.default_rng(20260121)
+    arrays, cases = {}, []
+    for ci in range(12):
+        k = int(rng.integers(1, 6))
+        w = [0] + sorted({int(x) for x in rng.integers(32, 300, size=k)})
+        mm = max(w) * int(rng.integers(2, 9)) + int(rng.integers(0, 40))
+        if ci % 4 == 0:
+            mm = (mm // 32 + 1) * 32 - 1
+        t = ref.set_up_mass_table(w, mm)
+        key = f"m{ci}"
+        arrays[key] = t
+        cases.append(dict(weights=w, max_mass=mm, key=key, sha256=sha(t)))
+    np.savez_compressed(GOLD / "mass_tables_small.npz", **arrays)
+    (GOLD / "mass_tables_small.json").write_text(json.dumps(cases) + "\n")
+    print(f"byte tables: {len(cases)} cases")
 
 
 def gen_table_shas(ref, full: bool):
@@ -288,7 +329,7 @@ def gen_explain_full(ref, table_sha: str):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--full", action="store_true", help="rebuild the full table with the reference loop (~200 s)")
-    ap.add_argument("--only", default="", help="comma list of: small_tables,shas,explain_small,explain_full")
+    ap.add_argument("--only", default="", help="comma list of: small_tables,mass_tables,shas,explain_small,explain_full")
     args = ap.parse_args()
     if not H.available():
         raise SystemExit("/root/reference not present: golden vectors can only be regenerated in the build container")
@@ -297,6 +338,8 @@ def main():
     only = set(filter(None, args.only.split(",")))
     if not only or "small_tables" in only:
         gen_small_tables(ref)
+    if not only or "mass_tables" in only:
+        gen_mass_tables(ref)
     doc = None
     if not only or "shas" in only:
         doc = gen_table_shas(ref, args.full)

@@ -92,6 +92,21 @@ def build_bit_table_closed_form(weights: Sequence[int], max_mass: int, compressi
     return packed
 
 
+def build_mass_table(weights: Sequence[int], max_mass: int) -> np.ndarray:
+    """Byte-per-mass table, mass_table.py:292-316: cell = 1 if reachable with earlier rows, + 2 if (mass - w_i) is a
+    non-zero cell of the same row (ascending in-place sweep = unbounded use of the row); cell (0, 0) = 3."""
+    R = len(weights)
+    t = np.zeros((R, max_mass + 1), dtype=np.uint8)
+    t[0, 0] = 3
+    for i in range(1, R):
+        w = int(weights[i])
+        t[i] = (t[i - 1] != 0).astype(np.uint8)
+        for start in range(0, max_mass + 1 - w, w):  # slabs of width w: sources of a slab are final before it is read
+            stop = min(start + w, max_mass + 1 - w)
+            t[i, start + w : stop + w] += 2 * (t[i, start:stop] != 0).astype(np.uint8)
+    return t
+
+
 def _cell(table: np.ndarray, row: int, mass: int, compression: int) -> int:
     """2-bit-aligned shifted cell value, mass_explanation.py:140-145 (low bits = cell of `mass`)."""
     return int(table[row, mass // compression]) >> (2 * (compression - 1 - mass % compression))

@@ -236,6 +236,8 @@ class Context:
     def valid_stage_f64(self, mass: np.ndarray, thr: Optional[np.ndarray], precision: float, tolerance: float):
         m = _arr(mass, np.float64)
         h = None if thr is None else _arr(thr, np.float64)
+        if h is not None and len(h) != len(m):
+            raise ValueError("per-probe arrays differ in length")
         self._check(self._lib.sst_valid_stage_f64(self._h, _p(m), _p(h), len(m), float(precision), float(tolerance)))
         self._staged_VP = len(m)
 

@@ -156,12 +156,47 @@ class Expr:
     def min(self) -> "Expr":
         return Expr(lambda df: [min(self._fn(df))], self._name)
 
+    @property
+    def str(self) -> "_StrNamespace":
+        return _StrNamespace(self)
+
+
+class _StrNamespace:
+    """``pl.col(x).str``: only the literal-substring test the prediction path uses."""
+
+    def __init__(self, expr: Expr):
+        self._expr = expr
+
+    def contains(self, pattern: str, literal: bool = False, **_kw) -> Expr:
+        import re as _re
+
+        rx = None if literal else _re.compile(pattern)
+        inner = self._expr
+        return Expr(lambda df: [(pattern in a) if rx is None else bool(rx.search(a)) for a in inner._fn(df)], inner._name)
+
+
+def struct(*names: Any) -> Expr:
+    """``pl.struct(a, b, ...)``: one dict per row (what ``map_elements`` callbacks index by column name)."""
+    flat: List[str] = []
+    for n in names:
+        flat.extend(n if isinstance(n, (list, tuple)) else [n])
+    return Expr(lambda df: [dict(zip(flat, row)) for row in zip(*(df._data[n] for n in flat))] if flat else [], flat[0] if flat else "struct")
+
+
+def concat(frames: Iterable["DataFrame"], **_kw) -> "DataFrame":
+    """Vertical concatenation of frames with the same columns."""
+    frames = list(frames)
+    if not frames:
+        return DataFrame()
+    cols = frames[0].columns
+    return DataFrame({c: [x for f in frames for x in f._data[c]] for c in cols})
+
 
 def col(name: str) -> Expr:
     return Expr(lambda df: list(df._data[name]), name)
 
 
-def lit(value: Any) -> Expr:
+def lit(value: Any, dtype: Any = None, **_kw) -> Expr:
     return Expr(lambda df: [value] * df.height, "literal")
 
 
@@ -296,9 +331,40 @@ class DataFrame:
         return DataFrame({k: [x for x, f in zip(v, keep) if f] for k, v in self._data.items()})
 
     def sort(self, by: Any, descending: bool = False) -> "DataFrame":
-        keys = [by] if isinstance(by, str) else list(by)
-        order = sorted(range(self.height), key=lambda i: tuple(self._data[k][i] for k in keys), reverse=descending)
+        keys = [by] if isinstance(by, (str, Expr)) else list(by)
+        cols = [self._data[k] if isinstance(k, str) else k._eval(self) for k in keys]
+        order = sorted(range(self.height), key=lambda i: tuple(c[i] for c in cols), reverse=descending)  # stable, like polars
         return DataFrame({k: [v[i] for i in order] for k, v in self._data.items()})
+
+    def drop(self, *names: Any) -> "DataFrame":
+        gone = set()
+        for n in names:
+            gone.update(n if isinstance(n, (list, tuple)) else [n])
+        return DataFrame({k: list(v) for k, v in self._data.items() if k not in gone})
+
+    def rename(self, mapping: Dict[str, str]) -> "DataFrame":
+        return DataFrame({mapping.get(k, k): list(v) for k, v in self._data.items()})
+
+    def with_row_index(self, name: str = "index", offset: int = 0) -> "DataFrame":
+        data = {name: list(range(offset, offset + self.height))}
+        data.update({k: list(v) for k, v in self._data.items()})
+        return DataFrame(data)
+
+    def write_csv(self, file: Any = None, separator: str = ",", **_kw):
+        def cell(x):
+            if x is None:
+                return ""
+            if isinstance(x, bool):
+                return "true" if x else "false"
+            return str(x)
+
+        lines = [separator.join(self.columns)] + [separator.join(cell(x) for x in row) for row in self.rows()]
+        text = "\n".join(lines) + "\n"
+        if file is None:
+            return text
+        with open(file, "w") as fh:
+            fh.write(text)
+        return None
 
     def sum(self) -> "DataFrame":
         return DataFrame({k: [sum(v)] for k, v in self._data.items()})
@@ -339,6 +405,25 @@ class DataFrame:
         return f"shape: {self.shape}\n{head}\n{body}"
 
 
+def read_csv(source: Any, separator: str = ",", **_kw) -> DataFrame:
+    """Typed read of a small delimited file: int, then float, then true/false, else string (per column)."""
+    with open(source) as fh:
+        rows = [line.rstrip("\n").split(separator) for line in fh if line.strip()]
+    header, body = rows[0], rows[1:]
+
+    def convert(vals: List[str]) -> list:
+        for conv in (int, float):
+            try:
+                return [conv(v) for v in vals]
+            except ValueError:
+                pass
+        if all(v in ("true", "false") for v in vals):
+            return [v == "true" for v in vals]
+        return vals
+
+    return DataFrame({h: convert([r[j] for r in body]) for j, h in enumerate(header)})
+
+
 def install_polars_shim() -> bool:
     """Make ``import polars`` work for the reference's unit test when polars is absent.
 
@@ -355,8 +440,8 @@ def install_polars_shim() -> bool:
     mod = types.ModuleType("polars")
     mod.__spectrseq_shim__ = True
     mod.__doc__ = "spectrseqtools_b200 minimal stand-in for polars (real polars not installed)"
-    for name, obj in dict(DataFrame=DataFrame, Series=Series, Expr=Expr, col=col, lit=lit,
-                          Float64=Float64, Int64=Int64, Utf8=Utf8, String=Utf8).items():
+    for name, obj in dict(DataFrame=DataFrame, Series=Series, Expr=Expr, col=col, lit=lit, struct=struct, concat=concat,
+                          read_csv=read_csv, Float64=Float64, Int64=Int64, Utf8=Utf8, String=Utf8, Boolean=bool).items():
         setattr(mod, name, obj)
     sys.modules["polars"] = mod
     return True

@@ -1021,7 +1021,6 @@ int sst_explain_run(sst_ctx* ctx, const sst_table* t, int rec_width, uint64_t me
         a.cta_tot = (unsigned long long*)ctx->d_blocksums.p;
         a.barrier = ctx->d_bar + 64 * (ctx->run_parity & 1);
         a.barrier_next = ctx->d_bar + 64 * ((ctx->run_parity + 1) & 1);
-        ctx->run_parity++;
         a.host_out = ctx->h_run_dev;
         a.leaf = LeafHash{t->leaf_mul};
         // enough CTAs that every thread gets about one entity of the longest list we can foresee (peaks, window
@@ -1036,6 +1035,7 @@ int sst_explain_run(sst_ctx* ctx, const sst_table* t, int rec_width, uint64_t me
             KTimer kt(ctx, SST_K_EXPLAIN_PASS);
             void* args[] = {(void*)&a};
             CK(cudaLaunchCooperativeKernel((const void*)kern, dim3(grid), dim3(kPassThreads), args, 0, ctx->stream));
+            ctx->run_parity++;  // only a launch that really started clears the other counter (a failed one would leave it stale)
             kt.stop(1);
         }
         // totals + timestamps + flags arrive in h_run by the kernel's own stores

@@ -70,6 +70,10 @@ def classify_observed(observed: Sequence[float], dp_table: DynamicProgrammingTab
     flags are waited for on first access (``.flags`` / ``.wait()``), so an ``explain_masses`` call issued in between
     overlaps it.  ``copy=False`` hands out the context's pinned buffer (valid until the next classification)."""
     observed = np.ascontiguousarray(observed, dtype=np.float64).reshape(-1)
+    if len(observed) and not np.isfinite(observed).all():  # upstream: int(round(nan)) / int(round(inf)) inside is_valid_mass
+        if np.isnan(observed).any():
+            raise ValueError("cannot convert float NaN to integer")
+        raise OverflowError("cannot convert float infinity to integer")
     weights = list(breakage_dict.keys())
     offsets = np.array([w * dp_table.precision for w in weights], dtype=np.float64)  # int * float, as upstream
     dev = dp_table.device_table()
@@ -135,7 +139,7 @@ def classify_fragments(fragment_masses, dp_table: DynamicProgrammingTable, break
     out["breakage"] = [str(labels[i]) for i in order]
     out["is_singleton"] = [bool(res.singleton[b_idx[i], f_idx[i]]) for i in order]
     frame = pl.DataFrame(out)
-    if output_file_path is not None and hasattr(frame, "write_csv"):
+    if output_file_path is not None:
         frame.write_csv(output_file_path, separator="\t")
     return frame
 

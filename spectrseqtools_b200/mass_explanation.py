@@ -68,8 +68,10 @@ def _budget_int(x) -> int:
     """Budgets are only tested with ``> 0`` and decremented by one: ceil() keeps that behaviour for floats."""
     if x is None:
         return _cabi.BUDGET_INF
-    if isinstance(x, float) and (math.isinf(x) or math.isnan(x)):
-        return _cabi.BUDGET_INF if x > 0 or math.isnan(x) else 0
+    if isinstance(x, float) and math.isnan(x):
+        return 0  # upstream tests the budget with `> 0`: NaN never allows a modification
+    if isinstance(x, float) and math.isinf(x):
+        return _cabi.BUDGET_INF if x > 0 else 0
     v = math.ceil(x)
     return max(0, min(int(v), _cabi.BUDGET_INF))
 
@@ -162,6 +164,18 @@ class ExplanationBatch:
         return sorted(tuple(int(r) for r in rec if r) for rec in self.rows(p))
 
 
+def _require_finite(masses: np.ndarray, thresholds: Optional[np.ndarray]):
+    """The reference integerises with ``int(round(x))`` / ``int(np.ceil(x))``: NaN raises ValueError, infinity
+    OverflowError (mass_explanation.py:51-58,107-114).  Raised here, before anything is staged, instead of feeding an
+    undefined float -> int cast to the device.  (A NaN *threshold* entry means "None" = relative in the batched API.)"""
+    if len(masses) and not np.isfinite(masses).all():
+        if np.isnan(masses).any():
+            raise ValueError("cannot convert float NaN to integer")
+        raise OverflowError("cannot convert float infinity to integer")
+    if thresholds is not None and len(thresholds) and np.isinf(thresholds).any():
+        raise OverflowError("cannot convert float infinity to integer")
+
+
 def _thr_array(thresholds, n: int) -> Optional[np.ndarray]:
     """Per-mass absolute thresholds as float64, NaN where the reference would use ``tolerance * mass``."""
     if thresholds is None:
@@ -189,6 +203,7 @@ def explain_masses(masses: Sequence[float], dp_table: DynamicProgrammingTable, m
     masses = np.ascontiguousarray(masses, dtype=np.float64).reshape(-1)
     P = len(masses)
     thr = _thr_array(thresholds, P)
+    _require_finite(masses, thr)
     if np.ndim(max_modifications) == 0:
         max_mods = _budget_int(max_modifications)  # one budget for the batch: filled on the device
     else:
@@ -231,6 +246,7 @@ def are_valid_masses(masses: Sequence[float], dp_table: DynamicProgrammingTable,
     """Batched ``is_valid_mass`` -> uint8 array of _cabi.VALID_* codes (2 = out of table)."""
     masses = np.ascontiguousarray(masses, dtype=np.float64).reshape(-1)
     thr = _thr_array(thresholds, len(masses))
+    _require_finite(masses, thr)
     dev = dp_table.device_table()
     ctx = dev.ctx
     ctx.valid_stage_f64(masses, thr, dp_table.precision, dp_table.tolerance)

@@ -123,15 +123,39 @@ def set_up_bit_table(integer_masses, max_mass: int, compression_rate: int):
     """2-bit reachability table as a host ndarray, bit-identical to the reference (mass_table.py:207-248).
 
     Built on the GPU and copied back; callers that only need the table for explanation calls should use
-    ``DynamicProgrammingTable`` (no copy).
+    ``DynamicProgrammingTable`` (no copy).  The device layout is 32 masses per ``uint64`` cell — the only one the
+    reference ever uses (``COMPRESSION_RATE``); the narrower layouts it also accepts (4 / 8 / 16 masses per
+    ``uint8`` / ``uint16`` / ``uint32`` cell) are re-packed on the host from a slightly wider device table, with that
+    layout's own last-column mask.  ``DynamicProgrammingTable`` itself is 32-per-cell only.
     """
-    return device_table(integer_masses, max_mass, compression_rate).download()
+    if compression_rate == 32:
+        return device_table(integer_masses, max_mass, compression_rate).download()
+    settings = select_table_building_settings(compression_rate)  # ValueError for anything but 4 / 8 / 16 / 32
+    weights = [int(w) for w in integer_masses]
+    if any(w < compression_rate for w in weights[1:]):
+        raise ValueError(f"weights below the compression rate ({compression_rate}): the reference's in-place word loop is not a closed form there")
+    mask = _last_column_mask(int(max_mass), compression_rate)    # numpy semantics (may raise OverflowError, as upstream)
+    ctype = settings["type"]
+    max_col = int(np.ceil((max_mass + 1) / compression_rate))
+    wide = device_table(weights, int(max_mass) + 64, 32).download()  # no masked cell below max_col * compression_rate
+    n = max_col * compression_rate
+    cells = np.zeros((wide.shape[0], wide.shape[1] * 32), dtype=np.uint8)
+    for k in range(32):
+        cells[:, k::32] = ((wide >> np.uint64(2 * (31 - k))) & np.uint64(3)).astype(np.uint8)
+    view = cells[:, :n].reshape(wide.shape[0], max_col, compression_rate)
+    out = np.zeros((wide.shape[0], max_col), dtype=ctype)
+    for k in range(compression_rate):
+        out |= view[:, :, k].astype(ctype) << ctype(2 * (compression_rate - 1 - k))
+    out[:, -1] &= ctype(mask)
+    return out
 
 
 def set_up_mass_table(integer_masses, max_mass):
     """Byte-per-mass variant (reference mass_table.py:292-316): value 1 = reachable with earlier rows,
-    +2 = one more copy of this row.  Derived from the packed device table (no separate kernel)."""
-    packed = set_up_bit_table(list(integer_masses), max_mass, 32)
+    +2 = one more copy of this row.  Derived from the packed device table (no separate kernel), which is built 64
+    masses wider than asked: the packed layout masks its last word (:246) — wiping it entirely when max_mass + 1 is
+    a multiple of 32 — while the byte table keeps every cell up to max_mass."""
+    packed = set_up_bit_table(list(integer_masses), max_mass + 64, 32)
     R, C = packed.shape
     out = np.zeros((R, C * 32), dtype=np.uint8)
     for k in range(32):
@@ -148,7 +172,7 @@ def set_table_path(precision, compression_rate):
 def load_dp_table(table_path, integer_masses):
     """Reference signature (mass_table.py:319-340).  The GPU rebuild is faster than reading 582 MB from
     disk, so nothing is cached on disk; the path only carries the compression rate, as upstream."""
-    compression_rate = int(table_path.split(".")[-1].rstrip("_per_cell"))
+    compression_rate = int(table_path.split(".")[-1].removesuffix("_per_cell"))
     max_mass = max(integer_masses) * MAX_SEQ_LENGTH
     if compression_rate == 1:
         return set_up_mass_table(integer_masses, max_mass)

@@ -16,19 +16,34 @@ def test_small_tables_bit_exact():
     arrays = np.load(Hh.GOLD / "tables_small.npz")
     done = 0
     for c in cases:
-        if c.get("raises") or c["compression"] != 32 or min(c["weights"][1:]) < 32:
+        if c.get("raises") or min(c["weights"][1:]) < 32:
             continue
-        got = MT.set_up_bit_table(c["weights"], c["max_mass"], 32)
+        got = MT.set_up_bit_table(c["weights"], c["max_mass"], c["compression"])  # 4 / 8 / 16 per cell: host re-pack
         want = arrays[c["key"]]
-        assert got.dtype == np.uint64 and got.shape == want.shape
+        assert got.dtype == want.dtype and got.shape == want.shape
         assert np.array_equal(got, want), c
         done += 1
-    assert done >= 8
+    assert done >= 23
+
+
+def test_byte_tables_bit_exact():
+    """set_up_mass_table / load_dp_table(rate 1) against tables made by the reference's own function
+    (mass_table.py:292-316), incl. widths where the packed table's last word is wiped by its mask."""
+    cases = Hh.load_json("mass_tables_small.json")
+    arrays = np.load(Hh.GOLD / "mass_tables_small.npz")
+    for c in cases:
+        MT.clear_table_cache()
+        got = MT.set_up_mass_table(c["weights"], c["max_mass"])
+        assert got.dtype == np.uint8 and got.shape == arrays[c["key"]].shape
+        assert np.array_equal(got, arrays[c["key"]]), c
+    assert any((c["max_mass"] + 1) % 32 == 0 for c in cases)
 
 
 def test_unsupported_tables_fail_loudly():
     with pytest.raises(ValueError):
-        MT.set_up_bit_table([0, 40, 50], 500, 16)      # only 32 masses per cell on the device
+        _cabi.context().build_table([0, 40, 50], 500, 16, 2**32 - 1)  # the device layout is 32 masses per cell only
+    with pytest.raises(ValueError):
+        MT.set_up_bit_table([0, 20, 50], 500, 16)      # narrow cells are re-packed from a device table: weights >= 32
     with pytest.raises(ValueError):
         MT.set_up_bit_table([0, 40, 50], 500, 5)       # not a rate the reference knows either
     with pytest.raises(ValueError):

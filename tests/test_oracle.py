@@ -28,6 +28,17 @@ def test_small_tables_match_reference():
             assert np.array_equal(OP.build_bit_table_closed_form(c["weights"], c["max_mass"], c["compression"]), want), c
 
 
+def test_byte_tables_match_reference():
+    """set_up_mass_table (mass_table.py:292-316): the numpy restatement against reference-made tables."""
+    cases = Hh.load_json("mass_tables_small.json")
+    arrays = np.load(Hh.GOLD / "mass_tables_small.npz")
+    assert len(cases) >= 10
+    for c in cases:
+        got = OP.build_mass_table(c["weights"], c["max_mass"])
+        assert got.dtype == np.uint8 and np.array_equal(got, arrays[c["key"]]), c
+        assert Hh.sha(got) == c["sha256"]
+
+
 @pytest.mark.parametrize("name", ["acgu", "quirk_365045", "full"])
 def test_big_table_sha(name):
     doc = Hh.load_json("tables_sha.json")[name]

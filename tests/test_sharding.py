@@ -142,5 +142,65 @@ def test_two_rank_gloo_gather_equals_single_rank():
     assert np.array_equal(valid, want_valid)
 
 
+# ---------------------------------------------------------------- GPU: the real device callback on two ranks
+def _gpu_workload():
+    from spectrseqtools_b200 import mass_table as MT
+    from spectrseqtools_b200 import synthetic as S
+
+    wl = S.make_workload("C2", 3000)
+    seq = MT.SequenceInformation(max_len=wl.max_len, su_mass=0.0, obs_mass=0.0, modification_rate=0.5)
+    dp = MT.DynamicProgrammingTable(S.alphabet_frame(wl.alphabet), 32, wl.ppm, 1e-3, seq, device=0)
+    masses = np.concatenate([wl.explain_mass, [1e9, 0.0002]])       # + an out-of-table mass and a zero-window mass
+    thr = np.concatenate([wl.explain_thr, [0.01, np.nan]])
+    return wl, dp, masses, thr
+
+
+def _gpu_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        wl, dp, masses, thr = _gpu_workload()
+        batch = sharding.explain_masses_sharded(masses, dp, max_modifications=wl.max_modifications, thresholds=thr)
+        valid = sharding.are_valid_masses_sharded(wl.valid_mass[:5000], dp, wl.valid_thr[:5000])
+        if rank == 0:
+            q.put((batch.status, batch.offsets, batch.records, valid))
+        else:
+            assert batch is None and valid is None
+            q.put("ok")
+    finally:
+        dist.destroy_process_group()
+
+
+import pytest  # noqa: E402
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_device_path_equals_single_rank(world):
+    """explain_masses_sharded / are_valid_masses_sharded with the CUDA callback on `world` ranks (one process per
+    rank, all on GPU 0 here; one GPU each under torchrun) == the single-rank batch call: status, offsets, records.
+    world = 3 leaves ragged shards; the appended out-of-table and zero-window masses land on different ranks."""
+    from spectrseqtools_b200 import mass_explanation as ME
+
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_gpu_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = [q.get(timeout=600) for _ in range(world)]
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    status, offsets, records, valid = next(g for g in got if not isinstance(g, str))
+    wl, dp, masses, thr = _gpu_workload()
+    one = ME.explain_masses(masses, dp, max_modifications=wl.max_modifications, thresholds=thr)
+    assert np.array_equal(status, one.status) and status[-2] == 2 and status[-1] & 1
+    assert np.array_equal(offsets, one.offsets) and offsets[-1] > 3000
+    W = min(records.shape[1], one.records.shape[1])
+    assert np.array_equal(records[:, :W], one.records[:, :W]) and not records[:, W:].any() and not one.records[:, W:].any()
+    assert np.array_equal(valid, ME.are_valid_masses(wl.valid_mass[:5000], dp, wl.valid_thr[:5000]))
+
+
 if __name__ == "__main__":
     sys.exit(0)
