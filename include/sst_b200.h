@@ -158,6 +158,17 @@ int sst_explain_stage_f64_uniform(sst_ctx* ctx, const sst_table* t, const double
 int sst_explain_run(sst_ctx* ctx, const sst_table* t, int rec_width, uint64_t memo_capacity, uint64_t* n_roots,
                     uint64_t* n_comps);
 int sst_explain_rec_width(const sst_ctx* ctx); /* record width of the last run */
+/* Which enumeration pass sst_explain_run uses: 0 = automatic (default: the depth-first pass — count -> scan -> fill over
+ * window values, one grid barrier — for batches of at most 16 nucleotides per composition, the level-synchronous pass
+ * for deeper ones and for batches the depth-first pass gives back because one window value has too many partial
+ * compositions for a single thread), 1 = always level-synchronous, 2 = depth-first or fail.  Both passes return the
+ * same compositions per peak; the order of the records inside a peak differs. */
+int sst_set_pass(sst_ctx* ctx, int which);
+int sst_last_pass(const sst_ctx* ctx); /* 1 = level-synchronous, 2 = depth-first produced the last result */
+/* diagnostics of the depth-first pass: enable != 0 makes the following runs record %globaltimer (ns) of every CTA at
+ * [0] start, [1] first tile's window values counted, [2] its roots written, [3] count phase done, [4] grid barrier
+ * passed, [5] fill phase done; out (may be NULL) receives [n_ctas][8] of the last recorded run */
+int sst_explain_cta_ns(sst_ctx* ctx, int enable, uint64_t* out, int cap_ctas, int* n_ctas);
 /* diagnostics: device timestamps (ns, %globaltimer, CTA 0's clock) at the phase boundaries of the last enumeration
  * pass, in order: [0] start, [1] window values counted, [2] level-0 nodes written, then for every level
  * [counted, grid barrier passed, written]; after the last level [per-level peak totals summed], [placement table

@@ -36,6 +36,7 @@ EXPORTS = [
     "sst_table_download_masks", "sst_table_destroy", "sst_is_valid", "sst_valid_stage", "sst_valid_run",
     "sst_valid_fetch", "sst_valid_stage_f64", "sst_explain", "sst_explain_stage", "sst_explain_stage_f64", "sst_explain_stage_f64_uniform", "sst_explain_rec_width", "sst_explain_phase_ns",
     "sst_explain_run", "sst_explain_fetch", "sst_classify", "sst_classify_stage", "sst_classify_run", "sst_classify_fetch", "sst_classify_launch", "sst_classify_async", "sst_classify_wait", "sst_length_bounds",
+    "sst_set_pass", "sst_last_pass", "sst_explain_cta_ns",
 ]
 
 
@@ -104,6 +105,9 @@ def load() -> C.CDLL:
             "sst_classify_launch": (C.c_int, [vp, vp, C.c_double, C.c_double]),
             "sst_classify_async": (C.c_int, [vp, vp, fp, C.c_int64, fp, C.c_int, C.c_double, C.c_double, u8p]),
             "sst_classify_wait": (C.c_int, [vp]),
+            "sst_set_pass": (C.c_int, [vp, C.c_int]),
+            "sst_last_pass": (C.c_int, [vp]),
+            "sst_explain_cta_ns": (C.c_int, [vp, C.c_int, u64p, C.c_int, C.POINTER(C.c_int)]),
             "sst_length_bounds": (C.c_int, [vp, vp, C.c_int64, C.c_int64, C.c_int32, C.c_int32, i32p, u8p, C.c_uint64,
                                             C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
         }
@@ -197,6 +201,21 @@ class Context:
     def set_item_limit(self, limit: int):
         """Blow-up guard: most partial compositions one level of a pass may hold (0 = device memory)."""
         self._check(self._lib.sst_set_item_limit(self._h, C.c_uint64(limit)))
+
+    def set_pass(self, which: int):
+        """0 = automatic, 1 = level-synchronous pass, 2 = depth-first pass (sst_set_pass)."""
+        self._check(self._lib.sst_set_pass(self._h, int(which)))
+
+    def last_pass(self) -> int:
+        return int(self._lib.sst_last_pass(self._h))
+
+    def cta_timestamps(self, enable: bool = True) -> np.ndarray:
+        """Switch the per-CTA phase timestamps of the depth-first pass on / off and return those of the last recorded
+        run as uint64[n_ctas, 8] (see sst_explain_cta_ns)."""
+        out = np.zeros((1024, 8), dtype=np.uint64)
+        n = C.c_int()
+        self._check(self._lib.sst_explain_cta_ns(self._h, 1 if enable else 0, _p(out), 1024, C.byref(n)))
+        return out[: n.value]
 
     def flush_l2(self, nbytes: int = 256 << 20):
         self._check(self._lib.sst_flush_l2(self._h, int(nbytes)))

@@ -11,6 +11,7 @@
 
 #include "../../include/sst_b200.h"
 #include "sst_common.cuh"
+#include "sst_enum.cuh"
 #include "sst_explain.cuh"
 #include "sst_table.cuh"
 
@@ -44,6 +45,8 @@ struct sst_table {
     int64_t w_host[128] = {0};
     uint64_t last_mask = ~0ULL;
     uint32_t leaf_mul = 0;  // collision-free multiplier of the weight -> row hash (0 = none found)
+    uint32_t* d_lamq = nullptr;  // scheduling cost model (CostModel): compositions per unit of mass, Q16, per coarse mass bucket
+    uint32_t lam_width = 1, lam_K = 0;
     float build_ms = 0.f, transpose_ms = 0.f;
     bool built_here = false;
 };
@@ -98,6 +101,15 @@ struct sst_ctx {
     bool have_result = false;
     uint64_t item_limit = ~0ULL;     // blow-up guard (items per level)
     int pass_grid_max[3] = {0, 0, 0};  // co-resident CTAs of the k_explain_pass instances on this device
+    int dfs_grid_max[4] = {0, 0, 0, 0};  // the same for the k_explain_dfs instances
+    int pass_grid_cap = 512;           // CTA-total scratch is sized for the largest grid of either pass
+    int pass_choice = 0;               // sst_set_pass: 0 automatic, 1 level-synchronous, 2 depth-first
+    int last_pass = 0;                 // which pass produced the last result
+    DevBuf d_rootvp, d_rootcnt, d_tilebase, d_ctans;
+    uint64_t pool_capacity = 0;        // items of the depth-first pass's pool
+    DevBuf d_peakcost, d_blkcost;      // scheduling costs of the staged batch (peak_cost(), sums per kCostBlock peaks)
+    bool want_cta_ns = false;          // diagnostics: per-CTA phase timestamps of the depth-first pass
+    int cta_ns_grid = 0;
     uint64_t phase_ns[32] = {0};
 };
 
@@ -287,6 +299,29 @@ int alloc_table(sst_ctx* ctx, sst_table* t, const int64_t* weights, int R, int64
         while (r < (size_t)R && weights[r] < (int64_t)(k << kWeightBucketShift)) r++;
         wb[k] = (uint8_t)r;  // R <= 128
     }
+    {   // coarse coin-change count over the row weights: how many compositions have a mass near k * width
+        const int64_t limit = C * 32;
+        int64_t width = w_min / 8 > 0 ? w_min / 8 : 1;
+        if (limit / width > 65536) width = limit / 65536 + 1;
+        const int64_t K = limit / width + 2;
+        std::vector<double> cnt((size_t)K + 1, 0.0);
+        cnt[0] = 1.0;
+        for (int r = 1; r < R; r++) {
+            int64_t cw = (weights[r] + width / 2) / width;
+            if (cw < 1) cw = 1;
+            for (int64_t k = cw; k <= K; k++) cnt[(size_t)k] += cnt[(size_t)(k - cw)];
+        }
+        std::vector<uint32_t> lamq((size_t)K);
+        for (int64_t k = 0; k < K; k++) {
+            const double v = cnt[(size_t)k] / (double)width * 65536.0 * 4.0;  // x4: real differences sit where compositions cluster
+            lamq[(size_t)k] = v < 1073741824.0 ? (uint32_t)v : 1073741824u;
+        }
+        t->lam_width = (uint32_t)width;
+        t->lam_K = (uint32_t)K;
+        CK(cudaMalloc(&t->d_lamq, (size_t)K * 4));
+        CK(cudaMemcpyAsync(t->d_lamq, lamq.data(), (size_t)K * 4, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
     CK(cudaMalloc(&t->d_wbucket, wb.size()));
     CK(cudaMemcpyAsync(t->d_wbucket, wb.data(), wb.size(), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(t->d_weights, w.data(), (size_t)R * 4, cudaMemcpyHostToDevice, ctx->stream));
@@ -303,6 +338,7 @@ void free_table(sst_table* t) {
     cudaFree(t->H);
     cudaFree(t->d_any);
     cudaFree(t->d_wbucket);
+    cudaFree(t->d_lamq);
     cudaFree(t->d_weights);
     cudaFree(t->d_step);
     cudaFree(t->d_shift);
@@ -367,7 +403,7 @@ void sst_ctx_destroy(sst_ctx* ctx) {
                       &ctx->d_memo_peaks, &ctx->d_status, &ctx->d_cnt, &ctx->d_peakoff, &ctx->d_recs,
                       &ctx->d_blocksums, &ctx->d_memo_keys, &ctx->d_memo_alive, &ctx->d_memo_top,
                       &ctx->d_memo_misc, &ctx->d_flush, &ctx->d_vtarget, &ctx->d_vthr, &ctx->d_vout,
-                      &ctx->d_scan, &ctx->d_vmass, &ctx->d_vthrf, &ctx->d_chunk_k, &ctx->d_chunk_r, &ctx->d_tmprecs, &ctx->d_tmppeak, &ctx->d_lvlcnt, &ctx->d_lvlA, &ctx->d_ctalvl, &ctx->d_nodemask, &ctx->d_cobs, &ctx->d_coff, &ctx->d_cout, &ctx->d_bkeys, &ctx->d_btop, &ctx->d_blower, &ctx->d_bupper, &ctx->d_bout,
+                      &ctx->d_scan, &ctx->d_vmass, &ctx->d_vthrf, &ctx->d_chunk_k, &ctx->d_chunk_r, &ctx->d_tmprecs, &ctx->d_tmppeak, &ctx->d_lvlcnt, &ctx->d_lvlA, &ctx->d_ctalvl, &ctx->d_nodemask, &ctx->d_cobs, &ctx->d_coff, &ctx->d_cout, &ctx->d_bkeys, &ctx->d_btop, &ctx->d_blower, &ctx->d_bupper, &ctx->d_bout, &ctx->d_rootvp, &ctx->d_rootcnt, &ctx->d_tilebase, &ctx->d_ctans, &ctx->d_peakcost, &ctx->d_blkcost,
                       &ctx->d_item_m[0], &ctx->d_item_m[1], &ctx->d_item_peak[0], &ctx->d_item_peak[1],
                       &ctx->d_item_meta[0], &ctx->d_item_meta[1], &ctx->d_item_all[0], &ctx->d_item_all[1],
                       &ctx->d_item_ind[0], &ctx->d_item_ind[1], &ctx->d_item_path[0], &ctx->d_item_path[1]};
@@ -802,6 +838,14 @@ int sst_explain_stage(sst_ctx* ctx, const sst_table* t, const int64_t* target, c
         if ((rc = reserve(ctx, ctx->d_memo_peaks, memo_peaks.size() * 4))) return rc;
         CK(cudaMemcpyAsync(ctx->d_memo_peaks.p, memo_peaks.data(), memo_peaks.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
     }
+    if ((rc = reserve(ctx, ctx->d_peakcost, (size_t)(P + 1) * 4))) return rc;
+    if ((rc = reserve(ctx, ctx->d_blkcost, (size_t)((P + kCostBlock - 1) / kCostBlock + 1) * 8))) return rc;
+    if (P) {
+        k_peak_costs<<<(unsigned)((P + kCostBlock - 1) / kCostBlock), kCostBlock, 0, ctx->stream>>>(
+            (const int64_t*)ctx->d_target.p, (const int64_t*)ctx->d_thr.p, P, t->C * 32, CostModel{t->d_lamq, t->lam_width, t->lam_K},
+            (uint32_t*)ctx->d_peakcost.p, (unsigned long long*)ctx->d_blkcost.p);
+        CK(cudaGetLastError());
+    }
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->P = P;
     ctx->R_staged = t->R;
@@ -848,6 +892,8 @@ int stage_f64(sst_ctx* ctx, const sst_table* t, const double* mass, const double
     if ((rc = reserve(ctx, ctx->d_vthrf, p8))) return rc;
     if ((rc = reserve(ctx, ctx->d_memo_peaks, p8 / 2))) return rc;
     if ((rc = reserve(ctx, ctx->d_scan, 512))) return rc;
+    if ((rc = reserve(ctx, ctx->d_peakcost, (size_t)(P + 1) * 4))) return rc;
+    if ((rc = reserve(ctx, ctx->d_blkcost, (size_t)((P + kCostBlock - 1) / kCostBlock + 1) * 8))) return rc;
     CK(cudaMemsetAsync(ctx->d_scan.p, 0, 32, ctx->stream));
     if (P) {
         CK(cudaMemcpyAsync(ctx->d_vmass.p, mass, (size_t)P * 8, cudaMemcpyHostToDevice, ctx->stream));
@@ -861,7 +907,8 @@ int stage_f64(sst_ctx* ctx, const sst_table* t, const double* mass, const double
             (const double*)ctx->d_vmass.p, thr ? (const double*)ctx->d_vthrf.p : nullptr, (int32_t*)ctx->d_maxmods.p, uniform_mods,
             max_mods ? 0 : 1, P, precision,
             tolerance, w_min_mod, hi_limit, with_memo ? SST_MODE_MEMO : SST_MODE_EXACT, t->C * 32, (int64_t*)ctx->d_target.p,
-            (int64_t*)ctx->d_thr.p, (uint8_t*)ctx->d_mode.p, (uint32_t*)ctx->d_memo_peaks.p, (unsigned long long*)ctx->d_scan.p);
+            (int64_t*)ctx->d_thr.p, (uint8_t*)ctx->d_mode.p, (uint32_t*)ctx->d_memo_peaks.p, (unsigned long long*)ctx->d_scan.p,
+            CostModel{t->d_lamq, t->lam_width, t->lam_K}, (uint32_t*)ctx->d_peakcost.p, (unsigned long long*)ctx->d_blkcost.p);
         CK(cudaGetLastError());
     }
     CK(cudaMemcpyAsync(ctx->h_misc, ctx->d_scan.p, 32, cudaMemcpyDeviceToHost, ctx->stream));
@@ -894,17 +941,187 @@ int sst_explain_stage_f64_uniform(sst_ctx* ctx, const sst_table* t, const double
     return stage_f64(ctx, t, mass, thr, nullptr, max_mods, P, ind, is_mod, precision, tolerance, with_memo);
 }
 
-int sst_explain_run(sst_ctx* ctx, const sst_table* t, int rec_width, uint64_t memo_capacity, uint64_t* n_roots,
-                    uint64_t* n_comps) {
-    CK(cudaSetDevice(ctx->device));
-    ctx->have_result = false;
+}  // extern "C"
+
+namespace {
+
+// MEMO mode: the first-visit replay (k_memo_phase_a) fills the hash map the enumeration reads its edges from.  Launched
+// once per run, before the pass; memo_check looks at its counters after the stream has been synchronised.
+int memo_launch(sst_ctx* ctx, const sst_table* t, uint64_t memo_capacity, MemoMap& mp) {
     const int64_t P = ctx->P;
-    if (ctx->R_staged != t->R) return fail(ctx, SST_ERR_STATE, "staged batch belongs to a table with %d rows", ctx->R_staged);
-    if (ctx->deepest > kMaxDepth - 3) return fail(ctx, SST_ERR_TOO_DEEP, "a composition may need %lld nucleotides (limit %d)", (long long)ctx->deepest, kMaxDepth - 3);
-    if (rec_width == 0) rec_width = (int)(8 * (ctx->deepest > 8 ? (ctx->deepest + 7) / 8 : 1));
-    if (rec_width < 8 || rec_width % 8 || rec_width > kMaxDepth) return fail(ctx, SST_ERR_BAD_ARG, "rec_width %d must be a multiple of 8 in [8, %d]", rec_width, kMaxDepth);
-    if (ctx->deepest > rec_width) return fail(ctx, SST_ERR_BAD_ARG, "a composition may need %lld nucleotides but rec_width is %d", (long long)ctx->deepest, rec_width);
-    // The whole pass is ONE cooperative launch and one small read-back (sst_explain.cuh, k_explain_pass).
+    uint64_t mcap = memo_capacity ? memo_capacity : ((uint64_t)1 << 20);
+    uint64_t pow2 = 1024;
+    while (pow2 < mcap) pow2 <<= 1;
+    if (pow2 > ((uint64_t)1 << 31)) return fail(ctx, SST_ERR_NOMEM, "memo capacity %llu too large", (unsigned long long)mcap);
+    int rc;
+    if ((rc = reserve(ctx, ctx->d_memo_keys, pow2 * 8))) return rc;
+    if ((rc = reserve(ctx, ctx->d_memo_alive, pow2 * 16))) return rc;
+    if ((rc = reserve(ctx, ctx->d_memo_top, pow2 * 4))) return rc;
+    if ((rc = reserve(ctx, ctx->d_memo_misc, 64))) return rc;
+    CK(cudaMemsetAsync(ctx->d_memo_keys.p, 0, pow2 * 8, ctx->stream));
+    CK(cudaMemsetAsync(ctx->d_memo_alive.p, 0, pow2 * 16, ctx->stream));
+    CK(cudaMemsetAsync(ctx->d_memo_top.p, 0, pow2 * 4, ctx->stream));
+    CK(cudaMemsetAsync(ctx->d_memo_misc.p, 0, 64, ctx->stream));
+    mp.keys = (unsigned long long*)ctx->d_memo_keys.p;
+    mp.alive = (uint4*)ctx->d_memo_alive.p;
+    mp.top = (uint32_t*)ctx->d_memo_top.p;
+    mp.cap_mask = (uint32_t)(pow2 - 1);
+    mp.fill = (unsigned int*)ctx->d_memo_misc.p;
+    mp.overflow = (int*)ctx->d_memo_misc.p + 1;
+    KTimer kt(ctx, SST_K_PHASE_A);
+    const int64_t frames = ctx->deepest + 2;  // the smallest stack instance that holds the deepest composition
+    auto phase_a = frames <= 16 ? k_memo_phase_a<16> : frames <= 40 ? k_memo_phase_a<40> : k_memo_phase_a<kMaxDepth>;
+    phase_a<<<(unsigned)((ctx->n_memo + 63) / 64), 64, 0, ctx->stream>>>(
+        view_of(t), RowMeta{(const int32_t*)ctx->d_ind.p, (const uint8_t*)ctx->d_ismod.p},
+        PeakBatch{(const int64_t*)ctx->d_target.p, (const int64_t*)ctx->d_thr.p, (const int32_t*)ctx->d_maxmods.p,
+                  (const uint8_t*)ctx->d_mode.p, P},
+        (const uint32_t*)ctx->d_memo_peaks.p, ctx->n_memo, mp);
+    kt.stop(1);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(ctx->h_misc + 100, ctx->d_memo_misc.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    return SST_OK;
+}
+
+// too small = an insertion failed, or the load factor passed 3/4 (the replay still finished, but probing a map that
+// full is slow: the caller grows it)
+int memo_check(sst_ctx* ctx, const MemoMap& mp) {
+    if (ctx->h_misc[101] || (unsigned)ctx->h_misc[100] > (mp.cap_mask >> 1) + (mp.cap_mask >> 2))
+        return fail(ctx, SST_ERR_MEMO_FULL, "first-visit map is too small (%d slots used)", ctx->h_misc[100]);
+    return SST_OK;
+}
+
+int grow_records(sst_ctx* ctx, unsigned long long comps, int rec_width) {
+    size_t free_b = 0, total_b = 0;
+    CK(cudaMemGetInfo(&free_b, &total_b));
+    const unsigned long long need = comps * (unsigned long long)rec_width;
+    if (need > (unsigned long long)free_b + ctx->d_recs.cap)
+        return fail(ctx, SST_ERR_NOMEM, "%llu compositions x %d bytes do not fit in device memory (%zu bytes free)", comps, rec_width, free_b);
+    return reserve(ctx, ctx->d_recs, (size_t)need + (need >> 2) + 8);
+}
+
+enum { PASS_DONE = 0, PASS_FALLBACK = -1 };
+
+// Depth-first pass (sst_enum.cuh): one cooperative launch, one grid barrier.  Returns PASS_FALLBACK when a root's
+// subtree is too large for one thread (the level-synchronous pass balances such batches across the machine).
+int run_dfs_pass(sst_ctx* ctx, const sst_table* t, int rec_width, const MemoMap& mp, bool memo_fresh, unsigned long long* roots,
+                 unsigned long long* comps) {
+    const int64_t P = ctx->P;
+    const int nw = rec_width / 8;
+    int rc;
+    auto kern = nw == 1 ? (ctx->has_exact ? k_explain_dfs<1, true> : k_explain_dfs<1, false>)
+                        : (ctx->has_exact ? k_explain_dfs<2, true> : k_explain_dfs<2, false>);
+    int& grid_max = ctx->dfs_grid_max[(nw == 1 ? 0 : 2) + (ctx->has_exact ? 1 : 0)];
+    if (!grid_max) {
+        int occ = 0;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kDfsThreads, 0));
+        if (occ < 1) return fail(ctx, SST_ERR_CUDA, "k_explain_dfs does not fit on an SM");
+        grid_max = occ * ctx->prop.multiProcessorCount;
+    }
+    // a CTA per 128 peaks, at most one co-resident wave: a single-peak call is one CTA and never waits at the barrier
+    int64_t want = (P + 127) / 128;
+    if (want < 1) want = 1;
+    const unsigned grid = (unsigned)(want < grid_max ? want : grid_max);
+    const size_t tile_cap = (size_t)(P / kDfsThreads) + 2 * (size_t)grid + 8;
+    if ((rc = reserve(ctx, ctx->d_status, (size_t)(P ? P : 1)))) return rc;
+    if ((rc = reserve(ctx, ctx->d_peakoff, (size_t)(P + 2) * 8))) return rc;
+    if ((rc = reserve(ctx, ctx->d_blocksums, (size_t)3 * (grid_max > ctx->pass_grid_cap ? grid_max : ctx->pass_grid_cap) * 8))) return rc;
+    if ((rc = reserve(ctx, ctx->d_cnt, (size_t)(P + 1) * 4))) return rc;
+    if ((rc = reserve(ctx, ctx->d_tilebase, tile_cap * 24))) return rc;
+    if (!ctx->d_recs.p && (rc = reserve(ctx, ctx->d_recs, (size_t)64 << 20))) return rc;
+    if (!ctx->h_run_dev || !ctx->d_bar) return fail(ctx, SST_ERR_NOMEM, "run summary buffers are missing");
+    // the item pool holds every tile's window roots and the lists of its split rounds; it keeps its size between runs
+    // and grows when a run reports that it was too small
+    if (ctx->pool_capacity < (uint64_t)(8 * P + 65536)) ctx->pool_capacity = ((uint64_t)(8 * P + 65536) + 31) & ~31ULL;
+    for (int attempt = 0;; attempt++) {
+        const size_t cap = (size_t)ctx->pool_capacity;
+        if ((rc = reserve(ctx, ctx->d_item_m[0], cap * 4))) return rc;
+        if ((rc = reserve(ctx, ctx->d_item_peak[0], cap * 4))) return rc;
+        if ((rc = reserve(ctx, ctx->d_item_meta[0], cap * 4))) return rc;
+        if ((rc = reserve(ctx, ctx->d_item_path[0], cap * 8 * (size_t)nw))) return rc;
+        if ((rc = reserve(ctx, ctx->d_rootcnt, cap * 4))) return rc;
+        if ((rc = reserve(ctx, ctx->d_rootvp, cap * 4))) return rc;
+        if ((rc = reserve(ctx, ctx->d_nodemask, cap * 16))) return rc;
+        if ((rc = reserve(ctx, ctx->d_chunk_k, (cap / 32 + 64) * 4))) return rc;
+        if (ctx->has_exact) {
+            if ((rc = reserve(ctx, ctx->d_item_all[0], cap * 4))) return rc;
+            if ((rc = reserve(ctx, ctx->d_item_ind[0], cap * 4))) return rc;
+        }
+        DfsArgs a{};
+        a.tv = view_of(t);
+        a.meta = RowMeta{(const int32_t*)ctx->d_ind.p, (const uint8_t*)ctx->d_ismod.p};
+        a.pk = PeakBatch{(const int64_t*)ctx->d_target.p, (const int64_t*)ctx->d_thr.p, (const int32_t*)ctx->d_maxmods.p,
+                         (const uint8_t*)ctx->d_mode.p, P};
+        a.mp = mp;
+        a.status = (uint8_t*)ctx->d_status.p;
+        a.peak_first = (uint32_t*)ctx->d_cnt.p;
+        a.pool = ItemPool{(uint32_t*)ctx->d_item_m[0].p, (uint32_t*)ctx->d_item_peak[0].p, (uint32_t*)ctx->d_item_meta[0].p,
+                          (unsigned long long*)ctx->d_item_path[0].p, (int32_t*)ctx->d_item_all[0].p, (int32_t*)ctx->d_item_ind[0].p,
+                          (uint4*)ctx->d_nodemask.p, (uint32_t*)ctx->d_rootcnt.p, (uint32_t*)ctx->d_rootvp.p, (uint32_t*)ctx->d_chunk_k.p,
+                          (unsigned long long)cap};
+        a.peak_cost = (const uint32_t*)ctx->d_peakcost.p;
+        a.blk_cost = (const unsigned long long*)ctx->d_blkcost.p;
+        a.tile_info = (unsigned long long*)ctx->d_tilebase.p;
+        a.tile_cap = (unsigned long long)tile_cap;
+        a.recs = (unsigned long long*)ctx->d_recs.p;
+        a.rec_capacity = (unsigned long long)(ctx->d_recs.cap / rec_width);
+        a.peak_off = (unsigned long long*)ctx->d_peakoff.p;
+        a.cta_tot = (unsigned long long*)ctx->d_blocksums.p;
+        a.sync = ctx->d_bar + 64 * (ctx->run_parity & 1);
+        a.sync_next = ctx->d_bar + 64 * ((ctx->run_parity + 1) & 1);
+        a.host_out = ctx->h_run_dev;
+        a.leaf = LeafHash{t->leaf_mul};
+        a.cta_ns = nullptr;
+        if (ctx->want_cta_ns) {
+            if ((rc = reserve(ctx, ctx->d_ctans, (size_t)grid * 64))) return rc;
+            a.cta_ns = (unsigned long long*)ctx->d_ctans.p;
+            ctx->cta_ns_grid = (int)grid;
+        }
+        {
+            KTimer kt(ctx, SST_K_EXPLAIN_PASS);
+            void* args[] = {(void*)&a};
+            CK(cudaLaunchCooperativeKernel((const void*)kern, dim3(grid), dim3(kDfsThreads), args, 0, ctx->stream));
+            ctx->run_parity++;  // only a launch that really started clears the other set
+            kt.stop(1);
+        }
+        CK(cudaEventRecord(ctx->ev_run, ctx->stream));  // the device is done here; what follows is the host waking up
+        CK(cudaStreamSynchronize(ctx->stream));
+        flush_timers(ctx);
+        const unsigned long long* h_tot = ctx->h_run;
+        const int* h_flags = reinterpret_cast<const int*>(ctx->h_run + 40);
+        *roots = h_tot[0];
+        *comps = h_tot[2];
+        ctx->levels = 1;
+        for (int i = 0; i < 32; i++) ctx->phase_ns[i] = h_tot[8 + i];
+        if (memo_fresh && attempt == 0 && (rc = memo_check(ctx, mp))) return rc;
+        if (h_flags[3]) return PASS_FALLBACK;
+        if (h_flags[2]) {  // the item pool was too small: grow and run the pass again
+            // a pool far beyond the batch size means combinatorial blow-up: that is the level-synchronous pass's job
+            // (it spreads single huge subtrees over the machine and enforces sst_set_item_limit)
+            unsigned long long most = 256ULL * (unsigned long long)(P > 0 ? P : 1);
+            if (most < (32ULL << 20)) most = 32ULL << 20;
+            if (ctx->item_limit < most) most = ctx->item_limit;
+            size_t free_b = 0, total_b = 0;
+            CK(cudaMemGetInfo(&free_b, &total_b));
+            const unsigned long long per_item = 37 + 8ULL * nw + (ctx->has_exact ? 8 : 0);
+            if (attempt >= 10 || ctx->pool_capacity * 2 > most || ctx->pool_capacity * per_item > (unsigned long long)free_b) return PASS_FALLBACK;
+            ctx->pool_capacity *= 2;
+            continue;
+        }
+        if (h_flags[1]) {  // records did not fit: grow and run the pass again
+            if (attempt >= 3) return fail(ctx, SST_ERR_CUDA, "record buffer kept overflowing (%llu compositions)", *comps);
+            if ((rc = grow_records(ctx, *comps, rec_width))) return rc;
+            continue;
+        }
+        break;
+    }
+    ctx->last_pass = 2;
+    return PASS_DONE;
+}
+
+// Level-synchronous pass (sst_explain.cuh, k_explain_pass): one cooperative launch, two grid barriers per level.
+int run_level_pass(sst_ctx* ctx, const sst_table* t, int rec_width, const MemoMap& mp, bool memo_fresh, unsigned long long* roots_out,
+                   unsigned long long* comps_out) {
+    const int64_t P = ctx->P;
     // Level-0 items are bounded by the summed window sizes (known to the host); the two item buffers and the
     // record buffer keep their capacity from earlier runs — a level that would overflow sets a flag and the pass
     // is repeated with larger buffers.
@@ -919,10 +1136,11 @@ int sst_explain_run(sst_ctx* ctx, const sst_table* t, int rec_width, uint64_t me
         if (occ < 1) return fail(ctx, SST_ERR_CUDA, "k_explain_pass does not fit on an SM");
         grid_max = occ * ctx->prop.multiProcessorCount;
         if (grid_max > kPassThreads) grid_max = kPassThreads;  // the slice totals are scanned by one CTA (balanced_range)
+        if (grid_max > ctx->pass_grid_cap) ctx->pass_grid_cap = grid_max;
     }
     if ((rc = reserve(ctx, ctx->d_status, (size_t)(P ? P : 1)))) return rc;
     if ((rc = reserve(ctx, ctx->d_peakoff, (size_t)(P + 2) * 8))) return rc;
-    if ((rc = reserve(ctx, ctx->d_blocksums, (size_t)3 * grid_max * 8))) return rc;
+    if ((rc = reserve(ctx, ctx->d_blocksums, (size_t)3 * ctx->pass_grid_cap * 8))) return rc;
     int lvl_cap = (int)ctx->deepest + 3;
     if (lvl_cap > kMaxLevels) lvl_cap = kMaxLevels;
     if ((rc = reserve(ctx, ctx->d_lvlcnt, (size_t)lvl_cap * (size_t)(P + 1) * 4))) return rc;
@@ -933,7 +1151,6 @@ int sst_explain_run(sst_ctx* ctx, const sst_table* t, int rec_width, uint64_t me
     if (!ctx->item_capacity) ctx->item_capacity = (uint64_t)1 << 20;
     if ((int64_t)ctx->item_capacity < root_bound + 1) ctx->item_capacity = (uint64_t)root_bound + 1;
 
-    MemoMap mp{};
     unsigned long long roots = 0, items = 0, comps = 0;
     for (int attempt = 0;; attempt++) {
         const size_t cap = (size_t)ctx->item_capacity;
@@ -959,37 +1176,6 @@ int sst_explain_run(sst_ctx* ctx, const sst_table* t, int rec_width, uint64_t me
         // totals, timestamps and flags live in shared memory of CTA 0 during the pass, which stores them to pinned host
         // memory on its way out (h_run: [0,40) totals and timestamps, then the flags)
         if (!ctx->h_run_dev || !ctx->d_bar) return fail(ctx, SST_ERR_NOMEM, "run summary buffers are missing");
-
-        if (ctx->n_memo && attempt == 0) {  // the first-visit map does not depend on the buffer sizes: built once
-            uint64_t mcap = memo_capacity ? memo_capacity : ((uint64_t)1 << 20);
-            uint64_t pow2 = 1024;
-            while (pow2 < mcap) pow2 <<= 1;
-            if (pow2 > ((uint64_t)1 << 31)) return fail(ctx, SST_ERR_NOMEM, "memo capacity %llu too large", (unsigned long long)mcap);
-            if ((rc = reserve(ctx, ctx->d_memo_keys, pow2 * 8))) return rc;
-            if ((rc = reserve(ctx, ctx->d_memo_alive, pow2 * 16))) return rc;
-            if ((rc = reserve(ctx, ctx->d_memo_top, pow2 * 4))) return rc;
-            if ((rc = reserve(ctx, ctx->d_memo_misc, 64))) return rc;
-            CK(cudaMemsetAsync(ctx->d_memo_keys.p, 0, pow2 * 8, ctx->stream));
-            CK(cudaMemsetAsync(ctx->d_memo_alive.p, 0, pow2 * 16, ctx->stream));
-            CK(cudaMemsetAsync(ctx->d_memo_top.p, 0, pow2 * 4, ctx->stream));
-            CK(cudaMemsetAsync(ctx->d_memo_misc.p, 0, 64, ctx->stream));
-            mp.keys = (unsigned long long*)ctx->d_memo_keys.p;
-            mp.alive = (uint4*)ctx->d_memo_alive.p;
-            mp.top = (uint32_t*)ctx->d_memo_top.p;
-            mp.cap_mask = (uint32_t)(pow2 - 1);
-            mp.fill = (unsigned int*)ctx->d_memo_misc.p;
-            mp.overflow = (int*)ctx->d_memo_misc.p + 1;
-            KTimer kt(ctx, SST_K_PHASE_A);
-            const int64_t frames = ctx->deepest + 2;  // the smallest stack instance that holds the deepest composition
-            auto phase_a = frames <= 16 ? k_memo_phase_a<16> : frames <= 40 ? k_memo_phase_a<40> : k_memo_phase_a<kMaxDepth>;
-            phase_a<<<(unsigned)((ctx->n_memo + 63) / 64), 64, 0, ctx->stream>>>(
-                view_of(t), RowMeta{(const int32_t*)ctx->d_ind.p, (const uint8_t*)ctx->d_ismod.p},
-                PeakBatch{(const int64_t*)ctx->d_target.p, (const int64_t*)ctx->d_thr.p, (const int32_t*)ctx->d_maxmods.p,
-                          (const uint8_t*)ctx->d_mode.p, P},
-                (const uint32_t*)ctx->d_memo_peaks.p, ctx->n_memo, mp);
-            kt.stop(1);
-            CK(cudaGetLastError());
-        }
 
         PassArgs a{};
         a.tv = view_of(t);
@@ -1039,7 +1225,6 @@ int sst_explain_run(sst_ctx* ctx, const sst_table* t, int rec_width, uint64_t me
             kt.stop(1);
         }
         // totals + timestamps + flags arrive in h_run by the kernel's own stores
-        if (ctx->n_memo && attempt == 0) CK(cudaMemcpyAsync(ctx->h_misc + 100, ctx->d_memo_misc.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaEventRecord(ctx->ev_run, ctx->stream));  // the device is done here; what follows is the host waking up
         CK(cudaStreamSynchronize(ctx->stream));
         flush_timers(ctx);
@@ -1051,11 +1236,7 @@ int sst_explain_run(sst_ctx* ctx, const sst_table* t, int rec_width, uint64_t me
         ctx->levels = (int)h_tot[3];
         if (!h_flags[2]) ctx->widest_level = items;
         for (int i = 0; i < 32; i++) ctx->phase_ns[i] = h_tot[8 + i];
-        // too small = an insertion failed, or the load factor passed 3/4 (the replay still finished, but probing a map
-        // that full is slow: the caller grows it, as before)
-        if (ctx->n_memo && attempt == 0 &&
-            (ctx->h_misc[101] || (unsigned)ctx->h_misc[100] > (mp.cap_mask >> 1) + (mp.cap_mask >> 2)))
-            return fail(ctx, SST_ERR_MEMO_FULL, "first-visit map is too small (%d slots used)", ctx->h_misc[100]);
+        if (memo_fresh && attempt == 0 && (rc = memo_check(ctx, mp))) return rc;
         if (h_flags[0])
             return fail(ctx, SST_ERR_NOMEM, "more than %llu partial compositions in one level (%llu): combinatorial blow-up (raise the limit with sst_set_item_limit)",
                         (unsigned long long)ctx->item_limit, items);
@@ -1072,18 +1253,75 @@ int sst_explain_run(sst_ctx* ctx, const sst_table* t, int rec_width, uint64_t me
         }
         if (h_flags[1]) {  // records did not fit: grow and run the pass again
             if (attempt >= 14) return fail(ctx, SST_ERR_CUDA, "record buffer kept overflowing (%llu compositions)", comps);
-            size_t free_b = 0, total_b = 0;
-            CK(cudaMemGetInfo(&free_b, &total_b));
-            const unsigned long long need = comps * (unsigned long long)rec_width;
-            if (need > (unsigned long long)free_b + ctx->d_recs.cap)
-                return fail(ctx, SST_ERR_NOMEM, "%llu compositions x %d bytes do not fit in device memory (%zu bytes free)", comps, rec_width, free_b);
-            if ((rc = reserve(ctx, ctx->d_recs, (size_t)need + (need >> 2) + 8))) return rc;
+            if ((rc = grow_records(ctx, comps, rec_width))) return rc;
             continue;
         }
         break;
     }
-    ctx->n_roots = roots;
     ctx->n_items = items;
+    ctx->last_pass = 1;
+    *roots_out = roots;
+    *comps_out = comps;
+    return PASS_DONE;
+}
+
+}  // namespace
+
+extern "C" {
+
+int sst_set_pass(sst_ctx* ctx, int which) {
+    if (which < 0 || which > 2) return fail(ctx, SST_ERR_BAD_ARG, "pass %d: 0 = automatic, 1 = level-synchronous, 2 = depth-first", which);
+    ctx->pass_choice = which;
+    return SST_OK;
+}
+
+int sst_last_pass(const sst_ctx* ctx) { return ctx->last_pass; }
+
+int sst_explain_cta_ns(sst_ctx* ctx, int enable, uint64_t* out, int cap_ctas, int* n_ctas) {
+    CK(cudaSetDevice(ctx->device));
+    ctx->want_cta_ns = enable != 0;
+    const int n = ctx->cta_ns_grid < cap_ctas ? ctx->cta_ns_grid : cap_ctas;
+    if (out && n > 0 && ctx->d_ctans.p) {
+        CK(cudaMemcpyAsync(out, ctx->d_ctans.p, (size_t)n * 64, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    if (n_ctas) *n_ctas = out ? n : 0;
+    return SST_OK;
+}
+
+int sst_explain_run(sst_ctx* ctx, const sst_table* t, int rec_width, uint64_t memo_capacity, uint64_t* n_roots,
+                    uint64_t* n_comps) {
+    CK(cudaSetDevice(ctx->device));
+    ctx->have_result = false;
+    if (ctx->R_staged != t->R) return fail(ctx, SST_ERR_STATE, "staged batch belongs to a table with %d rows", ctx->R_staged);
+    if (ctx->deepest > kMaxDepth - 3) return fail(ctx, SST_ERR_TOO_DEEP, "a composition may need %lld nucleotides (limit %d)", (long long)ctx->deepest, kMaxDepth - 3);
+    if (rec_width == 0) rec_width = (int)(8 * (ctx->deepest > 8 ? (ctx->deepest + 7) / 8 : 1));
+    if (rec_width < 8 || rec_width % 8 || rec_width > kMaxDepth) return fail(ctx, SST_ERR_BAD_ARG, "rec_width %d must be a multiple of 8 in [8, %d]", rec_width, kMaxDepth);
+    if (ctx->deepest > rec_width) return fail(ctx, SST_ERR_BAD_ARG, "a composition may need %lld nucleotides but rec_width is %d", (long long)ctx->deepest, rec_width);
+    // Depth-first pass for everything up to kDfsDepth nucleotides (ladder differences, singletons), level-synchronous
+    // pass for deeper batches and for those the depth-first pass gives back (a subtree too large for one thread).
+    const bool dfs_ok = ctx->deepest <= kDfsDepth && rec_width <= 16;
+    if (ctx->pass_choice == 2 && !dfs_ok)
+        return fail(ctx, SST_ERR_TOO_DEEP, "the depth-first pass holds at most %d nucleotides per composition (batch: %lld)", kDfsDepth, (long long)ctx->deepest);
+    bool use_dfs = ctx->pass_choice == 2 || (ctx->pass_choice == 0 && dfs_ok);
+    MemoMap mp{};
+    int rc;
+    if (ctx->n_memo && (rc = memo_launch(ctx, t, memo_capacity, mp))) return rc;
+    unsigned long long roots = 0, comps = 0;
+    bool memo_fresh = ctx->n_memo != 0;
+    if (use_dfs) {
+        rc = run_dfs_pass(ctx, t, rec_width, mp, memo_fresh, &roots, &comps);
+        if (rc == PASS_FALLBACK && ctx->pass_choice == 2)
+            return fail(ctx, SST_ERR_NOMEM, "a window value has more than %u partial compositions: too large for the depth-first pass", kDfsNodeCap);
+        if (rc == PASS_FALLBACK) {
+            use_dfs = false;
+            memo_fresh = false;  // already checked
+        } else if (rc) {
+            return rc;
+        }
+    }
+    if (!use_dfs && (rc = run_level_pass(ctx, t, rec_width, mp, memo_fresh, &roots, &comps))) return rc;
+    ctx->n_roots = roots;
     ctx->n_comps = comps;
     ctx->rec_width = rec_width;
     ctx->have_result = true;

@@ -145,6 +145,55 @@ __global__ void k_is_valid_f64(TableView tv, const double* __restrict__ mass, co
     out[p] = valid_code(tv, t, h);
 }
 
+// ---------------- scheduling cost of a peak ----------------
+// The depth-first pass deals the batch to CTAs by ESTIMATED work, not by peak count (one 5-nt ladder gap has 10^4
+// compositions, a 1-nt one has one).  The estimate needs no table access: lamq[k] is the number of compositions per
+// unit of mass around mass k * width, from a coarse coin-change count over the row weights made by the host when the
+// table is created (Q16, times an enrichment factor: the mass of a real fragment difference sits where compositions
+// cluster).  Window values that are reachable ~ W * min(1, lam), compositions ~ W * lam.
+struct CostModel {
+    const uint32_t* lamq;
+    uint32_t width;
+    uint32_t K;
+};
+constexpr int kCostBlock = 256;  // peaks per entry of the block-cost array
+__device__ __forceinline__ uint32_t peak_cost(const CostModel& cm, int64_t target, int64_t thr, int64_t limit) {
+    const int64_t lo = target - thr, hi = target + thr;
+    const int64_t a = lo < 1 ? 1 : lo, b = hi < limit - 1 ? hi : limit - 1;
+    const unsigned long long W = b >= a ? (unsigned long long)(b - a + 1) : 0ULL;
+    unsigned long long cost = 16ULL + (W >> 4);
+    if (W && cm.lamq) {
+        const int64_t mid = (a + b) >> 1;
+        unsigned long long k = ((unsigned long long)mid + (cm.width >> 1)) / cm.width;
+        if (k >= cm.K) k = cm.K - 1;
+        const unsigned long long lam = __ldg(cm.lamq + k);
+        const unsigned long long n_est = (W * (lam < 65536ULL ? lam : 65536ULL)) >> 16;
+        unsigned long long c_est = (W * lam) >> 16;
+        if (c_est < n_est) c_est = n_est;
+        cost += 6ULL * n_est + 4ULL * c_est;
+    }
+    return cost < 0x7FFFFFFFULL ? (uint32_t)cost : 0x7FFFFFFFu;
+}
+// CTA-wide: per-peak costs -> cost[p], their sum -> blk[blockIdx.x]   (blockDim.x == kCostBlock)
+__device__ __forceinline__ void store_costs(uint32_t c, int64_t p, int64_t P, uint32_t* __restrict__ cost, unsigned long long* __restrict__ blk) {
+    __shared__ unsigned long long s_blk;
+    if (threadIdx.x == 0) s_blk = 0ULL;
+    __syncthreads();
+    if (p < P) cost[p] = c;
+    unsigned long long v = p < P ? c : 0u;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+    if ((threadIdx.x & 31) == 0) atomicAdd(&s_blk, v);
+    __syncthreads();
+    if (threadIdx.x == 0) blk[blockIdx.x] = s_blk;
+}
+__global__ void __launch_bounds__(kCostBlock)
+k_peak_costs(const int64_t* __restrict__ target, const int64_t* __restrict__ thr, int64_t P, int64_t limit, CostModel cm,
+             uint32_t* __restrict__ cost, unsigned long long* __restrict__ blk) {
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    store_costs(p < P ? peak_cost(cm, target[p], thr[p], limit) : 0u, p, P, cost, blk);
+}
+
 // ---------------- staging of a float batch: integerise + budget mode + batch summary on the device ----------------
 // Same float operations as mass_explanation.py:107-114 (integerise above).  Mode: FREE when no composition inside
 // the window can exhaust a budget (max_mods >= hi / w_min_mod and hi < hi_limit, both from the host), else `slow`.
@@ -154,9 +203,10 @@ __global__ void __launch_bounds__(256)
 k_stage_f64(const double* __restrict__ mass, const double* __restrict__ thr, int32_t* __restrict__ max_mods, int32_t uniform_mods,
             int use_uniform, int64_t P, double precision, double tolerance, int64_t w_min_mod, int64_t hi_limit, int slow, int64_t limit,
             int64_t* __restrict__ target, int64_t* __restrict__ ithr, uint8_t* __restrict__ mode, uint32_t* __restrict__ memo_peaks,
-            unsigned long long* __restrict__ summary) {
+            unsigned long long* __restrict__ summary, CostModel cm, uint32_t* __restrict__ cost, unsigned long long* __restrict__ blk) {
     const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     unsigned long long win = 0, hi_u = 0;
+    uint32_t my_cost = 0;
     if (p < P) {
         int64_t t, h;
         integerise(mass[p], thr ? thr[p] : nan(""), precision, tolerance, t, h);
@@ -177,7 +227,9 @@ k_stage_f64(const double* __restrict__ mass, const double* __restrict__ thr, int
         mode[p] = (uint8_t)md;
         if (md == MODE_MEMO) memo_peaks[atomicAdd(summary + 2, 1ULL)] = (uint32_t)p;
         if (md == MODE_EXACT) atomicAdd(summary + 3, 1ULL);
+        my_cost = peak_cost(cm, t, h, limit);
     }
+    store_costs(my_cost, p, P, cost, blk);
 #pragma unroll
     for (int o = 16; o; o >>= 1) {
         win += __shfl_xor_sync(0xFFFFFFFFu, win, o);
@@ -1054,9 +1106,9 @@ __device__ __forceinline__ int item_kind(int mode, uint32_t m, uint32_t wmin) {
 // enabled LEFT edges of an open item.  EXACT mode filters by the budgets the item carries (reference
 // mass_explanation.py:165-172: a modification row needs all > 0 and ind > 0, where ind is the remaining budget
 // of the row the level was entered by, or IND[r] for any other row).
-__device__ __forceinline__ Mask128 open_children(const PassArgs& a, const RowTables& rt, int mode, uint32_t p, uint32_t m, int rmax,
+__device__ __forceinline__ Mask128 open_children(const TableView& tv, const MemoMap& mp, const RowTables& rt, int mode, uint32_t p, uint32_t m, int rmax,
                                                  int all, int ind) {
-    Mask128 c = child_mask(a.tv, a.mp, mode, p, m, rmax);
+    Mask128 c = child_mask(tv, mp, mode, p, m, rmax);
     if (mode == MODE_EXACT) {
         Mask128 scan = c;
         while (!mask_empty(scan)) {
@@ -1103,7 +1155,7 @@ k_explain_pass(const PassArgs a) {
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         for (int k = 0; k < 40; k++) s_sum.totals[k] = 0ULL;
         for (int k = 0; k < 4; k++) s_sum.flags[k] = 0;
-        *a.barrier_next = 0u;  // nobody uses it during this launch
+        for (int k = 0; k < 8; k++) a.barrier_next[k] = 0u;  // nobody uses the other set during this launch (the depth-first pass keeps a cursor and a flag there too)
         s_sum.totals[8] = globaltimer_ns();
     }
     // the run summary goes straight to pinned host memory when the pass ends (no copy operation after the launch)
@@ -1293,7 +1345,7 @@ k_explain_pass(const PassArgs a) {
                     r = (unsigned)mask_popc(c);
                 } else {
                     const int all = a.has_budget ? __ldcg(in.all + i) : 0, ind = a.has_budget ? __ldcg(in.ind + i) : 0;
-                    c = open_children(a, rt, mode, p, m, rmax, all, ind);
+                    c = open_children(tv, a.mp, rt, mode, p, m, rmax, all, ind);
                     k = (unsigned)mask_popc(c);
                 }
                 a.cnt[i] = k | (r << 16);

@@ -14,6 +14,16 @@ from spectrseqtools_b200 import masses as M
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(autouse=True, params=["auto", "level"])
+def enumeration_pass(request):
+    """Every test of this file runs twice: with the automatic choice (the depth-first pass wherever a composition has
+    at most 16 nucleotides, sst_enum.cuh) and with the level-synchronous pass forced (sst_explain.cuh)."""
+    ctx = _cabi.context()
+    ctx.set_pass(0 if request.param == "auto" else 1)
+    yield request.param
+    ctx.set_pass(0)
+
+
 def _canon(sols, w):
     index = {m: i for i, m in enumerate(w)}
     return sorted(tuple(index[x] for x in s) for s in sols if s)
@@ -73,13 +83,14 @@ def test_reference_unit_test_inputs(gold_full):
             assert Hh.digest(rec) == c["digest_recursion"] and tuple(c["seq"]) in rec
 
 
-def test_full_alphabet_random_differences(gold_full):
+def test_full_alphabet_random_differences(gold_full, enumeration_pass):
     for c in gold_full["random_cases"]:
         dp = Hh.full_dp_table(c["max_len"])
         for memo, tag in ((True, "memo"), (False, "nomemo")):
             res = ME.explain_mass_with_table(c["mass"], dp, max_modifications=c["max_modifications"], threshold=c["threshold"], with_memo=memo).explanations
             assert (None if res is None else len(res)) == c[f"n_{tag}"], c
             assert Hh.digest(res) == c[f"digest_{tag}"], c
+            assert _cabi.context().last_pass() == (2 if enumeration_pass == "auto" else 1)  # the pass under test really ran
 
 
 def test_full_alphabet_validity(gold_full):
