@@ -1021,17 +1021,16 @@ int run_dfs_pass(sst_ctx* ctx, const sst_table* t, int rec_width, const MemoMap&
     int64_t want = (P + 127) / 128;
     if (want < 1) want = 1;
     const unsigned grid = (unsigned)(want < grid_max ? want : grid_max);
-    const size_t tile_cap = (size_t)(P / kDfsThreads) + 2 * (size_t)grid + 8;
     if ((rc = reserve(ctx, ctx->d_status, (size_t)(P ? P : 1)))) return rc;
     if ((rc = reserve(ctx, ctx->d_peakoff, (size_t)(P + 2) * 8))) return rc;
     if ((rc = reserve(ctx, ctx->d_blocksums, (size_t)3 * (grid_max > ctx->pass_grid_cap ? grid_max : ctx->pass_grid_cap) * 8))) return rc;
     if ((rc = reserve(ctx, ctx->d_cnt, (size_t)(P + 1) * 4))) return rc;
-    if ((rc = reserve(ctx, ctx->d_tilebase, tile_cap * 24))) return rc;
+    if ((rc = reserve(ctx, ctx->d_tilebase, (size_t)grid * 24 + (size_t)(P / 32 + grid + 8) * 4))) return rc;
     if (!ctx->d_recs.p && (rc = reserve(ctx, ctx->d_recs, (size_t)64 << 20))) return rc;
     if (!ctx->h_run_dev || !ctx->d_bar) return fail(ctx, SST_ERR_NOMEM, "run summary buffers are missing");
     // the item pool holds every tile's window roots and the lists of its split rounds; it keeps its size between runs
     // and grows when a run reports that it was too small
-    if (ctx->pool_capacity < (uint64_t)(8 * P + 65536)) ctx->pool_capacity = ((uint64_t)(8 * P + 65536) + 31) & ~31ULL;
+    if (ctx->pool_capacity < (uint64_t)(32 * P + (1 << 20))) ctx->pool_capacity = ((uint64_t)(32 * P + (1 << 20)) + 63) & ~63ULL;
     for (int attempt = 0;; attempt++) {
         const size_t cap = (size_t)ctx->pool_capacity;
         if ((rc = reserve(ctx, ctx->d_item_m[0], cap * 4))) return rc;
@@ -1060,8 +1059,8 @@ int run_dfs_pass(sst_ctx* ctx, const sst_table* t, int rec_width, const MemoMap&
                           (unsigned long long)cap};
         a.peak_cost = (const uint32_t*)ctx->d_peakcost.p;
         a.blk_cost = (const unsigned long long*)ctx->d_blkcost.p;
-        a.tile_info = (unsigned long long*)ctx->d_tilebase.p;
-        a.tile_cap = (unsigned long long)tile_cap;
+        a.cta_info = (unsigned long long*)ctx->d_tilebase.p;
+        a.peak_cpre = (uint32_t*)((char*)ctx->d_tilebase.p + (size_t)grid * 24);
         a.recs = (unsigned long long*)ctx->d_recs.p;
         a.rec_capacity = (unsigned long long)(ctx->d_recs.cap / rec_width);
         a.peak_off = (unsigned long long*)ctx->d_peakoff.p;

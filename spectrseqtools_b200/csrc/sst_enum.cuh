@@ -15,12 +15,12 @@
 // Every CTA owns a contiguous stretch of the batch — contiguous in (peak, window value) order and equal in ESTIMATED
 // work (peak_cost(): compositions expected in the window, from a coarse count made by the host; no table access), so a
 // 5-nt ladder gap with 10^4 compositions is shared by several CTAs, each taking a sub-range of its window, while a
-// CTA of 1-nt differences takes a few hundred whole peaks.  A CTA works through its stretch in tiles of kDfsThreads
-// peaks, entirely on its own (no grid-wide step until the counts are complete):
-//   count phase, per tile
-//     roots:   thread per PEAK: window words -> number of roots; CTA scan; the roots are written to a stretch of the
-//              item pool in peak order (a peak with many roots is emitted by its whole warp).  Stretches are handed
-//              out by one atomic add per list on a global cursor; their order in the pool is irrelevant.
+// CTA of 1-nt differences takes a few hundred whole peaks.  A CTA works through its stretch entirely on its own (no
+// grid-wide step until the counts are complete), every step over ALL its peaks / items at once, so the number of
+// dependent steps does not grow with the batch:
+//   count phase
+//     roots:   thread per PEAK: window words -> number of roots; scan; the roots are written to a stretch of the
+//              item pool in peak order (a peak with many roots is emitted by its whole warp).
 //     split:   up to kMaxSplit rounds.  Every OPEN item is replaced by its children, closed items are carried over;
 //              thread per item, so every row-mask load of a round is in flight at once, and the list stays in
 //              peak order (depth-first order inside a peak).  Offsets come from warp scans over 32-item chunks plus
@@ -28,7 +28,7 @@
 //     count:   compositions below every item of the final list: closed forms, or — for what is left of deeper
 //              subtrees — a depth-first walk with an explicit stack of at most kDfsDepth frames.
 //   grid barrier: CTA totals -> record base of every CTA's slice (the only grid-wide dependency).
-//   fill phase, per tile: item i of the tile's final list starts at (records before the tile) + (exclusive scan of the
+//   fill phase: item i of the CTA's final list starts at (records of the CTAs before) + (exclusive scan of the
 //     counts), because items are in peak order; peak_off[p] is the start of the peak's first item.  Thread per item,
 //     8-byte record stores at the final positions; the masks are read back from the pool, not loaded again.
 // Inside a thread the items it handles are processed kU at a time, loads first, so that a CTA with a long list (one
@@ -45,7 +45,7 @@ namespace sst {
 
 constexpr int kDfsThreads = 512;
 constexpr int kDfsDepth = 16;               // frames of the per-thread stack = longest composition this pass accepts
-constexpr int kMaxSplit = 3;                // split rounds before the remaining subtrees are walked depth-first
+constexpr int kMaxSplit = 6;                // split rounds before the remaining subtrees are walked depth-first
 constexpr int kU = 2;                       // items a thread has in flight
 constexpr unsigned kDfsNodeCap = 1u << 15;  // edge expansions per item before the pass hands the batch to the level-synchronous one
 
@@ -69,17 +69,17 @@ struct DfsArgs {
     PeakBatch pk;
     MemoMap mp;
     uint8_t* status;                  // [P]
-    uint32_t* peak_first;             // [P] first item of every peak in its tile's final list
+    uint32_t* peak_first;             // [P] first item of every peak in its CTA's list (kept up to date through the split rounds)
+    uint32_t* peak_cpre;              // [P / 32 + gridDim.x + 1] roots of the 32-peak chunks before this one in its CTA's stretch
     ItemPool pool;
     const uint32_t* peak_cost;        // [P] estimated work of every peak (peak_cost(), written when the batch is staged)
     const unsigned long long* blk_cost;  // [ceil(P / kCostBlock)] their sums
-    unsigned long long* tile_info;    // [tile_cap][3] start, length and compositions of every tile's final list
-    unsigned long long tile_cap;
+    unsigned long long* cta_info;     // [gridDim.x][3] start, length and compositions of every CTA's final list
     unsigned long long* recs;         // [rec_capacity][nw] records, final order
     unsigned long long rec_capacity;
     unsigned long long* peak_off;     // [P+1]
     unsigned long long* cta_tot;      // [2][gridDim.x] compositions / roots of every CTA's slice
-    unsigned int* sync;               // this launch's words: [0] barrier arrivals, [2..3] pool cursor (u64), [4] fallback flag, [5] tile cursor
+    unsigned int* sync;               // this launch's words: [0] barrier arrivals, [2..3] pool cursor (u64), [4] fallback flag
     unsigned int* sync_next;          // the next launch's words: cleared by this one
     unsigned long long* host_out;     // pinned + mapped run summary (layout of PassSummary)
     LeafHash leaf;
@@ -261,7 +261,6 @@ k_explain_dfs(const DfsArgs a) {
     unsigned int* fallback = a.sync + 4;
     unsigned int gen = 0;
     int ts = 1;
-    unsigned int* tile_cursor = a.sync + 5;
 
     // ---- this CTA's stretch of the batch: costs [E*b/G, E*(b+1)/G) of the running sum over (peak, window value)
     __shared__ unsigned long long s_S[kDfsThreads + 1];
@@ -331,17 +330,25 @@ k_explain_dfs(const DfsArgs a) {
     const long long pb = s_loc_p[0], pe = s_loc_p[1];
     const unsigned long long rb = s_loc_r[0], eb = s_loc_e[0], re = s_loc_r[1], ee = s_loc_e[1];
     const long long p_last = re > 0 ? pe : pe - 1;
-    const int n_tiles = p_last >= pb ? (int)((p_last - pb + kDfsThreads) / kDfsThreads) : 0;
-    __shared__ unsigned int s_tile0;
-    if (threadIdx.x == 0) s_tile0 = n_tiles ? atomicAdd(tile_cursor, (unsigned)n_tiles) : 0u;
-    __syncthreads();
-    const unsigned long long tile0 = s_tile0;
-    const bool tiles_fit = tile0 + n_tiles <= a.tile_cap;
+    const long long n_mine = p_last >= pb ? p_last - pb + 1 : 0;  // peaks of this CTA (the first and the last possibly in part)
+    uint32_t* const my_cpre = a.peak_cpre + (pb >> 5) + blockIdx.x;  // chunk j = peaks pb + 32 j ..
 
-    // a stretch of the pool for a list of n items (whole 32-item chunks, so that chunk numbers are global)
+    // A stretch of the pool for a list of n items (whole 32-item chunks, so that chunk numbers are global).  The first
+    // half of the pool is divided among the CTAs up front — a bump pointer every thread keeps for itself, no atomic and
+    // no barrier — the second half is handed out by one atomic add per list on a global cursor once a CTA's share is
+    // used up.  The order of the stretches in the pool is irrelevant.
+    const unsigned long long share = ((pool.cap / 2) / gridDim.x) & ~31ULL;
+    unsigned long long bump = share * blockIdx.x;
+    const unsigned long long bump_end = bump + share;
     auto reserve = [&](unsigned long long n) -> unsigned long long {
+        const unsigned long long need = (n + 31ULL) & ~31ULL;
+        if (bump + need <= bump_end) {
+            const unsigned long long at = bump;
+            bump += need;
+            return at;
+        }
         __syncthreads();
-        if (threadIdx.x == 0) s_base = n ? atomicAdd(cursor, (n + 31ULL) & ~31ULL) : 0ULL;
+        if (threadIdx.x == 0) s_base = need ? (pool.cap / 2) + atomicAdd(cursor, need) : 0ULL;
         __syncthreads();
         return s_base;
     };
@@ -444,51 +451,91 @@ k_explain_dfs(const DfsArgs a) {
     // ---------------- count phase ----------------
     cta_stamp(a, 0);
     unsigned long long my_comps = 0, my_roots = 0;
-    bool overflow = !tiles_fit;
-    for (int t = 0; t < n_tiles && !overflow; t++) {
-        const long long p = pb + (long long)t * kDfsThreads + threadIdx.x;
-        const bool ok = p <= p_last;
-        const bool owner = ok && (p > pb || rb == 0);  // the peak starts in this CTA's stretch: it writes status and peak_off
-        uint32_t wa = 1, wb = 0;  // clamped window (masses fit 32 bits: the table is < 2^31 masses wide)
+    bool overflow = false;
+    // this CTA's part of the (clamped) window of peak p: [wa, wb], empty when wa > wb
+    auto window_of = [&](long long p, uint32_t& wa, uint32_t& wb, bool owner) {
+        wa = 1;
+        wb = 0;
+        const int64_t tg = a.pk.target[p], th = a.pk.thr[p];
+        const int64_t lo = tg - th, hi = tg + th;
+        if (owner) {  // the peak starts in this CTA's stretch: it writes status and peak_off
+            uint8_t st = 0;
+            if (lo <= 0 && 0 <= hi) st |= ST_ZERO_IN_WINDOW;
+            if (lo <= hi && hi >= limit) st |= ST_OUT_OF_TABLE;
+            a.status[p] = st;
+        }
+        int64_t ca = lo < 1 ? 1 : lo, cb = hi < limit - 1 ? hi : limit - 1;
+        if (ca <= cb) {  // a peak shared with the neighbouring CTAs
+            const unsigned long long W = (unsigned long long)(cb - ca + 1);
+            const int64_t full_a = ca;
+            if (p == pb && rb > 0) ca = full_a + (int64_t)((rb * W) / eb);
+            if (p == pe) cb = full_a + (int64_t)((re * W) / ee) - 1;
+        }
+        if (ca <= cb) {
+            wa = (uint32_t)ca;
+            wb = (uint32_t)cb;
+        }
+    };
+    // ---- roots of every peak; a warp handles 32 consecutive peaks at a time and scans their counts
+    const long long n_pchunks = (n_mine + 31) >> 5;
+    for (long long c = warp; c < n_pchunks; c += kWarps) {
+        const long long j = (c << 5) + lane, p = pb + j;
         unsigned int n = 0;
-        uint32_t meta0 = (uint32_t)top_row;
-        if (ok) {
-            const int64_t tg = a.pk.target[p], th = a.pk.thr[p];
-            const int64_t lo = tg - th, hi = tg + th;
-            if (owner) {
-                uint8_t st = 0;
-                if (lo <= 0 && 0 <= hi) st |= ST_ZERO_IN_WINDOW;
-                if (lo <= hi && hi >= limit) st |= ST_OUT_OF_TABLE;
-                a.status[p] = st;
-            }
-            meta0 |= (uint32_t)a.pk.mode[p] << 24;
-            int64_t ca = lo < 1 ? 1 : lo, cb = hi < limit - 1 ? hi : limit - 1;
-            if (ca <= cb) {  // a peak shared with the neighbouring CTAs: this one's part of the (clamped) window
-                const unsigned long long W = (unsigned long long)(cb - ca + 1);
-                const int64_t full_a = ca;
-                if (p == pb && rb > 0) ca = full_a + (int64_t)((rb * W) / eb);
-                if (p == pe) cb = full_a + (int64_t)((re * W) / ee) - 1;
-            }
-            if (ca <= cb) {
-                wa = (uint32_t)ca;
-                wb = (uint32_t)cb;
-                for_window_words(last, ca, cb, [&](int64_t, uint64_t x) { n += __popcll(x); });
-            }
+        if (j < n_mine) {
+            uint32_t wa, wb;
+            window_of(p, wa, wb, p > pb || rb == 0);
+            if (wa <= wb) for_window_words(last, (int64_t)wa, (int64_t)wb, [&](int64_t, uint64_t x) { n += __popcll(x); });
         }
         my_roots += n;
-        unsigned int NA;
-        unsigned int pf = block_scan32(n, &NA);  // the peak's first item in the tile's list
-        if (t == 0) cta_stamp(a, 1);
-        unsigned long long A = reserve(NA);
-        if (A + NA > pool.cap) {
-            overflow = true;
-            break;
+        unsigned int incl = n;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned int y = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+            if (lane >= o) incl += y;
         }
-        // ---- window roots in peak order; a peak with many roots is emitted by its whole warp (lane l takes window word l, l+32, ...)
-        {
-            const unsigned long long zero[NW] = {};
-            const int ind0 = s_ind[top_row];
-            const int all0 = (BUDGET && ok) ? a.pk.max_mods[p] : 0;
+        // (a first peak that started in the previous CTA's stretch keeps no entry: its part here starts at item 0, and
+        //  peak_first[p] belongs to the CTA the peak starts in)
+        if (j < n_mine && (p > pb || rb == 0)) a.peak_first[p] = incl - n;
+        if (lane == 31) my_cpre[c] = incl;
+    }
+    __syncthreads();
+    unsigned int NA = 0;
+    for (long long c0 = 0; c0 < n_pchunks; c0 += kDfsThreads) {  // exclusive scan of the chunk totals
+        const long long c = c0 + threadIdx.x;
+        const unsigned int x = c < n_pchunks ? my_cpre[c] : 0u;
+        unsigned int tot;
+        const unsigned int ex = block_scan32(x, &tot);
+        if (c < n_pchunks) my_cpre[c] = NA + ex;
+        NA += tot;
+    }
+    __syncthreads();
+    cta_stamp(a, 1);
+    unsigned long long A = reserve(NA);
+    if (A + NA > pool.cap) overflow = true;
+    // ---- window roots in peak order; a peak with many roots is emitted by its whole warp (lane l takes window word l, l+32, ...)
+    if (!overflow) {
+        const unsigned long long zero[NW] = {};
+        const int ind0 = s_ind[top_row];
+        for (long long c = warp; c < n_pchunks; c += kWarps) {
+            const long long j = (c << 5) + lane, p = pb + j;
+            const bool ok = j < n_mine;
+            uint32_t wa = 1, wb = 0, pf = 0, n = 0, meta0 = (uint32_t)top_row;
+            int all0 = 0;
+            if (ok) {
+                window_of(p, wa, wb, false);
+                if (p > pb || rb == 0) {
+                    pf = my_cpre[c] + a.peak_first[p];
+                    a.peak_first[p] = pf;
+                }
+                // roots of the peak = first item of the next peak - first item of this one (the last lane: chunk total)
+                meta0 |= (uint32_t)a.pk.mode[p] << 24;
+                if (BUDGET) all0 = a.pk.max_mods[p];
+            }
+            {
+                const uint32_t nxt = __shfl_down_sync(0xFFFFFFFFu, pf, 1);
+                const uint32_t chunk_end = c + 1 < n_pchunks ? my_cpre[c + 1] : NA;
+                n = ok ? ((lane == 31 || j + 1 >= n_mine) ? chunk_end : nxt) - pf : 0u;
+            }
             const bool heavy = n > 8;
             if (n && !heavy) {
                 unsigned long long o = A + pf;
@@ -516,14 +563,14 @@ k_explain_dfs(const DfsArgs a) {
                         if (wd == w0) x &= (1ULL << (2 * (31 - (int)(sa & 31)) + 1)) - 1ULL;
                         if (wd == w1) x &= ~0ULL << (2 * (31 - (int)(sb & 31)));
                     }
-                    const unsigned c = __popcll(x);
-                    unsigned incl = c;
+                    const unsigned cc = __popcll(x);
+                    unsigned incl = cc;
 #pragma unroll
                     for (int o = 1; o < 32; o <<= 1) {
                         const unsigned y = __shfl_up_sync(0xFFFFFFFFu, incl, o);
                         if (lane >= o) incl += y;
                     }
-                    unsigned long long o2 = run + (incl - c);
+                    unsigned long long o2 = run + (incl - cc);
                     while (x) {
                         const int pos = 63 - __clzll((long long)x);
                         x &= ~(1ULL << pos);
@@ -533,81 +580,83 @@ k_explain_dfs(const DfsArgs a) {
                 }
             }
         }
-        __syncthreads();  // the tile's roots are visible to the whole CTA
-        if (t == 0) cta_stamp(a, 2);
+    }
+    __syncthreads();  // the roots are visible to the whole CTA
+    cta_stamp(a, 2);
 
-        // ---- split rounds
-        for (int round = 0; round < kMaxSplit; round++) {
-            bool any_open = false;
-            unsigned long long unused = 0;
-            const unsigned int NB = count_pass(std::false_type{}, A, NA, any_open, unused);
-            if (!__syncthreads_or(any_open)) break;
-            const unsigned long long B = reserve(NB);
-            if (B + NB > pool.cap) {
-                overflow = true;
-                break;
+    // ---- split rounds
+    for (int round = 0; round < kMaxSplit && !overflow; round++) {
+        bool any_open = false;
+        unsigned long long unused = 0;
+        const unsigned int NB = count_pass(std::false_type{}, A, NA, any_open, unused);
+        if (!__syncthreads_or(any_open)) break;
+        const unsigned long long B = reserve(NB);
+        if (B + NB > pool.cap) {
+            overflow = true;
+            break;
+        }
+        for (unsigned int i0 = threadIdx.x; i0 < NA; i0 += kDfsThreads * kU) {
+            uint32_t m[kU], meta[kU], pk[kU], o[kU];
+            unsigned long long path[kU][NW];
+            int all[kU], ind[kU];
+            uint4 ch[kU];
+            bool valid[kU];
+#pragma unroll
+            for (int u = 0; u < kU; u++) {  // everything an item needs comes in one round of independent loads
+                const unsigned int i = i0 + u * kDfsThreads;
+                valid[u] = i < NA;
+                const unsigned long long at = A + (valid[u] ? i : 0u);
+                m[u] = pool.m[at];
+                meta[u] = pool.meta[at];
+                pk[u] = pool.peak[at];
+                o[u] = pool.cpre[at >> 5] + pool.off[at];
+                ch[u] = pool.mask[at];
+#pragma unroll
+                for (int q = 0; q < NW; q++) path[u][q] = pool.path[at * NW + q];
+                all[u] = BUDGET ? pool.all[at] : 0;
+                ind[u] = BUDGET ? pool.ind[at] : 0;
             }
-            for (unsigned int i0 = threadIdx.x; i0 < NA; i0 += kDfsThreads * kU) {
-                uint32_t m[kU], meta[kU], pk[kU], o[kU];
-                unsigned long long path[kU][NW];
-                int all[kU], ind[kU];
-                uint4 ch[kU];
-                bool valid[kU];
 #pragma unroll
-                for (int u = 0; u < kU; u++) {  // everything an item needs comes in one round of independent loads
-                    const unsigned int i = i0 + u * kDfsThreads;
-                    valid[u] = i < NA;
-                    const unsigned long long at = A + (valid[u] ? i : 0u);
-                    m[u] = pool.m[at];
-                    meta[u] = pool.meta[at];
-                    pk[u] = pool.peak[at];
-                    o[u] = pool.cpre[at >> 5] + pool.off[at];
-                    ch[u] = pool.mask[at];
+            for (int u = 0; u < kU; u++) {
+                if (!valid[u]) continue;
+                unsigned long long dst = B + o[u];
+                if (item_kind((meta[u] >> 24) & 3, m[u], rt.wmin) == KIND_OPEN) {
+                    const int rmax = meta[u] & 0xFF;
+                    Mask128 c = mk(ch[u]);
+                    while (!mask_empty(c)) {
+                        const int r = mask_pop_lowest(c);
+                        unsigned long long w[NW];
 #pragma unroll
-                    for (int q = 0; q < NW; q++) path[u][q] = pool.path[at * NW + q];
-                    all[u] = BUDGET ? pool.all[at] : 0;
-                    ind[u] = BUDGET ? pool.ind[at] : 0;
-                }
-#pragma unroll
-                for (int u = 0; u < kU; u++) {
-                    if (!valid[u]) continue;
-                    unsigned long long dst = B + o[u];
-                    if (item_kind((meta[u] >> 24) & 3, m[u], rt.wmin) == KIND_OPEN) {
-                        const int rmax = meta[u] & 0xFF;
-                        Mask128 c = mk(ch[u]);
-                        while (!mask_empty(c)) {
-                            const int r = mask_pop_lowest(c);
-                            unsigned long long w[NW];
-#pragma unroll
-                            for (int q = 0; q < NW; q++) w[q] = path[u][q];
-                            path_append(w, NW, r);
-                            const int mod = BUDGET ? s_mod[r] : 0;
-                            put_item(dst++, m[u] - (uint32_t)s_w[r], pk[u], (uint32_t)r | ((meta[u] & 0xFFFFFF00u) + 0x100u), w, all[u] - mod,
-                                     ((r == rmax) ? ind[u] : s_ind[r]) - mod);
-                        }
-                    } else {
-                        put_item(dst, m[u], pk[u], meta[u], path[u], all[u], ind[u]);
+                        for (int q = 0; q < NW; q++) w[q] = path[u][q];
+                        path_append(w, NW, r);
+                        const int mod = BUDGET ? s_mod[r] : 0;
+                        put_item(dst++, m[u] - (uint32_t)s_w[r], pk[u], (uint32_t)r | ((meta[u] & 0xFFFFFF00u) + 0x100u), w, all[u] - mod,
+                                 ((r == rmax) ? ind[u] : s_ind[r]) - mod);
                     }
+                } else {
+                    put_item(dst, m[u], pk[u], meta[u], path[u], all[u], ind[u]);
                 }
             }
-            pf = offset_of(A, pf, NA, NB);
-            A = B;
-            NA = NB;
-            __syncthreads();
         }
-        if (overflow) break;
-        if (t == 0) cta_stamp(a, 6);
+        for (long long j = (rb > 0 ? 1 : 0) + threadIdx.x; j < n_mine; j += kDfsThreads)  // (not a first peak that the previous CTA owns)
+            a.peak_first[pb + j] = offset_of(A, a.peak_first[pb + j], NA, NB);
+        A = B;
+        NA = NB;
+        __syncthreads();
+    }
+    cta_stamp(a, 6);
 
-        // ---- compositions below every item of the final list, and where its records start inside the tile
+    // ---- compositions below every item of the final list, and where its records start in the CTA's stretch
+    unsigned int my_recs = 0;
+    if (!overflow) {
         bool dummy = false;
-        const unsigned int tile_recs = count_pass(std::true_type{}, A, NA, dummy, my_comps);
-        if (threadIdx.x == 0) {
-            unsigned long long* ti = a.tile_info + (tile0 + t) * 3;
-            ti[0] = A;
-            ti[1] = NA;
-            ti[2] = tile_recs;
-        }
-        if (owner) a.peak_first[p] = pf;
+        my_recs = count_pass(std::true_type{}, A, NA, dummy, my_comps);
+    }
+    if (threadIdx.x == 0) {
+        unsigned long long* ci = a.cta_info + (size_t)blockIdx.x * 3;
+        ci[0] = A;
+        ci[1] = NA;
+        ci[2] = my_recs;
     }
     if (capped || overflow) atomicExch(fallback, overflow ? 2u : 1u);
     {
@@ -639,7 +688,7 @@ k_explain_dfs(const DfsArgs a) {
     const unsigned int fb = __ldcg(fallback);
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         s_sum.totals[0] = n_roots;
-        s_sum.totals[1] = __ldcg(cursor);                      // pool items used
+        s_sum.totals[1] = __ldcg(cursor);                      // pool items taken from the shared half
         s_sum.totals[2] = n_comps;
         s_sum.totals[3] = 1ULL;
         if (fb == 1u) s_sum.flags[3] = 1;                      // a subtree too large for one thread: level-synchronous pass
@@ -652,14 +701,16 @@ k_explain_dfs(const DfsArgs a) {
     }
 
     // ---------------- fill phase ----------------
-    unsigned long long run = rec_base;
-    for (int t = 0; t < n_tiles; t++) {
-        const long long p = pb + (long long)t * kDfsThreads + threadIdx.x;
-        const unsigned long long* ti = a.tile_info + (tile0 + t) * 3;
-        const unsigned long long A = ti[0];
-        const unsigned int NA = (unsigned int)ti[1], tile_recs = (unsigned int)ti[2];
+    {
+        const unsigned long long run = rec_base;
+        const unsigned long long* ci = a.cta_info + (size_t)blockIdx.x * 3;
+        const unsigned long long A = ci[0];
+        const unsigned int NA = (unsigned int)ci[1], my_recs = (unsigned int)ci[2];
         // peak role: a peak starts where its first item starts (items and records are both in peak order)
-        if (p <= p_last && (p > pb || rb == 0)) a.peak_off[p] = run + offset_of(A, a.peak_first[p], NA, tile_recs);
+        for (long long j = threadIdx.x; j < n_mine; j += kDfsThreads) {
+            const long long p = pb + j;
+            if (p > pb || rb == 0) a.peak_off[p] = run + offset_of(A, a.peak_first[p], NA, my_recs);
+        }
         // item role
         for (unsigned int i0 = threadIdx.x; i0 < NA; i0 += kDfsThreads * kU) {
             uint32_t m[kU], meta[kU], cnt[kU], o[kU];
@@ -710,7 +761,6 @@ k_explain_dfs(const DfsArgs a) {
                 }
             }
         }
-        run += tile_recs;
     }
     if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) a.peak_off[P] = n_comps;
     __syncthreads();
