@@ -124,6 +124,10 @@ int sst_classify_fetch(sst_ctx* ctx, uint8_t* out /* B*F */);
  * until sst_classify_wait returns); an enumeration pass issued in between overlaps it */
 int sst_classify_async(sst_ctx* ctx, const sst_table* t, const double* observed, int64_t F, const double* offsets, int B,
                        double precision, double tolerance, uint8_t* out /* B*F */);
+/* the same with two flags per byte: fragment f of breakage b in the low (f even) or high nibble of byte
+ * (b * Fp + f) / 2, Fp = F rounded up to even; out holds B * Fp / 2 bytes */
+int sst_classify_async_packed(sst_ctx* ctx, const sst_table* t, const double* observed, int64_t F, const double* offsets, int B,
+                              double precision, double tolerance, uint8_t* out /* B*Fp/2 */);
 int sst_classify_wait(sst_ctx* ctx);
 
 /* ---- sequence-length bounds: replaces compute_sequence_length_bound (mass_table.py:343-487), both directions in one
@@ -174,6 +178,20 @@ int sst_explain_cta_ns(sst_ctx* ctx, int enable, uint64_t* out, int cap_ctas, in
  * [counted, grid barrier passed, written]; after the last level [per-level peak totals summed], [placement table
  * written], [records permuted].  Right after a grid barrier that is every CTA's clock.  Unused slots are 0. */
 int sst_explain_phase_ns(const sst_ctx* ctx, uint64_t* out /* [32] */);
+/* The whole call — replaces a loop of calculate_explanations (common.py:47-65) — WITHOUT WAITING: the copy of the inputs,
+ * staging, the enumeration pass and the copy of the results are queued on the context's stream; sst_explain_collect
+ * waits for them.  One modification budget for the batch (what calculate_explanations passes).  All host pointers must
+ * stay valid until sst_explain_collect returns; status_out[P], off32_out[P+1] (peak offsets as uint32) and
+ * recs_out[recs_bytes] should be pinned (sst_host_alloc).  The record copy is sized by the previous batch (+ 25 %);
+ * sst_explain_collect fetches the rest if this batch is larger.  When the batch cannot be queued blindly (a
+ * modification budget that may bind, compositions longer than 16 nucleotides, a forced pass) the work is done inside
+ * sst_explain_collect instead.  SST_ERR_NOMEM from sst_explain_collect with *n_comps set: recs_out is too small —
+ * the result is still on the device, fetch it with sst_explain_fetch.  Two contexts on one device give two batches
+ * in flight: the copies of one overlap the kernels of the other. */
+int sst_explain_submit_f64(sst_ctx* ctx, const sst_table* t, const double* mass, const double* thr, int32_t max_mods, int64_t P,
+                           const int32_t* ind, const uint8_t* is_mod, double precision, double tolerance, int with_memo, uint8_t* status_out,
+                           uint32_t* off32_out, uint8_t* recs_out, uint64_t recs_bytes);
+int sst_explain_collect(sst_ctx* ctx, const sst_table* t, uint64_t* n_comps, int* rec_width);
 /* status[P]; peak_off[P+1] (compositions of peak p are records peak_off[p] .. peak_off[p+1]);
  * recs[n_comps * rec_width]: row indices in ascending order, 0-padded.  Any pointer may be NULL. */
 int sst_explain_fetch(sst_ctx* ctx, uint8_t* status, uint64_t* peak_off, uint8_t* recs);

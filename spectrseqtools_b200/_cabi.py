@@ -36,7 +36,7 @@ EXPORTS = [
     "sst_table_download_masks", "sst_table_destroy", "sst_is_valid", "sst_valid_stage", "sst_valid_run",
     "sst_valid_fetch", "sst_valid_stage_f64", "sst_explain", "sst_explain_stage", "sst_explain_stage_f64", "sst_explain_stage_f64_uniform", "sst_explain_rec_width", "sst_explain_phase_ns",
     "sst_explain_run", "sst_explain_fetch", "sst_classify", "sst_classify_stage", "sst_classify_run", "sst_classify_fetch", "sst_classify_launch", "sst_classify_async", "sst_classify_wait", "sst_length_bounds",
-    "sst_set_pass", "sst_last_pass", "sst_explain_cta_ns",
+    "sst_set_pass", "sst_last_pass", "sst_explain_cta_ns", "sst_explain_submit_f64", "sst_explain_collect", "sst_classify_async_packed",
 ]
 
 
@@ -104,7 +104,10 @@ def load() -> C.CDLL:
             "sst_classify_fetch": (C.c_int, [vp, u8p]),
             "sst_classify_launch": (C.c_int, [vp, vp, C.c_double, C.c_double]),
             "sst_classify_async": (C.c_int, [vp, vp, fp, C.c_int64, fp, C.c_int, C.c_double, C.c_double, u8p]),
+            "sst_classify_async_packed": (C.c_int, [vp, vp, fp, C.c_int64, fp, C.c_int, C.c_double, C.c_double, u8p]),
             "sst_classify_wait": (C.c_int, [vp]),
+            "sst_explain_submit_f64": (C.c_int, [vp, vp, fp, fp, C.c_int32, C.c_int64, i32p, u8p, C.c_double, C.c_double, C.c_int, u8p, u32p, u8p, C.c_uint64]),
+            "sst_explain_collect": (C.c_int, [vp, vp, C.POINTER(C.c_uint64), C.POINTER(C.c_int)]),
             "sst_set_pass": (C.c_int, [vp, C.c_int]),
             "sst_last_pass": (C.c_int, [vp]),
             "sst_explain_cta_ns": (C.c_int, [vp, C.c_int, u64p, C.c_int, C.POINTER(C.c_int)]),
@@ -300,12 +303,19 @@ class Context:
         """Queue the classification kernel without waiting (the next synchronous call on the context completes it)."""
         self._check(self._lib.sst_classify_launch(self._h, table._h, float(precision), float(tolerance)))
 
-    def classify_async(self, table: "DeviceTable", observed: np.ndarray, offsets: np.ndarray, precision: float, tolerance: float):
+    def classify_async(self, table: "DeviceTable", observed: np.ndarray, offsets: np.ndarray, precision: float, tolerance: float,
+                       packed: bool = False):
         """Whole classification on the side stream, no waiting; returns the pinned uint8[B, F] buffer the flags will
-        land in — valid after ``classify_wait()`` and until the next classification on this context."""
+        land in — valid after ``classify_wait()`` and until the next classification on this context.  ``packed``: two
+        flags per byte, uint8[B, ceil(F / 2)] (fragment f in the low nibble when f is even)."""
         o, b = _arr(observed, np.float64), _arr(offsets, np.float64)
         self._async_keep = (o, b)  # the copies are asynchronous: keep the host arrays alive
         B, F = len(b), len(o)
+        if packed:
+            half = (F + 1) // 2
+            buf = self._pinned("classify", B * half)[: B * half]
+            self._check(self._lib.sst_classify_async_packed(self._h, table._h, _p(o), F, _p(b), B, float(precision), float(tolerance), _p(buf)))
+            return buf.reshape(B, half)
         buf = self._pinned("classify", B * F)[: B * F]
         self._check(self._lib.sst_classify_async(self._h, table._h, _p(o), F, _p(b), B, float(precision), float(tolerance), _p(buf)))
         return buf.reshape(B, F)
@@ -348,6 +358,47 @@ class Context:
         self._check(self._lib.sst_explain_run(self._h, table._h, int(rec_width), C.c_uint64(memo_capacity), C.byref(nr), C.byref(nc)))
         self._last = (int(nr.value), int(nc.value), int(self._lib.sst_explain_rec_width(self._h)))
         return int(nr.value), int(nc.value)
+
+    def explain_submit_f64(self, table: "DeviceTable", mass, thr, max_mods: int, ind, is_mod, precision, tolerance, with_memo):
+        """Queue a whole enumeration call (inputs in, staging, pass, results out) without waiting; ``explain_collect``
+        completes it.  Results land in this context's pinned buffers."""
+        m = _arr(mass, np.float64)
+        h = None if thr is None else _arr(thr, np.float64)
+        iv, im = _arr(ind, np.int32), _arr(is_mod, np.uint8)
+        if h is not None and len(h) != len(m):
+            raise ValueError("per-peak arrays differ in length")
+        if len(iv) != table.R or len(im) != table.R:
+            raise ValueError("ind / is_mod need one entry per table row")
+        P = len(m)
+        status = self._pinned("status", P)[:P]
+        off = self._pinned("off32", 4 * (P + 1))[: 4 * (P + 1)].view(np.uint32)
+        recs = self._pinned("recs", max(self.__dict__.get("_recs_hint", 0), 1 << 20))
+        self._submitted = (m, h, iv, im, P, status, off, recs, table)  # the call reads the host arrays until it is collected
+        self._check(self._lib.sst_explain_submit_f64(self._h, table._h, _p(m), _p(h), int(max_mods), P, _p(iv), _p(im), float(precision),
+                                                     float(tolerance), 1 if with_memo else 0, _p(status), _p(off), _p(recs), recs.size))
+        self._staged_P = P
+
+    def explain_collect(self):
+        """-> (status uint8[P], offsets uint32[P+1], records uint8[n, W]): views of this context's pinned buffers,
+        valid until the next call on it."""
+        m, h, iv, im, P, status, off, recs, table = self._submitted
+        nc, W = C.c_uint64(), C.c_int()
+        rc = self._lib.sst_explain_collect(self._h, table._h, C.byref(nc), C.byref(W))
+        if rc == SST_ERR_NOMEM and nc.value and W.value:  # the pinned record buffer was too small: grow it, fetch from the device
+            need = nc.value * W.value
+            self._recs_hint = need + need // 4
+            recs = self._pinned("recs", self._recs_hint)
+            self._last = (0, int(nc.value), int(W.value))
+            off64 = np.empty(P + 1, dtype=np.uint64)
+            self._check(self._lib.sst_explain_fetch(self._h, _p(status), _p(off64), _p(recs[: need])))
+            off[:] = off64.astype(np.uint32)
+        else:
+            self._check(rc)
+        self._submitted = None
+        n, w = int(nc.value), int(W.value)
+        self._last = (0, n, w)
+        self._recs_hint = max(self.__dict__.get("_recs_hint", 0), n * w + n * w // 4)
+        return status, off, recs[: n * w].reshape(n, w)
 
     def explain_phase_ns(self) -> np.ndarray:
         """Device timestamps of the last enumeration pass (see sst_explain_phase_ns)."""
@@ -420,16 +471,19 @@ class DeviceTable:
         return out
 
 
-_contexts: Dict[int, Context] = {}
+_contexts: Dict[Tuple[int, int], Context] = {}
 
 
 def default_device() -> int:
     return int(os.environ.get("SST_DEVICE", os.environ.get("LOCAL_RANK", "0")))
 
 
-def context(device: Optional[int] = None) -> Context:
+def context(device: Optional[int] = None, slot: int = 0) -> Context:
+    """The context of a device.  ``slot`` > 0 gives further contexts on the same device (own streams, own scratch and
+    result buffers): batches submitted on different slots are in flight together — the copies of one overlap the
+    kernels of the other.  Tables built on slot 0 are used by every slot of the device."""
     d = default_device() if device is None else int(device)
-    ctx = _contexts.get(d)
+    ctx = _contexts.get((d, int(slot)))
     if ctx is None:
-        ctx = _contexts[d] = Context(d)
+        ctx = _contexts[(d, int(slot))] = Context(d)
     return ctx

@@ -108,6 +108,24 @@ struct sst_ctx {
     DevBuf d_rootvp, d_rootcnt, d_tilebase, d_ctans;
     uint64_t pool_capacity = 0;        // items of the depth-first pass's pool
     DevBuf d_peakcost, d_blkcost;      // scheduling costs of the staged batch (peak_cost(), sums per kCostBlock peaks)
+    DevBuf d_peakoff32;                // peak offsets as uint32 (what the asynchronous entry copies back)
+    // asynchronous whole call (sst_explain_submit_f64 / sst_explain_collect)
+    struct Pending {
+        bool active = false, done = false;
+        const double* mass = nullptr;
+        const double* thr = nullptr;
+        int32_t max_mods = 0;
+        int64_t P = 0;
+        const int32_t* ind = nullptr;
+        const uint8_t* is_mod = nullptr;
+        double precision = 0, tolerance = 0;
+        int with_memo = 0, rec_width = 0;
+        uint8_t* status = nullptr;
+        uint32_t* off32 = nullptr;
+        uint8_t* recs = nullptr;
+        uint64_t recs_bytes = 0, copied = 0;
+    } pend;
+    uint64_t last_comps = 0;           // compositions of the last batch: sizes the speculative copy of the next one
     bool want_cta_ns = false;          // diagnostics: per-CTA phase timestamps of the depth-first pass
     int cta_ns_grid = 0;
     uint64_t phase_ns[32] = {0};
@@ -403,7 +421,7 @@ void sst_ctx_destroy(sst_ctx* ctx) {
                       &ctx->d_memo_peaks, &ctx->d_status, &ctx->d_cnt, &ctx->d_peakoff, &ctx->d_recs,
                       &ctx->d_blocksums, &ctx->d_memo_keys, &ctx->d_memo_alive, &ctx->d_memo_top,
                       &ctx->d_memo_misc, &ctx->d_flush, &ctx->d_vtarget, &ctx->d_vthr, &ctx->d_vout,
-                      &ctx->d_scan, &ctx->d_vmass, &ctx->d_vthrf, &ctx->d_chunk_k, &ctx->d_chunk_r, &ctx->d_tmprecs, &ctx->d_tmppeak, &ctx->d_lvlcnt, &ctx->d_lvlA, &ctx->d_ctalvl, &ctx->d_nodemask, &ctx->d_cobs, &ctx->d_coff, &ctx->d_cout, &ctx->d_bkeys, &ctx->d_btop, &ctx->d_blower, &ctx->d_bupper, &ctx->d_bout, &ctx->d_rootvp, &ctx->d_rootcnt, &ctx->d_tilebase, &ctx->d_ctans, &ctx->d_peakcost, &ctx->d_blkcost,
+                      &ctx->d_scan, &ctx->d_vmass, &ctx->d_vthrf, &ctx->d_chunk_k, &ctx->d_chunk_r, &ctx->d_tmprecs, &ctx->d_tmppeak, &ctx->d_lvlcnt, &ctx->d_lvlA, &ctx->d_ctalvl, &ctx->d_nodemask, &ctx->d_cobs, &ctx->d_coff, &ctx->d_cout, &ctx->d_bkeys, &ctx->d_btop, &ctx->d_blower, &ctx->d_bupper, &ctx->d_bout, &ctx->d_rootvp, &ctx->d_rootcnt, &ctx->d_tilebase, &ctx->d_ctans, &ctx->d_peakcost, &ctx->d_blkcost, &ctx->d_peakoff32,
                       &ctx->d_item_m[0], &ctx->d_item_m[1], &ctx->d_item_peak[0], &ctx->d_item_peak[1],
                       &ctx->d_item_meta[0], &ctx->d_item_meta[1], &ctx->d_item_all[0], &ctx->d_item_all[1],
                       &ctx->d_item_ind[0], &ctx->d_item_ind[1], &ctx->d_item_path[0], &ctx->d_item_path[1]};
@@ -686,7 +704,7 @@ int sst_classify_launch(sst_ctx* ctx, const sst_table* t, double precision, doub
         KTimer kt(ctx, SST_K_CLASSIFY);
         k_classify<<<dim3((unsigned)((ctx->CF + 255) / 256), (unsigned)((ctx->CB + kClassifyPerThread - 1) / kClassifyPerThread)), 256, 0, ctx->stream>>>(view_of(t), (const double*)ctx->d_cobs.p, ctx->CF,
                                                                               (const double*)ctx->d_coff.p, ctx->CB, precision, tolerance,
-                                                                              (uint8_t*)ctx->d_cout.p);
+                                                                              (uint8_t*)ctx->d_cout.p, 0);
         kt.stop(1);
         CK(cudaGetLastError());
     }
@@ -704,8 +722,21 @@ int sst_classify_run(sst_ctx* ctx, const sst_table* t, double precision, double 
 // the whole classification on the context's SIDE stream, without waiting: stage (pinned `observed` / `offsets`
 // recommended), kernel, copy of the flags into `out` (pinned).  sst_classify_wait completes it.  An enumeration pass
 // issued in between runs concurrently on the main stream.
+static int classify_async(sst_ctx* ctx, const sst_table* t, const double* observed, int64_t F, const double* offsets, int B,
+                          double precision, double tolerance, uint8_t* out, int pack4);
+
 int sst_classify_async(sst_ctx* ctx, const sst_table* t, const double* observed, int64_t F, const double* offsets, int B,
                        double precision, double tolerance, uint8_t* out) {
+    return classify_async(ctx, t, observed, F, offsets, B, precision, tolerance, out, 0);
+}
+
+int sst_classify_async_packed(sst_ctx* ctx, const sst_table* t, const double* observed, int64_t F, const double* offsets, int B,
+                              double precision, double tolerance, uint8_t* out) {
+    return classify_async(ctx, t, observed, F, offsets, B, precision, tolerance, out, 1);
+}
+
+static int classify_async(sst_ctx* ctx, const sst_table* t, const double* observed, int64_t F, const double* offsets, int B,
+                          double precision, double tolerance, uint8_t* out, int pack4) {
     CK(cudaSetDevice(ctx->device));
     if (F < 0 || B < 0 || B > 65535) return fail(ctx, SST_ERR_BAD_ARG, "fragment / breakage count out of range");
     CK(cudaStreamSynchronize(ctx->stream2));  // an earlier asynchronous classification still owns the buffers
@@ -720,10 +751,10 @@ int sst_classify_async(sst_ctx* ctx, const sst_table* t, const double* observed,
     CK(cudaMemcpyAsync(ctx->d_coff.p, offsets, (size_t)B * 8, cudaMemcpyHostToDevice, ctx->stream2));
     k_classify<<<dim3((unsigned)((F + 255) / 256), (unsigned)((B + kClassifyPerThread - 1) / kClassifyPerThread)), 256, 0, ctx->stream2>>>(view_of(t), (const double*)ctx->d_cobs.p, F,
                                                                                        (const double*)ctx->d_coff.p, B, precision, tolerance,
-                                                                                       (uint8_t*)ctx->d_cout.p);
+                                                                                       (uint8_t*)ctx->d_cout.p, pack4);
     CK(cudaGetLastError());
     ctx->k_launches[SST_K_CLASSIFY] += 1;
-    CK(cudaMemcpyAsync(out, ctx->d_cout.p, (size_t)F * B, cudaMemcpyDeviceToHost, ctx->stream2));
+    CK(cudaMemcpyAsync(out, ctx->d_cout.p, pack4 ? (size_t)(((F + 1) & ~1LL) / 2) * B : (size_t)F * B, cudaMemcpyDeviceToHost, ctx->stream2));
     return SST_OK;
 }
 
@@ -863,8 +894,9 @@ int sst_explain_stage(sst_ctx* ctx, const sst_table* t, const int64_t* target, c
 
 namespace {
 // max_mods == nullptr: every peak has the budget `uniform_mods` (the array is filled on the device)
-int stage_f64(sst_ctx* ctx, const sst_table* t, const double* mass, const double* thr, const int32_t* max_mods, int32_t uniform_mods,
-              int64_t P, const int32_t* ind, const uint8_t* is_mod, double precision, double tolerance, int with_memo) {
+// everything of the staging that can be queued without waiting: copies in, k_stage_f64, the summary on its way to h_misc
+int stage_f64_enqueue(sst_ctx* ctx, const sst_table* t, const double* mass, const double* thr, const int32_t* max_mods, int32_t uniform_mods,
+                      int64_t P, const int32_t* ind, const uint8_t* is_mod, double precision, double tolerance, int with_memo) {
     CK(cudaSetDevice(ctx->device));
     ctx->have_result = false;
     if (P < 0) return fail(ctx, SST_ERR_BAD_ARG, "negative peak count");
@@ -912,10 +944,17 @@ int stage_f64(sst_ctx* ctx, const sst_table* t, const double* mass, const double
         CK(cudaGetLastError());
     }
     CK(cudaMemcpyAsync(ctx->h_misc, ctx->d_scan.p, 32, cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
-    const unsigned long long* h = (const unsigned long long*)ctx->h_misc;
     ctx->P = P;
     ctx->R_staged = t->R;
+    return SST_OK;
+}
+
+int stage_f64(sst_ctx* ctx, const sst_table* t, const double* mass, const double* thr, const int32_t* max_mods, int32_t uniform_mods,
+              int64_t P, const int32_t* ind, const uint8_t* is_mod, double precision, double tolerance, int with_memo) {
+    int rc = stage_f64_enqueue(ctx, t, mass, thr, max_mods, uniform_mods, P, ind, is_mod, precision, tolerance, with_memo);
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(ctx->stream));
+    const unsigned long long* h = (const unsigned long long*)ctx->h_misc;
     ctx->window_total = (int64_t)h[0];
     ctx->max_hi = (int64_t)h[1];
     ctx->n_memo = (int)h[2];
@@ -1003,8 +1042,7 @@ enum { PASS_DONE = 0, PASS_FALLBACK = -1 };
 
 // Depth-first pass (sst_enum.cuh): one cooperative launch, one grid barrier.  Returns PASS_FALLBACK when a root's
 // subtree is too large for one thread (the level-synchronous pass balances such batches across the machine).
-int run_dfs_pass(sst_ctx* ctx, const sst_table* t, int rec_width, const MemoMap& mp, bool memo_fresh, unsigned long long* roots,
-                 unsigned long long* comps) {
+int dfs_enqueue(sst_ctx* ctx, const sst_table* t, int rec_width, const MemoMap& mp) {
     const int64_t P = ctx->P;
     const int nw = rec_width / 8;
     int rc;
@@ -1031,7 +1069,8 @@ int run_dfs_pass(sst_ctx* ctx, const sst_table* t, int rec_width, const MemoMap&
     // the item pool holds every tile's window roots and the lists of its split rounds; it keeps its size between runs
     // and grows when a run reports that it was too small
     if (ctx->pool_capacity < (uint64_t)(32 * P + (1 << 20))) ctx->pool_capacity = ((uint64_t)(32 * P + (1 << 20)) + 63) & ~63ULL;
-    for (int attempt = 0;; attempt++) {
+    if ((rc = reserve(ctx, ctx->d_peakoff32, (size_t)(P + 2) * 4))) return rc;
+    {
         const size_t cap = (size_t)ctx->pool_capacity;
         if ((rc = reserve(ctx, ctx->d_item_m[0], cap * 4))) return rc;
         if ((rc = reserve(ctx, ctx->d_item_peak[0], cap * 4))) return rc;
@@ -1064,6 +1103,7 @@ int run_dfs_pass(sst_ctx* ctx, const sst_table* t, int rec_width, const MemoMap&
         a.recs = (unsigned long long*)ctx->d_recs.p;
         a.rec_capacity = (unsigned long long)(ctx->d_recs.cap / rec_width);
         a.peak_off = (unsigned long long*)ctx->d_peakoff.p;
+        a.peak_off32 = (uint32_t*)ctx->d_peakoff32.p;
         a.cta_tot = (unsigned long long*)ctx->d_blocksums.p;
         a.sync = ctx->d_bar + 64 * (ctx->run_parity & 1);
         a.sync_next = ctx->d_bar + 64 * ((ctx->run_parity + 1) & 1);
@@ -1083,34 +1123,57 @@ int run_dfs_pass(sst_ctx* ctx, const sst_table* t, int rec_width, const MemoMap&
             kt.stop(1);
         }
         CK(cudaEventRecord(ctx->ev_run, ctx->stream));  // the device is done here; what follows is the host waking up
+    }
+    return SST_OK;
+}
+
+enum { DFS_OK = 0, DFS_RETRY = -2 };
+// after the stream has been synchronised: what the pass left in the run summary
+int dfs_evaluate(sst_ctx* ctx, int rec_width, const MemoMap& mp, bool memo_fresh, int attempt, unsigned long long* roots, unsigned long long* comps) {
+    const int64_t P = ctx->P;
+    const int nw = rec_width / 8;
+    int rc;
+    flush_timers(ctx);
+    const unsigned long long* h_tot = ctx->h_run;
+    const int* h_flags = reinterpret_cast<const int*>(ctx->h_run + 40);
+    *roots = h_tot[0];
+    *comps = h_tot[2];
+    ctx->levels = 1;
+    for (int i = 0; i < 32; i++) ctx->phase_ns[i] = h_tot[8 + i];
+    if (memo_fresh && attempt == 0 && (rc = memo_check(ctx, mp))) return rc;
+    if (h_flags[3]) return PASS_FALLBACK;
+    if (h_flags[2]) {  // the item pool was too small: grow and run the pass again
+        // a pool far beyond the batch size means combinatorial blow-up: that is the level-synchronous pass's job
+        // (it spreads single huge subtrees over the machine and enforces sst_set_item_limit)
+        unsigned long long most = 256ULL * (unsigned long long)(P > 0 ? P : 1);
+        if (most < (32ULL << 20)) most = 32ULL << 20;
+        if (ctx->item_limit < most) most = ctx->item_limit;
+        size_t free_b = 0, total_b = 0;
+        CK(cudaMemGetInfo(&free_b, &total_b));
+        const unsigned long long per_item = 37 + 8ULL * nw + (ctx->has_exact ? 8 : 0);
+        if (attempt >= 10 || ctx->pool_capacity * 2 > most || ctx->pool_capacity * per_item > (unsigned long long)free_b) return PASS_FALLBACK;
+        ctx->pool_capacity *= 2;
+        return DFS_RETRY;
+    }
+    if (h_flags[1]) {  // records did not fit: grow and run the pass again
+        if (attempt >= 3) return fail(ctx, SST_ERR_CUDA, "record buffer kept overflowing (%llu compositions)", *comps);
+        if ((rc = grow_records(ctx, *comps, rec_width))) return rc;
+        return DFS_RETRY;
+    }
+    return DFS_OK;
+}
+
+// Depth-first pass (sst_enum.cuh): one cooperative launch, one grid barrier.  Returns PASS_FALLBACK when the batch
+// is not for it (a subtree too large for one thread, combinatorial blow-up of the item pool).
+int run_dfs_pass(sst_ctx* ctx, const sst_table* t, int rec_width, const MemoMap& mp, bool memo_fresh, unsigned long long* roots,
+                 unsigned long long* comps) {
+    for (int attempt = 0;; attempt++) {
+        int rc = dfs_enqueue(ctx, t, rec_width, mp);
+        if (rc) return rc;
         CK(cudaStreamSynchronize(ctx->stream));
-        flush_timers(ctx);
-        const unsigned long long* h_tot = ctx->h_run;
-        const int* h_flags = reinterpret_cast<const int*>(ctx->h_run + 40);
-        *roots = h_tot[0];
-        *comps = h_tot[2];
-        ctx->levels = 1;
-        for (int i = 0; i < 32; i++) ctx->phase_ns[i] = h_tot[8 + i];
-        if (memo_fresh && attempt == 0 && (rc = memo_check(ctx, mp))) return rc;
-        if (h_flags[3]) return PASS_FALLBACK;
-        if (h_flags[2]) {  // the item pool was too small: grow and run the pass again
-            // a pool far beyond the batch size means combinatorial blow-up: that is the level-synchronous pass's job
-            // (it spreads single huge subtrees over the machine and enforces sst_set_item_limit)
-            unsigned long long most = 256ULL * (unsigned long long)(P > 0 ? P : 1);
-            if (most < (32ULL << 20)) most = 32ULL << 20;
-            if (ctx->item_limit < most) most = ctx->item_limit;
-            size_t free_b = 0, total_b = 0;
-            CK(cudaMemGetInfo(&free_b, &total_b));
-            const unsigned long long per_item = 37 + 8ULL * nw + (ctx->has_exact ? 8 : 0);
-            if (attempt >= 10 || ctx->pool_capacity * 2 > most || ctx->pool_capacity * per_item > (unsigned long long)free_b) return PASS_FALLBACK;
-            ctx->pool_capacity *= 2;
-            continue;
-        }
-        if (h_flags[1]) {  // records did not fit: grow and run the pass again
-            if (attempt >= 3) return fail(ctx, SST_ERR_CUDA, "record buffer kept overflowing (%llu compositions)", *comps);
-            if ((rc = grow_records(ctx, *comps, rec_width))) return rc;
-            continue;
-        }
+        rc = dfs_evaluate(ctx, rec_width, mp, memo_fresh, attempt, roots, comps);
+        if (rc == DFS_RETRY) continue;
+        if (rc) return rc;
         break;
     }
     ctx->last_pass = 2;
@@ -1326,6 +1389,148 @@ int sst_explain_run(sst_ctx* ctx, const sst_table* t, int rec_width, uint64_t me
     ctx->have_result = true;
     if (n_roots) *n_roots = roots;
     if (n_comps) *n_comps = comps;
+    return SST_OK;
+}
+
+// ---- the whole call without waiting: inputs in, staging, pass, results out are queued on the context's stream ----
+int sst_explain_submit_f64(sst_ctx* ctx, const sst_table* t, const double* mass, const double* thr, int32_t max_mods, int64_t P,
+                           const int32_t* ind, const uint8_t* is_mod, double precision, double tolerance, int with_memo, uint8_t* status_out,
+                           uint32_t* off32_out, uint8_t* recs_out, uint64_t recs_bytes) {
+    CK(cudaSetDevice(ctx->device));
+    if (ctx->pend.active) return fail(ctx, SST_ERR_STATE, "a submitted batch has not been collected yet");
+    if (P < 0) return fail(ctx, SST_ERR_BAD_ARG, "negative peak count");
+    if (!t->H) return fail(ctx, SST_ERR_STATE, "table was built without row masks");
+    sst_ctx::Pending& pd = ctx->pend;
+    pd = sst_ctx::Pending{};
+    pd.mass = mass; pd.thr = thr; pd.max_mods = max_mods; pd.P = P; pd.ind = ind; pd.is_mod = is_mod;
+    pd.precision = precision; pd.tolerance = tolerance; pd.with_memo = with_memo;
+    pd.status = status_out; pd.off32 = off32_out; pd.recs = recs_out; pd.recs_bytes = recs_bytes;
+    pd.active = true;
+    ctx->have_result = false;
+    // Can everything be queued without a look at the staged batch?  Yes when a bound on the largest window end,
+    // taken from the host arrays, already shows that no budget can bind (every peak FREE) and that the depth-first
+    // pass holds the longest composition.  Otherwise the call is carried out synchronously in sst_explain_collect.
+    double m_max = 0.0, t_max = 0.0;
+    for (int64_t i = 0; i < P; i++) {
+        const double m = mass[i];
+        m_max = m > m_max ? m : m_max;
+    }
+    if (thr) {
+        for (int64_t i = 0; i < P; i++) {
+            const double x = thr[i];  // NaN = relative threshold: covered by tolerance * m_max below
+            t_max = x > t_max ? x : t_max;
+        }
+    }
+    const double rel = tolerance * m_max;
+    if (rel > t_max) t_max = rel;
+    const double hi_f = (m_max + t_max) / precision + 2.0;
+    bool fast = ctx->pass_choice != 1 && P > 0 && hi_f < 4.0e18;
+    int64_t hi_bound = 0;
+    if (fast) {
+        hi_bound = (int64_t)hi_f;
+        int64_t w_min_mod = 0, hi_limit = INT64_MAX;
+        for (int r = 1; r < t->R; r++)
+            if (is_mod[r]) {
+                const int64_t w = t->w_host[r];
+                if (!w_min_mod || w < w_min_mod) w_min_mod = w;
+                const int64_t lim = ((int64_t)ind[r] + 1) * w;
+                if (lim < hi_limit) hi_limit = lim;
+            }
+        if (w_min_mod && !((int64_t)max_mods >= hi_bound / w_min_mod && hi_bound < hi_limit)) fast = false;  // some budget may bind
+        const int64_t cap = t->C * 32 - 1;
+        const int64_t deepest = t->w_min > 0 ? (hi_bound < cap ? hi_bound : cap) / t->w_min : 0;
+        if (deepest > kDfsDepth) fast = false;
+        if (fast) {
+            ctx->deepest = deepest;
+            pd.rec_width = (int)(8 * (deepest > 8 ? (deepest + 7) / 8 : 1));
+        }
+    }
+    if (!fast) return SST_OK;  // sst_explain_collect does the work
+    int rc = stage_f64_enqueue(ctx, t, mass, thr, nullptr, max_mods, P, ind, is_mod, precision, tolerance, with_memo);
+    if (rc) {
+        pd.active = false;
+        return rc;
+    }
+    ctx->n_memo = 0;
+    ctx->has_exact = false;
+    ctx->window_total = 0;  // not known without the summary; only the level-synchronous pass sizes its buffers from it
+    ctx->max_hi = hi_bound;
+    MemoMap mp{};
+    if ((rc = dfs_enqueue(ctx, t, pd.rec_width, mp))) {
+        pd.active = false;
+        return rc;
+    }
+    // results on their way back: status, peak offsets, and as many records as the previous batch had (+ 25 %); a
+    // batch that turns out larger gets the rest in sst_explain_collect
+    CK(cudaMemcpyAsync(status_out, ctx->d_status.p, (size_t)P, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(off32_out, ctx->d_peakoff32.p, (size_t)(P + 1) * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    uint64_t guess = (ctx->last_comps + ctx->last_comps / 4) * (uint64_t)pd.rec_width + 4096;
+    if (guess > recs_bytes) guess = recs_bytes;
+    if (guess > ctx->d_recs.cap) guess = ctx->d_recs.cap;
+    if (guess) CK(cudaMemcpyAsync(recs_out, ctx->d_recs.p, (size_t)guess, cudaMemcpyDeviceToHost, ctx->stream));
+    pd.copied = guess;
+    pd.done = true;  // queued
+    return SST_OK;
+}
+
+int sst_explain_collect(sst_ctx* ctx, const sst_table* t, uint64_t* n_comps, int* rec_width) {
+    CK(cudaSetDevice(ctx->device));
+    sst_ctx::Pending& pd = ctx->pend;
+    if (!pd.active) return fail(ctx, SST_ERR_STATE, "no submitted batch to collect");
+    pd.active = false;
+    int rc;
+    bool redo = !pd.done;
+    unsigned long long roots = 0, comps = 0;
+    if (pd.done) {
+        CK(cudaStreamSynchronize(ctx->stream));
+        MemoMap mp{};
+        rc = dfs_evaluate(ctx, pd.rec_width, mp, false, 0, &roots, &comps);
+        if (rc == DFS_OK && comps < (1ULL << 32)) {
+            ctx->n_roots = roots;
+            ctx->n_comps = comps;
+            ctx->rec_width = pd.rec_width;
+            ctx->last_pass = 2;
+            ctx->have_result = true;
+            ctx->last_comps = comps;
+            const uint64_t need = comps * (uint64_t)pd.rec_width;
+            if (need > pd.recs_bytes) {  // the caller's buffer is too small: the result stays on the device for sst_explain_fetch
+                if (n_comps) *n_comps = comps;
+                if (rec_width) *rec_width = pd.rec_width;
+                return fail(ctx, SST_ERR_NOMEM, "record buffer of %llu bytes is too small for %llu compositions", (unsigned long long)pd.recs_bytes,
+                            (unsigned long long)comps);
+            }
+            if (need > pd.copied) {
+                CK(cudaMemcpyAsync(pd.recs + pd.copied, (const char*)ctx->d_recs.p + pd.copied, (size_t)(need - pd.copied), cudaMemcpyDeviceToHost,
+                                   ctx->stream));
+                CK(cudaStreamSynchronize(ctx->stream));
+            }
+        } else if (rc == DFS_OK || rc == DFS_RETRY || rc == PASS_FALLBACK) {
+            redo = true;  // larger buffers / the other pass / 64-bit offsets: the synchronous path sorts it out
+        } else {
+            return rc;
+        }
+    }
+    if (redo) {
+        rc = stage_f64(ctx, t, pd.mass, pd.thr, nullptr, pd.max_mods, pd.P, pd.ind, pd.is_mod, pd.precision, pd.tolerance, pd.with_memo);
+        if (rc) return rc;
+        uint64_t r64 = 0, c64 = 0;
+        if ((rc = sst_explain_run(ctx, t, 0, 0, &r64, &c64))) return rc;
+        comps = c64;
+        ctx->last_comps = comps;
+        if (comps >= (1ULL << 32)) return fail(ctx, SST_ERR_NOMEM, "%llu compositions: more than the 32-bit offsets of the asynchronous entry hold", (unsigned long long)comps);
+        const uint64_t need = comps * (uint64_t)ctx->rec_width;
+        if (n_comps) *n_comps = comps;
+        if (rec_width) *rec_width = ctx->rec_width;
+        if (need > pd.recs_bytes)
+            return fail(ctx, SST_ERR_NOMEM, "record buffer of %llu bytes is too small for %llu compositions", (unsigned long long)pd.recs_bytes,
+                        (unsigned long long)comps);
+        // 64-bit offsets -> 32-bit on the host (this path is the exception)
+        std::vector<uint64_t> off((size_t)pd.P + 1);
+        if ((rc = sst_explain_fetch(ctx, pd.status, off.data(), pd.recs))) return rc;
+        for (int64_t i = 0; i <= pd.P; i++) pd.off32[i] = (uint32_t)off[(size_t)i];
+    }
+    if (n_comps) *n_comps = ctx->n_comps;
+    if (rec_width) *rec_width = ctx->rec_width;
     return SST_OK;
 }
 

@@ -78,6 +78,7 @@ struct DfsArgs {
     unsigned long long* recs;         // [rec_capacity][nw] records, final order
     unsigned long long rec_capacity;
     unsigned long long* peak_off;     // [P+1]
+    uint32_t* peak_off32;             // [P+1] the same as uint32 (may be null; only meaningful below 2^32 compositions)
     unsigned long long* cta_tot;      // [2][gridDim.x] compositions / roots of every CTA's slice
     unsigned int* sync;               // this launch's words: [0] barrier arrivals, [2..3] pool cursor (u64), [4] fallback flag
     unsigned int* sync_next;          // the next launch's words: cleared by this one
@@ -709,7 +710,11 @@ k_explain_dfs(const DfsArgs a) {
         // peak role: a peak starts where its first item starts (items and records are both in peak order)
         for (long long j = threadIdx.x; j < n_mine; j += kDfsThreads) {
             const long long p = pb + j;
-            if (p > pb || rb == 0) a.peak_off[p] = run + offset_of(A, a.peak_first[p], NA, my_recs);
+            if (p > pb || rb == 0) {
+                const unsigned long long at = run + offset_of(A, a.peak_first[p], NA, my_recs);
+                a.peak_off[p] = at;
+                if (a.peak_off32) a.peak_off32[p] = (uint32_t)at;
+            }
         }
         // item role
         for (unsigned int i0 = threadIdx.x; i0 < NA; i0 += kDfsThreads * kU) {
@@ -762,7 +767,10 @@ k_explain_dfs(const DfsArgs a) {
             }
         }
     }
-    if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) a.peak_off[P] = n_comps;
+    if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) {
+        a.peak_off[P] = n_comps;
+        if (a.peak_off32) a.peak_off32[P] = (uint32_t)n_comps;
+    }
     __syncthreads();
     cta_stamp(a, 5);
     stamp(s_sum, ts++);

@@ -275,11 +275,11 @@ k_last_row_summary(const uint64_t* __restrict__ last, int64_t C, uint32_t* __res
 
 __global__ void __launch_bounds__(256)
 k_classify(TableView tv, const double* __restrict__ observed, int64_t F, const double* __restrict__ offsets, int B,
-           double precision, double tolerance, uint8_t* __restrict__ out) {
+           double precision, double tolerance, uint8_t* __restrict__ out, int pack4) {
     constexpr int K = kClassifyPerThread;
     const int32_t* __restrict__ s_w = tv.weights;  // <= 512 B, read-only: L1 resident, no per-CTA staging and no barrier
-    const int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (f >= F) return;
+    const int64_t f_real = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t f = f_real < F ? f_real : F - 1;  // lanes past the end repeat the last fragment (whole warps reach the packing shuffle)
     const double obs = observed[f];
     const int64_t h64 = (int64_t)ceil(__ddiv_rn(__dmul_rn(tolerance, obs), precision));  // the same for every offset
     const int b0 = blockIdx.y * K;
@@ -360,9 +360,18 @@ k_classify(TableView tv, const double* __restrict__ observed, int64_t F, const d
             if (x < tv.R && (int64_t)__ldg(s_w + x) <= hi) code[k] |= 4;
         }
     }
+    if (!pack4) {
 #pragma unroll
-    for (int k = 0; k < K; k++)
-        if (b0 + k < B) out[(int64_t)(b0 + k) * F + f] = code[k];
+        for (int k = 0; k < K; k++)
+            if (b0 + k < B && f_real < F) out[(int64_t)(b0 + k) * F + f] = code[k];
+    } else {  // two flags per byte: fragment f in the low nibble of byte (b * Fp + f) / 2, Fp = F rounded up to even
+        const int64_t Fp = (F + 1) & ~1LL;
+#pragma unroll
+        for (int k = 0; k < K; k++) {
+            const unsigned mine = code[k], next = __shfl_down_sync(0xFFFFFFFFu, mine, 1);
+            if (b0 + k < B && f_real < F && !(f_real & 1)) out[((int64_t)(b0 + k) * Fp + f_real) >> 1] = (uint8_t)(mine | ((f_real + 1 < F ? next : 0u) << 4));
+        }
+    }
 }
 
 // ---------------- MEMO phase A: sequential first-visit replay, one thread per peak ----------------

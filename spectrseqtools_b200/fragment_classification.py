@@ -25,12 +25,13 @@ class ClassifiedMasses:
     """Result of ``classify_observed``: one flag byte per (breakage, fragment), breakage-major."""
 
     def __init__(self, observed: np.ndarray, breakage_weights: List[int], labels: List[str], precision: float,
-                 flags: np.ndarray, pending=None):
+                 flags: np.ndarray, pending=None, packed: bool = False):
         self.observed = observed
         self.breakage_weights = breakage_weights
         self.labels = labels          # first label of every weight, like the reference's pl.lit(breakages[0])
         self.precision = precision
-        self._flags = flags           # uint8[B, F]
+        self._flags = flags           # uint8[B, F], or two flags per byte uint8[B, ceil(F / 2)] (unpacked on first use)
+        self._packed = packed
         self._pending = pending       # context of an asynchronous call that has not been waited for yet
 
     def wait(self) -> "ClassifiedMasses":
@@ -41,7 +42,14 @@ class ClassifiedMasses:
 
     @property
     def flags(self) -> np.ndarray:
-        return self.wait()._flags
+        self.wait()
+        if self._packed:
+            F = len(self.observed)
+            wide = np.empty((self._flags.shape[0], 2 * self._flags.shape[1]), dtype=np.uint8)
+            wide[:, 0::2] = self._flags & 15
+            wide[:, 1::2] = self._flags >> 4
+            self._flags, self._packed = wide[:, :F], False
+        return self._flags
 
     @property
     def valid(self) -> np.ndarray:
@@ -63,12 +71,13 @@ class ClassifiedMasses:
 
 
 def classify_observed(observed: Sequence[float], dp_table: DynamicProgrammingTable, breakage_dict: Dict[int, List[str]],
-                      copy: bool = True, wait: bool = True) -> ClassifiedMasses:
+                      copy: bool = True, wait: bool = True, slot: int = 0) -> ClassifiedMasses:
     """Validity + singleton flags of every observed mass under every breakage offset: one device pass.
 
     ``wait=False`` queues the whole call (copies and kernel) on the context's side stream and returns at once; the
     flags are waited for on first access (``.flags`` / ``.wait()``), so an ``explain_masses`` call issued in between
-    overlaps it.  ``copy=False`` hands out the context's pinned buffer (valid until the next classification)."""
+    overlaps it; the flags then cross the bus two per byte.  ``copy=False`` hands out the context's pinned buffer
+    (valid until the next classification on the same ``slot``, see ``_cabi.context``)."""
     observed = np.ascontiguousarray(observed, dtype=np.float64).reshape(-1)
     if len(observed) and not np.isfinite(observed).all():  # upstream: int(round(nan)) / int(round(inf)) inside is_valid_mass
         if np.isnan(observed).any():
@@ -77,11 +86,11 @@ def classify_observed(observed: Sequence[float], dp_table: DynamicProgrammingTab
     weights = list(breakage_dict.keys())
     offsets = np.array([w * dp_table.precision for w in weights], dtype=np.float64)  # int * float, as upstream
     dev = dp_table.device_table()
-    ctx = dev.ctx
+    ctx = dev.ctx if slot == 0 else _cabi.context(dev.ctx.device, slot)
     labels = [breakage_dict[w][0] for w in weights]
     if not wait:
-        flags = ctx.classify_async(dev, observed, offsets, dp_table.precision, dp_table.tolerance)
-        return ClassifiedMasses(observed, weights, labels, dp_table.precision, flags, pending=ctx)
+        flags = ctx.classify_async(dev, observed, offsets, dp_table.precision, dp_table.tolerance, packed=True)
+        return ClassifiedMasses(observed, weights, labels, dp_table.precision, flags, pending=ctx, packed=True)
     ctx.classify_stage(observed, offsets)
     ctx.classify_run(dev, dp_table.precision, dp_table.tolerance)
     flags = ctx.classify_fetch(copy=copy)

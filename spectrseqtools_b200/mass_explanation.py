@@ -121,16 +121,23 @@ class ExplanationBatch:
     """
 
     def __init__(self, status, offsets, records, weights, names_by_row):
-        self.status, self.offsets, self.records = status, offsets, records
+        self.status, self.records = status, records
+        self._offsets = offsets  # int64, or the uint32 the asynchronous entry brings back (widened on first use)
         self.weights = weights
         self._names_by_row = names_by_row
+
+    @property
+    def offsets(self) -> np.ndarray:
+        if self._offsets.dtype != np.int64:
+            self._offsets = self._offsets.astype(np.int64)
+        return self._offsets
 
     def __len__(self):
         return len(self.status)
 
     @property
     def n_compositions(self) -> int:
-        return int(self.offsets[-1])
+        return int(self._offsets[-1])
 
     def counts(self) -> np.ndarray:
         return np.diff(self.offsets)
@@ -187,16 +194,37 @@ def _thr_array(thresholds, n: int) -> Optional[np.ndarray]:
     return np.array([np.nan if x is None else x for x in thresholds], dtype=np.float64)
 
 
+class PendingExplanations:
+    """A batch submitted with ``explain_masses(..., wait=False)``: ``wait()`` gives the ``ExplanationBatch``."""
+
+    def __init__(self, ctx, dp_table, weights, copy):
+        self._ctx, self._dp, self._weights, self._copy = ctx, dp_table, weights, copy
+        self._batch = None
+
+    def wait(self) -> "ExplanationBatch":
+        if self._batch is None:
+            status, off, recs = self._ctx.explain_collect()
+            if self._copy:
+                status, off, recs = status.copy(), off.astype(np.int64), recs.copy()
+            self._batch = ExplanationBatch(status, off, recs, self._weights, [m.names for m in self._dp.masses])
+        return self._batch
+
+
 def explain_masses(masses: Sequence[float], dp_table: DynamicProgrammingTable, max_modifications=np.inf,
                    thresholds=None, with_memo: bool = True, compression_rate: Optional[int] = None,
-                   fetch_records: bool = True, copy: bool = True) -> ExplanationBatch:
+                   fetch_records: bool = True, copy: bool = True, wait: bool = True, slot: int = 0):
     """Batched ``explain_mass_with_table``: one device pass for all masses.
 
     ``max_modifications`` and ``thresholds`` may be scalars or per-mass sequences (``thresholds`` None, or a
     None / NaN entry, = relative ``dp_table.tolerance * mass``).  The float -> integer conversion and the
     choice of the budget mode happen inside the library (``sst_explain_stage_f64``) with the reference's
     float operations.  ``copy=False`` returns views of the context's pinned result buffers, valid until
-    the next call on the same device.
+    the next call on the same device and slot.
+
+    ``wait=False`` (one modification budget for the batch) queues the whole call — inputs in, staging, pass, results
+    out — and returns a ``PendingExplanations`` at once; with a different ``slot`` per call two batches are in flight
+    on the device, the copies of one under the kernels of the other (``masses`` / ``thresholds`` must not be modified
+    until ``wait()`` returns).
     """
     if compression_rate is not None and compression_rate != dp_table.compression_per_cell:
         raise ValueError("compression_rate must match the table's compression_per_cell")
@@ -209,14 +237,19 @@ def explain_masses(masses: Sequence[float], dp_table: DynamicProgrammingTable, m
     else:
         max_mods = np.array([_budget_int(x) for x in max_modifications], dtype=np.int32)
     dev = dp_table.device_table()
-    ctx = dev.ctx
+    ctx = dev.ctx if slot == 0 else _cabi.context(dev.ctx.device, slot)
     weights, is_mod, ind = _row_metadata(dp_table)
+    if not wait:
+        if np.ndim(max_modifications) != 0:
+            raise ValueError("wait=False takes one modification budget for the whole batch")
+        ctx.explain_submit_f64(dev, masses, thr, max_mods, ind, is_mod, dp_table.precision, dp_table.tolerance, with_memo)
+        return PendingExplanations(ctx, dp_table, weights, copy)
     ctx.explain_stage_f64(dev, masses, thr, max_mods, ind, is_mod, dp_table.precision, dp_table.tolerance, with_memo)
-    return _run_and_fetch(dp_table, dev, weights, fetch_records, copy)
+    return _run_and_fetch(dp_table, dev, weights, fetch_records, copy, ctx)
 
 
-def _run_and_fetch(dp_table, dev, weights, fetch_records=True, copy=True) -> ExplanationBatch:
-    ctx = dev.ctx
+def _run_and_fetch(dp_table, dev, weights, fetch_records=True, copy=True, ctx=None) -> ExplanationBatch:
+    ctx = ctx or dev.ctx
     cap = 0
     while True:
         try:
