@@ -257,6 +257,57 @@ void oracle_result_fetch(const void *r, uint8_t *rows, int64_t *off) {
 }
 void oracle_result_free(void *r) { if (r) { Result *res = (Result *)r; free(res->rows); free(res->off); free(res); } }
 
+/* ---------- batch front ends (the same per-call functions in a loop; what a full-batch parity gate calls) ---------- */
+
+/* codes[i] = 0 not valid, 1 valid, 2 out of table (NotImplementedError of mass_explanation.py:70-74) */
+int oracle_is_valid_batch(const void *table, int R, int64_t max_col, int compression, const int64_t *target,
+                          const int64_t *thr, int64_t n, uint8_t *codes) {
+    for (int64_t i = 0; i < n; i++) {
+        int ok = 0;
+        int rc = oracle_is_valid(table, R, max_col, compression, target[i], thr[i], &ok);
+        codes[i] = rc == OR_OUT_OF_TABLE ? 2 : (uint8_t)ok;
+    }
+    return OR_OK;
+}
+
+static int cmp_u64(const void *a, const void *b) {
+    uint64_t x = *(const uint64_t *)a, y = *(const uint64_t *)b;
+    return x < y ? -1 : x > y;
+}
+
+/* Every call of a batch through oracle_explain.  Each composition becomes one 8-byte key: its row indices in ascending
+ * order in bytes 0.., zero padded (compositions longer than 8 nucleotides: rc OR_BAD_COMPRESSION); the keys of a call
+ * are sorted ascending as little-endian uint64 — the canonical sort the parity tests apply to the device records.
+ * counts[i] = compositions of call i, or -1 when the call left the table.  keys holds up to cap keys; *n_keys is the
+ * number needed (call again with a larger buffer when it exceeds cap). */
+int oracle_explain_batch_keys(const void *table, int R, int64_t max_col, int compression, const int64_t *weights,
+                              const uint8_t *is_mod, const int64_t *ind, const int64_t *target, const int64_t *thr,
+                              int64_t n, int64_t max_mods, int with_memo, int64_t *counts, uint64_t *keys, int64_t cap,
+                              int64_t *n_keys) {
+    int64_t used = 0;
+    for (int64_t i = 0; i < n; i++) {
+        void *res = NULL;
+        int rc = oracle_explain(table, R, max_col, compression, weights, is_mod, ind, target[i], thr[i], max_mods, with_memo, &res);
+        if (rc == OR_OUT_OF_TABLE) { counts[i] = -1; continue; }
+        if (rc) return rc;
+        const Result *r = (const Result *)res;
+        counts[i] = r->n_sol;
+        int64_t first = used;
+        for (int64_t k = 0; k < r->n_sol; k++) {
+            int64_t len = r->off[k + 1] - r->off[k];
+            if (len > 8) { oracle_result_free(res); return OR_BAD_COMPRESSION; }
+            uint64_t key = 0;
+            for (int64_t q = 0; q < len; q++) key |= (uint64_t)r->rows[r->off[k] + q] << (8 * q);
+            if (used < cap) keys[used] = key;
+            used++;
+        }
+        if (used <= cap) qsort(keys + first, (size_t)(used - first), sizeof(uint64_t), cmp_u64);
+        oracle_result_free(res);
+    }
+    *n_keys = used;
+    return OR_OK;
+}
+
 /* ---------- sequence length bound, mass_table.py:343-487 ---------- */
 
 typedef struct {

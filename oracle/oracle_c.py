@@ -106,3 +106,39 @@ def length_bound(table: np.ndarray, compression: int, weights, is_mod, ind, targ
     if rc == 1:
         raise OutOfTable("value not in the DP table")
     return int(out.value)
+
+
+def is_valid_batch(table: np.ndarray, compression: int, target, thr) -> np.ndarray:
+    """oracle_is_valid over arrays -> uint8 codes: 0 not valid, 1 valid, 2 out of table."""
+    tg = np.ascontiguousarray(target, dtype=np.int64)
+    th = np.ascontiguousarray(thr, dtype=np.int64)
+    out = np.empty(len(tg), dtype=np.uint8)
+    lib().oracle_is_valid_batch(_ptr(table), C.c_int(table.shape[0]), C.c_int64(table.shape[1]), C.c_int(compression),
+                                _ptr(tg), _ptr(th), C.c_int64(len(tg)), _ptr(out))
+    return out
+
+
+def explain_batch_keys(table: np.ndarray, compression: int, weights, is_mod, ind, target, thr, max_mods,
+                       with_memo: bool = True):
+    """oracle_explain over arrays -> (counts int64[n] (-1 = out of table), keys uint64[sum]): every composition as
+    one little-endian 8-byte key (ascending row indices, zero padded), sorted ascending inside each call."""
+    w = np.ascontiguousarray(weights, dtype=np.int64)
+    im = np.ascontiguousarray(is_mod, dtype=np.uint8)
+    iv = np.ascontiguousarray(ind, dtype=np.int64)
+    tg = np.ascontiguousarray(target, dtype=np.int64)
+    th = np.ascontiguousarray(thr, dtype=np.int64)
+    mm = -1 if (max_mods is None or max_mods == float("inf")) else int(np.ceil(max(max_mods, 0)))
+    counts = np.empty(len(tg), dtype=np.int64)
+    cap = max(1024, 8 * len(tg))
+    while True:
+        keys = np.empty(cap, dtype=np.uint64)
+        need = C.c_int64(0)
+        rc = lib().oracle_explain_batch_keys(_ptr(table), C.c_int(table.shape[0]), C.c_int64(table.shape[1]),
+                                             C.c_int(compression), _ptr(w), _ptr(im), _ptr(iv), _ptr(tg), _ptr(th),
+                                             C.c_int64(len(tg)), C.c_int64(mm), C.c_int(1 if with_memo else 0),
+                                             _ptr(counts), _ptr(keys), C.c_int64(cap), C.byref(need))
+        if rc:
+            raise RuntimeError(f"oracle_explain_batch_keys rc={rc}")
+        if need.value <= cap:
+            return counts, keys[: need.value]
+        cap = int(need.value)

@@ -1,0 +1,82 @@
+"""GPU: the asynchronous whole-call entries (explain_masses(wait=False) -> sst_explain_submit_f64 / sst_explain_collect,
+classify_observed(wait=False) -> nibble-packed flags) on two context slots equal the synchronous calls, and the whole
+batch equals the C oracle call for call (oracle_explain_batch_keys / oracle_is_valid_batch)."""
+import numpy as np
+import pytest
+
+from oracle import oracle_c as OC
+from oracle import oracle_py as OP
+from spectrseqtools_b200 import fragment_classification as FC
+from spectrseqtools_b200 import mass_explanation as ME
+from spectrseqtools_b200 import mass_table as MT
+from spectrseqtools_b200 import synthetic as S
+
+pytestmark = pytest.mark.gpu
+
+
+def _table(wl):
+    seq = MT.SequenceInformation(max_len=wl.max_len, su_mass=0.0, obs_mass=0.0, modification_rate=0.5)
+    return MT.DynamicProgrammingTable(S.alphabet_frame(None if len(wl.alphabet) == 104 else wl.alphabet), 32, wl.ppm, 1e-3, seq)
+
+
+def _keys_per_call(batch):
+    recs = np.ascontiguousarray(batch.records)
+    assert recs.shape[1] == 8
+    keys = recs.view(np.uint64).reshape(-1)
+    call = np.repeat(np.arange(len(batch)), batch.counts())
+    return keys[np.lexsort((keys, call))]
+
+
+@pytest.mark.parametrize("config,n_peaks", [("C2", 6000), ("C4", 20000)])
+def test_async_slots_equal_sync_and_oracle(config, n_peaks):
+    wl = S.make_workload(config, n_peaks)
+    dp = _table(wl)
+    sync = ME.explain_masses(wl.explain_mass, dp, max_modifications=wl.max_modifications, thresholds=wl.explain_thr)
+    flags = FC.classify_observed(wl.observed, dp, wl.breakage).flags.copy()
+    # two batches in flight: the second half of the calls on slot 1 while slot 0 holds the first half, then both again
+    half = len(wl.explain_mass) // 2
+    parts = [(slice(0, half), 0), (slice(half, None), 1)]
+    for _round in range(2):
+        pend = [(ME.explain_masses(wl.explain_mass[s], dp, max_modifications=wl.max_modifications, thresholds=wl.explain_thr[s],
+                                   wait=False, slot=k),
+                 FC.classify_observed(wl.observed, dp, wl.breakage, wait=False, slot=k), s) for s, k in parts]
+        for pe, pc, s in pend:
+            b = pe.wait()
+            lo = s.start or 0
+            hi = lo + len(b)
+            assert np.array_equal(b.status, sync.status[lo:hi])
+            assert np.array_equal(b.counts(), sync.counts()[lo:hi])
+            assert np.array_equal(b.records, sync.records[sync.offsets[lo]:sync.offsets[hi]])
+            assert np.array_equal(pc.flags, flags)
+    # the whole batch against the C oracle, every call
+    w = [m.mass for m in dp.masses]
+    tab = OC.build_bit_table(w, max(w) * wl.max_seq_length, 32)
+    rows = [OP.Row(m.mass, m.is_modification, m.modification_rate) for m in dp.masses]
+    ind = OP.individual_budgets(rows, dp.seq.max_len)
+    tg, th = ME._integerise_many(wl.explain_mass, wl.explain_thr, dp)
+    counts, keys = OC.explain_batch_keys(tab, 32, w, [r.is_modification for r in rows], ind, tg, th, wl.max_modifications, True)
+    assert np.array_equal(np.where(counts < 0, 0, counts), sync.counts())
+    assert np.array_equal(counts < 0, (sync.status & 2) != 0)
+    assert np.array_equal(_keys_per_call(sync), keys)
+    vt, vh = ME._integerise_many(wl.valid_mass, wl.valid_thr, dp)
+    codes = OC.is_valid_batch(tab, 32, vt, vh)
+    assert np.array_equal(np.ascontiguousarray(flags.T).reshape(-1) & 3, codes)
+
+
+def test_async_falls_back_when_budgets_bind():
+    """A batch whose budgets can bind cannot be queued blind: collect() carries it out synchronously, same result."""
+    wl = S.make_workload("C2", 3000)
+    dp = _table(wl)
+    want = ME.explain_masses(wl.explain_mass, dp, max_modifications=1, thresholds=wl.explain_thr)
+    got = ME.explain_masses(wl.explain_mass, dp, max_modifications=1, thresholds=wl.explain_thr, wait=False).wait()
+    assert np.array_equal(got.status, want.status) and np.array_equal(got.offsets, want.offsets)
+    assert np.array_equal(got.records, want.records)
+
+
+def test_packed_flags_odd_fragment_count():
+    wl = S.make_workload("C2", 1001)
+    dp = _table(wl)
+    obs = wl.observed[:1001]
+    want = FC.classify_observed(obs, dp, wl.breakage).flags.copy()
+    got = FC.classify_observed(obs, dp, wl.breakage, wait=False).flags
+    assert got.shape == want.shape and np.array_equal(got, want)
