@@ -162,13 +162,17 @@ int sst_explain_stage_f64_uniform(sst_ctx* ctx, const sst_table* t, const double
 int sst_explain_run(sst_ctx* ctx, const sst_table* t, int rec_width, uint64_t memo_capacity, uint64_t* n_roots,
                     uint64_t* n_comps);
 int sst_explain_rec_width(const sst_ctx* ctx); /* record width of the last run */
-/* Which enumeration pass sst_explain_run uses: 0 = automatic (default: the depth-first pass — count -> scan -> fill over
- * window values, one grid barrier — for batches of at most 16 nucleotides per composition, the level-synchronous pass
- * for deeper ones and for batches the depth-first pass gives back because one window value has too many partial
- * compositions for a single thread), 1 = always level-synchronous, 2 = depth-first or fail.  Both passes return the
- * same compositions per peak; the order of the records inside a peak differs. */
+/* Which enumeration pass sst_explain_run uses.  0 = automatic (default): the depth-first ITEM pass (sst_enum.cuh: count ->
+ * scan -> fill over partial compositions in peak order, one grid barrier) for batches of ladder differences (at most 16
+ * nucleotides per composition, a handful of compositions per peak by the staged batch's cost estimate); the
+ * LEVEL-synchronous pass (sst_explain.cuh) for deeper compositions, for batches with thousands of compositions per
+ * peak (it spreads single huge subtrees over the machine) and for batches the item pass gives back.  1 = always
+ * level-synchronous, 2 = item pass or fail, 3 = DIRECT pass or fail (sst_direct.cuh: per-peak counts looked up in a
+ * composition-count table built once per alphabet, scan, output-balanced fill; batches whose budgets cannot bind, at
+ * most 16 nucleotides, windows below 2^22 integer masses), -3 = the same as 0.  All passes return the same
+ * compositions per peak; direct and item pass also the same record order (depth-first), the level pass another. */
 int sst_set_pass(sst_ctx* ctx, int which);
-int sst_last_pass(const sst_ctx* ctx); /* 1 = level-synchronous, 2 = depth-first produced the last result */
+int sst_last_pass(const sst_ctx* ctx); /* 1 = level-synchronous, 2 = depth-first items, 3 = direct produced the last result */
 /* diagnostics of the depth-first pass: enable != 0 makes the following runs record %globaltimer (ns) of every CTA at
  * [0] start, [1] first tile's window values counted, [2] its roots written, [3] count phase done, [4] grid barrier
  * passed, [5] fill phase done; out (may be NULL) receives [n_ctas][8] of the last recorded run */

@@ -27,7 +27,7 @@ STATUS_ZERO_IN_WINDOW, STATUS_OUT_OF_TABLE = 1, 2
 VALID_NO, VALID_YES, VALID_OUT_OF_TABLE = 0, 1, 2
 CLASS_VALID, CLASS_OUT_OF_TABLE, CLASS_SINGLETON = 1, 2, 4
 BUDGET_INF = 1 << 30
-KERNEL_SLOTS = ["build", "transpose", "is_valid", "phase_a", "explain_pass", "classify", "length_bound", "spare"]
+KERNEL_SLOTS = ["build", "transpose", "is_valid", "phase_a", "explain_pass", "classify", "length_bound", "count_table"]
 
 EXPORTS = [
     "sst_ctx_create", "sst_ctx_destroy", "sst_last_error", "sst_device_info", "sst_host_alloc", "sst_host_free",
@@ -206,7 +206,8 @@ class Context:
         self._check(self._lib.sst_set_item_limit(self._h, C.c_uint64(limit)))
 
     def set_pass(self, which: int):
-        """0 = automatic, 1 = level-synchronous pass, 2 = depth-first pass (sst_set_pass)."""
+        """0 = automatic (item pass for light batches, level-synchronous for heavy or deep ones), 1 = level-synchronous
+        pass, 2 = depth-first item pass, 3 = direct pass (count table) (sst_set_pass)."""
         self._check(self._lib.sst_set_pass(self._h, int(which)))
 
     def last_pass(self) -> int:

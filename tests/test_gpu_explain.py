@@ -16,10 +16,11 @@ pytestmark = pytest.mark.gpu
 
 @pytest.fixture(autouse=True, params=["auto", "level"])
 def enumeration_pass(request):
-    """Every test of this file runs twice: with the automatic choice (the depth-first pass wherever a composition has
-    at most 16 nucleotides, sst_enum.cuh) and with the level-synchronous pass forced (sst_explain.cuh)."""
+    """Every test of this file runs twice: with the automatic choice (the depth-first item pass, sst_enum.cuh, wherever a
+    composition has at most 16 nucleotides and the batch is light) and with the level-synchronous pass forced
+    (sst_explain.cuh).  The direct pass (sst_direct.cuh) has its own file, tests/test_gpu_direct.py."""
     ctx = _cabi.context()
-    ctx.set_pass(0 if request.param == "auto" else 1)
+    ctx.set_pass({"auto": 0, "level": 1}[request.param])
     yield request.param
     ctx.set_pass(0)
 
@@ -90,7 +91,7 @@ def test_full_alphabet_random_differences(gold_full, enumeration_pass):
             res = ME.explain_mass_with_table(c["mass"], dp, max_modifications=c["max_modifications"], threshold=c["threshold"], with_memo=memo).explanations
             assert (None if res is None else len(res)) == c[f"n_{tag}"], c
             assert Hh.digest(res) == c[f"digest_{tag}"], c
-            assert _cabi.context().last_pass() == (2 if enumeration_pass == "auto" else 1)  # the pass under test really ran
+            assert _cabi.context().last_pass() == {"auto": 2, "level": 1}[enumeration_pass]  # the pass under test really ran
 
 
 def test_full_alphabet_validity(gold_full):

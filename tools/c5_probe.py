@@ -19,10 +19,12 @@ print("calls", len(em), "by nt", np.bincount(wl.explain_nt[sel]), "table", dev.R
 weights, is_mod, ind = ME._row_metadata(dp)
 mm = np.full(len(em), wl.max_modifications, dtype=np.int32)
 ctx.explain_stage_f64(dev, em, et, mm, ind, is_mod, dp.precision, dp.tolerance, True)
-t0 = time.perf_counter(); nr, nc = ctx.explain_run(dev, 0); t1 = time.perf_counter()
-print("first run (buffers grow): %.1f ms, roots %d comps %d" % ((t1 - t0) * 1e3, nr, nc))
-ctx.stats_reset()
-for _ in range(3):
-    ctx.flush_l2(); ctx.timer_start(); nr, nc = ctx.explain_run(dev, 0); ms = ctx.timer_stop()
-    print("run: %.3f ms  %.3g comps/s  records %.1f MB -> %.0f GB/s written" % (ms, nc / ms * 1e3, nc * 8 / 1e6, nc * 8 / ms / 1e6))
-print(ctx.kernel_stats()["explain_pass"], [round(float(x) * 1e-3, 1) for x in np.diff(ctx.explain_phase_ns().astype(np.int64)[ctx.explain_phase_ns() > 0])])
+for which in (1, -3, 3):
+    ctx.set_pass(which)
+    t0 = time.perf_counter(); nr, nc = ctx.explain_run(dev, 0); t1 = time.perf_counter()
+    print("pass choice %d (ran %d): first run (buffers grow): %.1f ms, roots %d comps %d" % (which, ctx.last_pass(), (t1 - t0) * 1e3, nr, nc))
+    ctx.stats_reset()
+    for _ in range(3):
+        ctx.flush_l2(); ctx.timer_start(); nr, nc = ctx.explain_run(dev, 0); ms = ctx.timer_stop()
+        print("  run: %.3f ms  %.3g comps/s  records %.1f MB -> %.0f GB/s written" % (ms, nc / ms * 1e3, nc * 8 / 1e6, nc * 8 / ms / 1e6))
+    print(" ", ctx.kernel_stats()["explain_pass"], [round(float(x) * 1e-3, 1) for x in np.diff(ctx.explain_phase_ns().astype(np.int64)[ctx.explain_phase_ns() > 0])])

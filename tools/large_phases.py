@@ -13,12 +13,12 @@ dev = dp.device_table(); ctx = dev.ctx
 mass, thr = np.tile(wl.explain_mass, f), np.tile(wl.explain_thr, f)
 weights, is_mod, ind = ME._row_metadata(dp)
 ctx.explain_stage_f64(dev, mass, thr, wl.max_modifications, ind, is_mod, dp.precision, dp.tolerance, True)
-for mode in (1, 2):
+for mode in (2, 3):
     ctx.set_pass(mode)
     for _ in range(3):
         ctx.explain_run(dev, 0)
     ctx.stats_reset()
-    if mode == 2:
+    if mode == 3:
         ctx.cta_timestamps(True)
     for _ in range(5):
         ctx.flush_l2()
@@ -27,8 +27,8 @@ for mode in (1, 2):
     ph = ctx.explain_phase_ns().astype(np.int64); ph = ph[ph > 0]
     print(f"pass {mode} x{f}: {len(mass)} calls, {r} roots, {c} compositions, pass {st['explain_pass'][0] / 5:.3f} ms")
     print("  phases (us):", [round(float(x) * 1e-3, 1) for x in np.diff(ph)])
-    if mode == 2:
+    if mode == 3:
         cs = ctx.cta_timestamps(False).astype(np.int64)
         d = (cs[:, :8] - cs[:, 0].min()) * 1e-3
-        for k, nm in enumerate(["start", "win counted", "roots written", "count done", "barrier", "fill done", "rounds done"]):
+        for k, nm in enumerate(["start", "counted", "barrier 1", "scanned", "barrier 2", "searched", "roots (last)", "fill done"]):
             print(f"  {nm:14s} min {d[:, k].min():8.1f} p50 {np.median(d[:, k]):8.1f} p90 {np.percentile(d[:, k], 90):8.1f} max {d[:, k].max():8.1f}")

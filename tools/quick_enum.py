@@ -9,13 +9,13 @@ seq = MT.SequenceInformation(max_len=wl.max_len, su_mass=0.0, obs_mass=0.0, modi
 dp = MT.DynamicProgrammingTable(S.alphabet_frame(None), 32, wl.ppm, 1e-3, seq)
 res = {}
 flush = "--warm" not in sys.argv
-for mode in (1, 2):
+for mode in (2, 3):
     ctx.set_pass(mode)
     b = ME.explain_masses(wl.explain_mass, dp, max_modifications=wl.max_modifications, thresholds=wl.explain_thr)
     res[mode] = b
     dev = dp.device_table()
     ts = []
-    if mode == 2:
+    if mode == 3:
         ctx.cta_timestamps(True)
     for _ in range(10):
         if flush:
@@ -23,18 +23,18 @@ for mode in (1, 2):
         ctx.stats_reset(); ctx.explain_run(dev, 0); ts.append(ctx.kernel_stats()["explain_pass"][0])
     ph = ctx.explain_phase_ns().astype(np.int64); ph = ph[ph > 0]
     print("pass", mode, "last", ctx.last_pass(), "comps", b.n_compositions, "ms", np.round(ts, 4), "phases us", np.diff(ph) * 1e-3)
-    if mode == 2:
+    if mode == 3:
         c = ctx.cta_timestamps(False).astype(np.int64)
         t0 = c[:, 0].min()
         d = (c[:, :8] - t0) * 1e-3
-        names = ["start", "win counted", "roots written", "count done", "barrier", "fill done", "rounds done"]
+        names = ["start", "counted", "barrier 1", "scanned", "barrier 2", "searched", "roots (last)", "fill done"]
         for k, nm in enumerate(names):
             print(f"  {nm:14s} min {d[:, k].min():8.1f} p50 {np.median(d[:, k]):8.1f} p90 {np.percentile(d[:, k], 90):8.1f} max {d[:, k].max():8.1f}")
-        print("  count phase per CTA us: p10/p50/p90/max", np.percentile(d[:, 3] - d[:, 0], [10, 50, 90, 100]).round(1),
-              " fill: ", np.percentile(d[:, 5] - d[:, 4], [10, 50, 90, 100]).round(1))
-a, b = res[1], res[2]
+        print("  count phase per CTA us: p10/p50/p90/max", np.percentile(d[:, 1] - d[:, 0], [10, 50, 90, 100]).round(1),
+              " fill: ", np.percentile(d[:, 7] - d[:, 4], [10, 50, 90, 100]).round(1))
+a, b = res[2], res[3]
 print("status", np.array_equal(a.status, b.status), "offsets", np.array_equal(a.offsets, b.offsets))
 ka = a.records.view(np.uint64).reshape(-1); kb = b.records.view(np.uint64).reshape(-1)
 pk = np.repeat(np.arange(len(a)), a.counts())
 oa = np.lexsort((ka, pk)); ob = np.lexsort((kb, pk))
-print("records (sorted per peak) equal:", np.array_equal(ka[oa], kb[ob]))
+print("records (sorted per peak) equal:", np.array_equal(ka[oa], kb[ob]), " same order:", np.array_equal(ka, kb))
