@@ -40,7 +40,9 @@ enum {
     SST_ERR_NOMEM = 7,         /* result or scratch does not fit in device memory -> MemoryError */
     SST_ERR_MEMO_FULL = 8,     /* first-visit map too small: call again with a larger memo_capacity */
     SST_ERR_STATE = 9,         /* fetch without a preceding run */
-    SST_ERR_OUT_OF_TABLE = 10  /* a probed mass lies beyond the table -> NotImplementedError */
+    SST_ERR_OUT_OF_TABLE = 10, /* a probed mass lies beyond the table -> NotImplementedError */
+    SST_ERR_NAN = 11,          /* a NaN mass: the reference's int(round(nan)) -> ValueError (mass_explanation.py:51,107) */
+    SST_ERR_INF = 12           /* an infinite mass or threshold: int(round(inf)) / int(np.ceil(inf)) -> OverflowError */
 };
 
 /* per-peak budget modes for sst_explain (see DESIGN.md "Budget semantics") */

@@ -22,6 +22,7 @@ LIB_PATH = _HERE / "libsst_b200.so"
 SST_OK, SST_ERR_CUDA, SST_ERR_NO_DEVICE, SST_ERR_BAD_ARG, SST_ERR_COMPRESSION = 0, 1, 2, 3, 4
 SST_ERR_TOO_MANY_ROWS, SST_ERR_TOO_DEEP, SST_ERR_NOMEM, SST_ERR_MEMO_FULL, SST_ERR_STATE = 5, 6, 7, 8, 9
 SST_ERR_OUT_OF_TABLE = 10
+SST_ERR_NAN, SST_ERR_INF = 11, 12
 MODE_FREE, MODE_EXACT, MODE_MEMO = 0, 1, 2
 STATUS_ZERO_IN_WINDOW, STATUS_OUT_OF_TABLE = 1, 2
 VALID_NO, VALID_YES, VALID_OUT_OF_TABLE = 0, 1, 2
@@ -150,6 +151,10 @@ class Context:
         msg = (self._lib.sst_last_error(self._h) or b"").decode(errors="replace")
         if rc in (SST_ERR_BAD_ARG, SST_ERR_COMPRESSION, SST_ERR_TOO_MANY_ROWS):
             raise ValueError(msg)
+        if rc == SST_ERR_NAN:  # the reference's int(round(nan))
+            raise ValueError(msg)
+        if rc == SST_ERR_INF:  # int(round(inf)) / int(np.ceil(inf))
+            raise OverflowError(msg)
         if rc == SST_ERR_TOO_DEEP:
             raise NotImplementedError(msg)
         if rc == SST_ERR_NOMEM:

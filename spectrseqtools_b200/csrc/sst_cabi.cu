@@ -47,6 +47,7 @@ struct sst_table {
     uint64_t last_mask = ~0ULL;
     uint32_t leaf_mul = 0;  // collision-free multiplier of the weight -> row hash (0 = none found)
     uint32_t* d_lamq = nullptr;  // scheduling cost model (CostModel): compositions per unit of mass, Q16, per coarse mass bucket
+    std::vector<uint32_t> h_lamq;  // the same on the host (the asynchronous entry estimates a batch's cost from a sample)
     uint32_t lam_width = 1, lam_K = 0;
     float build_ms = 0.f, transpose_ms = 0.f;
     bool built_here = false;
@@ -137,6 +138,9 @@ struct sst_ctx {
         uint64_t recs_bytes = 0, copied = 0;
     } pend;
     uint64_t last_comps = 0;           // compositions of the last batch: sizes the speculative copy of the next one
+    int32_t up_ind[128] = {0};         // what d_ind / d_ismod hold (the per-row budgets rarely change between batches)
+    uint8_t up_ismod[128] = {0};
+    int up_R = -1;
     unsigned long long* h_blk = nullptr;  // pinned: block sums of the staged batch's scheduling costs
     size_t h_blk_cap = 0;
     double est_cost_per_peak = 0.0;    // mean peak_cost() of the staged batch (the automatic choice of the pass looks at it)
@@ -164,6 +168,48 @@ int fail(sst_ctx* ctx, int code, const char* fmt, ...) {
             return fail(ctx, e_ == cudaErrorMemoryAllocation ? SST_ERR_NOMEM : SST_ERR_CUDA, "%s: %s (%s:%d)", #call, \
                         cudaGetErrorString(e_), __FILE__, __LINE__);                                      \
     } while (0)
+
+// One pass over a host array of doubles: the largest value (NaN drops out of the compares), whether a NaN and whether
+// an infinity occurs.  Eight independent accumulators: a single dependent chain of compares over 10^5 values costs
+// more than all the CUDA calls of a staging function together.
+struct F64Scan {
+    double max = 0.0;
+    bool has_nan = false, has_inf = false;
+};
+F64Scan scan_f64(const double* x, int64_t n) {
+    double acc[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0}, mag[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    int nan[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    int64_t i = 0;
+    for (; i + 8 <= n; i += 8)
+        for (int k = 0; k < 8; k++) {
+            const double v = x[i + k], a = v < 0.0 ? -v : v;
+            acc[k] = v > acc[k] ? v : acc[k];
+            mag[k] = a > mag[k] ? a : mag[k];
+            nan[k] |= v != v;
+        }
+    for (; i < n; i++) {
+        const double v = x[i], a = v < 0.0 ? -v : v;
+        acc[0] = v > acc[0] ? v : acc[0];
+        mag[0] = a > mag[0] ? a : mag[0];
+        nan[0] |= v != v;
+    }
+    F64Scan r;
+    double m = 0.0;
+    for (int k = 0; k < 8; k++) {
+        r.max = acc[k] > r.max ? acc[k] : r.max;
+        m = mag[k] > m ? mag[k] : m;
+        r.has_nan |= nan[k] != 0;
+    }
+    r.has_inf = m > 1.7976931348623157e308;
+    return r;
+}
+// the reference's int(round(x)) / int(np.ceil(x)) on a non-finite value (mass_explanation.py:51-58,107-114): NaN is a
+// ValueError, infinity an OverflowError.  A NaN THRESHOLD means "None" (relative) in the batched entries.
+int check_finite(sst_ctx* ctx, const F64Scan& s, bool nan_allowed) {
+    if (s.has_nan && !nan_allowed) return fail(ctx, SST_ERR_NAN, "cannot convert float NaN to integer");
+    if (s.has_inf) return fail(ctx, SST_ERR_INF, "cannot convert float infinity to integer");
+    return SST_OK;
+}
 
 int reserve(sst_ctx* ctx, DevBuf& b, size_t bytes) {
     if (bytes <= b.cap && b.p) return SST_OK;
@@ -350,6 +396,7 @@ int alloc_table(sst_ctx* ctx, sst_table* t, const int64_t* weights, int R, int64
         }
         t->lam_width = (uint32_t)width;
         t->lam_K = (uint32_t)K;
+        t->h_lamq = lamq;
         CK(cudaMalloc(&t->d_lamq, (size_t)K * 4));
         CK(cudaMemcpyAsync(t->d_lamq, lamq.data(), (size_t)K * 4, cudaMemcpyHostToDevice, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
@@ -702,6 +749,8 @@ int sst_valid_stage_f64(sst_ctx* ctx, const double* mass, const double* thr, int
     CK(cudaSetDevice(ctx->device));
     if (P < 0) return fail(ctx, SST_ERR_BAD_ARG, "negative probe count");
     int rc;
+    if ((rc = check_finite(ctx, scan_f64(mass, P), false))) return rc;
+    if (thr && (rc = check_finite(ctx, scan_f64(thr, P), true))) return rc;
     if ((rc = reserve(ctx, ctx->d_vmass, (size_t)(P ? P : 1) * 8))) return rc;
     if ((rc = reserve(ctx, ctx->d_vthrf, (size_t)(P ? P : 1) * 8))) return rc;
     if ((rc = reserve(ctx, ctx->d_vout, (size_t)(P ? P : 1)))) return rc;
@@ -756,6 +805,7 @@ int sst_classify_stage(sst_ctx* ctx, const double* observed, int64_t F, const do
     CK(cudaStreamSynchronize(ctx->stream2));  // an asynchronous classification may still own the buffers
     if (F < 0 || B < 0 || B > 65535) return fail(ctx, SST_ERR_BAD_ARG, "fragment / breakage count out of range");
     int rc;
+    if ((rc = check_finite(ctx, scan_f64(observed, F), false))) return rc;
     if ((rc = reserve(ctx, ctx->d_cobs, (size_t)(F ? F : 1) * 8))) return rc;
     if ((rc = reserve(ctx, ctx->d_coff, (size_t)(B ? B : 1) * 8))) return rc;
     if ((rc = reserve(ctx, ctx->d_cout, (size_t)(F * B ? F * B : 1)))) return rc;
@@ -811,6 +861,7 @@ static int classify_async(sst_ctx* ctx, const sst_table* t, const double* observ
     if (F < 0 || B < 0 || B > 65535) return fail(ctx, SST_ERR_BAD_ARG, "fragment / breakage count out of range");
     CK(cudaStreamSynchronize(ctx->stream2));  // an earlier asynchronous classification still owns the buffers
     int rc;
+    if ((rc = check_finite(ctx, scan_f64(observed, F), false))) return rc;
     if ((rc = reserve(ctx, ctx->d_cobs, (size_t)(F ? F : 1) * 8))) return rc;
     if ((rc = reserve(ctx, ctx->d_coff, (size_t)(B ? B : 1) * 8))) return rc;
     if ((rc = reserve(ctx, ctx->d_cout, (size_t)(F * B ? F * B : 1)))) return rc;
@@ -871,6 +922,7 @@ int sst_length_bounds(sst_ctx* ctx, const sst_table* t, int64_t target, int64_t 
     CK(cudaMemsetAsync(ctx->d_bkeys.p, 0, pow2 * 4, ctx->stream));
     CK(cudaMemsetAsync(ctx->d_btop.p, 0, pow2, ctx->stream));
     CK(cudaMemsetAsync(ctx->d_bout.p, 0, 64, ctx->stream));
+    ctx->up_R = -1;  // (d_ind / d_ismod no longer hold what stage_f64_enqueue remembers)
     CK(cudaMemcpyAsync(ctx->d_ind.p, ind, (size_t)t->R * 4, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(ctx->d_ismod.p, is_mod, (size_t)t->R, cudaMemcpyHostToDevice, ctx->stream));
     ctx->have_result = false;  // d_ind / d_ismod of a staged enumeration batch are gone: it has to be staged again
@@ -932,6 +984,7 @@ int sst_explain_stage(sst_ctx* ctx, const sst_table* t, const int64_t* target, c
         CK(cudaMemcpyAsync(ctx->d_maxmods.p, max_mods, (size_t)P * 4, cudaMemcpyHostToDevice, ctx->stream));
         CK(cudaMemcpyAsync(ctx->d_mode.p, mode, (size_t)P, cudaMemcpyHostToDevice, ctx->stream));
     }
+    ctx->up_R = -1;  // (d_ind / d_ismod no longer hold what stage_f64_enqueue remembers)
     CK(cudaMemcpyAsync(ctx->d_ind.p, ind, (size_t)t->R * 4, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(ctx->d_ismod.p, is_mod, (size_t)t->R, cudaMemcpyHostToDevice, ctx->stream));
     ctx->n_memo = (int)memo_peaks.size();
@@ -973,6 +1026,11 @@ int stage_f64_enqueue(sst_ctx* ctx, const sst_table* t, const double* mass, cons
     ctx->have_result = false;
     if (P < 0) return fail(ctx, SST_ERR_BAD_ARG, "negative peak count");
     if (!t->H) return fail(ctx, SST_ERR_STATE, "table was built without row masks");
+    if (!ctx->pend.active) {  // (sst_explain_submit_f64 has looked at the arrays already)
+        int rcf = check_finite(ctx, scan_f64(mass, P), false);
+        if (!rcf && thr) rcf = check_finite(ctx, scan_f64(thr, P), true);
+        if (rcf) return rcf;
+    }
     // Integerisation (the float operations of mass_explanation.py:107-114), the choice of the budget mode and
     // the batch summary all run on the device (k_stage_f64): the host only derives the two mode thresholds
     // from the per-row budgets.  FREE when no composition inside the window can exhaust a budget.
@@ -1004,8 +1062,13 @@ int stage_f64_enqueue(sst_ctx* ctx, const sst_table* t, const double* mass, cons
         if (thr) CK(cudaMemcpyAsync(ctx->d_vthrf.p, thr, (size_t)P * 8, cudaMemcpyHostToDevice, ctx->stream));
         if (max_mods) CK(cudaMemcpyAsync(ctx->d_maxmods.p, max_mods, (size_t)P * 4, cudaMemcpyHostToDevice, ctx->stream));
     }
-    CK(cudaMemcpyAsync(ctx->d_ind.p, ind, (size_t)t->R * 4, cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaMemcpyAsync(ctx->d_ismod.p, is_mod, (size_t)t->R, cudaMemcpyHostToDevice, ctx->stream));
+    if (ctx->up_R != t->R || memcmp(ctx->up_ind, ind, (size_t)t->R * 4) || memcmp(ctx->up_ismod, is_mod, (size_t)t->R)) {
+        memcpy(ctx->up_ind, ind, (size_t)t->R * 4);  // (the copies below read the context's arrays: the caller's may go away)
+        memcpy(ctx->up_ismod, is_mod, (size_t)t->R);
+        ctx->up_R = t->R;
+        CK(cudaMemcpyAsync(ctx->d_ind.p, ctx->up_ind, (size_t)t->R * 4, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(ctx->d_ismod.p, ctx->up_ismod, (size_t)t->R, cudaMemcpyHostToDevice, ctx->stream));
+    }
     if (P) {
         k_stage_f64<<<(unsigned)((P + 255) / 256), 256, 0, ctx->stream>>>(
             (const double*)ctx->d_vmass.p, thr ? (const double*)ctx->d_vthrf.p : nullptr, (int32_t*)ctx->d_maxmods.p, uniform_mods,
@@ -1643,17 +1706,17 @@ int sst_explain_submit_f64(sst_ctx* ctx, const sst_table* t, const double* mass,
     // Can everything be queued without a look at the staged batch?  Yes when a bound on the largest window end,
     // taken from the host arrays, already shows that no budget can bind (every peak FREE) and that the depth-first
     // pass holds the longest composition.  Otherwise the call is carried out synchronously in sst_explain_collect.
-    double m_max = 0.0, t_max = 0.0;
-    for (int64_t i = 0; i < P; i++) {
-        const double m = mass[i];
-        m_max = m > m_max ? m : m_max;
-    }
-    if (thr) {
-        for (int64_t i = 0; i < P; i++) {
-            const double x = thr[i];  // NaN = relative threshold: covered by tolerance * m_max below
-            t_max = x > t_max ? x : t_max;
+    const F64Scan sm = scan_f64(mass, P), st = thr ? scan_f64(thr, P) : F64Scan{};
+    {
+        int rcf = check_finite(ctx, sm, false);
+        if (!rcf) rcf = check_finite(ctx, st, true);
+        if (rcf) {
+            pd.active = false;
+            return rcf;
         }
     }
+    const double m_max = sm.max;
+    double t_max = st.max;  // NaN = relative threshold: covered by tolerance * m_max below
     const double rel = tolerance * m_max;
     if (rel > t_max) t_max = rel;
     const double hi_f = (m_max + t_max) / precision + 2.0;
@@ -1672,7 +1735,25 @@ int sst_explain_submit_f64(sst_ctx* ctx, const sst_table* t, const double* mass,
         if (w_min_mod && !((int64_t)max_mods >= hi_bound / w_min_mod && hi_bound < hi_limit)) fast = false;  // some budget may bind
         const int64_t cap = t->C * 32 - 1;
         const int64_t deepest = t->w_min > 0 ? (hi_bound < cap ? hi_bound : cap) / t->w_min : 0;
-        if (deepest > 4) fast = false;  // windows that reach 5 nucleotides: thousands of compositions per peak, the synchronous path picks the pass by cost
+        if (deepest > kDfsDepth) fast = false;
+        if (fast && !t->h_lamq.empty()) {  // peak_cost() of every 16th peak: a heavy batch goes the synchronous way, which picks the pass by cost
+            double sum = 0.0;
+            int64_t n = 0;
+            const double th_fix = thr ? 0.0 : 1.0;
+            for (int64_t i = 0; i < P; i += 16, n++) {
+                const double tg = mass[i] / precision;
+                double th = (thr && !(thr[i] != thr[i])) ? thr[i] / precision : tolerance * mass[i] / precision;
+                (void)th_fix;
+                if (!(tg > 0.0) || !(th >= 0.0)) continue;
+                const double W = 2.0 * th + 1.0;
+                size_t k = (size_t)((tg + 0.5 * t->lam_width) / t->lam_width);
+                if (k >= t->h_lamq.size()) k = t->h_lamq.size() - 1;
+                const double lam = (double)t->h_lamq[k] / 65536.0;
+                const double n_est = W * (lam < 1.0 ? lam : 1.0), c_est = W * lam > n_est ? W * lam : n_est;
+                sum += 16.0 + W / 16.0 + 6.0 * n_est + 4.0 * c_est;
+            }
+            if (n && sum / (double)n > kHeavyCostPerPeak) fast = false;
+        }
         if (fast) {
             ctx->deepest = deepest;
             pd.rec_width = (int)(8 * (deepest > 8 ? (deepest + 7) / 8 : 1));

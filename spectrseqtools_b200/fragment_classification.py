@@ -70,6 +70,9 @@ class ClassifiedMasses:
         return self.observed[None, :] - off[:, None]
 
 
+_OFFSET_CACHE: dict = {}  # the offsets / labels of the last breakage dictionary (same object, same size: same offsets)
+
+
 def classify_observed(observed: Sequence[float], dp_table: DynamicProgrammingTable, breakage_dict: Dict[int, List[str]],
                       copy: bool = True, wait: bool = True, slot: int = 0) -> ClassifiedMasses:
     """Validity + singleton flags of every observed mass under every breakage offset: one device pass.
@@ -79,15 +82,18 @@ def classify_observed(observed: Sequence[float], dp_table: DynamicProgrammingTab
     overlaps it; the flags then cross the bus two per byte.  ``copy=False`` hands out the context's pinned buffer
     (valid until the next classification on the same ``slot``, see ``_cabi.context``)."""
     observed = np.ascontiguousarray(observed, dtype=np.float64).reshape(-1)
-    if len(observed) and not np.isfinite(observed).all():  # upstream: int(round(nan)) / int(round(inf)) inside is_valid_mass
-        if np.isnan(observed).any():
-            raise ValueError("cannot convert float NaN to integer")
-        raise OverflowError("cannot convert float infinity to integer")
-    weights = list(breakage_dict.keys())
-    offsets = np.array([w * dp_table.precision for w in weights], dtype=np.float64)  # int * float, as upstream
+    # (NaN / infinite masses: the library raises what upstream's int(round(x)) inside is_valid_mass raises)
+    key = (id(breakage_dict), len(breakage_dict), dp_table.precision)
+    hit = _OFFSET_CACHE.get("last")
+    if hit is not None and hit[0] == key and hit[1] is breakage_dict:
+        _k, _d, weights, offsets, labels = hit
+    else:
+        weights = list(breakage_dict.keys())
+        offsets = np.array([w * dp_table.precision for w in weights], dtype=np.float64)  # int * float, as upstream
+        labels = [breakage_dict[w][0] for w in weights]
+        _OFFSET_CACHE["last"] = (key, breakage_dict, weights, offsets, labels)
     dev = dp_table.device_table()
     ctx = dev.ctx if slot == 0 else _cabi.context(dev.ctx.device, slot)
-    labels = [breakage_dict[w][0] for w in weights]
     if not wait:
         flags = ctx.classify_async(dev, observed, offsets, dp_table.precision, dp_table.tolerance, packed=True)
         return ClassifiedMasses(observed, weights, labels, dp_table.precision, flags, pending=ctx, packed=True)

@@ -171,18 +171,6 @@ class ExplanationBatch:
         return sorted(tuple(int(r) for r in rec if r) for rec in self.rows(p))
 
 
-def _require_finite(masses: np.ndarray, thresholds: Optional[np.ndarray]):
-    """The reference integerises with ``int(round(x))`` / ``int(np.ceil(x))``: NaN raises ValueError, infinity
-    OverflowError (mass_explanation.py:51-58,107-114).  Raised here, before anything is staged, instead of feeding an
-    undefined float -> int cast to the device.  (A NaN *threshold* entry means "None" = relative in the batched API.)"""
-    if len(masses) and not np.isfinite(masses).all():
-        if np.isnan(masses).any():
-            raise ValueError("cannot convert float NaN to integer")
-        raise OverflowError("cannot convert float infinity to integer")
-    if thresholds is not None and len(thresholds) and np.isinf(thresholds).any():
-        raise OverflowError("cannot convert float infinity to integer")
-
-
 def _thr_array(thresholds, n: int) -> Optional[np.ndarray]:
     """Per-mass absolute thresholds as float64, NaN where the reference would use ``tolerance * mass``."""
     if thresholds is None:
@@ -231,7 +219,6 @@ def explain_masses(masses: Sequence[float], dp_table: DynamicProgrammingTable, m
     masses = np.ascontiguousarray(masses, dtype=np.float64).reshape(-1)
     P = len(masses)
     thr = _thr_array(thresholds, P)
-    _require_finite(masses, thr)
     if np.ndim(max_modifications) == 0:
         max_mods = _budget_int(max_modifications)  # one budget for the batch: filled on the device
     else:
@@ -279,7 +266,6 @@ def are_valid_masses(masses: Sequence[float], dp_table: DynamicProgrammingTable,
     """Batched ``is_valid_mass`` -> uint8 array of _cabi.VALID_* codes (2 = out of table)."""
     masses = np.ascontiguousarray(masses, dtype=np.float64).reshape(-1)
     thr = _thr_array(thresholds, len(masses))
-    _require_finite(masses, thr)
     dev = dp_table.device_table()
     ctx = dev.ctx
     ctx.valid_stage_f64(masses, thr, dp_table.precision, dp_table.tolerance)

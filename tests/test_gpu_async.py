@@ -80,3 +80,39 @@ def test_packed_flags_odd_fragment_count():
     want = FC.classify_observed(obs, dp, wl.breakage).flags.copy()
     got = FC.classify_observed(obs, dp, wl.breakage, wait=False).flags
     assert got.shape == want.shape and np.array_equal(got, want)
+
+
+def test_non_finite_inputs_raise_like_the_reference():
+    """int(round(nan)) is a ValueError, int(round(inf)) / int(np.ceil(inf)) an OverflowError upstream
+    (mass_explanation.py:51-58,107-114); the library finds them in the host arrays before anything is staged."""
+    wl = S.make_workload("C2", 600)
+    dp = _table(wl)
+    good = wl.explain_mass[:64].copy()
+    for bad, exc in ((np.nan, ValueError), (np.inf, OverflowError), (-np.inf, OverflowError)):
+        m = good.copy()
+        m[37] = bad
+        for kw in ({}, {"wait": False}):
+            with pytest.raises(exc):
+                r = ME.explain_masses(m, dp, max_modifications=wl.max_modifications, thresholds=wl.explain_thr[:64], **kw)
+                r.wait()
+        with pytest.raises(exc):
+            ME.are_valid_masses(m, dp, wl.explain_thr[:64])
+        with pytest.raises(exc):
+            FC.classify_observed(m, dp, wl.breakage)
+        with pytest.raises(exc):
+            FC.classify_observed(m, dp, wl.breakage, wait=False).wait()
+        with pytest.raises(exc):
+            ME.explain_mass_with_table(float(bad), dp)
+        with pytest.raises(exc):
+            ME.is_valid_mass(float(bad), dp)
+    t = wl.explain_thr[:64].copy()
+    t[5] = np.inf
+    with pytest.raises(OverflowError):
+        ME.explain_masses(good, dp, thresholds=t)
+    t[5] = np.nan  # = None: relative threshold
+    a = ME.explain_masses(good, dp, max_modifications=wl.max_modifications, thresholds=t)
+    t2 = [None if np.isnan(x) else float(x) for x in t]
+    b = ME.explain_masses(good, dp, max_modifications=wl.max_modifications, thresholds=t2)
+    assert np.array_equal(a.offsets, b.offsets) and np.array_equal(a.records, b.records)
+    # the context still works after the refusals
+    assert len(ME.explain_masses(good, dp, max_modifications=wl.max_modifications, thresholds=wl.explain_thr[:64], wait=False).wait()) == 64
