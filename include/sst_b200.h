@@ -184,6 +184,10 @@ int sst_explain_cta_ns(sst_ctx* ctx, int enable, uint64_t* out, int cap_ctas, in
  * [counted, grid barrier passed, written]; after the last level [per-level peak totals summed], [placement table
  * written], [records permuted].  Right after a grid barrier that is every CTA's clock.  Unused slots are 0. */
 int sst_explain_phase_ns(const sst_ctx* ctx, uint64_t* out /* [32] */);
+/* diagnostics: host wall time (ns) and number of visits per section of the asynchronous entries since the last call
+ * (sections are the marks in sst_cabi.cu: 0-12 sst_explain_submit_f64, 13 the wait in sst_explain_collect, 16-20
+ * sst_classify_async); returns the sums, clears them and switches the stopwatch on or off (process-wide) */
+int sst_host_profile(int enable, uint64_t* ns_out /* [32] or NULL */, uint64_t* calls_out /* [32] or NULL */);
 /* The whole call — replaces a loop of calculate_explanations (common.py:47-65) — WITHOUT WAITING: the copy of the inputs,
  * staging, the enumeration pass and the copy of the results are queued on the context's stream; sst_explain_collect
  * waits for them.  One modification budget for the batch (what calculate_explanations passes).  All host pointers must

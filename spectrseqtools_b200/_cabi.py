@@ -37,7 +37,7 @@ EXPORTS = [
     "sst_table_download_masks", "sst_table_destroy", "sst_is_valid", "sst_valid_stage", "sst_valid_run",
     "sst_valid_fetch", "sst_valid_stage_f64", "sst_explain", "sst_explain_stage", "sst_explain_stage_f64", "sst_explain_stage_f64_uniform", "sst_explain_rec_width", "sst_explain_phase_ns",
     "sst_explain_run", "sst_explain_fetch", "sst_classify", "sst_classify_stage", "sst_classify_run", "sst_classify_fetch", "sst_classify_launch", "sst_classify_async", "sst_classify_wait", "sst_length_bounds",
-    "sst_set_pass", "sst_last_pass", "sst_explain_cta_ns", "sst_explain_submit_f64", "sst_explain_collect", "sst_classify_async_packed",
+    "sst_set_pass", "sst_last_pass", "sst_explain_cta_ns", "sst_explain_submit_f64", "sst_explain_collect", "sst_classify_async_packed", "sst_host_profile",
 ]
 
 
@@ -109,6 +109,7 @@ def load() -> C.CDLL:
             "sst_classify_wait": (C.c_int, [vp]),
             "sst_explain_submit_f64": (C.c_int, [vp, vp, fp, fp, C.c_int32, C.c_int64, i32p, u8p, C.c_double, C.c_double, C.c_int, u8p, u32p, u8p, C.c_uint64]),
             "sst_explain_collect": (C.c_int, [vp, vp, C.POINTER(C.c_uint64), C.POINTER(C.c_int)]),
+            "sst_host_profile": (C.c_int, [C.c_int, u64p, u64p]),
             "sst_set_pass": (C.c_int, [vp, C.c_int]),
             "sst_last_pass": (C.c_int, [vp]),
             "sst_explain_cta_ns": (C.c_int, [vp, C.c_int, u64p, C.c_int, C.POINTER(C.c_int)]),
@@ -405,6 +406,12 @@ class Context:
         self._last = (0, n, w)
         self._recs_hint = max(self.__dict__.get("_recs_hint", 0), n * w + n * w // 4)
         return status, off, recs[: n * w].reshape(n, w)
+
+    def host_profile(self, enable: bool):
+        """(ns[32], visits[32]) per section of the asynchronous entries since the last call (sst_host_profile)."""
+        ns, calls = np.zeros(32, dtype=np.uint64), np.zeros(32, dtype=np.uint64)
+        self._check(self._lib.sst_host_profile(1 if enable else 0, _p(ns), _p(calls)))
+        return ns, calls
 
     def explain_phase_ns(self) -> np.ndarray:
         """Device timestamps of the last enumeration pass (see sst_explain_phase_ns)."""

@@ -4,6 +4,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
+#include <time.h>
 
 #include <cmath>
 #include <new>
@@ -21,6 +22,30 @@ using namespace sst;
 namespace {
 
 constexpr int kMaxPending = 32;
+
+// Host-side stopwatch of the asynchronous entries (diagnostics, sst_host_profile): wall time between marks inside the
+// submitting calls, summed per section.  Off unless switched on; a mark is two loads when off.
+struct HostProf {
+    bool on = false;
+    uint64_t ns[32] = {0}, calls[32] = {0};
+    uint64_t last = 0;
+};
+HostProf g_hp;
+inline uint64_t host_now_ns() {
+    timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return (uint64_t)ts.tv_sec * 1000000000ULL + (uint64_t)ts.tv_nsec;
+}
+inline void hp_begin() {
+    if (g_hp.on) g_hp.last = host_now_ns();
+}
+inline void hp_mark(int k) {
+    if (!g_hp.on) return;
+    const uint64_t t = host_now_ns();
+    g_hp.ns[k] += t - g_hp.last;
+    g_hp.calls[k]++;
+    g_hp.last = t;
+}
 
 struct DevBuf {  // grow-only device scratch
     void* p = nullptr;
@@ -97,6 +122,8 @@ struct sst_ctx {
     DevBuf d_bkeys, d_btop, d_blower, d_bupper, d_bout;  // sequence-length bounds
     int64_t CF = 0;
     int CB = 0;
+    const uint8_t* c_async_out = nullptr;  // where the last asynchronous classification lands (sst_classify_wait looks at its first row)
+    bool c_async_pack4 = false;
     int64_t VP = 0;
     int* h_misc = nullptr;             // pinned: run summary read back with one copy
     unsigned long long* h_run = nullptr;  // pinned + mapped: the enumeration pass writes its summary here itself
@@ -138,6 +165,8 @@ struct sst_ctx {
         uint64_t recs_bytes = 0, copied = 0;
     } pend;
     uint64_t last_comps = 0;           // compositions of the last batch: sizes the speculative copy of the next one
+    bool spec_ok = true;               // sst_explain_submit_f64 queues blindly (the last batch it had to redo would have fitted, or none yet)
+    int spec_rec_width = 8;            // with this record width
     int32_t up_ind[128] = {0};         // what d_ind / d_ismod hold (the per-row budgets rarely change between batches)
     uint8_t up_ismod[128] = {0};
     int up_R = -1;
@@ -169,46 +198,24 @@ int fail(sst_ctx* ctx, int code, const char* fmt, ...) {
                         cudaGetErrorString(e_), __FILE__, __LINE__);                                      \
     } while (0)
 
-// One pass over a host array of doubles: the largest value (NaN drops out of the compares), whether a NaN and whether
-// an infinity occurs.  Eight independent accumulators: a single dependent chain of compares over 10^5 values costs
-// more than all the CUDA calls of a staging function together.
-struct F64Scan {
-    double max = 0.0;
-    bool has_nan = false, has_inf = false;
-};
-F64Scan scan_f64(const double* x, int64_t n) {
-    double acc[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0}, mag[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-    int nan[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    int64_t i = 0;
-    for (; i + 8 <= n; i += 8)
-        for (int k = 0; k < 8; k++) {
-            const double v = x[i + k], a = v < 0.0 ? -v : v;
-            acc[k] = v > acc[k] ? v : acc[k];
-            mag[k] = a > mag[k] ? a : mag[k];
-            nan[k] |= v != v;
-        }
-    for (; i < n; i++) {
-        const double v = x[i], a = v < 0.0 ? -v : v;
-        acc[0] = v > acc[0] ? v : acc[0];
-        mag[0] = a > mag[0] ? a : mag[0];
-        nan[0] |= v != v;
-    }
-    F64Scan r;
-    double m = 0.0;
-    for (int k = 0; k < 8; k++) {
-        r.max = acc[k] > r.max ? acc[k] : r.max;
-        m = mag[k] > m ? mag[k] : m;
-        r.has_nan |= nan[k] != 0;
-    }
-    r.has_inf = m > 1.7976931348623157e308;
-    return r;
-}
-// the reference's int(round(x)) / int(np.ceil(x)) on a non-finite value (mass_explanation.py:51-58,107-114): NaN is a
-// ValueError, infinity an OverflowError.  A NaN THRESHOLD means "None" (relative) in the batched entries.
-int check_finite(sst_ctx* ctx, const F64Scan& s, bool nan_allowed) {
-    if (s.has_nan && !nan_allowed) return fail(ctx, SST_ERR_NAN, "cannot convert float NaN to integer");
-    if (s.has_inf) return fail(ctx, SST_ERR_INF, "cannot convert float infinity to integer");
+// Non-finite inputs are found by the kernels that integerise (non_finite() in sst_explain.cuh) and reported here: the
+// reference's int(round(x)) / int(np.ceil(x)) raise ValueError for NaN, OverflowError for an infinity
+// (mass_explanation.py:51-58,107-114).  No pass over the host arrays: at 10^5 peaks that cost more than every CUDA call
+// of a submission together.
+int nf_error(sst_ctx* ctx, unsigned long long bits) {
+    if (bits & NF_NAN) return fail(ctx, SST_ERR_NAN, "cannot convert float NaN to integer");
+    if (bits & NF_INF) return fail(ctx, SST_ERR_INF, "cannot convert float infinity to integer");
     return SST_OK;
+}
+// the same from a row of result codes: `nan_code` / `inf_code` in a byte (or, packed, in either nibble)
+int nf_error_codes(sst_ctx* ctx, const uint8_t* codes, int64_t n, int nan_code, int inf_code, bool nibbles) {
+    unsigned seen = 0;
+    if (nibbles) {
+        for (int64_t i = 0; i < n; i++) seen |= 1u << (codes[i] & 15) | 1u << (codes[i] >> 4);
+    } else {
+        for (int64_t i = 0; i < n; i++) seen |= 1u << (codes[i] & 15);
+    }
+    return nf_error(ctx, ((seen >> nan_code) & 1u ? NF_NAN : 0) | ((seen >> inf_code) & 1u ? NF_INF : 0));
 }
 
 int reserve(sst_ctx* ctx, DevBuf& b, size_t bytes) {
@@ -749,8 +756,6 @@ int sst_valid_stage_f64(sst_ctx* ctx, const double* mass, const double* thr, int
     CK(cudaSetDevice(ctx->device));
     if (P < 0) return fail(ctx, SST_ERR_BAD_ARG, "negative probe count");
     int rc;
-    if ((rc = check_finite(ctx, scan_f64(mass, P), false))) return rc;
-    if (thr && (rc = check_finite(ctx, scan_f64(thr, P), true))) return rc;
     if ((rc = reserve(ctx, ctx->d_vmass, (size_t)(P ? P : 1) * 8))) return rc;
     if ((rc = reserve(ctx, ctx->d_vthrf, (size_t)(P ? P : 1) * 8))) return rc;
     if ((rc = reserve(ctx, ctx->d_vout, (size_t)(P ? P : 1)))) return rc;
@@ -790,6 +795,7 @@ int sst_valid_fetch(sst_ctx* ctx, uint8_t* out) {
     CK(cudaSetDevice(ctx->device));
     if (ctx->VP) CK(cudaMemcpyAsync(out, ctx->d_vout.p, (size_t)ctx->VP, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
+    if (ctx->valid_f64) return nf_error_codes(ctx, out, ctx->VP, VALID_CODE_NAN, VALID_CODE_INF, false);
     return SST_OK;
 }
 
@@ -805,7 +811,6 @@ int sst_classify_stage(sst_ctx* ctx, const double* observed, int64_t F, const do
     CK(cudaStreamSynchronize(ctx->stream2));  // an asynchronous classification may still own the buffers
     if (F < 0 || B < 0 || B > 65535) return fail(ctx, SST_ERR_BAD_ARG, "fragment / breakage count out of range");
     int rc;
-    if ((rc = check_finite(ctx, scan_f64(observed, F), false))) return rc;
     if ((rc = reserve(ctx, ctx->d_cobs, (size_t)(F ? F : 1) * 8))) return rc;
     if ((rc = reserve(ctx, ctx->d_coff, (size_t)(B ? B : 1) * 8))) return rc;
     if ((rc = reserve(ctx, ctx->d_cout, (size_t)(F * B ? F * B : 1)))) return rc;
@@ -857,11 +862,12 @@ int sst_classify_async_packed(sst_ctx* ctx, const sst_table* t, const double* ob
 
 static int classify_async(sst_ctx* ctx, const sst_table* t, const double* observed, int64_t F, const double* offsets, int B,
                           double precision, double tolerance, uint8_t* out, int pack4) {
+    hp_begin();
     CK(cudaSetDevice(ctx->device));
     if (F < 0 || B < 0 || B > 65535) return fail(ctx, SST_ERR_BAD_ARG, "fragment / breakage count out of range");
     CK(cudaStreamSynchronize(ctx->stream2));  // an earlier asynchronous classification still owns the buffers
+    hp_mark(16);
     int rc;
-    if ((rc = check_finite(ctx, scan_f64(observed, F), false))) return rc;
     if ((rc = reserve(ctx, ctx->d_cobs, (size_t)(F ? F : 1) * 8))) return rc;
     if ((rc = reserve(ctx, ctx->d_coff, (size_t)(B ? B : 1) * 8))) return rc;
     if ((rc = reserve(ctx, ctx->d_cout, (size_t)(F * B ? F * B : 1)))) return rc;
@@ -870,18 +876,29 @@ static int classify_async(sst_ctx* ctx, const sst_table* t, const double* observ
     if (!F || !B) return SST_OK;
     CK(cudaMemcpyAsync(ctx->d_cobs.p, observed, (size_t)F * 8, cudaMemcpyHostToDevice, ctx->stream2));
     CK(cudaMemcpyAsync(ctx->d_coff.p, offsets, (size_t)B * 8, cudaMemcpyHostToDevice, ctx->stream2));
+    hp_mark(18);
     k_classify<<<dim3((unsigned)((F + 255) / 256), (unsigned)((B + kClassifyPerThread - 1) / kClassifyPerThread)), 256, 0, ctx->stream2>>>(view_of(t), (const double*)ctx->d_cobs.p, F,
                                                                                        (const double*)ctx->d_coff.p, B, precision, tolerance,
                                                                                        (uint8_t*)ctx->d_cout.p, pack4);
     CK(cudaGetLastError());
+    hp_mark(19);
     ctx->k_launches[SST_K_CLASSIFY] += 1;
     CK(cudaMemcpyAsync(out, ctx->d_cout.p, pack4 ? (size_t)(((F + 1) & ~1LL) / 2) * B : (size_t)F * B, cudaMemcpyDeviceToHost, ctx->stream2));
+    hp_mark(20);
+    ctx->c_async_out = out;
+    ctx->c_async_pack4 = pack4 != 0;
     return SST_OK;
 }
 
 int sst_classify_wait(sst_ctx* ctx) {
     CK(cudaSetDevice(ctx->device));
     CK(cudaStreamSynchronize(ctx->stream2));
+    if (ctx->c_async_out && ctx->CF && ctx->CB) {  // a non-finite observed mass marks every breakage row: the first one tells
+        const uint8_t* row0 = ctx->c_async_out;
+        ctx->c_async_out = nullptr;
+        return nf_error_codes(ctx, row0, ctx->c_async_pack4 ? (ctx->CF + 1) / 2 : ctx->CF, CLASS_CODE_NAN, CLASS_CODE_INF, ctx->c_async_pack4);
+    }
+    ctx->c_async_out = nullptr;
     return SST_OK;
 }
 
@@ -889,6 +906,7 @@ int sst_classify_fetch(sst_ctx* ctx, uint8_t* out) {
     CK(cudaSetDevice(ctx->device));
     if (ctx->CF && ctx->CB) CK(cudaMemcpyAsync(out, ctx->d_cout.p, (size_t)ctx->CF * ctx->CB, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
+    if (ctx->CF && ctx->CB) return nf_error_codes(ctx, out, ctx->CF, CLASS_CODE_NAN, CLASS_CODE_INF, false);
     return SST_OK;
 }
 
@@ -1026,11 +1044,6 @@ int stage_f64_enqueue(sst_ctx* ctx, const sst_table* t, const double* mass, cons
     ctx->have_result = false;
     if (P < 0) return fail(ctx, SST_ERR_BAD_ARG, "negative peak count");
     if (!t->H) return fail(ctx, SST_ERR_STATE, "table was built without row masks");
-    if (!ctx->pend.active) {  // (sst_explain_submit_f64 has looked at the arrays already)
-        int rcf = check_finite(ctx, scan_f64(mass, P), false);
-        if (!rcf && thr) rcf = check_finite(ctx, scan_f64(thr, P), true);
-        if (rcf) return rcf;
-    }
     // Integerisation (the float operations of mass_explanation.py:107-114), the choice of the budget mode and
     // the batch summary all run on the device (k_stage_f64): the host only derives the two mode thresholds
     // from the per-row budgets.  FREE when no composition inside the window can exhaust a budget.
@@ -1056,7 +1069,9 @@ int stage_f64_enqueue(sst_ctx* ctx, const sst_table* t, const double* mass, cons
     if ((rc = reserve(ctx, ctx->d_scan, 512))) return rc;
     if ((rc = reserve(ctx, ctx->d_peakcost, (size_t)(P + 1) * 4))) return rc;
     if ((rc = reserve(ctx, ctx->d_blkcost, (size_t)((P + kCostBlock - 1) / kCostBlock + 1) * 8))) return rc;
-    CK(cudaMemsetAsync(ctx->d_scan.p, 0, 32, ctx->stream));
+    hp_mark(2);
+    CK(cudaMemsetAsync(ctx->d_scan.p, 0, 64, ctx->stream));
+    hp_mark(3);
     if (P) {
         CK(cudaMemcpyAsync(ctx->d_vmass.p, mass, (size_t)P * 8, cudaMemcpyHostToDevice, ctx->stream));
         if (thr) CK(cudaMemcpyAsync(ctx->d_vthrf.p, thr, (size_t)P * 8, cudaMemcpyHostToDevice, ctx->stream));
@@ -1069,6 +1084,7 @@ int stage_f64_enqueue(sst_ctx* ctx, const sst_table* t, const double* mass, cons
         CK(cudaMemcpyAsync(ctx->d_ind.p, ctx->up_ind, (size_t)t->R * 4, cudaMemcpyHostToDevice, ctx->stream));
         CK(cudaMemcpyAsync(ctx->d_ismod.p, ctx->up_ismod, (size_t)t->R, cudaMemcpyHostToDevice, ctx->stream));
     }
+    hp_mark(4);
     if (P) {
         k_stage_f64<<<(unsigned)((P + 255) / 256), 256, 0, ctx->stream>>>(
             (const double*)ctx->d_vmass.p, thr ? (const double*)ctx->d_vthrf.p : nullptr, (int32_t*)ctx->d_maxmods.p, uniform_mods,
@@ -1078,7 +1094,9 @@ int stage_f64_enqueue(sst_ctx* ctx, const sst_table* t, const double* mass, cons
             CostModel{t->d_lamq, t->lam_width, t->lam_K}, (uint32_t*)ctx->d_peakcost.p, (unsigned long long*)ctx->d_blkcost.p);
         CK(cudaGetLastError());
     }
-    CK(cudaMemcpyAsync(ctx->h_misc, ctx->d_scan.p, 32, cudaMemcpyDeviceToHost, ctx->stream));
+    hp_mark(5);
+    CK(cudaMemcpyAsync(ctx->h_misc, ctx->d_scan.p, 64, cudaMemcpyDeviceToHost, ctx->stream));
+    hp_mark(6);
     ctx->P = P;
     ctx->R_staged = t->R;
     return SST_OK;
@@ -1092,6 +1110,7 @@ int stage_f64(sst_ctx* ctx, const sst_table* t, const double* mass, const double
     CK(cudaStreamSynchronize(ctx->stream));
     fetch_costs_finish(ctx, P);
     const unsigned long long* h = (const unsigned long long*)ctx->h_misc;
+    if ((rc = nf_error(ctx, h[4]))) return rc;
     ctx->window_total = (int64_t)h[0];
     ctx->max_hi = (int64_t)h[1];
     ctx->n_memo = (int)h[2];
@@ -1275,7 +1294,7 @@ int direct_enqueue(sst_ctx* ctx, sst_table* t, int rec_width) {
 
 // Depth-first pass (sst_enum.cuh): one cooperative launch, one grid barrier.  Returns PASS_FALLBACK when a root's
 // subtree is too large for one thread (the level-synchronous pass balances such batches across the machine).
-int dfs_enqueue(sst_ctx* ctx, const sst_table* t, int rec_width, const MemoMap& mp) {
+int dfs_enqueue(sst_ctx* ctx, const sst_table* t, int rec_width, const MemoMap& mp, const SpecGuard* guard = nullptr) {
     const int64_t P = ctx->P;
     const int nw = rec_width / 8;
     int rc;
@@ -1348,14 +1367,19 @@ int dfs_enqueue(sst_ctx* ctx, const sst_table* t, int rec_width, const MemoMap& 
             a.cta_ns = (unsigned long long*)ctx->d_ctans.p;
             ctx->cta_ns_grid = (int)grid;
         }
+        a.guard = guard ? *guard : SpecGuard{};
+        hp_mark(7);
         {
             KTimer kt(ctx, SST_K_EXPLAIN_PASS);
+            hp_mark(8);
             void* args[] = {(void*)&a};
             CK(cudaLaunchCooperativeKernel((const void*)kern, dim3(grid), dim3(kDfsThreads), args, 0, ctx->stream));
+            hp_mark(9);
             ctx->run_parity++;  // only a launch that really started clears the other set
             kt.stop(1);
         }
         CK(cudaEventRecord(ctx->ev_run, ctx->stream));  // the device is done here; what follows is the host waking up
+        hp_mark(10);
     }
     return SST_OK;
 }
@@ -1692,6 +1716,7 @@ int sst_explain_run(sst_ctx* ctx, const sst_table* t, int rec_width, uint64_t me
 int sst_explain_submit_f64(sst_ctx* ctx, const sst_table* t, const double* mass, const double* thr, int32_t max_mods, int64_t P,
                            const int32_t* ind, const uint8_t* is_mod, double precision, double tolerance, int with_memo, uint8_t* status_out,
                            uint32_t* off32_out, uint8_t* recs_out, uint64_t recs_bytes) {
+    hp_begin();
     CK(cudaSetDevice(ctx->device));
     if (ctx->pend.active) return fail(ctx, SST_ERR_STATE, "a submitted batch has not been collected yet");
     if (P < 0) return fail(ctx, SST_ERR_BAD_ARG, "negative peak count");
@@ -1703,62 +1728,19 @@ int sst_explain_submit_f64(sst_ctx* ctx, const sst_table* t, const double* mass,
     pd.status = status_out; pd.off32 = off32_out; pd.recs = recs_out; pd.recs_bytes = recs_bytes;
     pd.active = true;
     ctx->have_result = false;
-    // Can everything be queued without a look at the staged batch?  Yes when a bound on the largest window end,
-    // taken from the host arrays, already shows that no budget can bind (every peak FREE) and that the depth-first
-    // pass holds the longest composition.  Otherwise the call is carried out synchronously in sst_explain_collect.
-    const F64Scan sm = scan_f64(mass, P), st = thr ? scan_f64(thr, P) : F64Scan{};
-    {
-        int rcf = check_finite(ctx, sm, false);
-        if (!rcf) rcf = check_finite(ctx, st, true);
-        if (rcf) {
-            pd.active = false;
-            return rcf;
-        }
-    }
-    const double m_max = sm.max;
-    double t_max = st.max;  // NaN = relative threshold: covered by tolerance * m_max below
-    const double rel = tolerance * m_max;
-    if (rel > t_max) t_max = rel;
-    const double hi_f = (m_max + t_max) / precision + 2.0;
-    bool fast = ctx->pass_choice != 1 && P > 0 && hi_f < 4.0e18;
-    int64_t hi_bound = 0;
+    // Everything is queued without a look at the batch, on the assumption that it is like the previous ones: no budget
+    // binds (every peak FREE), compositions fit the record width of last time, the depth-first pass is the right one.
+    // The staging kernel's summary (largest window end, MEMO / EXACT peaks, non-finite inputs, summed cost estimate)
+    // stays on the device, where the pass checks it before it does anything; a batch that breaks an assumption comes
+    // back untouched and is carried out synchronously in sst_explain_collect, which also decides whether the next
+    // submission speculates again.  No pass over the host arrays.
+    const bool fast = ctx->pass_choice != 1 && ctx->pass_choice != 3 && P > 0 && ctx->spec_ok;
+    hp_mark(0);
     if (fast) {
-        hi_bound = (int64_t)hi_f;
-        int64_t w_min_mod = 0, hi_limit = INT64_MAX;
-        for (int r = 1; r < t->R; r++)
-            if (is_mod[r]) {
-                const int64_t w = t->w_host[r];
-                if (!w_min_mod || w < w_min_mod) w_min_mod = w;
-                const int64_t lim = ((int64_t)ind[r] + 1) * w;
-                if (lim < hi_limit) hi_limit = lim;
-            }
-        if (w_min_mod && !((int64_t)max_mods >= hi_bound / w_min_mod && hi_bound < hi_limit)) fast = false;  // some budget may bind
-        const int64_t cap = t->C * 32 - 1;
-        const int64_t deepest = t->w_min > 0 ? (hi_bound < cap ? hi_bound : cap) / t->w_min : 0;
-        if (deepest > kDfsDepth) fast = false;
-        if (fast && !t->h_lamq.empty()) {  // peak_cost() of every 16th peak: a heavy batch goes the synchronous way, which picks the pass by cost
-            double sum = 0.0;
-            int64_t n = 0;
-            const double th_fix = thr ? 0.0 : 1.0;
-            for (int64_t i = 0; i < P; i += 16, n++) {
-                const double tg = mass[i] / precision;
-                double th = (thr && !(thr[i] != thr[i])) ? thr[i] / precision : tolerance * mass[i] / precision;
-                (void)th_fix;
-                if (!(tg > 0.0) || !(th >= 0.0)) continue;
-                const double W = 2.0 * th + 1.0;
-                size_t k = (size_t)((tg + 0.5 * t->lam_width) / t->lam_width);
-                if (k >= t->h_lamq.size()) k = t->h_lamq.size() - 1;
-                const double lam = (double)t->h_lamq[k] / 65536.0;
-                const double n_est = W * (lam < 1.0 ? lam : 1.0), c_est = W * lam > n_est ? W * lam : n_est;
-                sum += 16.0 + W / 16.0 + 6.0 * n_est + 4.0 * c_est;
-            }
-            if (n && sum / (double)n > kHeavyCostPerPeak) fast = false;
-        }
-        if (fast) {
-            ctx->deepest = deepest;
-            pd.rec_width = (int)(8 * (deepest > 8 ? (deepest + 7) / 8 : 1));
-        }
+        ctx->deepest = ctx->spec_rec_width;
+        pd.rec_width = ctx->spec_rec_width;
     }
+    hp_mark(1);
     if (!fast) return SST_OK;  // sst_explain_collect does the work
     int rc = stage_f64_enqueue(ctx, t, mass, thr, nullptr, max_mods, P, ind, is_mod, precision, tolerance, with_memo);
     if (rc) {
@@ -1768,21 +1750,32 @@ int sst_explain_submit_f64(sst_ctx* ctx, const sst_table* t, const double* mass,
     ctx->n_memo = 0;
     ctx->has_exact = false;
     ctx->window_total = 0;  // not known without the summary; only the level-synchronous pass sizes its buffers from it
-    ctx->max_hi = hi_bound;
     MemoMap mp{};
-    pd.direct = ctx->pass_choice == 3 && direct_eligible(ctx, t, pd.rec_width);
-    if ((rc = pd.direct ? direct_enqueue(ctx, const_cast<sst_table*>(t), pd.rec_width) : dfs_enqueue(ctx, t, pd.rec_width, mp))) {
+    pd.direct = false;
+    SpecGuard g{};
+    g.summary = (const unsigned long long*)ctx->d_scan.p;
+    {
+        const int64_t cap = t->C * 32 - 1;
+        const bool table_bounds = t->w_min > 0 && cap / t->w_min <= (int64_t)pd.rec_width;  // no window value of this table is deeper
+        g.max_hi = (t->w_min > 0 && !table_bounds) ? (unsigned long long)((int64_t)(pd.rec_width + 1) * t->w_min - 1) : ~0ULL;
+        ctx->max_hi = g.max_hi < (unsigned long long)cap ? (int64_t)g.max_hi : cap;
+        const double heavy = kHeavyCostPerPeak * (double)P;
+        g.max_cost = heavy < 1.8e19 ? (unsigned long long)heavy : ~0ULL;
+    }
+    if ((rc = dfs_enqueue(ctx, t, pd.rec_width, mp, &g))) {
         pd.active = false;
         return rc;
     }
     // results on their way back: status, peak offsets, and as many records as the previous batch had (+ 25 %); a
     // batch that turns out larger gets the rest in sst_explain_collect
     CK(cudaMemcpyAsync(status_out, ctx->d_status.p, (size_t)P, cudaMemcpyDeviceToHost, ctx->stream));
+    hp_mark(11);
     CK(cudaMemcpyAsync(off32_out, ctx->d_peakoff32.p, (size_t)(P + 1) * 4, cudaMemcpyDeviceToHost, ctx->stream));
     uint64_t guess = (ctx->last_comps + ctx->last_comps / 4) * (uint64_t)pd.rec_width + 4096;
     if (guess > recs_bytes) guess = recs_bytes;
     if (guess > ctx->d_recs.cap) guess = ctx->d_recs.cap;
     if (guess) CK(cudaMemcpyAsync(recs_out, ctx->d_recs.p, (size_t)guess, cudaMemcpyDeviceToHost, ctx->stream));
+    hp_mark(12);
     pd.copied = guess;
     pd.done = true;  // queued
     return SST_OK;
@@ -1797,10 +1790,21 @@ int sst_explain_collect(sst_ctx* ctx, const sst_table* t, uint64_t* n_comps, int
     bool redo = !pd.done;
     unsigned long long roots = 0, comps = 0;
     if (pd.done) {
+        hp_begin();
         CK(cudaStreamSynchronize(ctx->stream));
+        hp_mark(13);
+        const unsigned long long* hs = (const unsigned long long*)ctx->h_misc;  // the staging kernel's summary
+        if ((rc = nf_error(ctx, hs[4]))) return rc;
         MemoMap mp{};
         rc = pd.direct ? direct_evaluate(ctx, pd.rec_width, 0, &roots, &comps) : dfs_evaluate(ctx, pd.rec_width, mp, false, 0, &roots, &comps);
         if (rc == DFS_OK && comps < (1ULL << 32)) {
+            {
+                const int64_t cap = t->C * 32 - 1, max_hi = (int64_t)hs[1];
+                ctx->max_hi = max_hi;
+                ctx->window_total = (int64_t)hs[0];
+                ctx->deepest = t->w_min > 0 ? (max_hi < cap ? max_hi : cap) / t->w_min : 0;
+                if (ctx->deepest <= 8) ctx->spec_rec_width = 8;  // (a batch of short compositions after longer ones)
+            }
             ctx->n_roots = roots;
             ctx->n_comps = comps;
             ctx->rec_width = pd.rec_width;
@@ -1832,6 +1836,9 @@ int sst_explain_collect(sst_ctx* ctx, const sst_table* t, uint64_t* n_comps, int
         if ((rc = sst_explain_run(ctx, t, 0, 0, &r64, &c64))) return rc;
         comps = c64;
         ctx->last_comps = comps;
+        // would the speculative path have carried this batch?  Then the next submission takes it.
+        ctx->spec_ok = ctx->last_pass == 2 && !ctx->n_memo && !ctx->has_exact && ctx->rec_width <= 16;
+        if (ctx->spec_ok) ctx->spec_rec_width = ctx->rec_width;
         if (comps >= (1ULL << 32)) return fail(ctx, SST_ERR_NOMEM, "%llu compositions: more than the 32-bit offsets of the asynchronous entry hold", (unsigned long long)comps);
         const uint64_t need = comps * (uint64_t)ctx->rec_width;
         if (n_comps) *n_comps = comps;
@@ -1846,6 +1853,15 @@ int sst_explain_collect(sst_ctx* ctx, const sst_table* t, uint64_t* n_comps, int
     }
     if (n_comps) *n_comps = ctx->n_comps;
     if (rec_width) *rec_width = ctx->rec_width;
+    return SST_OK;
+}
+
+int sst_host_profile(int enable, uint64_t* ns_out, uint64_t* calls_out) {
+    if (ns_out) memcpy(ns_out, g_hp.ns, sizeof(g_hp.ns));
+    if (calls_out) memcpy(calls_out, g_hp.calls, sizeof(g_hp.calls));
+    memset(g_hp.ns, 0, sizeof(g_hp.ns));
+    memset(g_hp.calls, 0, sizeof(g_hp.calls));
+    g_hp.on = enable != 0;
     return SST_OK;
 }
 

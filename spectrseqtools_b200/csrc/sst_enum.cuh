@@ -63,6 +63,15 @@ struct ItemPool {
     unsigned long long cap;       // items (a multiple of 32)
 };
 
+// Speculative launch (sst_explain_submit_f64): the batch was staged but its summary has not been looked at by the host.
+// The pass reads it first and leaves the batch alone when a peak is not FREE, a window reaches further than the record
+// width holds, an input was not finite, or the batch is too heavy for this pass (summary layout: k_stage_f64).
+struct SpecGuard {
+    const unsigned long long* summary;  // null: no speculation
+    unsigned long long max_hi;          // largest window end the launch can take
+    unsigned long long max_cost;        // largest summed peak_cost()
+};
+
 struct DfsArgs {
     TableView tv;
     RowMeta meta;
@@ -85,6 +94,7 @@ struct DfsArgs {
     unsigned long long* host_out;     // pinned + mapped run summary (layout of PassSummary)
     LeafHash leaf;
     unsigned long long* cta_ns;       // diagnostics (may be null): [gridDim.x][8] %globaltimer of every CTA at its phase boundaries
+    SpecGuard guard;
 };
 
 __device__ __forceinline__ void cta_stamp(const DfsArgs& a, int k) {
@@ -249,6 +259,18 @@ k_explain_dfs(const DfsArgs a) {
         }
     };
     __syncthreads();
+    if (a.guard.summary) {  // the same answer in every CTA: nobody reaches the grid barrier
+        const unsigned long long* g = a.guard.summary;
+        if (__ldcg(g + 1) > a.guard.max_hi || __ldcg(g + 2) || __ldcg(g + 3) || __ldcg(g + 4) || __ldcg(g + 5) > a.guard.max_cost) {
+            if (blockIdx.x == 0 && threadIdx.x == 0) {
+                s_sum.flags[3] = 1;
+                a.host_out[0] = 0ULL;
+                a.host_out[2] = 0ULL;
+            }
+            publish();
+            return;
+        }
+    }
     leaf_table_init(s_leaf, s_w, tv.R, a.leaf);
     __syncthreads();
     const RowTables rt{s_w, s_ind, s_mod, s_leaf, a.leaf, tv.R > 1 ? (uint32_t)s_w[1] : 0u};

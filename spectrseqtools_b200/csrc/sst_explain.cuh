@@ -111,6 +111,17 @@ __device__ __forceinline__ void integerise(double mass, double thr, double preci
     ithr = (int64_t)ceil(__ddiv_rn(t, precision));
 }
 
+// Non-finite inputs: the reference integerises with int(round(x)) / int(np.ceil(x)) (mass_explanation.py:51-58,107-114),
+// which raises ValueError for NaN and OverflowError for an infinity.  The kernels that integerise report them instead of
+// casting: a NaN mass, an infinite mass (its relative threshold is infinite too) or an infinite threshold.  A NaN
+// threshold means "None" (relative) in the batched entries.
+enum : int { NF_NAN = 1, NF_INF = 2 };
+enum : int { VALID_CODE_NAN = 3, VALID_CODE_INF = 4 };  // k_is_valid_f64's codes for them (0 / 1 / 2 are answers)
+enum : int { CLASS_CODE_NAN = 8, CLASS_CODE_INF = 9 };  // k_classify's (bit 3 is set by nothing else)
+__device__ __forceinline__ int non_finite(double mass, double thr) {
+    return (isnan(mass) ? NF_NAN : 0) | ((isinf(mass) || isinf(thr)) ? NF_INF : 0);
+}
+
 // out[p] = 0 not valid, 1 valid, 2 out-of-table value met before any hit (-> NotImplementedError)
 __device__ __forceinline__ uint8_t valid_code(const TableView& tv, int64_t target, int64_t thr) {
     const int64_t limit = tv.C * 32;
@@ -140,8 +151,14 @@ __global__ void k_is_valid_f64(TableView tv, const double* __restrict__ mass, co
                                double precision, double tolerance, int64_t P, uint8_t* __restrict__ out) {
     const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= P) return;
+    const double m = mass[p], th = thr ? thr[p] : nan("");
+    const int bad = non_finite(m, th);
+    if (bad) {  // the reference's int(round(nan)) / int(round(inf)): the host turns the code into the exception
+        out[p] = (uint8_t)(bad & NF_NAN ? VALID_CODE_NAN : VALID_CODE_INF);
+        return;
+    }
     int64_t t, h;
-    integerise(mass[p], thr ? thr[p] : nan(""), precision, tolerance, t, h);
+    integerise(m, th, precision, tolerance, t, h);
     out[p] = valid_code(tv, t, h);
 }
 
@@ -198,7 +215,7 @@ k_peak_costs(const int64_t* __restrict__ target, const int64_t* __restrict__ thr
 // Same float operations as mass_explanation.py:107-114 (integerise above).  Mode: FREE when no composition inside
 // the window can exhaust a budget (max_mods >= hi / w_min_mod and hi < hi_limit, both from the host), else `slow`.
 // summary: [0] summed window sizes (upper bound for level-0 items), [1] largest window end, [2] MEMO peaks (their
-// indices are appended to memo_peaks), [3] EXACT peaks.
+// indices are appended to memo_peaks), [3] EXACT peaks, [4] NF_* bits of non-finite inputs, [5] summed peak_cost().
 __global__ void __launch_bounds__(256)
 k_stage_f64(const double* __restrict__ mass, const double* __restrict__ thr, int32_t* __restrict__ max_mods, int32_t uniform_mods,
             int use_uniform, int64_t P, double precision, double tolerance, int64_t w_min_mod, int64_t hi_limit, int slow, int64_t limit,
@@ -209,7 +226,15 @@ k_stage_f64(const double* __restrict__ mass, const double* __restrict__ thr, int
     uint32_t my_cost = 0;
     if (p < P) {
         int64_t t, h;
-        integerise(mass[p], thr ? thr[p] : nan(""), precision, tolerance, t, h);
+        const double m = mass[p], th = thr ? thr[p] : nan("");
+        const int bad = non_finite(m, th);
+        if (bad) {  // reported in the summary; the peak itself becomes an empty window
+            atomicOr(summary + 4, (unsigned long long)bad);
+            t = 0;
+            h = -1;
+        } else {
+            integerise(m, th, precision, tolerance, t, h);
+        }
         target[p] = t;
         ithr[p] = h;
         int64_t hi = t + h;
@@ -236,9 +261,13 @@ k_stage_f64(const double* __restrict__ mass, const double* __restrict__ thr, int
         const unsigned long long y = __shfl_xor_sync(0xFFFFFFFFu, hi_u, o);
         hi_u = y > hi_u ? y : hi_u;
     }
+    unsigned long long csum = my_cost;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) csum += __shfl_xor_sync(0xFFFFFFFFu, csum, o);
     if ((threadIdx.x & 31) == 0) {
         if (win) atomicAdd(summary, win);
         if (hi_u) atomicMax(summary + 1, hi_u);
+        atomicAdd(summary + 5, csum);
     }
 }
 
@@ -294,7 +323,10 @@ k_classify(TableView tv, const double* __restrict__ observed, int64_t F, const d
         lean = lean && t64[k] > -(1LL << 30) && t64[k] < (1LL << 30);
     }
     uint8_t code[K];
-    if (lean) {
+    if (!isfinite(obs)) {
+#pragma unroll
+        for (int k = 0; k < K; k++) code[k] = (uint8_t)(isnan(obs) ? CLASS_CODE_NAN : CLASS_CODE_INF);
+    } else if (lean) {
         const int h = (int)h64;
         const int w_top = __ldg(s_w + tv.R - 1);
         int lo[K], hi[K], a[K], e[K];

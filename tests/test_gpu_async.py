@@ -116,3 +116,41 @@ def test_non_finite_inputs_raise_like_the_reference():
     assert np.array_equal(a.offsets, b.offsets) and np.array_equal(a.records, b.records)
     # the context still works after the refusals
     assert len(ME.explain_masses(good, dp, max_modifications=wl.max_modifications, thresholds=wl.explain_thr[:64], wait=False).wait()) == 64
+
+
+def test_speculation_recovers_after_every_kind_of_refusal():
+    """sst_explain_submit_f64 queues blindly and the pass checks the staged summary on the device.  A batch it refuses
+    (binding budgets, compositions longer than the record width, a heavy batch) is redone synchronously by collect()
+    and the following light batch is queued blindly again — every result equals the synchronous call."""
+    from spectrseqtools_b200 import _cabi
+
+    wl = S.make_workload("C2", 3000)
+    dp = _table(wl)
+    ctx = _cabi.context()
+
+    def both(masses, thr, mm):
+        want = ME.explain_masses(masses, dp, max_modifications=mm, thresholds=thr)
+        got = ME.explain_masses(masses, dp, max_modifications=mm, thresholds=thr, wait=False).wait()
+        assert np.array_equal(got.status, want.status) and np.array_equal(got.offsets, want.offsets)
+        assert got.records.shape == want.records.shape and np.array_equal(got.records, want.records)
+        return got
+
+    light = (wl.explain_mass, wl.explain_thr, wl.max_modifications)
+    both(*light)
+    both(wl.explain_mass, wl.explain_thr, 1)          # budgets bind: refused on the device, redone
+    assert both(*light).records.shape[1] == 8          # and the light batch after it
+    # 9 .. 12 nucleotides: 16-byte records, refused once, then queued blindly with the wider record
+    w = sorted(m.mass for m in dp.masses if m.mass > 0)[:4]
+    rng = np.random.default_rng(11)
+    deep = np.array([sum(rng.choice(w, size=rng.integers(9, 13))) for _ in range(40)], dtype=np.float64) * dp.precision
+    thr = np.full(len(deep), 2 * dp.precision)
+    for _ in range(2):
+        b = both(deep, thr, wl.max_modifications)
+        assert b.records.shape[1] == 16 and b.n_compositions > 0
+    assert both(*light).records.shape[1] == 8          # back to 8-byte records
+    # a heavy batch (wide windows a few nucleotides up: thousands of compositions per peak) goes to the level pass
+    heavy_m = np.array([sum(rng.choice(w, size=5)) for _ in range(64)], dtype=np.float64) * dp.precision
+    heavy_t = np.full(len(heavy_m), 4000 * dp.precision)
+    both(heavy_m, heavy_t, wl.max_modifications)
+    both(*light)
+    assert ctx.last_pass() == 2

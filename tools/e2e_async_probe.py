@@ -46,5 +46,16 @@ for depth in (1, 2):
     n = 200
     t0 = time.perf_counter(); loop(n, depth); dt = time.perf_counter() - t0
     print(f"depth {depth}: step {dt / n * 1e6:.1f} us;  " + "  ".join(f"{k} {v / n * 1e6:.1f}" for k, v in T.items()))
+ctx.host_profile(True)
+n = 200
+loop(n, 2)
+ns, calls = ctx.host_profile(False)
+names = {0: "submit: scans of the host arrays", 1: "submit: mode bound + cost sample", 2: "stage: reserves", 3: "stage: memset", 4: "stage: H2D copies",
+         5: "stage: k_stage_f64 launch", 6: "stage: summary D2H", 7: "dfs: reserves + args", 8: "dfs: timer event", 9: "dfs: cooperative launch",
+         10: "dfs: 2 event records", 11: "D2H status", 12: "D2H offsets + records", 13: "collect: stream wait", 16: "classify: wait stream2",
+         17: "classify: scan", 18: "classify: 2 H2D", 19: "classify: launch", 20: "classify: D2H"}
+for k in range(32):
+    if calls[k]:
+        print(f"  [{k:2d}] {names.get(k, ''):36s} {ns[k] / n * 1e-3:8.1f} us/step  ({int(calls[k])} visits)")
 pr = cProfile.Profile(); pr.enable(); loop(200, 2); pr.disable()
-pstats.Stats(pr).sort_stats("tottime").print_stats(25)
+pstats.Stats(pr).sort_stats("tottime").print_stats(8)
