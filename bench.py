@@ -7,7 +7,7 @@
 One step = one pass of the mass-explanation hot path over one batch: validity probes for every
 (peak x breakage offset) + enumeration for every ladder difference of the batch.
 `value` times the kernels with inputs resident in HBM; `e2e` times the public Python API with host
-buffers (H2D + kernels + D2H of all results), two batches in flight on two context slots (the copies of
+buffers (H2D + kernels + D2H of all results), three batches in flight on three context slots (the copies of
 one under the kernels of the other).  Multi-GPU: one process per GPU (torchrun).  Default `--scaling weak`:
 every rank explains its own 10^5-peak batch (no data-path collective), time = max over ranks.
 `--scaling strong`: ONE fixed workload (the C4 batch tiled `--strong-factor` times) is partitioned over the
@@ -479,8 +479,8 @@ def main():
         peaks_all, comps_all = float(wl.n_peaks), float(n_comps)
     value = peaks_all * args.steps / (total_ms * 1e-3)
 
-    # ---- e2e: public API, host buffers in, host arrays out (H2D + kernels + D2H of every result), two batches in
-    # flight on two context slots: step i+1 is submitted before step i is collected, so the copies of one batch run
+    # ---- e2e: public API, host buffers in, host arrays out (H2D + kernels + D2H of every result), three batches in
+    # flight on three context slots: steps i+1 and i+2 are submitted before step i is collected, so the copies of one batch run
     # under the kernels of the other.  Strong scaling: every rank publishes its block in shared memory and rank 0
     # gathers all blocks inside the timed region.
     def submit(slot):
@@ -500,16 +500,18 @@ def main():
                 return v, batch, gather.collect(seq_no)
         return v, batch, None
 
+    E2E_DEPTH = 3  # batches in flight: three context slots keep the copy engines and the SMs busy at the same time
+
     def e2e_loop(n, seq0):
-        pend = submit(0)
+        pend = [submit(k) for k in range(min(E2E_DEPTH - 1, n))]
         out = None
         for i in range(n):
-            nxt = submit((i + 1) & 1) if i + 1 < n else None
-            out = finish(pend, seq0 + i)
-            pend = nxt
+            if i + E2E_DEPTH - 1 < n:
+                pend.append(submit((i + E2E_DEPTH - 1) % E2E_DEPTH))
+            out = finish(pend.pop(0), seq0 + i)
         return out
 
-    e2e_loop(3, 1)
+    e2e_loop(2 * E2E_DEPTH, 1)
     if dist is not None:
         dist.barrier()
     sampler.period = 0.05
@@ -527,7 +529,8 @@ def main():
         e2e_s = float(t.item())
     rec_width = batch.records.shape[1] if batch.records.ndim == 2 else 8
     h2d = 8 * len(observed) + 8 * len(offsets) + 16 * len(e_target) + 5 * dev.R  # masses + thresholds; the batch-wide budget is a scalar
-    d2h = int(valid._flags.size) + len(e_target) + 4 * (len(e_target) + 1) + int(batch.n_compositions) * rec_width
+    # flags (two per byte) + the result block of the enumeration (header, status, uint32 offsets, records incl. the copy margin)
+    d2h = int(valid._flags.size) + _cabi.context(local_rank, (args.steps - 1) % E2E_DEPTH).explain_d2h_bytes()
     e2e_value = peaks_all * args.steps / e2e_s
 
     # ---- the reference-shaped scalar entries (one mass per call: what prediction.py / skeleton_building.py do)
@@ -619,7 +622,7 @@ def main():
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "ms_per_step": 1e3 * e2e_s / args.steps,
                 "how": "public API (classify_observed + explain_masses, wait=False), pinned host inputs, results in pinned host "
-                       "arrays; two batches in flight on two context slots" + ("; every rank's block gathered on rank 0 through POSIX shared memory inside the timed region" if gather is not None else "")},
+                       "arrays; three batches in flight on three context slots" + ("; every rank's block gathered on rank 0 through POSIX shared memory inside the timed region" if gather is not None else "")},
         "scalar_latency_us": scalar,
         "gpu_launches": int(launches),
         "roofline": roofline, "kernels": kernels, "pass_phase_us": phase_us, "large_batch": large, "table_build": table_info,

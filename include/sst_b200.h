@@ -188,19 +188,32 @@ int sst_explain_phase_ns(const sst_ctx* ctx, uint64_t* out /* [32] */);
  * (sections are the marks in sst_cabi.cu: 0-12 sst_explain_submit_f64, 13 the wait in sst_explain_collect, 16-20
  * sst_classify_async); returns the sums, clears them and switches the stopwatch on or off (process-wide) */
 int sst_host_profile(int enable, uint64_t* ns_out /* [32] or NULL */, uint64_t* calls_out /* [32] or NULL */);
+/* diagnostics: device timeline (ms since a process-wide origin) of the last batch queued by sst_explain_submit_f64 on
+ * this context, once it has been collected: [0] first operation, [1] inputs on the device, [2] staged, [3] pass done,
+ * [4] results in host memory; -1 = not recorded.  enable switches the recording on or off for the following batches */
+int sst_trace_ms(sst_ctx* ctx, int enable, float* out /* [8] or NULL */);
 /* The whole call — replaces a loop of calculate_explanations (common.py:47-65) — WITHOUT WAITING: the copy of the inputs,
- * staging, the enumeration pass and the copy of the results are queued on the context's stream; sst_explain_collect
+ * staging, the enumeration pass and ONE copy of the results are queued on the context's stream; sst_explain_collect
  * waits for them.  One modification budget for the batch (what calculate_explanations passes).  All host pointers must
- * stay valid until sst_explain_collect returns; status_out[P], off32_out[P+1] (peak offsets as uint32) and
- * recs_out[recs_bytes] should be pinned (sst_host_alloc).  The record copy is sized by the previous batch (+ 25 %);
- * sst_explain_collect fetches the rest if this batch is larger.  When the batch cannot be queued blindly (a
- * modification budget that may bind, compositions longer than 16 nucleotides, a forced pass) the work is done inside
- * sst_explain_collect instead.  SST_ERR_NOMEM from sst_explain_collect with *n_comps set: recs_out is too small —
- * the result is still on the device, fetch it with sst_explain_fetch.  Two contexts on one device give two batches
- * in flight: the copies of one overlap the kernels of the other. */
+ * stay valid until sst_explain_collect returns.  Results arrive in out_block (pinned: sst_host_alloc), laid out as
+ * sst_explain_block_layout(P) says: a 512-byte header the library uses, status[P], peak offsets as uint32[P + 1],
+ * records; block_bytes - recs_off bytes are available for records.  The copy carries as many records as the previous
+ * batch had (+ 2 %); sst_explain_collect fetches the rest if this batch is larger.
+ *
+ * Nothing looks at the host arrays: the batch is queued on the assumption that it is like the previous one (no
+ * modification budget binds, compositions fit the record width of last time, a handful of compositions per peak), and
+ * the pass checks the staged batch's summary ON THE DEVICE before it does anything.  A batch that breaks an assumption
+ * comes back untouched and is carried out synchronously inside sst_explain_collect (so are batches after it, until
+ * one of them would have fitted again).  Non-finite masses / thresholds: SST_ERR_NAN / SST_ERR_INF from
+ * sst_explain_collect.  SST_ERR_NOMEM from sst_explain_collect with *n_comps set: the block is too small for the
+ * records — the result is still on the device, fetch it with sst_explain_fetch.  Several contexts on one device give
+ * several batches in flight: the copies of one overlap the kernels of another (three keep the copy engine busy). */
 int sst_explain_submit_f64(sst_ctx* ctx, const sst_table* t, const double* mass, const double* thr, int32_t max_mods, int64_t P,
-                           const int32_t* ind, const uint8_t* is_mod, double precision, double tolerance, int with_memo, uint8_t* status_out,
-                           uint32_t* off32_out, uint8_t* recs_out, uint64_t recs_bytes);
+                           const int32_t* ind, const uint8_t* is_mod, double precision, double tolerance, int with_memo,
+                           uint8_t* out_block, uint64_t block_bytes);
+int sst_explain_block_layout(int64_t P, uint64_t* status_off, uint64_t* off32_off, uint64_t* recs_off);
+/* bytes the last collected submission copied device -> host (block header, status, offsets, records incl. the margin) */
+uint64_t sst_explain_d2h_bytes(const sst_ctx* ctx);
 int sst_explain_collect(sst_ctx* ctx, const sst_table* t, uint64_t* n_comps, int* rec_width);
 /* status[P]; peak_off[P+1] (compositions of peak p are records peak_off[p] .. peak_off[p+1]);
  * recs[n_comps * rec_width]: row indices in ascending order, 0-padded.  Any pointer may be NULL. */

@@ -37,7 +37,7 @@ EXPORTS = [
     "sst_table_download_masks", "sst_table_destroy", "sst_is_valid", "sst_valid_stage", "sst_valid_run",
     "sst_valid_fetch", "sst_valid_stage_f64", "sst_explain", "sst_explain_stage", "sst_explain_stage_f64", "sst_explain_stage_f64_uniform", "sst_explain_rec_width", "sst_explain_phase_ns",
     "sst_explain_run", "sst_explain_fetch", "sst_classify", "sst_classify_stage", "sst_classify_run", "sst_classify_fetch", "sst_classify_launch", "sst_classify_async", "sst_classify_wait", "sst_length_bounds",
-    "sst_set_pass", "sst_last_pass", "sst_explain_cta_ns", "sst_explain_submit_f64", "sst_explain_collect", "sst_classify_async_packed", "sst_host_profile",
+    "sst_set_pass", "sst_last_pass", "sst_explain_cta_ns", "sst_explain_submit_f64", "sst_explain_collect", "sst_classify_async_packed", "sst_host_profile", "sst_trace_ms", "sst_explain_block_layout", "sst_explain_d2h_bytes",
 ]
 
 
@@ -107,9 +107,12 @@ def load() -> C.CDLL:
             "sst_classify_async": (C.c_int, [vp, vp, fp, C.c_int64, fp, C.c_int, C.c_double, C.c_double, u8p]),
             "sst_classify_async_packed": (C.c_int, [vp, vp, fp, C.c_int64, fp, C.c_int, C.c_double, C.c_double, u8p]),
             "sst_classify_wait": (C.c_int, [vp]),
-            "sst_explain_submit_f64": (C.c_int, [vp, vp, fp, fp, C.c_int32, C.c_int64, i32p, u8p, C.c_double, C.c_double, C.c_int, u8p, u32p, u8p, C.c_uint64]),
+            "sst_explain_submit_f64": (C.c_int, [vp, vp, fp, fp, C.c_int32, C.c_int64, i32p, u8p, C.c_double, C.c_double, C.c_int, u8p, C.c_uint64]),
+            "sst_explain_block_layout": (C.c_int, [C.c_int64, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
             "sst_explain_collect": (C.c_int, [vp, vp, C.POINTER(C.c_uint64), C.POINTER(C.c_int)]),
             "sst_host_profile": (C.c_int, [C.c_int, u64p, u64p]),
+            "sst_trace_ms": (C.c_int, [vp, C.c_int, fp]),
+            "sst_explain_d2h_bytes": (C.c_uint64, [vp]),
             "sst_set_pass": (C.c_int, [vp, C.c_int]),
             "sst_last_pass": (C.c_int, [vp]),
             "sst_explain_cta_ns": (C.c_int, [vp, C.c_int, u64p, C.c_int, C.POINTER(C.c_int)]),
@@ -377,12 +380,15 @@ class Context:
         if len(iv) != table.R or len(im) != table.R:
             raise ValueError("ind / is_mod need one entry per table row")
         P = len(m)
-        status = self._pinned("status", P)[:P]
-        off = self._pinned("off32", 4 * (P + 1))[: 4 * (P + 1)].view(np.uint32)
-        recs = self._pinned("recs", max(self.__dict__.get("_recs_hint", 0), 1 << 20))
+        so, oo, ro = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        self._check(self._lib.sst_explain_block_layout(P, C.byref(so), C.byref(oo), C.byref(ro)))
+        block = self._pinned("block", ro.value + max(self.__dict__.get("_recs_hint", 0), 64 * P, 1 << 20))  # one block: one copy brings it back
+        status = block[so.value: so.value + P]
+        off = block[oo.value: oo.value + 4 * (P + 1)].view(np.uint32)
+        recs = block[ro.value:]
         self._submitted = (m, h, iv, im, P, status, off, recs, table)  # the call reads the host arrays until it is collected
         self._check(self._lib.sst_explain_submit_f64(self._h, table._h, _p(m), _p(h), int(max_mods), P, _p(iv), _p(im), float(precision),
-                                                     float(tolerance), 1 if with_memo else 0, _p(status), _p(off), _p(recs), recs.size))
+                                                     float(tolerance), 1 if with_memo else 0, _p(block), block.size))
         self._staged_P = P
 
     def explain_collect(self):
@@ -394,7 +400,7 @@ class Context:
         if rc == SST_ERR_NOMEM and nc.value and W.value:  # the pinned record buffer was too small: grow it, fetch from the device
             need = nc.value * W.value
             self._recs_hint = need + need // 4
-            recs = self._pinned("recs", self._recs_hint)
+            recs = self._pinned("recs", self._recs_hint)  # (the block is too small; the next submission allocates a larger one)
             self._last = (0, int(nc.value), int(W.value))
             off64 = np.empty(P + 1, dtype=np.uint64)
             self._check(self._lib.sst_explain_fetch(self._h, _p(status), _p(off64), _p(recs[: need])))
@@ -406,6 +412,16 @@ class Context:
         self._last = (0, n, w)
         self._recs_hint = max(self.__dict__.get("_recs_hint", 0), n * w + n * w // 4)
         return status, off, recs[: n * w].reshape(n, w)
+
+    def explain_d2h_bytes(self) -> int:
+        """Bytes the last collected submission copied device -> host."""
+        return int(self._lib.sst_explain_d2h_bytes(self._h))
+
+    def trace_ms(self, enable: bool) -> np.ndarray:
+        """Device timeline (ms) of the last batch submitted on this context (sst_trace_ms)."""
+        out = np.zeros(8, dtype=np.float32)
+        self._check(self._lib.sst_trace_ms(self._h, 1 if enable else 0, _p(out)))
+        return out
 
     def host_profile(self, enable: bool):
         """(ns[32], visits[32]) per section of the asynchronous entries since the last call (sst_host_profile)."""

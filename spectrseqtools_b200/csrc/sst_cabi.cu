@@ -3,6 +3,7 @@
 #include <stdarg.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <time.h>
 
@@ -31,6 +32,7 @@ struct HostProf {
     uint64_t last = 0;
 };
 HostProf g_hp;
+cudaEvent_t g_trace_base = nullptr;  // common origin of every context's trace events
 inline uint64_t host_now_ns() {
     timespec ts;
     clock_gettime(CLOCK_MONOTONIC, &ts);
@@ -128,6 +130,7 @@ struct sst_ctx {
     int* h_misc = nullptr;             // pinned: run summary read back with one copy
     unsigned long long* h_run = nullptr;  // pinned + mapped: the enumeration pass writes its summary here itself
     unsigned long long* h_run_dev = nullptr;
+    unsigned long long* d_run = nullptr;  // the same summary in device memory (pipelined submissions copy it out)
     unsigned int* d_bar = nullptr;     // two grid-barrier counters (64 words apart) that alternate between launches
     unsigned run_parity = 0;
     uint64_t n_roots = 0, n_comps = 0;
@@ -163,10 +166,17 @@ struct sst_ctx {
         uint32_t* off32 = nullptr;
         uint8_t* recs = nullptr;
         uint64_t recs_bytes = 0, copied = 0;
+        uint8_t* block = nullptr;      // the caller's result block (layout: BlockLayout)
     } pend;
+    DevBuf d_block;                    // the same block on the device: the pass writes into it, ONE copy brings it back
     uint64_t last_comps = 0;           // compositions of the last batch: sizes the speculative copy of the next one
     bool spec_ok = true;               // sst_explain_submit_f64 queues blindly (the last batch it had to redo would have fitted, or none yet)
     int spec_rec_width = 8;            // with this record width
+    cudaEvent_t trace_ev[8] = {nullptr};  // diagnostics (sst_trace_ms): device timeline of the last submitted batch
+    bool trace_on = false;
+    int spec_margin_pct = 2;           // records copied back blindly: the previous batch's plus this much (SST_SPEC_MARGIN_PCT);
+                                       // every percent is bus time of every batch, a larger batch costs one more small copy
+    uint64_t last_d2h_bytes = 0;       // bytes the last collected submission brought back
     int32_t up_ind[128] = {0};         // what d_ind / d_ismod hold (the per-row budgets rarely change between batches)
     uint8_t up_ismod[128] = {0};
     int up_R = -1;
@@ -202,6 +212,19 @@ int fail(sst_ctx* ctx, int code, const char* fmt, ...) {
 // reference's int(round(x)) / int(np.ceil(x)) raise ValueError for NaN, OverflowError for an infinity
 // (mass_explanation.py:51-58,107-114).  No pass over the host arrays: at 10^5 peaks that cost more than every CUDA call
 // of a submission together.
+// Result block of the asynchronous entry, the same on the device and in the caller's (pinned) memory, so that one copy
+// brings everything back: [0, 352) run summary of the pass, [384, 448) summary of the staging kernel, then status[P],
+// off32[P + 1] and the records, each 16-byte aligned.
+struct BlockLayout {
+    uint64_t status, off32, recs;
+    explicit BlockLayout(int64_t P) {
+        status = 512;
+        off32 = status + (((uint64_t)P + 15) & ~15ULL);
+        recs = off32 + ((4 * ((uint64_t)P + 1) + 15) & ~15ULL);
+    }
+};
+constexpr uint64_t kBlockStageSummary = 384;
+
 int nf_error(sst_ctx* ctx, unsigned long long bits) {
     if (bits & NF_NAN) return fail(ctx, SST_ERR_NAN, "cannot convert float NaN to integer");
     if (bits & NF_INF) return fail(ctx, SST_ERR_INF, "cannot convert float infinity to integer");
@@ -209,6 +232,20 @@ int nf_error(sst_ctx* ctx, unsigned long long bits) {
 }
 // the same from a row of result codes: `nan_code` / `inf_code` in a byte (or, packed, in either nibble)
 int nf_error_codes(sst_ctx* ctx, const uint8_t* codes, int64_t n, int nan_code, int inf_code, bool nibbles) {
+    // both codes have bit 3 set, which no answer has: one OR over the row, 32 bytes at a time, says whether there is
+    // anything to look for
+    {
+        uint64_t acc[4] = {0, 0, 0, 0};
+        int64_t i = 0;
+        for (; i + 32 <= n; i += 32) {
+            uint64_t w[4];
+            memcpy(w, codes + i, 32);
+            acc[0] |= w[0]; acc[1] |= w[1]; acc[2] |= w[2]; acc[3] |= w[3];
+        }
+        uint64_t any = acc[0] | acc[1] | acc[2] | acc[3];
+        for (; i < n; i++) any |= (uint64_t)codes[i];
+        if (!(any & 0x8888888888888888ULL)) return SST_OK;
+    }
     unsigned seen = 0;
     if (nibbles) {
         for (int64_t i = 0; i < n; i++) seen |= 1u << (codes[i] & 15) | 1u << (codes[i] >> 4);
@@ -250,6 +287,10 @@ struct KTimer {  // brackets one kernel family with a pair of pooled events; tim
         if (idx >= 0) cudaEventRecord(ctx->kev[2 * idx + 1], ctx->stream);
     }
 };
+
+inline void trace_mark(sst_ctx* ctx, int k) {
+    if (ctx->trace_on) cudaEventRecord(ctx->trace_ev[k], ctx->stream);
+}
 
 // call after the stream has been synchronised
 void flush_timers(sst_ctx* ctx) {
@@ -531,6 +572,11 @@ int sst_ctx_create(int device, sst_ctx** out) {
     cudaHostAlloc((void**)&ctx->h_run, 512, cudaHostAllocMapped);
     if (ctx->h_run) cudaHostGetDevicePointer((void**)&ctx->h_run_dev, ctx->h_run, 0);
     if (cudaMalloc(&ctx->d_bar, 512) == cudaSuccess) cudaMemset(ctx->d_bar, 0, 512);
+    if (const char* e = getenv("SST_SPEC_MARGIN_PCT")) {
+        const int v = atoi(e);
+        if (v >= -100 && v <= 1000) ctx->spec_margin_pct = v;
+    }
+    if (cudaMalloc(&ctx->d_run, 512) == cudaSuccess) cudaMemset(ctx->d_run, 0, 512);
     *out = ctx;
     return SST_OK;
 }
@@ -551,6 +597,7 @@ void sst_ctx_destroy(sst_ctx* ctx) {
     if (ctx->h_misc) cudaFreeHost(ctx->h_misc);
     if (ctx->h_run) cudaFreeHost(ctx->h_run);
     cudaFree(ctx->d_bar);
+    cudaFree(ctx->d_run);
     for (DevBuf* b : bufs) cudaFree(b->p);
     cudaEventDestroy(ctx->ev_a);
     cudaEventDestroy(ctx->ev_b);
@@ -1039,7 +1086,9 @@ namespace {
 // max_mods == nullptr: every peak has the budget `uniform_mods` (the array is filled on the device)
 // everything of the staging that can be queued without waiting: copies in, k_stage_f64, the summary on its way to h_misc
 int stage_f64_enqueue(sst_ctx* ctx, const sst_table* t, const double* mass, const double* thr, const int32_t* max_mods, int32_t uniform_mods,
-                      int64_t P, const int32_t* ind, const uint8_t* is_mod, double precision, double tolerance, int with_memo) {
+                      int64_t P, const int32_t* ind, const uint8_t* is_mod, double precision, double tolerance, int with_memo,
+                      unsigned long long* summary_at = nullptr) {
+    const bool summary_later = summary_at != nullptr;  // (part of a result block that is copied out as a whole)
     CK(cudaSetDevice(ctx->device));
     ctx->have_result = false;
     if (P < 0) return fail(ctx, SST_ERR_BAD_ARG, "negative peak count");
@@ -1070,7 +1119,9 @@ int stage_f64_enqueue(sst_ctx* ctx, const sst_table* t, const double* mass, cons
     if ((rc = reserve(ctx, ctx->d_peakcost, (size_t)(P + 1) * 4))) return rc;
     if ((rc = reserve(ctx, ctx->d_blkcost, (size_t)((P + kCostBlock - 1) / kCostBlock + 1) * 8))) return rc;
     hp_mark(2);
-    CK(cudaMemsetAsync(ctx->d_scan.p, 0, 64, ctx->stream));
+    trace_mark(ctx, 0);
+    unsigned long long* const summary = summary_at ? summary_at : (unsigned long long*)ctx->d_scan.p;
+    CK(cudaMemsetAsync(summary, 0, 64, ctx->stream));
     hp_mark(3);
     if (P) {
         CK(cudaMemcpyAsync(ctx->d_vmass.p, mass, (size_t)P * 8, cudaMemcpyHostToDevice, ctx->stream));
@@ -1085,18 +1136,22 @@ int stage_f64_enqueue(sst_ctx* ctx, const sst_table* t, const double* mass, cons
         CK(cudaMemcpyAsync(ctx->d_ismod.p, ctx->up_ismod, (size_t)t->R, cudaMemcpyHostToDevice, ctx->stream));
     }
     hp_mark(4);
+    trace_mark(ctx, 1);
     if (P) {
         k_stage_f64<<<(unsigned)((P + 255) / 256), 256, 0, ctx->stream>>>(
             (const double*)ctx->d_vmass.p, thr ? (const double*)ctx->d_vthrf.p : nullptr, (int32_t*)ctx->d_maxmods.p, uniform_mods,
             max_mods ? 0 : 1, P, precision,
             tolerance, w_min_mod, hi_limit, with_memo ? SST_MODE_MEMO : SST_MODE_EXACT, t->C * 32, (int64_t*)ctx->d_target.p,
-            (int64_t*)ctx->d_thr.p, (uint8_t*)ctx->d_mode.p, (uint32_t*)ctx->d_memo_peaks.p, (unsigned long long*)ctx->d_scan.p,
+            (int64_t*)ctx->d_thr.p, (uint8_t*)ctx->d_mode.p, (uint32_t*)ctx->d_memo_peaks.p, summary,
             CostModel{t->d_lamq, t->lam_width, t->lam_K}, (uint32_t*)ctx->d_peakcost.p, (unsigned long long*)ctx->d_blkcost.p);
         CK(cudaGetLastError());
     }
     hp_mark(5);
-    CK(cudaMemcpyAsync(ctx->h_misc, ctx->d_scan.p, 64, cudaMemcpyDeviceToHost, ctx->stream));
+    // (a pipelined submission gets the summary with the result block: a copy between staging and pass would make the pass
+    //  wait for the copy engine, which is still busy with the previous batch's records)
+    if (!summary_later) CK(cudaMemcpyAsync(ctx->h_misc, ctx->d_scan.p, 64, cudaMemcpyDeviceToHost, ctx->stream));
     hp_mark(6);
+    trace_mark(ctx, 2);
     ctx->P = P;
     ctx->R_staged = t->R;
     return SST_OK;
@@ -1294,7 +1349,13 @@ int direct_enqueue(sst_ctx* ctx, sst_table* t, int rec_width) {
 
 // Depth-first pass (sst_enum.cuh): one cooperative launch, one grid barrier.  Returns PASS_FALLBACK when a root's
 // subtree is too large for one thread (the level-synchronous pass balances such batches across the machine).
-int dfs_enqueue(sst_ctx* ctx, const sst_table* t, int rec_width, const MemoMap& mp, const SpecGuard* guard = nullptr) {
+struct OutBlock {  // where a pipelined submission wants status, 32-bit offsets, records and the run summary
+    uint8_t* base;
+    BlockLayout at;
+    uint64_t rec_bytes;
+};
+int dfs_enqueue(sst_ctx* ctx, const sst_table* t, int rec_width, const MemoMap& mp, const SpecGuard* guard = nullptr,
+                const OutBlock* ob = nullptr) {
     const int64_t P = ctx->P;
     const int nw = rec_width / 8;
     int rc;
@@ -1317,7 +1378,7 @@ int dfs_enqueue(sst_ctx* ctx, const sst_table* t, int rec_width, const MemoMap& 
     if ((rc = reserve(ctx, ctx->d_cnt, (size_t)(P + 1) * 4))) return rc;
     if ((rc = reserve(ctx, ctx->d_tilebase, (size_t)grid * 24 + (size_t)(P / 32 + grid + 8) * 4))) return rc;
     if (!ctx->d_recs.p && (rc = reserve(ctx, ctx->d_recs, (size_t)64 << 20))) return rc;
-    if (!ctx->h_run_dev || !ctx->d_bar) return fail(ctx, SST_ERR_NOMEM, "run summary buffers are missing");
+    if (!ctx->h_run_dev || !ctx->d_bar || !ctx->d_run) return fail(ctx, SST_ERR_NOMEM, "run summary buffers are missing");
     // the item pool holds every tile's window roots and the lists of its split rounds; it keeps its size between runs
     // and grows when a run reports that it was too small
     if (ctx->pool_capacity < (uint64_t)(32 * P + (1 << 20))) ctx->pool_capacity = ((uint64_t)(32 * P + (1 << 20)) + 63) & ~63ULL;
@@ -1368,6 +1429,13 @@ int dfs_enqueue(sst_ctx* ctx, const sst_table* t, int rec_width, const MemoMap& 
             ctx->cta_ns_grid = (int)grid;
         }
         a.guard = guard ? *guard : SpecGuard{};
+        if (ob) {  // everything the host wants back lies in one block
+            a.status = ob->base + ob->at.status;
+            a.peak_off32 = (uint32_t*)(ob->base + ob->at.off32);
+            a.recs = (unsigned long long*)(ob->base + ob->at.recs);
+            a.rec_capacity = (unsigned long long)(ob->rec_bytes / rec_width);
+            a.host_out = (unsigned long long*)ob->base;
+        }
         hp_mark(7);
         {
             KTimer kt(ctx, SST_K_EXPLAIN_PASS);
@@ -1378,6 +1446,7 @@ int dfs_enqueue(sst_ctx* ctx, const sst_table* t, int rec_width, const MemoMap& 
             ctx->run_parity++;  // only a launch that really started clears the other set
             kt.stop(1);
         }
+        if (guard) trace_mark(ctx, 3);
         CK(cudaEventRecord(ctx->ev_run, ctx->stream));  // the device is done here; what follows is the host waking up
         hp_mark(10);
     }
@@ -1714,8 +1783,8 @@ int sst_explain_run(sst_ctx* ctx, const sst_table* t, int rec_width, uint64_t me
 
 // ---- the whole call without waiting: inputs in, staging, pass, results out are queued on the context's stream ----
 int sst_explain_submit_f64(sst_ctx* ctx, const sst_table* t, const double* mass, const double* thr, int32_t max_mods, int64_t P,
-                           const int32_t* ind, const uint8_t* is_mod, double precision, double tolerance, int with_memo, uint8_t* status_out,
-                           uint32_t* off32_out, uint8_t* recs_out, uint64_t recs_bytes) {
+                           const int32_t* ind, const uint8_t* is_mod, double precision, double tolerance, int with_memo, uint8_t* out_block,
+                           uint64_t block_bytes) {
     hp_begin();
     CK(cudaSetDevice(ctx->device));
     if (ctx->pend.active) return fail(ctx, SST_ERR_STATE, "a submitted batch has not been collected yet");
@@ -1725,7 +1794,10 @@ int sst_explain_submit_f64(sst_ctx* ctx, const sst_table* t, const double* mass,
     pd = sst_ctx::Pending{};
     pd.mass = mass; pd.thr = thr; pd.max_mods = max_mods; pd.P = P; pd.ind = ind; pd.is_mod = is_mod;
     pd.precision = precision; pd.tolerance = tolerance; pd.with_memo = with_memo;
-    pd.status = status_out; pd.off32 = off32_out; pd.recs = recs_out; pd.recs_bytes = recs_bytes;
+    const BlockLayout lay(P);
+    if (!out_block || block_bytes < lay.recs) return fail(ctx, SST_ERR_BAD_ARG, "result block of %llu bytes: %llu are needed before the first record", (unsigned long long)block_bytes, (unsigned long long)lay.recs);
+    pd.block = out_block;
+    pd.status = out_block + lay.status; pd.off32 = (uint32_t*)(out_block + lay.off32); pd.recs = out_block + lay.recs; pd.recs_bytes = block_bytes - lay.recs;
     pd.active = true;
     ctx->have_result = false;
     // Everything is queued without a look at the batch, on the assumption that it is like the previous ones: no budget
@@ -1742,7 +1814,21 @@ int sst_explain_submit_f64(sst_ctx* ctx, const sst_table* t, const double* mass,
     }
     hp_mark(1);
     if (!fast) return SST_OK;  // sst_explain_collect does the work
-    int rc = stage_f64_enqueue(ctx, t, mass, thr, nullptr, max_mods, P, ind, is_mod, precision, tolerance, with_memo);
+    // the device block: room for twice the records that are copied back blindly (a larger batch gets the rest in collect)
+    uint64_t guess = (ctx->last_comps + ctx->last_comps * (uint64_t)ctx->spec_margin_pct / 100) * (uint64_t)pd.rec_width + 4096;
+    if (guess > pd.recs_bytes) guess = pd.recs_bytes;
+    int rc;
+    {
+        uint64_t dev_recs = 2 * guess > ((uint64_t)16 << 20) ? 2 * guess : ((uint64_t)16 << 20);
+        if (dev_recs < pd.recs_bytes && pd.recs_bytes <= ((uint64_t)1 << 30)) dev_recs = pd.recs_bytes;
+        if ((rc = reserve(ctx, ctx->d_block, (size_t)(lay.recs + dev_recs)))) {
+            pd.active = false;
+            return rc;
+        }
+    }
+    const OutBlock ob{(uint8_t*)ctx->d_block.p, lay, (uint64_t)ctx->d_block.cap - lay.recs};
+    rc = stage_f64_enqueue(ctx, t, mass, thr, nullptr, max_mods, P, ind, is_mod, precision, tolerance, with_memo,
+                           (unsigned long long*)(ob.base + kBlockStageSummary));
     if (rc) {
         pd.active = false;
         return rc;
@@ -1753,7 +1839,7 @@ int sst_explain_submit_f64(sst_ctx* ctx, const sst_table* t, const double* mass,
     MemoMap mp{};
     pd.direct = false;
     SpecGuard g{};
-    g.summary = (const unsigned long long*)ctx->d_scan.p;
+    g.summary = (const unsigned long long*)(ob.base + kBlockStageSummary);
     {
         const int64_t cap = t->C * 32 - 1;
         const bool table_bounds = t->w_min > 0 && cap / t->w_min <= (int64_t)pd.rec_width;  // no window value of this table is deeper
@@ -1762,22 +1848,29 @@ int sst_explain_submit_f64(sst_ctx* ctx, const sst_table* t, const double* mass,
         const double heavy = kHeavyCostPerPeak * (double)P;
         g.max_cost = heavy < 1.8e19 ? (unsigned long long)heavy : ~0ULL;
     }
-    if ((rc = dfs_enqueue(ctx, t, pd.rec_width, mp, &g))) {
+    if ((rc = dfs_enqueue(ctx, t, pd.rec_width, mp, &g, &ob))) {
         pd.active = false;
         return rc;
     }
-    // results on their way back: status, peak offsets, and as many records as the previous batch had (+ 25 %); a
-    // batch that turns out larger gets the rest in sst_explain_collect
-    CK(cudaMemcpyAsync(status_out, ctx->d_status.p, (size_t)P, cudaMemcpyDeviceToHost, ctx->stream));
+    // the result block on its way back in ONE copy: summaries, status, peak offsets and as many records as the previous
+    // batch had (+ spec_margin_pct); a batch that turns out larger gets the rest in sst_explain_collect
+    CK(cudaMemcpyAsync(out_block, ob.base, (size_t)(lay.recs + guess), cudaMemcpyDeviceToHost, ctx->stream));
     hp_mark(11);
-    CK(cudaMemcpyAsync(off32_out, ctx->d_peakoff32.p, (size_t)(P + 1) * 4, cudaMemcpyDeviceToHost, ctx->stream));
-    uint64_t guess = (ctx->last_comps + ctx->last_comps / 4) * (uint64_t)pd.rec_width + 4096;
-    if (guess > recs_bytes) guess = recs_bytes;
-    if (guess > ctx->d_recs.cap) guess = ctx->d_recs.cap;
-    if (guess) CK(cudaMemcpyAsync(recs_out, ctx->d_recs.p, (size_t)guess, cudaMemcpyDeviceToHost, ctx->stream));
     hp_mark(12);
+    trace_mark(ctx, 4);
     pd.copied = guess;
     pd.done = true;  // queued
+    return SST_OK;
+}
+
+uint64_t sst_explain_d2h_bytes(const sst_ctx* ctx) { return ctx->last_d2h_bytes; }
+
+int sst_explain_block_layout(int64_t P, uint64_t* status_off, uint64_t* off32_off, uint64_t* recs_off) {
+    if (P < 0) return SST_ERR_BAD_ARG;
+    const BlockLayout lay(P);
+    if (status_off) *status_off = lay.status;
+    if (off32_off) *off32_off = lay.off32;
+    if (recs_off) *recs_off = lay.recs;
     return SST_OK;
 }
 
@@ -1793,6 +1886,8 @@ int sst_explain_collect(sst_ctx* ctx, const sst_table* t, uint64_t* n_comps, int
         hp_begin();
         CK(cudaStreamSynchronize(ctx->stream));
         hp_mark(13);
+        memcpy(ctx->h_run, pd.block, 352);  // where the evaluation below looks
+        memcpy(ctx->h_misc, pd.block + kBlockStageSummary, 64);
         const unsigned long long* hs = (const unsigned long long*)ctx->h_misc;  // the staging kernel's summary
         if ((rc = nf_error(ctx, hs[4]))) return rc;
         MemoMap mp{};
@@ -1809,18 +1904,17 @@ int sst_explain_collect(sst_ctx* ctx, const sst_table* t, uint64_t* n_comps, int
             ctx->n_comps = comps;
             ctx->rec_width = pd.rec_width;
             ctx->last_pass = pd.direct ? 3 : 2;
-            ctx->have_result = true;
+            ctx->have_result = false;  // (delivered; nothing is left in the buffers sst_explain_fetch reads)
             ctx->last_comps = comps;
             const uint64_t need = comps * (uint64_t)pd.rec_width;
-            if (need > pd.recs_bytes) {  // the caller's buffer is too small: the result stays on the device for sst_explain_fetch
-                if (n_comps) *n_comps = comps;
-                if (rec_width) *rec_width = pd.rec_width;
-                return fail(ctx, SST_ERR_NOMEM, "record buffer of %llu bytes is too small for %llu compositions", (unsigned long long)pd.recs_bytes,
-                            (unsigned long long)comps);
+            if (need > pd.recs_bytes) {  // the caller's block is too small: the synchronous path leaves the result on the device for sst_explain_fetch
+                redo = true;
             }
-            if (need > pd.copied) {
-                CK(cudaMemcpyAsync(pd.recs + pd.copied, (const char*)ctx->d_recs.p + pd.copied, (size_t)(need - pd.copied), cudaMemcpyDeviceToHost,
-                                   ctx->stream));
+            ctx->last_d2h_bytes = BlockLayout(pd.P).recs + (need > pd.copied ? need : pd.copied);
+            if (need <= pd.recs_bytes && need > pd.copied) {
+                const BlockLayout lay(pd.P);
+                CK(cudaMemcpyAsync(pd.recs + pd.copied, (const char*)ctx->d_block.p + lay.recs + pd.copied, (size_t)(need - pd.copied),
+                                   cudaMemcpyDeviceToHost, ctx->stream));
                 CK(cudaStreamSynchronize(ctx->stream));
             }
         } else if (rc == DFS_OK || rc == DFS_RETRY || rc == PASS_FALLBACK) {
@@ -1853,6 +1947,27 @@ int sst_explain_collect(sst_ctx* ctx, const sst_table* t, uint64_t* n_comps, int
     }
     if (n_comps) *n_comps = ctx->n_comps;
     if (rec_width) *rec_width = ctx->rec_width;
+    return SST_OK;
+}
+
+int sst_trace_ms(sst_ctx* ctx, int enable, float* out) {
+    CK(cudaSetDevice(ctx->device));
+    if (!g_trace_base) {
+        CK(cudaEventCreate(&g_trace_base));
+        CK(cudaEventRecord(g_trace_base, ctx->stream));
+        CK(cudaEventSynchronize(g_trace_base));
+    }
+    if (out)
+        for (int k = 0; k < 8; k++) {
+            out[k] = -1.f;
+            if (ctx->trace_ev[k] && cudaEventElapsedTime(&out[k], g_trace_base, ctx->trace_ev[k]) != cudaSuccess) {
+                out[k] = -1.f;
+                cudaGetLastError();
+            }
+        }
+    if (enable && !ctx->trace_ev[0])
+        for (auto& e : ctx->trace_ev) CK(cudaEventCreate(&e));
+    ctx->trace_on = enable != 0;
     return SST_OK;
 }
 

@@ -116,7 +116,7 @@ __device__ __forceinline__ void integerise(double mass, double thr, double preci
 // casting: a NaN mass, an infinite mass (its relative threshold is infinite too) or an infinite threshold.  A NaN
 // threshold means "None" (relative) in the batched entries.
 enum : int { NF_NAN = 1, NF_INF = 2 };
-enum : int { VALID_CODE_NAN = 3, VALID_CODE_INF = 4 };  // k_is_valid_f64's codes for them (0 / 1 / 2 are answers)
+enum : int { VALID_CODE_NAN = 8, VALID_CODE_INF = 9 };  // k_is_valid_f64's codes for them (0 / 1 / 2 are answers; bit 3 is set by nothing else)
 enum : int { CLASS_CODE_NAN = 8, CLASS_CODE_INF = 9 };  // k_classify's (bit 3 is set by nothing else)
 __device__ __forceinline__ int non_finite(double mass, double thr) {
     return (isnan(mass) ? NF_NAN : 0) | ((isinf(mass) || isinf(thr)) ? NF_INF : 0);

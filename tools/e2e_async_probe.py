@@ -15,10 +15,21 @@ em = ctx.pinned_empty(wl.explain_mass.shape, np.float64); em[...] = wl.explain_m
 et = ctx.pinned_empty(wl.explain_thr.shape, np.float64); et[...] = wl.explain_thr
 T = {"submit_classify": 0.0, "submit_explain": 0.0, "wait_classify": 0.0, "collect_explain": 0.0}
 
+WHAT = {"classify": True, "explain": True}
+
+
+class _Done:
+    def wait(self):
+        return None
+
+
 def submit(slot):
     t0 = time.perf_counter()
-    v = FC.classify_observed(obs, dp, wl.breakage, copy=False, wait=False, slot=slot)
+    v = FC.classify_observed(obs, dp, wl.breakage, copy=False, wait=False, slot=slot) if WHAT["classify"] else _Done()
     t1 = time.perf_counter()
+    if not WHAT["explain"]:
+        T["submit_classify"] += t1 - t0
+        return v, _Done()
     b = ME.explain_masses(em, dp, max_modifications=wl.max_modifications, thresholds=et, copy=False, wait=False, slot=slot)
     t2 = time.perf_counter()
     T["submit_classify"] += t1 - t0; T["submit_explain"] += t2 - t1
@@ -40,12 +51,47 @@ def loop(n, depth=2):
             pend.append(submit((i + depth - 1) % depth))
         finish(pend.pop(0))
 
-for depth in (1, 2):
+for depth, what in ((1, "ce"), (2, "ce"), (3, "ce"), (4, "ce"), (2, "e"), (3, "e"), (2, "c"), (3, "c")):
+    WHAT["classify"], WHAT["explain"] = "c" in what, "e" in what
     loop(10, depth)
     for k in T: T[k] = 0.0
     n = 200
     t0 = time.perf_counter(); loop(n, depth); dt = time.perf_counter() - t0
-    print(f"depth {depth}: step {dt / n * 1e6:.1f} us;  " + "  ".join(f"{k} {v / n * 1e6:.1f}" for k, v in T.items()))
+    print(f"depth {depth} {what}: step {dt / n * 1e6:.1f} us;  " + "  ".join(f"{k} {v / n * 1e6:.1f}" for k, v in T.items()))
+# device timeline of the enumeration pass in the pipelined loop (CTA 0's %globaltimer at start / end of every launch)
+from spectrseqtools_b200 import _cabi
+for depth, what in ((3, "e"), (3, "ce")):
+    WHAT["classify"], WHAT["explain"] = "c" in what, "e" in what
+    loop(10, depth)
+    stamps = []
+    for k in range(depth):
+        _cabi.context(0, k).trace_ms(True)
+    trace, host = [], []
+    pend = [submit(k) for k in range(depth - 1)]
+    n = 60
+    t_host = []
+    for i in range(n):
+        if i + depth - 1 < n:
+            pend.append(submit((i + depth - 1) % depth))
+        finish(pend.pop(0))
+        t_host.append(time.perf_counter())
+        trace.append(_cabi.context(0, i % depth).trace_ms(True)[:5].astype(np.float64) * 1e3)
+        ph = _cabi.context(0, i % depth).explain_phase_ns().astype(np.int64)
+        ph = ph[ph > 0]
+        stamps.append((ph[0], ph[-1]))
+    st = np.array(stamps, dtype=np.int64)
+    dur = (st[:, 1] - st[:, 0]) * 1e-3
+    gap = (st[1:, 0] - st[:-1, 1]) * 1e-3
+    per = np.diff(st[:, 0]) * 1e-3
+    print(f"timeline depth {depth} {what}: kernel us p50 {np.median(dur):.1f} max {dur.max():.1f}; start-to-start p50 {np.median(per):.1f}; gap after a kernel p50 {np.median(gap):.1f} min {gap.min():.1f} max {gap.max():.1f}")
+    tr = np.array(trace)[10:]
+    seg = np.diff(tr, axis=1)
+    print("   per batch us p50: H2D", np.median(seg[:, 0]).round(1), " stage", np.median(seg[:, 1]).round(1), " pass (with waiting)", np.median(seg[:, 2]).round(1),
+          " D2H", np.median(seg[:, 3]).round(1), " whole chain", np.median(tr[:, 4] - tr[:, 0]).round(1), " period", np.median(np.diff(tr[:, 4])).round(1))
+    for r in tr[20:26]:
+        print("     ", (r - tr[20, 0]).round(1))
+    print("   host collect-to-collect us p50", round(float(np.median(np.diff(t_host))) * 1e6, 1))
+WHAT["classify"] = WHAT["explain"] = True
 ctx.host_profile(True)
 n = 200
 loop(n, 2)
