@@ -23,6 +23,7 @@ using namespace sst;
 namespace {
 
 constexpr int kMaxPending = 32;
+constexpr size_t kReplaySmemLimit = 200 * 1024;  // dynamic shared memory a replay CTA may ask for (k_memo_phase_a)
 
 // Host-side stopwatch of the asynchronous entries (diagnostics, sst_host_profile): wall time between marks inside the
 // submitting calls, summed per section.  Off unless switched on; a mark is two loads when off.
@@ -170,6 +171,7 @@ struct sst_ctx {
     } pend;
     DevBuf d_block;                    // the same block on the device: the pass writes into it, ONE copy brings it back
     uint64_t last_comps = 0;           // compositions of the last batch: sizes the speculative copy of the next one
+    bool replay_attr_set = false;      // k_memo_phase_a's dynamic shared-memory limit has been raised on this device
     bool spec_ok = true;               // sst_explain_submit_f64 queues blindly (the last batch it had to redo would have fitted, or none yet)
     int spec_rec_width = 8;            // with this record width
     cudaEvent_t trace_ev[8] = {nullptr};  // diagnostics (sst_trace_ms): device timeline of the last submitted batch
@@ -561,6 +563,9 @@ int sst_ctx_create(int device, sst_ctx** out) {
         delete ctx;
         return SST_ERR_NO_DEVICE;
     }
+    // Every kernel's per-thread stack is at most ~1.4 KB (the depth-first walk of the enumeration pass); asking for that
+    // now makes the driver size its local-memory pool here, once, instead of inside the first launch that needs it.
+    cudaDeviceSetLimit(cudaLimitStackSize, 2048);
     cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
     cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking);
     cudaEventCreate(&ctx->ev_a);
@@ -996,11 +1001,8 @@ int sst_length_bounds(sst_ctx* ctx, const sst_table* t, int64_t target, int64_t 
                 (uint32_t)(pow2 - 1), (int*)((char*)ctx->d_bout.p + 32)};
     {
         KTimer kt(ctx, SST_K_LENGTH_BOUND);
-        // smallest stack instance that holds the deepest walk (see k_memo_phase_a)
-        const int64_t frames = (t->w_min > 0 ? (target + thr) / t->w_min : 0) + 2;
-        auto kern = frames <= 16 ? k_length_bounds<16> : frames <= 40 ? k_length_bounds<40> : k_length_bounds<kMaxDepth>;
-        kern<<<1, 32, 0, ctx->stream>>>(view_of(t), RowMeta{(const int32_t*)ctx->d_ind.p, (const uint8_t*)ctx->d_ismod.p}, target, thr,
-                                        max_mods, max_len, mp, (int64_t*)ctx->d_bout.p);
+        k_length_bounds<<<1, 32, 0, ctx->stream>>>(view_of(t), RowMeta{(const int32_t*)ctx->d_ind.p, (const uint8_t*)ctx->d_ismod.p}, target, thr,
+                                                   max_mods, max_len, mp, (int64_t*)ctx->d_bout.p);
         kt.stop(1);
         CK(cudaGetLastError());
     }
@@ -1219,13 +1221,19 @@ int memo_launch(sst_ctx* ctx, const sst_table* t, uint64_t memo_capacity, MemoMa
     mp.fill = (unsigned int*)ctx->d_memo_misc.p;
     mp.overflow = (int*)ctx->d_memo_misc.p + 1;
     KTimer kt(ctx, SST_K_PHASE_A);
-    const int64_t frames = ctx->deepest + 2;  // the smallest stack instance that holds the deepest composition
-    auto phase_a = frames <= 16 ? k_memo_phase_a<16> : frames <= 40 ? k_memo_phase_a<40> : k_memo_phase_a<kMaxDepth>;
-    phase_a<<<(unsigned)((ctx->n_memo + 63) / 64), 64, 0, ctx->stream>>>(
+    // the replay stack lives in shared memory: frames for the deepest composition, as many threads per CTA as fit
+    const int64_t frames = ctx->deepest + 3;
+    const int threads = replay_threads(frames, kReplaySmemLimit);
+    if (!threads) return fail(ctx, SST_ERR_TOO_DEEP, "a composition may need %lld nucleotides: the replay stack does not fit in shared memory", (long long)ctx->deepest);
+    if (!ctx->replay_attr_set) {
+        CK(cudaFuncSetAttribute((const void*)k_memo_phase_a, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kReplaySmemLimit));
+        ctx->replay_attr_set = true;
+    }
+    k_memo_phase_a<<<(unsigned)((ctx->n_memo + threads - 1) / threads), threads, (size_t)frames * threads * kReplayFrameBytes, ctx->stream>>>(
         view_of(t), RowMeta{(const int32_t*)ctx->d_ind.p, (const uint8_t*)ctx->d_ismod.p},
         PeakBatch{(const int64_t*)ctx->d_target.p, (const int64_t*)ctx->d_thr.p, (const int32_t*)ctx->d_maxmods.p,
                   (const uint8_t*)ctx->d_mode.p, P},
-        (const uint32_t*)ctx->d_memo_peaks.p, ctx->n_memo, mp);
+        (const uint32_t*)ctx->d_memo_peaks.p, ctx->n_memo, mp, (int)frames);
     kt.stop(1);
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(ctx->h_misc + 100, ctx->d_memo_misc.p, 8, cudaMemcpyDeviceToHost, ctx->stream));

@@ -407,13 +407,57 @@ k_classify(TableView tv, const double* __restrict__ observed, int64_t F, const d
 }
 
 // ---------------- MEMO phase A: sequential first-visit replay, one thread per peak ----------------
-// DEPTH = frames of the explicit stack (one per nucleotide on the current path): the host picks the smallest instance
-// that holds the longest composition the staged batch can have, because the per-thread stack decides how much local
-// memory the driver reserves for EVERY resident thread of the device (4.8 KB x 303 104 threads = 1.5 GB at DEPTH 96).
-template <int DEPTH>
+// The explicit stack (one frame per nucleotide on the current path, `frames` of them) lives in DYNAMIC SHARED MEMORY,
+// field-major and thread-minor, not in local memory: a per-thread stack decides how much local memory the driver
+// reserves for EVERY resident thread of the device (4.8 KB x 303 104 threads = 1.5 GB for 96 frames) and the first
+// launch of such a kernel in a process pays for resizing that pool (hundreds of ms).  The host sizes the CTA so that
+// frames x threads x kReplayFrameBytes fits (replay_threads()).
+constexpr int kReplayFrameBytes = 52;  // m, slot, all, ind (4 each), pend, fresh (16 each), rin, cur (1 each), padded
+struct ReplayStack {
+    uint32_t* m;
+    int* slot;
+    int* all;
+    int* ind;
+    uint32_t* pend;   // [frames][4][T]
+    uint32_t* fresh;  // [frames][4][T]
+    uint8_t* rin;
+    uint8_t* cur;
+    int T, tid;
+    __device__ ReplayStack(unsigned char* base, int frames, int threads, int thread) : T(threads), tid(thread) {
+        const size_t n = (size_t)frames * threads;
+        m = reinterpret_cast<uint32_t*>(base);
+        slot = reinterpret_cast<int*>(m + n);
+        all = slot + n;
+        ind = all + n;
+        pend = reinterpret_cast<uint32_t*>(ind + n);
+        fresh = pend + 4 * n;
+        rin = reinterpret_cast<uint8_t*>(fresh + 4 * n);
+        cur = rin + n;
+    }
+    __device__ __forceinline__ int at(int d) const { return d * T + tid; }
+    __device__ __forceinline__ Mask128 get(const uint32_t* plane, int d) const {
+        Mask128 r;
+#pragma unroll
+        for (int k = 0; k < 4; k++) r.w[k] = plane[(d * 4 + k) * T + tid];
+        return r;
+    }
+    __device__ __forceinline__ void put(uint32_t* plane, int d, const Mask128& v) const {
+#pragma unroll
+        for (int k = 0; k < 4; k++) plane[(d * 4 + k) * T + tid] = v.w[k];
+    }
+    __device__ __forceinline__ void set_bit(uint32_t* plane, int d, int r) const { plane[(d * 4 + (r >> 5)) * T + tid] |= 1u << (r & 31); }
+};
+// threads per CTA of a replay kernel whose deepest walk needs `frames` frames (0: does not fit at all)
+inline int replay_threads(int64_t frames, size_t smem_limit) {
+    for (int t = 64; t >= 8; t >>= 1)
+        if ((size_t)frames * t * kReplayFrameBytes + 2048 <= smem_limit) return t;
+    return 0;
+}
+
 __global__ void __launch_bounds__(64)
 k_memo_phase_a(TableView tv, RowMeta meta, PeakBatch pk, const uint32_t* __restrict__ memo_peaks, int n_memo,
-               MemoMap mp) {
+               MemoMap mp, int frames) {
+    extern __shared__ __align__(16) unsigned char s_dyn[];
     __shared__ int32_t s_w[kMaxRows];
     __shared__ int32_t s_ind[kMaxRows];
     __shared__ uint8_t s_mod[kMaxRows];
@@ -433,12 +477,8 @@ k_memo_phase_a(TableView tv, RowMeta meta, PeakBatch pk, const uint32_t* __restr
     const int64_t b = hi < limit - 1 ? hi : limit - 1;
     const int top_row = tv.R - 1;
 
-    // explicit recursion stack (one frame per mass on the current path)
-    uint32_t f_m[DEPTH + 1];
-    int f_slot[DEPTH + 1];
-    uint8_t f_rin[DEPTH + 1], f_cur[DEPTH + 1];
-    int f_all[DEPTH + 1], f_ind[DEPTH + 1];
-    Mask128 f_pend[DEPTH + 1], f_new[DEPTH + 1];
+    // explicit recursion stack (one frame per mass on the current path), in shared memory
+    ReplayStack f(s_dyn, frames, blockDim.x, threadIdx.x);
     int sp = 0;
 
     // arrival at (m, r_in) with budgets; either answers from the map (returns false, sets alive) or
@@ -447,7 +487,7 @@ k_memo_phase_a(TableView tv, RowMeta meta, PeakBatch pk, const uint32_t* __restr
     auto arrive = [&](uint32_t m, int r_in, int all, int ind, bool& alive) -> bool {
         alive = false;
         const int slot = memo_find_or_insert(mp, memo_key(p, m), inserted);
-        if (slot < 0 || sp > DEPTH) {
+        if (slot < 0 || sp >= frames) {
             *mp.overflow = 1;
             return false;
         }
@@ -461,9 +501,10 @@ k_memo_phase_a(TableView tv, RowMeta meta, PeakBatch pk, const uint32_t* __restr
         Mask128 pend = mk(ld_nc_u4(tv.H + m));
         mask_keep_le(pend, r_in);
         mask_keep_gt(pend, top);
-        f_m[sp] = m; f_slot[sp] = slot; f_rin[sp] = (uint8_t)r_in; f_all[sp] = all; f_ind[sp] = ind;
-        f_pend[sp] = pend;
-        f_new[sp].w[0] = f_new[sp].w[1] = f_new[sp].w[2] = f_new[sp].w[3] = 0u;
+        const int o = f.at(sp);
+        f.m[o] = m; f.slot[o] = slot; f.rin[o] = (uint8_t)r_in; f.all[o] = all; f.ind[o] = ind;
+        f.put(f.pend, sp, pend);
+        f.put(f.fresh, sp, Mask128{{0u, 0u, 0u, 0u}});
         sp++;
         return true;
     };
@@ -473,33 +514,36 @@ k_memo_phase_a(TableView tv, RowMeta meta, PeakBatch pk, const uint32_t* __restr
         bool alive;
         if (!arrive((uint32_t)v, top_row, pk.max_mods[p], s_ind[top_row], alive)) continue;
         while (sp > 0) {
-            const int d = sp - 1;
-            if (mask_empty(f_pend[d])) {  // all new rows of this mass expanded: publish and return
-                const int slot = f_slot[d];
+            const int d = sp - 1, o = f.at(d);
+            Mask128 pend = f.get(f.pend, d);
+            if (mask_empty(pend)) {  // all new rows of this mass expanded: publish and return
+                const int slot = f.slot[o];
+                const Mask128 fresh = f.get(f.fresh, d);
                 uint4 A = mp.alive[slot];
-                A.x |= f_new[d].w[0]; A.y |= f_new[d].w[1]; A.z |= f_new[d].w[2]; A.w |= f_new[d].w[3];
+                A.x |= fresh.w[0]; A.y |= fresh.w[1]; A.z |= fresh.w[2]; A.w |= fresh.w[3];
                 mp.alive[slot] = A;
-                mp.top[slot] = f_rin[d];
+                mp.top[slot] = f.rin[o];
                 Mask128 t = mk(A);
-                mask_keep_le(t, f_rin[d]);
+                mask_keep_le(t, f.rin[o]);
                 const bool ok = !mask_empty(t);
                 sp--;
-                if (sp > 0 && ok) mask_set(f_new[sp - 1], f_cur[sp - 1]);
+                if (sp > 0 && ok) f.set_bit(f.fresh, sp - 1, f.cur[f.at(sp - 1)]);
                 continue;
             }
-            const int r = mask_pop_lowest(f_pend[d]);  // LEFT edges fire in ascending row order (UP first)
-            f_cur[d] = (uint8_t)r;
-            const int ind_here = (r == f_rin[d]) ? f_ind[d] : s_ind[r];
+            const int r = mask_pop_lowest(pend);  // LEFT edges fire in ascending row order (UP first)
+            f.put(f.pend, d, pend);
+            f.cur[o] = (uint8_t)r;
+            const int ind_here = (r == f.rin[o]) ? f.ind[o] : s_ind[r];
             const int mod = s_mod[r];
-            if (mod && !(f_all[d] > 0 && ind_here > 0)) continue;
-            const uint32_t m2 = f_m[d] - (uint32_t)s_w[r];
+            if (mod && !(f.all[o] > 0 && ind_here > 0)) continue;
+            const uint32_t m2 = f.m[o] - (uint32_t)s_w[r];
             if (m2 == 0u) {
-                mask_set(f_new[d], r);
+                f.set_bit(f.fresh, d, r);
                 continue;
             }
             bool child_alive;
-            if (!arrive(m2, r, f_all[d] - mod, ind_here - mod, child_alive)) {
-                if (child_alive) mask_set(f_new[d], r);
+            if (!arrive(m2, r, f.all[o] - mod, ind_here - mod, child_alive)) {
+                if (child_alive) f.set_bit(f.fresh, d, r);
             }
         }
     }
@@ -540,7 +584,6 @@ __device__ inline int bound_slot(const BoundMap& mp, uint32_t m, unsigned int* f
 }
 
 // out[0] = lower bound, out[1] = upper bound, out[2] = 1 if a window value lies beyond the table (the reference raises)
-template <int DEPTH>  // stack frames, as in k_memo_phase_a
 __global__ void __launch_bounds__(32)
 k_length_bounds(TableView tv, RowMeta meta, int64_t target, int64_t thr, int max_mods, int max_len, BoundMap mp, int64_t* __restrict__ out) {
     __shared__ int32_t s_w[kMaxRows];
@@ -563,13 +606,15 @@ k_length_bounds(TableView tv, RowMeta meta, int64_t target, int64_t thr, int max
     }
     unsigned int fill = 0;
 
-    // one frame per mass on the current path
-    uint32_t f_m[DEPTH + 2];
-    int f_slot[DEPTH + 2];
-    uint8_t f_rin[DEPTH + 2], f_cur[DEPTH + 2], f_fill[DEPTH + 2];
-    int f_all[DEPTH + 2], f_ind[DEPTH + 2];
-    int8_t f_lo[DEPTH + 2], f_up[DEPTH + 2];  // running min / max
-    Mask128 f_pend[DEPTH + 2];
+    // one frame per mass on the current path; the one working thread keeps them in shared memory (3.6 KB), not in a
+    // per-thread stack (see k_memo_phase_a)
+    constexpr int DEPTH = kMaxDepth;
+    __shared__ uint32_t f_m[DEPTH + 2];
+    __shared__ int f_slot[DEPTH + 2];
+    __shared__ uint8_t f_rin[DEPTH + 2], f_cur[DEPTH + 2], f_fill[DEPTH + 2];
+    __shared__ int f_all[DEPTH + 2], f_ind[DEPTH + 2];
+    __shared__ int8_t f_lo[DEPTH + 2], f_up[DEPTH + 2];  // running min / max
+    __shared__ Mask128 f_pend[DEPTH + 2];
     int sp = 0;
     int ret_lo = 0, ret_up = 0;  // value of the node an arrival / a finished frame stands for
 

@@ -15,14 +15,22 @@ for mode in (2, 3):
     res[mode] = b
     dev = dp.device_table()
     ts = []
-    if mode == 3:
-        ctx.cta_timestamps(True)
+    ctx.cta_timestamps(True)
     for _ in range(10):
         if flush:
             ctx.flush_l2()
         ctx.stats_reset(); ctx.explain_run(dev, 0); ts.append(ctx.kernel_stats()["explain_pass"][0])
     ph = ctx.explain_phase_ns().astype(np.int64); ph = ph[ph > 0]
     print("pass", mode, "last", ctx.last_pass(), "comps", b.n_compositions, "ms", np.round(ts, 4), "phases us", np.diff(ph) * 1e-3)
+    if mode == 2:
+        c = ctx.cta_timestamps(False).astype(np.int64)
+        t0 = c[:, 0].min()
+        d = (c[:, :8] - t0) * 1e-3
+        for k, nm in ((0, "start"), (1, "win counted"), (2, "roots written"), (6, "rounds done"), (3, "count done"), (4, "barrier"), (5, "fill done")):
+            print(f"  {nm:14s} min {d[:, k].min():8.1f} p10 {np.percentile(d[:, k], 10):8.1f} p50 {np.median(d[:, k]):8.1f} p90 {np.percentile(d[:, k], 90):8.1f} max {d[:, k].max():8.1f}")
+        seg = {"windows": d[:, 1] - d[:, 0], "roots": d[:, 2] - d[:, 1], "rounds": d[:, 6] - d[:, 2], "final count": d[:, 3] - d[:, 6], "fill": d[:, 5] - d[:, 4]}
+        for nm, v in seg.items():
+            print(f"    {nm:12s} per CTA us p10/p50/p90/max", np.percentile(v, [10, 50, 90, 100]).round(1))
     if mode == 3:
         c = ctx.cta_timestamps(False).astype(np.int64)
         t0 = c[:, 0].min()
