@@ -184,6 +184,33 @@ int sst_explain_cta_ns(sst_ctx* ctx, int enable, uint64_t* out, int cap_ctas, in
  * [counted, grid barrier passed, written]; after the last level [per-level peak totals summed], [placement table
  * written], [records permuted].  Right after a grid barrier that is every CTA's clock.  Unused slots are 0. */
 int sst_explain_phase_ns(const sst_ctx* ctx, uint64_t* out /* [32] */);
+/* ---- N3 + N4: ladder differences and the explanation-based alphabet reduction on a fragment frame that
+ * stays on the device between the rounds (kernels: sst_ladder.cuh).
+ *
+ * sst_ladder_stage: the classified fragments, sorted by standard-unit mass as prediction.py:68-72 leaves them —
+ * su[F], observed[F], flags[F] (1 = breakage contains START, 2 = contains END, 4 = is_singleton).  Every fragment
+ * starts alive.
+ *
+ * sst_ladder_round replaces Predictor.collect_diff_explanations_for_su (prediction.py:261-329) for the alive fragments:
+ * the two-pointer window of each side (`diff > max_weight` restart, tail behaviour once `end` sits on the last
+ * fragment), the l1 error threshold tolerance * (obs1 + obs2) (common.py:37-44), then the singletons (su, tolerance *
+ * obs) — generated on the device straight into a staged batch, enumerated by sst_explain_run's machinery, deduplicated
+ * by key as the reference's dicts do (the last entering call with a key wins; a pair enters with >= 1 explanation, a
+ * singleton always).  mask_out[4]: bit r set = table row r occurs in a winning explanation — what
+ * Predictor.filter_by_explanation (:170-202) turns into the reduced alphabet.  Only that mask and two counters cross
+ * the bus.  The explanations themselves stay available: sst_explain_fetch (calls in generation order) +
+ * sst_ladder_fetch (keys, thresholds, per-call flags: 1 = entered its dict, 2 = is the surviving entry of its key).
+ *
+ * sst_ladder_revalidate replaces the loop of Predictor._reduce_alphabet (:204-227) after the table has been rebuilt for
+ * the reduced alphabet: is_valid_mass(su, tolerance * observed) of every alive fragment; the ones that fail die.
+ * SST_ERR_OUT_OF_TABLE as is_valid_mass raises. */
+int sst_ladder_stage(sst_ctx* ctx, const double* su, const double* observed, const uint8_t* flags, int64_t F);
+int sst_ladder_round(sst_ctx* ctx, const sst_table* t, double max_weight, double precision, double tolerance, int32_t max_mods,
+                     const int32_t* ind, const uint8_t* is_mod, int with_memo, uint32_t* mask_out /* [4] */, uint64_t* n_calls,
+                     uint64_t* n_comps);
+int sst_ladder_revalidate(sst_ctx* ctx, const sst_table* t, double precision, double tolerance, int64_t* n_alive);
+int sst_ladder_fetch(sst_ctx* ctx, uint8_t* alive_out /* [F] */, double* key_out /* [n_calls] */, double* thr_out /* [n_calls] */,
+                     uint8_t* call_flags_out /* [n_calls] */);
 /* diagnostics: host wall time (ns) and number of visits per section of the asynchronous entries since the last call
  * (sections are the marks in sst_cabi.cu: 0-12 sst_explain_submit_f64, 13 the wait in sst_explain_collect, 16-20
  * sst_classify_async); returns the sums, clears them and switches the stopwatch on or off (process-wide) */

@@ -38,6 +38,7 @@ EXPORTS = [
     "sst_valid_fetch", "sst_valid_stage_f64", "sst_explain", "sst_explain_stage", "sst_explain_stage_f64", "sst_explain_stage_f64_uniform", "sst_explain_rec_width", "sst_explain_phase_ns",
     "sst_explain_run", "sst_explain_fetch", "sst_classify", "sst_classify_stage", "sst_classify_run", "sst_classify_fetch", "sst_classify_launch", "sst_classify_async", "sst_classify_wait", "sst_length_bounds",
     "sst_set_pass", "sst_last_pass", "sst_explain_cta_ns", "sst_explain_submit_f64", "sst_explain_collect", "sst_classify_async_packed", "sst_host_profile", "sst_trace_ms", "sst_explain_block_layout", "sst_explain_d2h_bytes",
+    "sst_ladder_stage", "sst_ladder_round", "sst_ladder_revalidate", "sst_ladder_fetch",
 ]
 
 
@@ -112,6 +113,11 @@ def load() -> C.CDLL:
             "sst_explain_collect": (C.c_int, [vp, vp, C.POINTER(C.c_uint64), C.POINTER(C.c_int)]),
             "sst_host_profile": (C.c_int, [C.c_int, u64p, u64p]),
             "sst_trace_ms": (C.c_int, [vp, C.c_int, fp]),
+            "sst_ladder_stage": (C.c_int, [vp, fp, fp, u8p, C.c_int64]),
+            "sst_ladder_round": (C.c_int, [vp, vp, C.c_double, C.c_double, C.c_double, C.c_int32, i32p, u8p, C.c_int, u32p,
+                                           C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
+            "sst_ladder_revalidate": (C.c_int, [vp, vp, C.c_double, C.c_double, C.POINTER(C.c_int64)]),
+            "sst_ladder_fetch": (C.c_int, [vp, u8p, fp, fp, u8p]),
             "sst_explain_d2h_bytes": (C.c_uint64, [vp]),
             "sst_set_pass": (C.c_int, [vp, C.c_int]),
             "sst_last_pass": (C.c_int, [vp]),
@@ -412,6 +418,42 @@ class Context:
         self._last = (0, n, w)
         self._recs_hint = max(self.__dict__.get("_recs_hint", 0), n * w + n * w // 4)
         return status, off, recs[: n * w].reshape(n, w)
+
+    # ---- N3 / N4 on a device-resident fragment frame (sst_ladder_*)
+    def ladder_stage(self, su, observed, flags):
+        s, o, f = _arr(su, np.float64), _arr(observed, np.float64), _arr(flags, np.uint8)
+        if not (len(s) == len(o) == len(f)):
+            raise ValueError("per-fragment arrays differ in length")
+        self._check(self._lib.sst_ladder_stage(self._h, _p(s), _p(o), _p(f), len(s)))
+        self._ladder_F = len(s)
+
+    def ladder_round(self, table: "DeviceTable", max_weight: float, precision: float, tolerance: float, max_mods: int, ind, is_mod,
+                     with_memo: bool = True):
+        """-> (row mask as a Python int, number of calls, number of compositions) of one round over the alive fragments."""
+        iv, im = _arr(ind, np.int32), _arr(is_mod, np.uint8)
+        if len(iv) != table.R or len(im) != table.R:
+            raise ValueError("ind / is_mod need one entry per table row")
+        mask = np.zeros(4, dtype=np.uint32)
+        nc, nk = C.c_uint64(), C.c_uint64()
+        self._check(self._lib.sst_ladder_round(self._h, table._h, float(max_weight), float(precision), float(tolerance), int(max_mods), _p(iv), _p(im),
+                                               1 if with_memo else 0, _p(mask), C.byref(nc), C.byref(nk)))
+        self._staged_P = int(nc.value)
+        self._last = (0, int(nk.value), int(self._lib.sst_explain_rec_width(self._h)))
+        self._ladder_calls = int(nc.value)
+        return sum(int(w) << (32 * k) for k, w in enumerate(mask)), int(nc.value), int(nk.value)
+
+    def ladder_revalidate(self, table: "DeviceTable", precision: float, tolerance: float) -> int:
+        n = C.c_int64()
+        self._check(self._lib.sst_ladder_revalidate(self._h, table._h, float(precision), float(tolerance), C.byref(n)))
+        return int(n.value)
+
+    def ladder_fetch(self, calls: bool = True):
+        """-> (alive uint8[F], keys float64[n], thresholds float64[n], call flags uint8[n]) of the last round."""
+        alive = np.zeros(self._ladder_F, dtype=np.uint8)
+        n = self._ladder_calls if calls else 0
+        keys, thr, fl = np.zeros(n, dtype=np.float64), np.zeros(n, dtype=np.float64), np.zeros(n, dtype=np.uint8)
+        self._check(self._lib.sst_ladder_fetch(self._h, _p(alive), _p(keys) if n else None, _p(thr) if n else None, _p(fl) if n else None))
+        return alive, keys, thr, fl
 
     def explain_d2h_bytes(self) -> int:
         """Bytes the last collected submission copied device -> host."""

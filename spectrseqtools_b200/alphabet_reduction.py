@@ -101,10 +101,93 @@ def reduce_alphabet(nucleotides: Set[str], su_masses: Sequence[float], observed_
     return codes == _cabi.VALID_YES
 
 
+class DeviceLadder:
+    """The classified-fragment frame on the device (rows N3 + N4): pairs, thresholds, enumeration, dedup by key, the
+    union of observed table rows and the re-validation all run there; per round the host sees a 128-bit row mask and
+    two counters (``sst_ladder_*``, kernels in csrc/sst_ladder.cuh).
+
+    ``su_masses`` must ascend (prediction.py:68-72 sorts the frame before ``filter_by_explanation``)."""
+
+    def __init__(self, su_masses: Sequence[float], observed_masses: Sequence[float], breakages: Sequence[str],
+                 is_singleton: Sequence[bool], dp_table: DynamicProgrammingTable, explanation_masses):
+        self.dp = dp_table
+        self.max_weight = _max_weight(explanation_masses)
+        su = np.ascontiguousarray(su_masses, dtype=np.float64)
+        flags = np.array([(1 if "START" in b else 0) | (2 if "END" in b else 0) | (4 if s else 0)
+                          for b, s in zip(breakages, is_singleton)], dtype=np.uint8)
+        self.ctx = dp_table.device_table().ctx
+        self.ctx.ladder_stage(su, np.ascontiguousarray(observed_masses, dtype=np.float64), flags)
+        self.n_calls = self.n_compositions = 0
+
+    def round(self) -> Set[str]:
+        """One ``collect_diff_explanations_for_su`` over the alive fragments -> the nucleosides that occur in any
+        surviving explanation (every name of every table row used, as ``convert_nucleotide_masses_to_names`` expands)."""
+        from .common import _budget
+        from .mass_explanation import MASS_NAMES, _row_metadata
+
+        dp = self.dp
+        dev = dp.device_table()
+        weights, is_mod, ind = _row_metadata(dp)
+        mask, self.n_calls, self.n_compositions = self.ctx.ladder_round(dev, self.max_weight, dp.precision, dp.tolerance, _budget(dp), ind,
+                                                                        is_mod, True)
+        self._weights = weights
+        return {name for r in range(1, len(weights)) if (mask >> r) & 1 for name in MASS_NAMES[int(weights[r])]}
+
+    def revalidate(self) -> int:
+        """``Predictor._reduce_alphabet``'s loop over the fragments against the current (rebuilt) table -> fragments alive."""
+        return self.ctx.ladder_revalidate(self.dp.device_table(), self.dp.precision, self.dp.tolerance)
+
+    def alive(self) -> np.ndarray:
+        return self.ctx.ladder_fetch(calls=False)[0].astype(bool)
+
+    def calls(self):
+        """(keys, thresholds, flags) of the last round in generation order (START pairs, END pairs, singletons);
+        flag bit 0: the call entered its dict, bit 1: it is the entry that survives under its key."""
+        _alive, keys, thr, fl = self.ctx.ladder_fetch()
+        return keys, thr, fl
+
+    def explanations(self) -> Dict[float, Optional[List[Explanation]]]:
+        """The dict ``collect_diff_explanations_for_su`` returns for the last round (surviving entries only are read back)."""
+        from .mass_explanation import ExplanationBatch
+
+        keys, _thr, fl = self.calls()
+        out: Dict[float, Optional[List[Explanation]]] = {}
+        if not len(keys):
+            return out
+        status, off, recs = self.ctx.explain_fetch(copy=False)
+        batch = ExplanationBatch(status, off, recs, self._weights, [m.names for m in self.dp.masses])
+        order: Dict[float, int] = {}
+        for i in np.nonzero(fl & 1)[0]:  # key order = first insertion, value = the last entering call's
+            order.setdefault(float(keys[i]), 0)
+        for i in np.nonzero(fl & 2)[0]:
+            found = batch.explanations(int(i)).explanations
+            order[float(keys[i])] = None if found is None else [Explanation(*names) for names in found]
+        out.update(order)
+        return out
+
+
+def filter_by_explanation_device(su_masses: Sequence[float], observed_masses: Sequence[float], breakages: Sequence[str],
+                                 is_singleton: Sequence[bool], dp_table: DynamicProgrammingTable, explanation_masses):
+    """``Predictor.filter_by_explanation`` (prediction.py:170-202) with the fragment frame resident on the device: per
+    round one generated-and-enumerated batch, one table rebuild, one re-validation; the host only turns the 128-bit row
+    mask into the reduced alphabet.  Returns (indices of the surviving fragments, explanations of the last round)."""
+    lad = DeviceLadder(su_masses, observed_masses, breakages, is_singleton, dp_table, explanation_masses)
+    old_size = -1
+    while old_size != len(dp_table.masses):
+        old_size = len(dp_table.masses)
+        nucleotides = lad.round()
+        dp_table.adapt_individual_modification_rates_by_alphabet_reduction(nucleotides)
+        lad.revalidate()
+    # the last round left the alphabet — and with it the table and its row numbering — as it was: its explanations
+    # are still on the device
+    return np.nonzero(lad.alive())[0], lad.explanations()
+
+
 def filter_by_explanation(su_masses: Sequence[float], observed_masses: Sequence[float], breakages: Sequence[str],
                           is_singleton: Sequence[bool], dp_table: DynamicProgrammingTable, explanation_masses):
     """``Predictor.filter_by_explanation`` (prediction.py:170-202): repeat explanation -> reduction until the
-    alphabet is stable.  Returns (indices of the surviving fragments, explanations of the last round)."""
+    alphabet is stable.  Returns (indices of the surviving fragments, explanations of the last round).  (Host loop
+    over batched device calls; ``filter_by_explanation_device`` keeps the frame on the device.)"""
     su = np.asarray(su_masses, dtype=np.float64)
     obs = np.asarray(observed_masses, dtype=np.float64)
     brk = list(breakages)

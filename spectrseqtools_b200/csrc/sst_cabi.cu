@@ -16,6 +16,7 @@
 #include "sst_direct.cuh"
 #include "sst_enum.cuh"
 #include "sst_explain.cuh"
+#include "sst_ladder.cuh"
 #include "sst_table.cuh"
 
 using namespace sst;
@@ -169,6 +170,10 @@ struct sst_ctx {
         uint64_t recs_bytes = 0, copied = 0;
         uint8_t* block = nullptr;      // the caller's result block (layout: BlockLayout)
     } pend;
+    // N3 / N4: the classified-fragment frame that stays on the device between the rounds of the alphabet reduction
+    DevBuf d_lsu, d_lobs, d_lflags, d_lalive, d_lidx, d_lreach, d_lfirst, d_lhdr, d_lkeys, d_llast, d_lcall;
+    int64_t LF = -1;                   // fragments of the staged frame (-1: none)
+    uint64_t l_calls = 0;              // calls of the last round
     DevBuf d_block;                    // the same block on the device: the pass writes into it, ONE copy brings it back
     uint64_t last_comps = 0;           // compositions of the last batch: sizes the speculative copy of the next one
     bool replay_attr_set = false;      // k_memo_phase_a's dynamic shared-memory limit has been raised on this device
@@ -595,7 +600,7 @@ void sst_ctx_destroy(sst_ctx* ctx) {
                       &ctx->d_memo_peaks, &ctx->d_status, &ctx->d_cnt, &ctx->d_peakoff, &ctx->d_recs,
                       &ctx->d_blocksums, &ctx->d_memo_keys, &ctx->d_memo_alive, &ctx->d_memo_top,
                       &ctx->d_memo_misc, &ctx->d_flush, &ctx->d_vtarget, &ctx->d_vthr, &ctx->d_vout,
-                      &ctx->d_scan, &ctx->d_vmass, &ctx->d_vthrf, &ctx->d_chunk_k, &ctx->d_chunk_r, &ctx->d_tmprecs, &ctx->d_tmppeak, &ctx->d_lvlcnt, &ctx->d_lvlA, &ctx->d_ctalvl, &ctx->d_nodemask, &ctx->d_cobs, &ctx->d_coff, &ctx->d_cout, &ctx->d_bkeys, &ctx->d_btop, &ctx->d_blower, &ctx->d_bupper, &ctx->d_bout, &ctx->d_rootvp, &ctx->d_rootcnt, &ctx->d_tilebase, &ctx->d_ctans, &ctx->d_peakcost, &ctx->d_blkcost, &ctx->d_peakoff32, &ctx->d_bag_m, &ctx->d_bag_meta, &ctx->d_bag_cnt, &ctx->d_bag_off, &ctx->d_bag_path, &ctx->d_roots, &ctx->d_tiles,
+                      &ctx->d_scan, &ctx->d_vmass, &ctx->d_vthrf, &ctx->d_chunk_k, &ctx->d_chunk_r, &ctx->d_tmprecs, &ctx->d_tmppeak, &ctx->d_lvlcnt, &ctx->d_lvlA, &ctx->d_ctalvl, &ctx->d_nodemask, &ctx->d_cobs, &ctx->d_coff, &ctx->d_cout, &ctx->d_bkeys, &ctx->d_btop, &ctx->d_blower, &ctx->d_bupper, &ctx->d_bout, &ctx->d_rootvp, &ctx->d_rootcnt, &ctx->d_tilebase, &ctx->d_ctans, &ctx->d_peakcost, &ctx->d_blkcost, &ctx->d_peakoff32, &ctx->d_bag_m, &ctx->d_bag_meta, &ctx->d_bag_cnt, &ctx->d_bag_off, &ctx->d_bag_path, &ctx->d_roots, &ctx->d_tiles, &ctx->d_block, &ctx->d_lsu, &ctx->d_lobs, &ctx->d_lflags, &ctx->d_lalive, &ctx->d_lidx, &ctx->d_lreach, &ctx->d_lfirst, &ctx->d_lhdr, &ctx->d_lkeys, &ctx->d_llast, &ctx->d_lcall,
                       &ctx->d_item_m[0], &ctx->d_item_m[1], &ctx->d_item_peak[0], &ctx->d_item_peak[1],
                       &ctx->d_item_meta[0], &ctx->d_item_meta[1], &ctx->d_item_all[0], &ctx->d_item_all[1],
                       &ctx->d_item_ind[0], &ctx->d_item_ind[1], &ctx->d_item_path[0], &ctx->d_item_path[1]};
@@ -1089,7 +1094,7 @@ namespace {
 // everything of the staging that can be queued without waiting: copies in, k_stage_f64, the summary on its way to h_misc
 int stage_f64_enqueue(sst_ctx* ctx, const sst_table* t, const double* mass, const double* thr, const int32_t* max_mods, int32_t uniform_mods,
                       int64_t P, const int32_t* ind, const uint8_t* is_mod, double precision, double tolerance, int with_memo,
-                      unsigned long long* summary_at = nullptr) {
+                      unsigned long long* summary_at = nullptr, bool inputs_on_device = false) {
     const bool summary_later = summary_at != nullptr;  // (part of a result block that is copied out as a whole)
     CK(cudaSetDevice(ctx->device));
     ctx->have_result = false;
@@ -1125,11 +1130,11 @@ int stage_f64_enqueue(sst_ctx* ctx, const sst_table* t, const double* mass, cons
     unsigned long long* const summary = summary_at ? summary_at : (unsigned long long*)ctx->d_scan.p;
     CK(cudaMemsetAsync(summary, 0, 64, ctx->stream));
     hp_mark(3);
-    if (P) {
+    if (P && !inputs_on_device) {  // (the ladder generator writes masses and thresholds into d_vmass / d_vthrf itself)
         CK(cudaMemcpyAsync(ctx->d_vmass.p, mass, (size_t)P * 8, cudaMemcpyHostToDevice, ctx->stream));
         if (thr) CK(cudaMemcpyAsync(ctx->d_vthrf.p, thr, (size_t)P * 8, cudaMemcpyHostToDevice, ctx->stream));
-        if (max_mods) CK(cudaMemcpyAsync(ctx->d_maxmods.p, max_mods, (size_t)P * 4, cudaMemcpyHostToDevice, ctx->stream));
     }
+    if (P && max_mods) CK(cudaMemcpyAsync(ctx->d_maxmods.p, max_mods, (size_t)P * 4, cudaMemcpyHostToDevice, ctx->stream));
     if (ctx->up_R != t->R || memcmp(ctx->up_ind, ind, (size_t)t->R * 4) || memcmp(ctx->up_ismod, is_mod, (size_t)t->R)) {
         memcpy(ctx->up_ind, ind, (size_t)t->R * 4);  // (the copies below read the context's arrays: the caller's may go away)
         memcpy(ctx->up_ismod, is_mod, (size_t)t->R);
@@ -1160,8 +1165,10 @@ int stage_f64_enqueue(sst_ctx* ctx, const sst_table* t, const double* mass, cons
 }
 
 int stage_f64(sst_ctx* ctx, const sst_table* t, const double* mass, const double* thr, const int32_t* max_mods, int32_t uniform_mods,
-              int64_t P, const int32_t* ind, const uint8_t* is_mod, double precision, double tolerance, int with_memo) {
-    int rc = stage_f64_enqueue(ctx, t, mass, thr, max_mods, uniform_mods, P, ind, is_mod, precision, tolerance, with_memo);
+              int64_t P, const int32_t* ind, const uint8_t* is_mod, double precision, double tolerance, int with_memo,
+              bool inputs_on_device = false) {
+    int rc = stage_f64_enqueue(ctx, t, mass, thr, max_mods, uniform_mods, P, ind, is_mod, precision, tolerance, with_memo, nullptr,
+                               inputs_on_device);
     if (rc) return rc;
     if ((rc = fetch_costs_enqueue(ctx, P))) return rc;
     CK(cudaStreamSynchronize(ctx->stream));
@@ -1976,6 +1983,136 @@ int sst_trace_ms(sst_ctx* ctx, int enable, float* out) {
     if (enable && !ctx->trace_ev[0])
         for (auto& e : ctx->trace_ev) CK(cudaEventCreate(&e));
     ctx->trace_on = enable != 0;
+    return SST_OK;
+}
+
+// ---------------- N3 / N4: ladder differences and alphabet reduction on a device-resident frame (sst_ladder.cuh) ----------------
+int sst_ladder_stage(sst_ctx* ctx, const double* su, const double* obs, const uint8_t* flags, int64_t F) {
+    CK(cudaSetDevice(ctx->device));
+    if (F < 0 || F >= ((int64_t)1 << 31)) return fail(ctx, SST_ERR_BAD_ARG, "fragment count out of range");
+    ctx->LF = -1;
+    int rc;
+    const size_t n = (size_t)(F ? F : 1);
+    if ((rc = reserve(ctx, ctx->d_lsu, n * 8))) return rc;
+    if ((rc = reserve(ctx, ctx->d_lobs, n * 8))) return rc;
+    if ((rc = reserve(ctx, ctx->d_lflags, n))) return rc;
+    if ((rc = reserve(ctx, ctx->d_lalive, n))) return rc;
+    if ((rc = reserve(ctx, ctx->d_lidx, 3 * n * 4))) return rc;
+    if ((rc = reserve(ctx, ctx->d_lreach, 2 * n * 4))) return rc;
+    if ((rc = reserve(ctx, ctx->d_lfirst, 2 * n * 8))) return rc;
+    if ((rc = reserve(ctx, ctx->d_lhdr, kLadderHdrWords * 8))) return rc;
+    if (F) {
+        for (int64_t i = 1; i < F; i++)  // the window walks sorted masses (prediction.py:68-72 sorts the frame first)
+            if (su[i] < su[i - 1]) return fail(ctx, SST_ERR_BAD_ARG, "standard-unit masses must ascend (fragment %lld)", (long long)i);
+        CK(cudaMemcpyAsync(ctx->d_lsu.p, su, (size_t)F * 8, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(ctx->d_lobs.p, obs, (size_t)F * 8, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(ctx->d_lflags.p, flags, (size_t)F, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemsetAsync(ctx->d_lalive.p, 1, (size_t)F, ctx->stream));
+    }
+    CK(cudaMemsetAsync(ctx->d_lhdr.p, 0, kLadderHdrWords * 8, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->LF = F;
+    ctx->l_calls = 0;
+    return SST_OK;
+}
+
+int sst_ladder_round(sst_ctx* ctx, const sst_table* t, double max_weight, double precision, double tolerance, int32_t max_mods,
+                     const int32_t* ind, const uint8_t* is_mod, int with_memo, uint32_t* mask_out, uint64_t* n_calls, uint64_t* n_comps) {
+    CK(cudaSetDevice(ctx->device));
+    if (ctx->LF < 0) return fail(ctx, SST_ERR_STATE, "no fragment frame staged (sst_ladder_stage)");
+    const int64_t F = ctx->LF;
+    int rc;
+    ctx->l_calls = 0;
+    ctx->have_result = false;
+    if (mask_out) mask_out[0] = mask_out[1] = mask_out[2] = mask_out[3] = 0u;
+    if (n_calls) *n_calls = 0;
+    if (n_comps) *n_comps = 0;
+    if (!F) return SST_OK;
+    LadderFrame fr{(const double*)ctx->d_lsu.p, (const double*)ctx->d_lobs.p, (const uint8_t*)ctx->d_lflags.p, (uint8_t*)ctx->d_lalive.p, F};
+    unsigned long long* hdr = (unsigned long long*)ctx->d_lhdr.p;
+    uint32_t* idx = (uint32_t*)ctx->d_lidx.p;
+    uint32_t* reach = (uint32_t*)ctx->d_lreach.p;
+    unsigned long long* first = (unsigned long long*)ctx->d_lfirst.p;
+    const unsigned gx = (unsigned)((F + 255) / 256);
+    k_ladder_sides<<<1, kPassThreads, 0, ctx->stream>>>(fr, idx, hdr);
+    k_ladder_reach<<<dim3(gx, 2), 256, 0, ctx->stream>>>(fr, idx, hdr, max_weight, reach);
+    k_ladder_scan<<<1, kPassThreads, 0, ctx->stream>>>(fr, hdr, reach, first);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(ctx->h_misc, hdr, kLadderHdrWords * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    const unsigned long long* h = (const unsigned long long*)ctx->h_misc;
+    const uint64_t calls = h[7], pairs = h[5] + h[6];
+    if (calls >= ((uint64_t)1 << 32) - 1) return fail(ctx, SST_ERR_NOMEM, "%llu ladder differences: more than one batch holds", (unsigned long long)calls);
+    if (n_calls) *n_calls = calls;
+    if (!calls) return SST_OK;
+    if ((rc = reserve(ctx, ctx->d_vmass, (size_t)calls * 8))) return rc;
+    if ((rc = reserve(ctx, ctx->d_vthrf, (size_t)calls * 8))) return rc;
+    k_ladder_fill<<<dim3(gx, 3), 256, 0, ctx->stream>>>(fr, idx, hdr, reach, first, tolerance, (double*)ctx->d_vmass.p, (double*)ctx->d_vthrf.p);
+    CK(cudaGetLastError());
+    // the calls are a staged batch now: integerise, budget modes, enumeration — nothing has left the device
+    if ((rc = stage_f64(ctx, t, (const double*)ctx->d_vmass.p, (const double*)ctx->d_vthrf.p, nullptr, max_mods, (int64_t)calls, ind, is_mod, precision,
+                        tolerance, with_memo, true)))
+        return rc;
+    uint64_t roots = 0, comps = 0;
+    for (uint64_t memo_cap = 0;;) {  // (MEMO mode: a first-visit map that turns out too small is enlarged, the staged batch run again)
+        rc = sst_explain_run(ctx, t, 0, memo_cap, &roots, &comps);
+        if (rc != SST_ERR_MEMO_FULL) break;
+        memo_cap = (memo_cap ? memo_cap : ((uint64_t)1 << 20)) * 4;
+        if (memo_cap > ((uint64_t)1 << 30)) break;
+    }
+    if (rc) return rc;
+    if (n_comps) *n_comps = comps;
+    // dedup by key + union of the rows the winners use
+    uint64_t pow2 = 1024;
+    while (pow2 < 2 * calls) pow2 <<= 1;
+    if ((rc = reserve(ctx, ctx->d_lkeys, (size_t)pow2 * 8))) return rc;
+    if ((rc = reserve(ctx, ctx->d_llast, (size_t)pow2 * 4))) return rc;
+    if ((rc = reserve(ctx, ctx->d_lcall, (size_t)calls))) return rc;
+    CK(cudaMemsetAsync(ctx->d_lkeys.p, 0, (size_t)pow2 * 8, ctx->stream));
+    CK(cudaMemsetAsync(ctx->d_llast.p, 0, (size_t)pow2 * 4, ctx->stream));
+    KeyTable kt{(unsigned long long*)ctx->d_lkeys.p, (unsigned int*)ctx->d_llast.p, (uint32_t)(pow2 - 1)};
+    const unsigned gc = (unsigned)((calls + 255) / 256);
+    k_ladder_enter<<<gc, 256, 0, ctx->stream>>>((const double*)ctx->d_vmass.p, (const unsigned long long*)ctx->d_peakoff.p, calls, pairs, kt,
+                                                (uint8_t*)ctx->d_lcall.p);
+    k_ladder_union<<<gc, 256, 0, ctx->stream>>>((const double*)ctx->d_vmass.p, (const unsigned long long*)ctx->d_peakoff.p,
+                                                (const unsigned long long*)ctx->d_recs.p, ctx->rec_width / 8, calls, kt, (uint8_t*)ctx->d_lcall.p, hdr);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(ctx->h_misc, hdr, kLadderHdrWords * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (mask_out) memcpy(mask_out, h + 8, 16);
+    ctx->l_calls = calls;
+    return SST_OK;
+}
+
+int sst_ladder_revalidate(sst_ctx* ctx, const sst_table* t, double precision, double tolerance, int64_t* n_alive) {
+    CK(cudaSetDevice(ctx->device));
+    if (ctx->LF < 0) return fail(ctx, SST_ERR_STATE, "no fragment frame staged (sst_ladder_stage)");
+    const int64_t F = ctx->LF;
+    if (n_alive) *n_alive = 0;
+    if (!F) return SST_OK;
+    LadderFrame fr{(const double*)ctx->d_lsu.p, (const double*)ctx->d_lobs.p, (const uint8_t*)ctx->d_lflags.p, (uint8_t*)ctx->d_lalive.p, F};
+    unsigned long long* hdr = (unsigned long long*)ctx->d_lhdr.p;
+    CK(cudaMemsetAsync(hdr + 12, 0, 16, ctx->stream));
+    k_ladder_revalidate<<<(unsigned)((F + 255) / 256), 256, 0, ctx->stream>>>(view_of(t), fr, precision, tolerance, hdr);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(ctx->h_misc, hdr, kLadderHdrWords * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    const unsigned long long* h = (const unsigned long long*)ctx->h_misc;
+    if (h[13]) return fail(ctx, SST_ERR_OUT_OF_TABLE, "A value of the mass window is not in the DP table. Extend its size if you want to compute larger masses.");
+    if (n_alive) *n_alive = (int64_t)h[12];
+    return SST_OK;
+}
+
+int sst_ladder_fetch(sst_ctx* ctx, uint8_t* alive_out, double* key_out, double* thr_out, uint8_t* call_flags_out) {
+    CK(cudaSetDevice(ctx->device));
+    if (ctx->LF < 0) return fail(ctx, SST_ERR_STATE, "no fragment frame staged (sst_ladder_stage)");
+    if (alive_out && ctx->LF) CK(cudaMemcpyAsync(alive_out, ctx->d_lalive.p, (size_t)ctx->LF, cudaMemcpyDeviceToHost, ctx->stream));
+    if (ctx->l_calls) {
+        if (key_out) CK(cudaMemcpyAsync(key_out, ctx->d_vmass.p, (size_t)ctx->l_calls * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        if (thr_out) CK(cudaMemcpyAsync(thr_out, ctx->d_vthrf.p, (size_t)ctx->l_calls * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        if (call_flags_out) CK(cudaMemcpyAsync(call_flags_out, ctx->d_lcall.p, (size_t)ctx->l_calls, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    CK(cudaStreamSynchronize(ctx->stream));
     return SST_OK;
 }
 

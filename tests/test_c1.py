@@ -158,6 +158,83 @@ def test_c1_fixed_point_matches_the_reference(name):
         assert (None if v is None else sorted(list(e.nucleosides) for e in v)) == want[k], k
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["acgu", "mods12"])
+def test_c1_device_ladder_first_round_is_the_reference_window(name):
+    """N3 on the device: the generated calls (differences, l1 thresholds; START pairs, END pairs, singletons) are the
+    reference's first-round calls bit for bit and in order, and the surviving dict entries are the reference's."""
+    case = CASES[name]
+    dp = _dp(case)
+    cl = case["classified"]
+    lad = AR.DeviceLadder(cl["standard_unit_mass"], cl["observed_mass"], cl["breakage"], cl["is_singleton"], dp, _frame_for(set(case["alphabet"])))
+    names = lad.round()
+    keys, thr, fl = lad.calls()
+    first_round = [c for c in case["explain_calls"] if c[3] == len(case["start_weights"])]
+    assert [float(k) for k in keys] == [c[0] for c in first_round]
+    assert [float(t) for t in thr] == [c[1] for c in first_round]
+    # the host generator + batched enumeration build the same dict (keys, order of first insertion, surviving values)
+    want = AR.collect_diff_explanations(cl["standard_unit_mass"], cl["observed_mass"], cl["breakage"], cl["is_singleton"], dp, _frame_for(set(case["alphabet"])))
+    lad.round()
+    got = lad.explanations()
+    assert list(got) == list(want)
+    for k in want:
+        assert (None if got[k] is None else sorted(e.nucleosides for e in got[k])) == (None if want[k] is None else sorted(e.nucleosides for e in want[k])), k
+    assert names == AR.observed_nucleotides(want)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["acgu", "mods12"])
+def test_c1_device_fixed_point_matches_the_reference(name):
+    """N4 with the frame resident on the device: the reference's fixed point, surviving fragments and final explanations."""
+    case = CASES[name]
+    dp = _dp(case)
+    cl = case["classified"]
+    alive, expl = AR.filter_by_explanation_device(cl["standard_unit_mass"], cl["observed_mass"], cl["breakage"], cl["is_singleton"], dp,
+                                                  _frame_for(set(case["alphabet"])))
+    assert [int(i) for i in alive] == case["final_orig_index"]
+    assert [m.mass for m in dp.masses] == case["final_weights"]
+    assert [list(m.names) for m in dp.masses] == case["final_names"]
+    want = {k: v for k, v in case["explanations"]}
+    assert set(expl) == set(want)
+    for k, v in expl.items():
+        assert (None if v is None else sorted(list(e.nucleosides) for e in v)) == want[k], k
+
+
+@pytest.mark.gpu
+def test_device_ladder_random_frames_equal_the_host_generator():
+    """Dense random ladders with repeated masses (equal keys on both sides and among the singletons), fragments that die
+    in a round, empty sides: pairs, thresholds, dict and row mask equal the host generator's, round after round."""
+    rng = np.random.default_rng(5)
+    case = CASES["mods12"]
+    frame = _frame_for(set(case["alphabet"]))
+    w = [x for x in case["start_weights"] if x]
+    for trial in range(6):
+        dp = _dp(case)
+        n = [0, 1, 2, 40, 300, 1500][trial]
+        ladders = [np.cumsum(rng.choice(w, size=25)) * 1e-3 for _ in range(n // 25 + 1)]  # (25 nucleotides stay inside the table)
+        su = np.concatenate(ladders)[:n]
+        su = np.sort(np.concatenate([su, su[: n // 3]]))  # a third of the masses twice
+        obs = su + rng.choice([0.0, 18.0105, 97.9769], size=len(su))
+        brk = [["START_c/y", "c/y_END", "START_END", "c/y_c/y"][k] for k in rng.integers(0, 4, size=len(su))]
+        single = (rng.random(len(su)) < 0.5) & (np.arange(len(su)) < 12)  # singletons are light fragments (heavy ones leave the table)
+        lad = AR.DeviceLadder(su, obs, brk, single, dp, frame)
+        names = lad.round()
+        want = AR.collect_diff_explanations(su, obs, brk, single, dp, frame)
+        got = lad.explanations()
+        assert list(got) == list(want), trial
+        for k in want:
+            assert (None if got[k] is None else sorted(e.nucleosides for e in got[k])) == (None if want[k] is None else sorted(e.nucleosides for e in want[k])), (trial, k)
+        assert names == AR.observed_nucleotides(want), trial
+        if len(su):
+            keep = AR.reduce_alphabet(names, su, obs, dp)  # host path: rebuilds the table, validity batch
+            assert lad.revalidate() == int(keep.sum())
+            assert np.array_equal(lad.alive(), keep), trial
+            want2 = AR.collect_diff_explanations(su[keep], obs[keep], [b for b, k in zip(brk, keep) if k], single[keep], dp, frame)
+            lad.round()
+            got2 = lad.explanations()
+            assert list(got2) == list(want2), trial
+
+
 def _reference_checkout():
     for cand in (pathlib.Path("/root/reference"), pathlib.Path(__file__).resolve().parents[1] / "baseline" / "_ref"):
         if (cand / "spectrseqtools" / "prediction.py").is_file():
