@@ -552,6 +552,32 @@ def main():
         scalar = {"explain_mass_with_table": spread(te), "is_valid_mass": spread(tv), "calls": int(k),
                   "note": "wall time of one reference-shaped call (a batch of one), names included"}
 
+    # ---- rows N3 / N4 on the device: one round of the explanation-based alphabet reduction over a fragment frame that
+    # stays on the device (pairs + thresholds generated, enumerated, deduplicated by key, rows united, fragments
+    # re-validated); wall time of the calls a Predictor.filter_by_explanation round makes
+    ladder = None
+    if rank == 0 and not strong:
+        from spectrseqtools_b200 import alphabet_reduction as AR
+
+        ladder = {}
+        for tag, n_oligos in (("one_spectrum", 3), ("merged_100_oligos", 100)):
+            su, obs_f, brk, single = S.make_frame(n_oligos, names=None if len(wl.alphabet) == 104 else wl.alphabet)
+            lad = AR.DeviceLadder(su, obs_f, brk, single, dp, S.alphabet_frame(None if len(wl.alphabet) == 104 else wl.alphabet))
+            lad.round(); lad.revalidate()
+            tr, tv = [], []
+            for _ in range(20):
+                t1 = time.perf_counter()
+                lad.round()
+                t2 = time.perf_counter()
+                lad.revalidate()
+                t3 = time.perf_counter()
+                tr.append((t2 - t1) * 1e6)
+                tv.append((t3 - t2) * 1e6)
+            ladder[tag] = {"fragments": int(len(su)), "calls": int(lad.n_calls), "compositions": int(lad.n_compositions),
+                           "round_us": spread(tr), "revalidate_us": spread(tv)}
+        ladder["note"] = ("sst_ladder_round / sst_ladder_revalidate: wall time per call; per round the host receives a 128-bit row mask "
+                          "and two counters (the table rebuild between them is table_build)")
+
     # ---- roofline of the enumeration pass (K2a + K2b family) from the live per-kernel event times
     win_words = ((2 * e_thr + 1 + 31) // 32 + 1).sum()
     comp_len = int((batch.records > 0).sum()) if batch.records is not None and batch.records.size else 0
@@ -624,6 +650,7 @@ def main():
                 "how": "public API (classify_observed + explain_masses, wait=False), pinned host inputs, results in pinned host "
                        "arrays; three batches in flight on three context slots" + ("; every rank's block gathered on rank 0 through POSIX shared memory inside the timed region" if gather is not None else "")},
         "scalar_latency_us": scalar,
+        "ladder_round": ladder,
         "gpu_launches": int(launches),
         "roofline": roofline, "kernels": kernels, "pass_phase_us": phase_us, "large_batch": large, "table_build": table_info,
     }

@@ -41,6 +41,8 @@ class Workload:
     max_modifications: int
     observed: Optional[np.ndarray] = None   # float64 observed peak masses, n_peaks (valid_* = observed x breakage)
     breakage: Optional[dict] = None         # breakage weight (integer mDa, ascending) -> labels
+    observed_decoy: Optional[np.ndarray] = None   # bool, n_peaks: the peak is an "a-B" decoy (C4)
+    explain_decoy: Optional[np.ndarray] = None    # bool per explanation call: one of its rungs is a decoy
 
 
 def alphabet_frame(names: Optional[List[str]]):
@@ -65,6 +67,36 @@ def _rows(names: Optional[List[str]]):
     reps = [reps[i] for i in order]
     is_mod = np.array([r not in M.UNMODIFIED_BASES for r in reps])
     return ims, reps, is_mod
+
+
+NEUTRAL_BASE_MASSES = np.array([135.05450, 111.04326, 151.04941, 112.02728])  # adenine, cytosine, guanine, uracil
+
+
+def make_frame(n_oligos: int, length: int = 25, seed: int = 7, names=None, miss_p: float = 0.2, ppm: float = 10e-6):
+    """A classified-fragment frame for the ladder rows (N3 / N4): both ladders of ``n_oligos`` random oligos, some rungs
+    missing, sorted by standard-unit mass as prediction.py:68-72 leaves them.  -> (su, observed, breakage labels,
+    is_singleton): the columns ``Predictor.filter_by_explanation`` reads."""
+    rng = np.random.default_rng(seed)
+    ims, reps, is_mod = _rows(names)
+    plain, mods = np.nonzero(~is_mod)[0], np.nonzero(is_mod)[0]
+    breakage = M.build_breakage_dict(555.1294, 455.1491)
+    label_of = {v: k for k, vs in breakage.items() for v in vs}
+    off5, off3 = label_of["START_c/y"] * 1e-3, label_of["c/y_END"] * 1e-3
+    su_all, obs_all, brk, single = [], [], [], []
+    for _ in range(n_oligos):
+        pick = np.where(rng.random(length) < 0.15, rng.choice(mods, size=length), rng.choice(plain, size=length))
+        w = ims[pick] * 1e-3
+        for ladder, (off, tag) in enumerate(((off5, "START_c/y"), (off3, "c/y_END"))):
+            su = np.cumsum(w if ladder == 0 else w[::-1])
+            obs = (su + off) * (1 + rng.uniform(-ppm / 2, ppm / 2, size=length))
+            kept = np.nonzero(rng.random(length) >= miss_p)[0]
+            su_all.append((obs - off)[kept])
+            obs_all.append(obs[kept])
+            brk += [tag] * len(kept)
+            single += [bool(k == 0) for k in kept]
+    su, obs = np.concatenate(su_all), np.concatenate(obs_all)
+    order = np.argsort(su, kind="stable")
+    return su[order], obs[order], [brk[i] for i in order], np.array(single, dtype=bool)[order]
 
 
 def make_workload(config: str, n_peaks: int = 100_000, seed_offset: int = 0) -> Workload:
@@ -100,7 +132,7 @@ def make_workload(config: str, n_peaks: int = 100_000, seed_offset: int = 0) -> 
         off5_alt = label_of["START_a/w"] * 1e-3
         off3_alt = label_of["a/w_END"] * 1e-3
 
-    v_mass, v_thr, e_mass, e_thr, e_nt, all_obs = [], [], [], [], [], []
+    v_mass, v_thr, e_mass, e_thr, e_nt, all_obs, all_decoy, e_decoy = [], [], [], [], [], [], [], []
     peaks = 0
     longest = 0
     while peaks < n_peaks:
@@ -119,7 +151,16 @@ def make_workload(config: str, n_peaks: int = 100_000, seed_offset: int = 0) -> 
             if full_dict and rng.random() < 0.5:
                 off = (off5_alt if ladder == 0 else off3_alt)
             obs = (su + off) * (1 + rng.uniform(-ppm / 2, ppm / 2, size=L))
+            if full_dict and ladder == 0 and off == off5_alt:
+                # C4's "a-B" ions: the reference does not model them — an a-type fragment that has lost its
+                # last nucleobase, i.e. the a/w offset minus a neutral base mass.  They are decoys: mostly invalid under
+                # every breakage offset, and their differences to the neighbouring rungs explain nothing.
+                decoy = rng.random(L) < 0.08
+                obs = np.where(decoy, obs - rng.choice(NEUTRAL_BASE_MASSES, size=L), obs)
+            else:
+                decoy = np.zeros(L, dtype=bool)
             all_obs.append(obs)
+            all_decoy.append(decoy)
             # validity: every peak against every breakage offset
             cand = obs[:, None] - offsets[None, :] * 1e-3
             v_mass.append(cand.ravel())
@@ -131,6 +172,7 @@ def make_workload(config: str, n_peaks: int = 100_000, seed_offset: int = 0) -> 
                 e_mass.append(np.array([su_obs[0]]))
                 e_thr.append(np.array([ppm * obs[0]]))
                 e_nt.append(np.array([1]))
+                e_decoy.append(decoy[:1])
             if len(kept) > 1:
                 gap = np.diff(kept)
                 ok = gap <= max_gap
@@ -138,6 +180,7 @@ def make_workload(config: str, n_peaks: int = 100_000, seed_offset: int = 0) -> 
                 e_mass.append(su_obs[b] - su_obs[a])
                 e_thr.append(ppm * (obs[a] + obs[b]))
                 e_nt.append(gap[ok])
+                e_decoy.append(decoy[a] | decoy[b])
             peaks += L
     min_w = float(ims[0]) * 1e-3
     max_len = int(longest / min_w)
@@ -147,12 +190,14 @@ def make_workload(config: str, n_peaks: int = 100_000, seed_offset: int = 0) -> 
                   n_peaks=peaks, valid_mass=cat(v_mass, np.float64), valid_thr=cat(v_thr, np.float64),
                   explain_mass=cat(e_mass, np.float64), explain_thr=cat(e_thr, np.float64),
                   explain_nt=cat(e_nt, np.int64), max_modifications=round(0.5 * max_len),
-                  observed=cat(all_obs, np.float64), breakage={int(k): breakage[int(k)] for k in offsets})
+                  observed=cat(all_obs, np.float64), breakage={int(k): breakage[int(k)] for k in offsets},
+                  observed_decoy=cat(all_decoy, bool), explain_decoy=cat(e_decoy, bool))
     # trim to exactly n_peaks peaks (validity arrays are peak-major)
     if peaks > n_peaks:
         wl.valid_mass = wl.valid_mass[: n_peaks * n_off]
         wl.valid_thr = wl.valid_thr[: n_peaks * n_off]
         wl.observed = wl.observed[:n_peaks]
+        wl.observed_decoy = wl.observed_decoy[:n_peaks]
         wl.n_peaks = n_peaks
     return wl
 
@@ -166,4 +211,6 @@ def shard(wl: Workload, rank: int, world: int) -> Workload:
                     max_seq_length=wl.max_seq_length, n_peaks=len(vm), valid_mass=vm.ravel(), valid_thr=vt.ravel(),
                     explain_mass=wl.explain_mass[rank::world], explain_thr=wl.explain_thr[rank::world],
                     explain_nt=wl.explain_nt[rank::world], max_modifications=wl.max_modifications,
-                    observed=None if wl.observed is None else wl.observed[rank::world], breakage=wl.breakage)
+                    observed=None if wl.observed is None else wl.observed[rank::world], breakage=wl.breakage,
+                    observed_decoy=None if wl.observed_decoy is None else wl.observed_decoy[rank::world],
+                    explain_decoy=None if wl.explain_decoy is None else wl.explain_decoy[rank::world])
