@@ -511,13 +511,13 @@ def main():
             out = finish(pend.pop(0), seq0 + i)
         return out
 
-    e2e_loop(2 * E2E_DEPTH, 1)
+    e2e_loop(2 * E2E_DEPTH, 1)  # (the gather numbers its steps consecutively: the timed loop continues at 2 * E2E_DEPTH + 1)
     if dist is not None:
         dist.barrier()
     sampler.period = 0.05
     sampler.active.set()
     t0 = time.perf_counter()
-    valid, batch, gathered = e2e_loop(args.steps, 100)
+    valid, batch, gathered = e2e_loop(args.steps, 2 * E2E_DEPTH + 1)
     e2e_s = time.perf_counter() - t0
     sampler.active.clear()
     sampler.stop()

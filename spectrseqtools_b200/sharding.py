@@ -177,8 +177,9 @@ def partition_contiguous(masses, thresholds, world: int, dp_table) -> List[int]:
 class ShmGather:
     """Host-side gather on ONE box through POSIX shared memory: every rank owns a segment, writes its arrays plus a
     small header into it, and rank 0 maps all segments and reads them in place (views, no pickling, no socket).
-    ``publish(seq, arrays)`` then ``collect(seq)`` on rank 0; a segment is reused for the next step once rank 0 has
-    acknowledged ``seq`` (``publish`` of the step after next waits for it: two steps may be in flight)."""
+    ``publish(seq, arrays)`` then ``collect(seq)`` on rank 0, steps numbered consecutively from 1.  A segment has two
+    halves that alternate; rank 0 hands out VIEWS, so a half is written again only after rank 0 has released the step
+    that used it (``collect(seq + 1)`` releases ``seq``): a publisher runs at most one step ahead of the reader."""
 
     HEADER = 4096
 
@@ -214,14 +215,28 @@ class ShmGather:
         _shm, hdr, data = self._peers[r]
         return hdr, data
 
+    @staticmethod
+    def _spin(waiting, what: str, timeout: float = 60.0) -> None:
+        """Busy-wait while ``waiting()``; a peer that never arrives is an error, not a hang."""
+        import time
+
+        n, deadline = 0, None
+        while waiting():
+            n += 1
+            if n & 0xFFFF == 0:
+                now = time.monotonic()
+                deadline = deadline or now + timeout
+                if now > deadline:
+                    raise TimeoutError(f"ShmGather: {what} within {timeout:.0f} s")
+
     def publish(self, seq: int, arrays: Sequence[np.ndarray]) -> None:
         """header: [0] seq (written last), [1] acknowledged seq (written by rank 0), [2] number of arrays, then per
         array (dtype code, ndim, shape0, shape1, byte offset)."""
         hdr, data = self._hdr, self._data
         half = len(data) // 2
         base = (seq & 1) * half  # two halves alternate, so the step in flight is not overwritten
-        while seq >= 2 and hdr[1] < seq - 2 and self.rank != 0:  # the half is free once rank 0 has read step seq - 2
-            pass
+        # the half is free once rank 0 has read step seq - 2 (steps are numbered consecutively from 1)
+        self._spin(lambda: seq >= 3 and hdr[1] < seq - 2 and self.rank != 0, f"rank 0 never acknowledged step {seq - 2}")
         at = base
         slot = 8 + (seq & 1) * 128
         hdr[slot] = len(arrays)
@@ -236,13 +251,21 @@ class ShmGather:
             at += (nb + 63) & ~63
         hdr[0] = seq
 
+    def release(self, seq: int) -> None:
+        """Rank 0 is done with the views of every step up to ``seq``: their segment halves may be written again."""
+        for r in range(self.world):
+            hdr = self._peer(r)[0]
+            if hdr[1] < seq:
+                hdr[1] = seq
+
     def collect(self, seq: int):
-        """Rank 0: the arrays of every rank for step ``seq`` (views of the shared segments), in rank order."""
+        """Rank 0: the arrays of every rank for step ``seq`` (views of the shared segments), in rank order.  The views
+        stay valid until the next ``collect`` (which releases step ``seq - 1``) or an explicit ``release``."""
+        self.release(seq - 1)
         out = []
         for r in range(self.world):
             hdr, data = self._peer(r)
-            while hdr[0] < seq:
-                pass
+            self._spin(lambda: hdr[0] < seq, f"rank {r} never published step {seq}")
             slot = 8 + (seq & 1) * 128
             arrs = []
             for k in range(int(hdr[slot])):
@@ -252,8 +275,6 @@ class ShmGather:
                 a = data[at:at + n * dt.itemsize].view(dt)
                 arrs.append(a.reshape(s0, s1) if ndim > 1 else a)
             out.append(arrs)
-        for r in range(self.world):
-            self._peer(r)[0][1] = seq
         return out
 
     def close(self) -> None:

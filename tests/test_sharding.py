@@ -204,3 +204,50 @@ def test_sharded_device_path_equals_single_rank(world):
 
 if __name__ == "__main__":
     sys.exit(0)
+
+
+def _shm_worker(rank, world, tag, steps, q):
+    """One rank of the shared-memory gather: publishes `steps` consecutive steps, rank 0 collects and checks them."""
+    import numpy as np
+
+    from spectrseqtools_b200 import sharding
+
+    g = sharding.ShmGather(tag, rank, world, capacity=1 << 20)
+    try:
+        ok = True
+        for seq in range(1, steps + 1):
+            a = np.full(100 + rank, seq * 10 + rank, dtype=np.uint32)
+            b = np.arange(6, dtype=np.uint8).reshape(3, 2) + seq + rank
+            g.publish(seq, [a, b])
+            if rank == 0:
+                got = g.collect(seq)
+                for r, (ga, gb) in enumerate(got):
+                    ok &= ga.shape == (100 + r,) and bool((ga == seq * 10 + r).all())
+                    ok &= gb.shape == (3, 2) and bool((gb == (np.arange(6, dtype=np.uint8).reshape(3, 2) + seq + r)).all())
+        if rank == 0:
+            g.release(steps)
+            q.put(ok)
+        else:  # stay until rank 0 has read the last step
+            sharding.ShmGather._spin(lambda: g._hdr[1] < steps, "last acknowledgement", timeout=30.0)
+            q.put(True)
+    finally:
+        g.close()
+
+
+def test_shm_gather_many_consecutive_steps():
+    """The gather the strong-scaling bench uses: consecutive step numbers, a segment half reused every second step, the
+    publisher waits for the release of step seq - 2 (a gap in the numbering used to hang it for ever, and an
+    acknowledgement sent before the views were read let the publisher overwrite them)."""
+    import multiprocessing as mp
+    import os
+
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    tag = f"sstb200_test_{os.getpid()}"
+    procs = [ctx.Process(target=_shm_worker, args=(r, 2, tag, 40, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=30)
+    assert all(res)
