@@ -66,6 +66,10 @@ const char* sst_last_error(const sst_ctx* ctx);
 int sst_device_info(sst_ctx* ctx, int* sm_count, int* cc_major, int* cc_minor, uint64_t* free_bytes, uint64_t* total_bytes);
 void* sst_host_alloc(sst_ctx* ctx, size_t bytes); /* pinned host memory, NULL on failure */
 void sst_host_free(sst_ctx* ctx, void* p);
+/* page-lock / release memory the caller owns (e.g. a POSIX shared-memory segment: results copied there are visible to
+ * the other processes of the box without a further copy — the host-side gather of SURVEY §8e) */
+int sst_host_register(sst_ctx* ctx, void* p, size_t bytes);
+int sst_host_unregister(sst_ctx* ctx, void* p);
 /* CUDA-event stopwatch on the context's stream (what bench.py times with) */
 int sst_timer_start(sst_ctx* ctx);
 int sst_timer_stop(sst_ctx* ctx, float* ms);

@@ -38,7 +38,7 @@ EXPORTS = [
     "sst_valid_fetch", "sst_valid_stage_f64", "sst_explain", "sst_explain_stage", "sst_explain_stage_f64", "sst_explain_stage_f64_uniform", "sst_explain_rec_width", "sst_explain_phase_ns",
     "sst_explain_run", "sst_explain_fetch", "sst_classify", "sst_classify_stage", "sst_classify_run", "sst_classify_fetch", "sst_classify_launch", "sst_classify_async", "sst_classify_wait", "sst_length_bounds",
     "sst_set_pass", "sst_last_pass", "sst_explain_cta_ns", "sst_explain_submit_f64", "sst_explain_collect", "sst_classify_async_packed", "sst_host_profile", "sst_trace_ms", "sst_explain_block_layout", "sst_explain_d2h_bytes",
-    "sst_ladder_stage", "sst_ladder_round", "sst_ladder_revalidate", "sst_ladder_fetch",
+    "sst_ladder_stage", "sst_ladder_round", "sst_ladder_revalidate", "sst_ladder_fetch", "sst_host_register", "sst_host_unregister",
 ]
 
 
@@ -113,6 +113,8 @@ def load() -> C.CDLL:
             "sst_explain_collect": (C.c_int, [vp, vp, C.POINTER(C.c_uint64), C.POINTER(C.c_int)]),
             "sst_host_profile": (C.c_int, [C.c_int, u64p, u64p]),
             "sst_trace_ms": (C.c_int, [vp, C.c_int, fp]),
+            "sst_host_register": (C.c_int, [vp, vp, C.c_size_t]),
+            "sst_host_unregister": (C.c_int, [vp, vp]),
             "sst_ladder_stage": (C.c_int, [vp, fp, fp, u8p, C.c_int64]),
             "sst_ladder_round": (C.c_int, [vp, vp, C.c_double, C.c_double, C.c_double, C.c_int32, i32p, u8p, C.c_int, u32p,
                                            C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
@@ -320,7 +322,7 @@ class Context:
         self._check(self._lib.sst_classify_launch(self._h, table._h, float(precision), float(tolerance)))
 
     def classify_async(self, table: "DeviceTable", observed: np.ndarray, offsets: np.ndarray, precision: float, tolerance: float,
-                       packed: bool = False):
+                       packed: bool = False, out: Optional[np.ndarray] = None):
         """Whole classification on the side stream, no waiting; returns the pinned uint8[B, F] buffer the flags will
         land in — valid after ``classify_wait()`` and until the next classification on this context.  ``packed``: two
         flags per byte, uint8[B, ceil(F / 2)] (fragment f in the low nibble when f is even)."""
@@ -329,7 +331,9 @@ class Context:
         B, F = len(b), len(o)
         if packed:
             half = (F + 1) // 2
-            buf = self._pinned("classify", B * half)[: B * half]
+            buf = self._pinned("classify", B * half)[: B * half] if out is None else out[: B * half]
+            if buf.size < B * half:
+                raise ValueError("out is too small for the packed flags")
             self._check(self._lib.sst_classify_async_packed(self._h, table._h, _p(o), F, _p(b), B, float(precision), float(tolerance), _p(buf)))
             return buf.reshape(B, half)
         buf = self._pinned("classify", B * F)[: B * F]
@@ -375,9 +379,17 @@ class Context:
         self._last = (int(nr.value), int(nc.value), int(self._lib.sst_explain_rec_width(self._h)))
         return int(nr.value), int(nc.value)
 
-    def explain_submit_f64(self, table: "DeviceTable", mass, thr, max_mods: int, ind, is_mod, precision, tolerance, with_memo):
+    def host_register(self, arr: np.ndarray):
+        """Page-lock a caller-owned buffer (sst_host_register); ``host_unregister`` before it is freed."""
+        self._check(self._lib.sst_host_register(self._h, _p(arr), arr.nbytes))
+
+    def host_unregister(self, arr: np.ndarray):
+        self._check(self._lib.sst_host_unregister(self._h, _p(arr)))
+
+    def explain_submit_f64(self, table: "DeviceTable", mass, thr, max_mods: int, ind, is_mod, precision, tolerance, with_memo, out_block=None):
         """Queue a whole enumeration call (inputs in, staging, pass, results out) without waiting; ``explain_collect``
-        completes it.  Results land in this context's pinned buffers."""
+        completes it.  Results land in this context's pinned result block, or in ``out_block`` (uint8, page-locked by
+        the caller, e.g. a registered shared-memory region)."""
         m = _arr(mass, np.float64)
         h = None if thr is None else _arr(thr, np.float64)
         iv, im = _arr(ind, np.int32), _arr(is_mod, np.uint8)
@@ -388,7 +400,12 @@ class Context:
         P = len(m)
         so, oo, ro = C.c_uint64(), C.c_uint64(), C.c_uint64()
         self._check(self._lib.sst_explain_block_layout(P, C.byref(so), C.byref(oo), C.byref(ro)))
-        block = self._pinned("block", ro.value + max(self.__dict__.get("_recs_hint", 0), 64 * P, 1 << 20))  # one block: one copy brings it back
+        if out_block is not None:
+            block = out_block
+            if block.dtype != np.uint8 or block.ndim != 1 or block.size <= ro.value:
+                raise ValueError("out_block must be a flat uint8 array larger than the block's fixed part")
+        else:
+            block = self._pinned("block", ro.value + max(self.__dict__.get("_recs_hint", 0), 64 * P, 1 << 20))  # one block: one copy brings it back
         status = block[so.value: so.value + P]
         off = block[oo.value: oo.value + 4 * (P + 1)].view(np.uint32)
         recs = block[ro.value:]

@@ -644,6 +644,20 @@ void* sst_host_alloc(sst_ctx* ctx, size_t bytes) {
     return p;
 }
 
+// page-lock memory the caller owns (a POSIX shared-memory segment: results that land there are gathered without a copy)
+int sst_host_register(sst_ctx* ctx, void* p, size_t bytes) {
+    CK(cudaSetDevice(ctx->device));
+    if (!p || !bytes) return fail(ctx, SST_ERR_BAD_ARG, "nothing to register");
+    CK(cudaHostRegister(p, bytes, cudaHostRegisterPortable));
+    return SST_OK;
+}
+
+int sst_host_unregister(sst_ctx* ctx, void* p) {
+    CK(cudaSetDevice(ctx->device));
+    if (p) CK(cudaHostUnregister(p));
+    return SST_OK;
+}
+
 void sst_host_free(sst_ctx* ctx, void* p) {
     (void)ctx;
     if (p) cudaFreeHost(p);

@@ -74,13 +74,14 @@ _OFFSET_CACHE: dict = {}  # the offsets / labels of the last breakage dictionary
 
 
 def classify_observed(observed: Sequence[float], dp_table: DynamicProgrammingTable, breakage_dict: Dict[int, List[str]],
-                      copy: bool = True, wait: bool = True, slot: int = 0) -> ClassifiedMasses:
+                      copy: bool = True, wait: bool = True, slot: int = 0, out=None) -> ClassifiedMasses:
     """Validity + singleton flags of every observed mass under every breakage offset: one device pass.
 
     ``wait=False`` queues the whole call (copies and kernel) on the context's side stream and returns at once; the
     flags are waited for on first access (``.flags`` / ``.wait()``), so an ``explain_masses`` call issued in between
     overlaps it; the flags then cross the bus two per byte.  ``copy=False`` hands out the context's pinned buffer
-    (valid until the next classification on the same ``slot``, see ``_cabi.context``)."""
+    (valid until the next classification on the same ``slot``, see ``_cabi.context``).  ``out`` (with ``wait=False``): a
+    page-locked uint8 buffer of the caller's for the packed flags (see ``explain_masses(out_block=...)``)."""
     observed = np.ascontiguousarray(observed, dtype=np.float64).reshape(-1)
     # (NaN / infinite masses: the library raises what upstream's int(round(x)) inside is_valid_mass raises)
     key = (id(breakage_dict), len(breakage_dict), dp_table.precision)
@@ -95,7 +96,7 @@ def classify_observed(observed: Sequence[float], dp_table: DynamicProgrammingTab
     dev = dp_table.device_table()
     ctx = dev.ctx if slot == 0 else _cabi.context(dev.ctx.device, slot)
     if not wait:
-        flags = ctx.classify_async(dev, observed, offsets, dp_table.precision, dp_table.tolerance, packed=True)
+        flags = ctx.classify_async(dev, observed, offsets, dp_table.precision, dp_table.tolerance, packed=True, out=out)
         return ClassifiedMasses(observed, weights, labels, dp_table.precision, flags, pending=ctx, packed=True)
     ctx.classify_stage(observed, offsets)
     ctx.classify_run(dev, dp_table.precision, dp_table.tolerance)

@@ -200,7 +200,7 @@ class PendingExplanations:
 
 def explain_masses(masses: Sequence[float], dp_table: DynamicProgrammingTable, max_modifications=np.inf,
                    thresholds=None, with_memo: bool = True, compression_rate: Optional[int] = None,
-                   fetch_records: bool = True, copy: bool = True, wait: bool = True, slot: int = 0):
+                   fetch_records: bool = True, copy: bool = True, wait: bool = True, slot: int = 0, out_block=None):
     """Batched ``explain_mass_with_table``: one device pass for all masses.
 
     ``max_modifications`` and ``thresholds`` may be scalars or per-mass sequences (``thresholds`` None, or a
@@ -212,7 +212,9 @@ def explain_masses(masses: Sequence[float], dp_table: DynamicProgrammingTable, m
     ``wait=False`` (one modification budget for the batch) queues the whole call — inputs in, staging, pass, results
     out — and returns a ``PendingExplanations`` at once; with a different ``slot`` per call two batches are in flight
     on the device, the copies of one under the kernels of the other (``masses`` / ``thresholds`` must not be modified
-    until ``wait()`` returns).
+    until ``wait()`` returns).  ``out_block``: a page-locked uint8 buffer of the caller's (``_cabi.Context.host_register``)
+    the result block is copied into instead of the context's own — e.g. a region of a shared-memory segment, so that the
+    other processes of the box see the result without a further copy (``sharding.ShmGather``).
     """
     if compression_rate is not None and compression_rate != dp_table.compression_per_cell:
         raise ValueError("compression_rate must match the table's compression_per_cell")
@@ -229,7 +231,7 @@ def explain_masses(masses: Sequence[float], dp_table: DynamicProgrammingTable, m
     if not wait:
         if np.ndim(max_modifications) != 0:
             raise ValueError("wait=False takes one modification budget for the whole batch")
-        ctx.explain_submit_f64(dev, masses, thr, max_mods, ind, is_mod, dp_table.precision, dp_table.tolerance, with_memo)
+        ctx.explain_submit_f64(dev, masses, thr, max_mods, ind, is_mod, dp_table.precision, dp_table.tolerance, with_memo, out_block=out_block)
         return PendingExplanations(ctx, dp_table, weights, copy)
     ctx.explain_stage_f64(dev, masses, thr, max_mods, ind, is_mod, dp_table.precision, dp_table.tolerance, with_memo)
     return _run_and_fetch(dp_table, dev, weights, fetch_records, copy, ctx)

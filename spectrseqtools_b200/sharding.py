@@ -175,24 +175,38 @@ def partition_contiguous(masses, thresholds, world: int, dp_table) -> List[int]:
 
 
 class ShmGather:
-    """Host-side gather on ONE box through POSIX shared memory: every rank owns a segment, writes its arrays plus a
-    small header into it, and rank 0 maps all segments and reads them in place (views, no pickling, no socket).
-    ``publish(seq, arrays)`` then ``collect(seq)`` on rank 0, steps numbered consecutively from 1.  A segment has two
-    halves that alternate; rank 0 hands out VIEWS, so a half is written again only after rank 0 has released the step
-    that used it (``collect(seq + 1)`` releases ``seq``): a publisher runs at most one step ahead of the reader."""
+    """Host-side gather on ONE box through POSIX shared memory: every rank owns a segment, puts its arrays plus a small
+    header into it, and rank 0 maps all segments and reads them in place (views, no pickling, no socket).
+
+    The segment is cut into ``REGIONS`` regions used round-robin by consecutive steps (numbered from 1).  A rank can
+    have its results written STRAIGHT INTO a region — ``register(ctx)`` page-locks the segment, ``region(seq)`` is the
+    buffer to hand to ``explain_masses(out_block=...)`` / ``classify_observed(out=...)`` — so that the device-to-host
+    copy is the gather and ``publish`` only writes a header; arrays that live elsewhere are copied in.
+    ``publish(seq, arrays)`` then ``collect(seq)`` on rank 0.  Rank 0 hands out VIEWS: a region is written again only
+    after rank 0 has released the step that used it (``collect(seq + 1)`` releases ``seq``)."""
 
     HEADER = 4096
+    REGIONS = 4
+    SLOT = 96  # header words per region: count + 5 per array (at most 19 arrays)
 
     def __init__(self, tag: str, rank: int, world: int, capacity: int = 256 << 20):
         from multiprocessing import shared_memory
 
         self.rank, self.world, self.tag = rank, world, tag
-        self._shm = shared_memory.SharedMemory(name=f"{tag}_{rank}", create=True, size=self.HEADER + capacity)
+        self._rs = (capacity // self.REGIONS) & ~4095
+        self._shm = shared_memory.SharedMemory(name=f"{tag}_{rank}", create=True, size=self.HEADER + self._rs * self.REGIONS)
         self._hdr = np.ndarray(self.HEADER // 8, dtype=np.int64, buffer=self._shm.buf)
         self._hdr[:] = 0
-        self._data = np.ndarray(capacity, dtype=np.uint8, buffer=self._shm.buf, offset=self.HEADER)
+        self._data = np.ndarray(self._rs * self.REGIONS, dtype=np.uint8, buffer=self._shm.buf, offset=self.HEADER)
+        self._base = self._data.__array_interface__["data"][0]
         self._peers = {}
         self._sm = shared_memory
+        self._registered = None
+
+    def register(self, ctx) -> None:
+        """Page-lock this rank's segment (``_cabi.Context.host_register``) so that results can be copied straight into it."""
+        ctx.host_register(self._data)
+        self._registered = ctx
 
     def _peer(self, r: int):
         if r == self.rank:
@@ -229,30 +243,46 @@ class ShmGather:
                 if now > deadline:
                     raise TimeoutError(f"ShmGather: {what} within {timeout:.0f} s")
 
+    def region(self, seq: int) -> np.ndarray:
+        """The region step ``seq`` may write (uint8 view), once rank 0 has released the step that used it last."""
+        hdr = self._hdr
+        self._spin(lambda: seq > self.REGIONS and hdr[1] < seq - self.REGIONS, f"rank 0 never released step {seq - self.REGIONS}")
+        k = seq % self.REGIONS
+        return self._data[k * self._rs:(k + 1) * self._rs]
+
     def publish(self, seq: int, arrays: Sequence[np.ndarray]) -> None:
-        """header: [0] seq (written last), [1] acknowledged seq (written by rank 0), [2] number of arrays, then per
-        array (dtype code, ndim, shape0, shape1, byte offset)."""
-        hdr, data = self._hdr, self._data
-        half = len(data) // 2
-        base = (seq & 1) * half  # two halves alternate, so the step in flight is not overwritten
-        # the half is free once rank 0 has read step seq - 2 (steps are numbered consecutively from 1)
-        self._spin(lambda: seq >= 3 and hdr[1] < seq - 2 and self.rank != 0, f"rank 0 never acknowledged step {seq - 2}")
-        at = base
-        slot = 8 + (seq & 1) * 128
-        hdr[slot] = len(arrays)
-        for k, a in enumerate(arrays):
+        """header: [0] seq (written last), [1] released seq (written by rank 0), then per region a slot of
+        [number of arrays, (dtype code, ndim, shape0, shape1, byte offset) per array]."""
+        hdr = self._hdr
+        reg = self.region(seq)
+        r0 = (seq % self.REGIONS) * self._rs
+        if len(arrays) * 5 + 1 > self.SLOT:
+            raise ValueError("too many arrays for one step")
+        # arrays that already live in this step's region stay where they are; the others are copied behind them
+        placed, cursor = [], 0
+        for a in arrays:
             a = np.ascontiguousarray(a)
-            nb = a.nbytes
-            if at + nb > base + half:
-                raise MemoryError("ShmGather segment too small for this step")
-            data[at:at + nb] = a.reshape(-1).view(np.uint8)
+            off = a.__array_interface__["data"][0] - self._base - r0 if a.size else -1
+            inside = 0 <= off and off + a.nbytes <= self._rs
+            placed.append((a, off if inside else None))
+            if inside:
+                cursor = max(cursor, off + a.nbytes)
+        slot = 8 + (seq % self.REGIONS) * self.SLOT
+        hdr[slot] = len(arrays)
+        for k, (a, off) in enumerate(placed):
+            if off is None:
+                cursor = (cursor + 63) & ~63
+                if cursor + a.nbytes > self._rs:
+                    raise MemoryError("ShmGather region too small for this step")
+                reg[cursor:cursor + a.nbytes] = a.reshape(-1).view(np.uint8)
+                off = cursor
+                cursor += a.nbytes
             hdr[slot + 1 + 5 * k: slot + 6 + 5 * k] = [_DT.index(a.dtype.str), a.ndim, a.shape[0] if a.ndim else 1,
-                                                      a.shape[1] if a.ndim > 1 else 1, at]
-            at += (nb + 63) & ~63
+                                                      a.shape[1] if a.ndim > 1 else 1, r0 + off]
         hdr[0] = seq
 
     def release(self, seq: int) -> None:
-        """Rank 0 is done with the views of every step up to ``seq``: their segment halves may be written again."""
+        """Rank 0 is done with the views of every step up to ``seq``: their regions may be written again."""
         for r in range(self.world):
             hdr = self._peer(r)[0]
             if hdr[1] < seq:
@@ -266,7 +296,7 @@ class ShmGather:
         for r in range(self.world):
             hdr, data = self._peer(r)
             self._spin(lambda: hdr[0] < seq, f"rank {r} never published step {seq}")
-            slot = 8 + (seq & 1) * 128
+            slot = 8 + (seq % self.REGIONS) * self.SLOT
             arrs = []
             for k in range(int(hdr[slot])):
                 code, ndim, s0, s1, at = (int(x) for x in hdr[slot + 1 + 5 * k: slot + 6 + 5 * k])
@@ -278,6 +308,12 @@ class ShmGather:
         return out
 
     def close(self) -> None:
+        if self._registered is not None:
+            try:
+                self._registered.host_unregister(self._data)
+            except Exception:
+                pass
+            self._registered = None
         for shm, _h, _d in self._peers.values():
             shm.close()
         self._peers = {}
