@@ -65,7 +65,7 @@ for depth, what in ((3, "e"), (3, "ce")):
     loop(10, depth)
     stamps = []
     for k in range(depth):
-        _cabi.context(0, k).trace_ms(True)
+        _cabi.context(ctx.device, k).trace_ms(True)
     trace, host = [], []
     pend = [submit(k) for k in range(depth - 1)]
     n = 60
@@ -75,8 +75,8 @@ for depth, what in ((3, "e"), (3, "ce")):
             pend.append(submit((i + depth - 1) % depth))
         finish(pend.pop(0))
         t_host.append(time.perf_counter())
-        trace.append(_cabi.context(0, i % depth).trace_ms(True)[:5].astype(np.float64) * 1e3)
-        ph = _cabi.context(0, i % depth).explain_phase_ns().astype(np.int64)
+        trace.append(_cabi.context(ctx.device, i % depth).trace_ms(True)[:5].astype(np.float64) * 1e3)
+        ph = _cabi.context(ctx.device, i % depth).explain_phase_ns().astype(np.int64)
         ph = ph[ph > 0]
         stamps.append((ph[0], ph[-1]))
     st = np.array(stamps, dtype=np.int64)
