@@ -140,7 +140,7 @@ struct sst_ctx {
     bool have_result = false;
     uint64_t item_limit = ~0ULL;     // blow-up guard (items per level)
     int pass_grid_max[3] = {0, 0, 0};  // co-resident CTAs of the k_explain_pass instances on this device
-    int dfs_grid_max[4] = {0, 0, 0, 0};  // the same for the k_explain_dfs instances
+    int dfs_grid_max[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // the same for the k_explain_dfs instances (two CTA shapes)
     int pass_grid_cap = 512;           // CTA-total scratch is sized for the largest grid of either pass
     int pass_choice = 0;               // sst_set_pass: 0 automatic, 1 level-synchronous, 2 depth-first (items), 3 direct (count table)
     int dir_grid_max[2] = {0, 0};      // co-resident CTAs of the k_explain_direct instances
@@ -1388,12 +1388,16 @@ int dfs_enqueue(sst_ctx* ctx, const sst_table* t, int rec_width, const MemoMap& 
     const int64_t P = ctx->P;
     const int nw = rec_width / 8;
     int rc;
-    auto kern = nw == 1 ? (ctx->has_exact ? k_explain_dfs<1, true> : k_explain_dfs<1, false>)
-                        : (ctx->has_exact ? k_explain_dfs<2, true> : k_explain_dfs<2, false>);
-    int& grid_max = ctx->dfs_grid_max[(nw == 1 ? 0 : 2) + (ctx->has_exact ? 1 : 0)];
+    const bool wide = P <= kDfsWideMaxPeaks;  // one 1024-thread CTA per SM for batches in the latency regime
+    const int threads = wide ? kDfsThreadsWide : kDfsThreads;
+    auto kern = wide ? (nw == 1 ? (ctx->has_exact ? k_explain_dfs<1, true, kDfsThreadsWide> : k_explain_dfs<1, false, kDfsThreadsWide>)
+                                : (ctx->has_exact ? k_explain_dfs<2, true, kDfsThreadsWide> : k_explain_dfs<2, false, kDfsThreadsWide>))
+                     : (nw == 1 ? (ctx->has_exact ? k_explain_dfs<1, true, kDfsThreads> : k_explain_dfs<1, false, kDfsThreads>)
+                                : (ctx->has_exact ? k_explain_dfs<2, true, kDfsThreads> : k_explain_dfs<2, false, kDfsThreads>));
+    int& grid_max = ctx->dfs_grid_max[(wide ? 4 : 0) + (nw == 1 ? 0 : 2) + (ctx->has_exact ? 1 : 0)];
     if (!grid_max) {
         int occ = 0;
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kDfsThreads, 0));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, 0));
         if (occ < 1) return fail(ctx, SST_ERR_CUDA, "k_explain_dfs does not fit on an SM");
         grid_max = occ * ctx->prop.multiProcessorCount;
     }
@@ -1470,7 +1474,7 @@ int dfs_enqueue(sst_ctx* ctx, const sst_table* t, int rec_width, const MemoMap& 
             KTimer kt(ctx, SST_K_EXPLAIN_PASS);
             hp_mark(8);
             void* args[] = {(void*)&a};
-            CK(cudaLaunchCooperativeKernel((const void*)kern, dim3(grid), dim3(kDfsThreads), args, 0, ctx->stream));
+            CK(cudaLaunchCooperativeKernel((const void*)kern, dim3(grid), dim3(threads), args, 0, ctx->stream));
             hp_mark(9);
             ctx->run_parity++;  // only a launch that really started clears the other set
             kt.stop(1);

@@ -43,7 +43,12 @@
 
 namespace sst {
 
-constexpr int kDfsThreads = 512;
+constexpr int kDfsThreads = 512;             // threads per CTA, two CTAs per SM: the throughput shape (large batches)
+constexpr int kDfsThreadsWide = 1024;        // one CTA per SM: half as many stretches, each with twice the threads — a heavy
+                                             // stretch needs half as many steps and the estimate errors average out over
+                                             // twice as many peaks; measured 82 against 88 us on the C4 batch, 0.54 against
+                                             // 0.53 ms on the batch tiled 16x, so the host picks by batch size
+constexpr int64_t kDfsWideMaxPeaks = 400000; // batches up to this many peaks take the wide shape
 constexpr int kDfsDepth = 16;               // frames of the per-thread stack = longest composition this pass accepts
 constexpr int kMaxSplit = 6;                // split rounds before the remaining subtrees are walked depth-first
 constexpr int kU = 2;                       // items a thread has in flight
@@ -229,9 +234,10 @@ __device__ __noinline__ unsigned int dfs_item(const DfsArgs& a, const RowTables&
     return total;
 }
 
-template <int NW, bool BUDGET>
-__global__ void __launch_bounds__(kDfsThreads, 2)
+template <int NW, bool BUDGET, int THREADS>
+__global__ void __launch_bounds__(THREADS, 1024 / THREADS)
 k_explain_dfs(const DfsArgs a) {
+    constexpr int kDfsThreads = THREADS;  // (shadows the namespace constant: everything below is per instance)
     __shared__ int32_t s_w[kMaxRows];
     __shared__ int32_t s_ind[kMaxRows];
     __shared__ uint8_t s_mod[kMaxRows];
@@ -680,6 +686,7 @@ k_explain_dfs(const DfsArgs a) {
         ci[0] = A;
         ci[1] = NA;
         ci[2] = my_recs;
+        if (a.cta_ns) a.cta_ns[(size_t)blockIdx.x * 8 + 7] = ((unsigned long long)n_mine << 44) | ((unsigned long long)NA << 22) | my_recs;  // diagnostics
     }
     if (capped || overflow) atomicExch(fallback, overflow ? 2u : 1u);
     {

@@ -888,10 +888,10 @@ __device__ __forceinline__ void stamp(PassSummary& sum, int k) {
     if (blockIdx.x == 0 && threadIdx.x == 0 && k < 32) sum.totals[8 + k] = globaltimer_ns();
 }
 
-// exclusive scan of one value per thread across the CTA; *total = CTA sum.  Warp scans, then warp 0 scans the
-// per-warp totals (three barriers, ~50 instructions per warp).
+// exclusive scan of one value per thread across the CTA (any whole number of warps up to 32); *total = CTA sum.  Warp
+// scans, then warp 0 scans the per-warp totals (three barriers, ~50 instructions per warp).
 __device__ __forceinline__ unsigned long long block_scan(unsigned long long x, unsigned long long* total) {
-    __shared__ unsigned long long s_w64[kPassThreads / 32];
+    __shared__ unsigned long long s_w64[32];
     __shared__ unsigned long long s_tot64;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     unsigned long long incl = x;
@@ -903,15 +903,15 @@ __device__ __forceinline__ unsigned long long block_scan(unsigned long long x, u
     if (lane == 31) s_w64[w] = incl;
     __syncthreads();
     if (w == 0) {
-        const unsigned long long v = lane < kPassThreads / 32 ? s_w64[lane] : 0ULL;
+        const unsigned long long v = lane < (int)(blockDim.x >> 5) ? s_w64[lane] : 0ULL;
         unsigned long long inc = v;
 #pragma unroll
-        for (int o = 1; o < kPassThreads / 32; o <<= 1) {
+        for (int o = 1; o < 32; o <<= 1) {
             const unsigned long long y = __shfl_up_sync(0xFFFFFFFFu, inc, o);
             if (lane >= o) inc += y;
         }
-        if (lane < kPassThreads / 32) s_w64[lane] = inc - v;
-        if (lane == kPassThreads / 32 - 1) s_tot64 = inc;
+        if (lane < (int)(blockDim.x >> 5)) s_w64[lane] = inc - v;
+        if (lane == 31) s_tot64 = inc;
     }
     __syncthreads();
     const unsigned long long r = s_w64[w] + incl - x;
@@ -922,7 +922,7 @@ __device__ __forceinline__ unsigned long long block_scan(unsigned long long x, u
 
 // 32-bit flavour for the per-round scans (a round's counts always fit): ~35 instructions per warp, 3 barriers
 __device__ __forceinline__ unsigned int block_scan32(unsigned int x, unsigned int* total) {
-    __shared__ unsigned int s_w32[kPassThreads / 32];
+    __shared__ unsigned int s_w32[32];
     __shared__ unsigned int s_tot32;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     unsigned int incl = x;
@@ -934,15 +934,15 @@ __device__ __forceinline__ unsigned int block_scan32(unsigned int x, unsigned in
     if (lane == 31) s_w32[w] = incl;
     __syncthreads();
     if (w == 0) {
-        const unsigned int v = lane < kPassThreads / 32 ? s_w32[lane] : 0u;
+        const unsigned int v = lane < (int)(blockDim.x >> 5) ? s_w32[lane] : 0u;
         unsigned int inc = v;
 #pragma unroll
-        for (int o = 1; o < kPassThreads / 32; o <<= 1) {
+        for (int o = 1; o < 32; o <<= 1) {
             const unsigned int y = __shfl_up_sync(0xFFFFFFFFu, inc, o);
             if (lane >= o) inc += y;
         }
-        if (lane < kPassThreads / 32) s_w32[lane] = inc - v;
-        if (lane == kPassThreads / 32 - 1) s_tot32 = inc;
+        if (lane < (int)(blockDim.x >> 5)) s_w32[lane] = inc - v;
+        if (lane == 31) s_tot32 = inc;
     }
     __syncthreads();
     const unsigned int r = s_w32[w] + incl - x;
@@ -956,7 +956,7 @@ __device__ __forceinline__ unsigned long long block_sum(unsigned long long x);
 
 // four independent 32-bit scans at once (the per-level scans over the peaks share their barriers)
 __device__ __forceinline__ void block_scan32x4(unsigned int (&x)[4], unsigned int (&tot)[4]) {
-    __shared__ unsigned int s_w4[kPassThreads / 32][4];
+    __shared__ unsigned int s_w4[32][4];
     __shared__ unsigned int s_t4[4];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     unsigned int incl[4];
@@ -974,15 +974,15 @@ __device__ __forceinline__ void block_scan32x4(unsigned int (&x)[4], unsigned in
     if (w == 0) {
 #pragma unroll
         for (int k = 0; k < 4; k++) {
-            const unsigned int v = lane < kPassThreads / 32 ? s_w4[lane][k] : 0u;
+            const unsigned int v = lane < (int)(blockDim.x >> 5) ? s_w4[lane][k] : 0u;
             unsigned int inc = v;
 #pragma unroll
-            for (int o = 1; o < kPassThreads / 32; o <<= 1) {
+            for (int o = 1; o < 32; o <<= 1) {
                 const unsigned int y = __shfl_up_sync(0xFFFFFFFFu, inc, o);
                 if (lane >= o) inc += y;
             }
-            if (lane < kPassThreads / 32) s_w4[lane][k] = inc - v;
-            if (lane == kPassThreads / 32 - 1) s_t4[k] = inc;
+            if (lane < (int)(blockDim.x >> 5)) s_w4[lane][k] = inc - v;
+            if (lane == 31) s_t4[k] = inc;
         }
     }
     __syncthreads();
@@ -997,7 +997,7 @@ __device__ __forceinline__ void block_scan32x4(unsigned int (&x)[4], unsigned in
 // handful of shared-memory accesses per thread — every thread re-adding all partials cost ~2.5 us per call)
 template <int N>
 __device__ __forceinline__ void block_sum_n(unsigned long long (&v)[N]) {
-    __shared__ unsigned long long s_part[kPassThreads / 32][N];
+    __shared__ unsigned long long s_part[32][N];
     __shared__ unsigned long long s_res[N];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
 #pragma unroll
@@ -1010,7 +1010,7 @@ __device__ __forceinline__ void block_sum_n(unsigned long long (&v)[N]) {
     if (w == 0) {
 #pragma unroll
         for (int k = 0; k < N; k++) {
-            unsigned long long t = lane < kPassThreads / 32 ? s_part[lane][k] : 0ULL;
+            unsigned long long t = lane < (int)(blockDim.x >> 5) ? s_part[lane][k] : 0ULL;
 #pragma unroll
             for (int o = 16; o; o >>= 1) t += __shfl_xor_sync(0xFFFFFFFFu, t, o);
             if (lane == 0) s_res[k] = t;

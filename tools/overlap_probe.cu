@@ -38,6 +38,27 @@ int main() {
             printf("%s %7zu KB: %7.1f us  %6.1f GB/s\n", dir ? "D2H" : "H2D", sz >> 10, best * 1e3, sz / (best * 1e-3) / 1e9);
         }
     }
+    // launch cost seen by a pair of events around ONE kernel of 296 x 512 threads that spins for 50 us: plain vs cooperative
+    for (int coop = 0; coop < 2; coop++) {
+        float best = 1e9, sum = 0;
+        for (int r = 0; r < 20; r++) {
+            cudaDeviceSynchronize();
+            unsigned long long ns = 50000; unsigned long long* outp = nullptr;
+            cudaEventRecord(e0, st[0]);
+            if (coop) {
+                void* args[] = {&ns, &outp};
+                cudaLaunchCooperativeKernel((const void*)spin, dim3(296), dim3(512), args, 0, st[0]);
+            } else {
+                spin<<<296, 512, 0, st[0]>>>(ns, outp);
+            }
+            cudaEventRecord(e1, st[0]);
+            cudaEventSynchronize(e1);
+            float ms; cudaEventElapsedTime(&ms, e0, e1);
+            if (ms < best) best = ms;
+            if (r >= 4) sum += ms;
+        }
+        printf("%s launch of a 50 us kernel, event to event: best %.1f us, mean %.1f us\n", coop ? "cooperative" : "plain", best * 1e3, sum / 16 * 1e3);
+    }
     // pipeline: per step H2D 2 MB -> kernel 100 us -> D2H 5 MB, on `depth` streams round robin, 200 steps
     for (int coop = 0; coop < 2; coop++)
     for (int depth = 1; depth <= 4; depth++) {

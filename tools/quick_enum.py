@@ -31,6 +31,16 @@ for mode in (2, 3):
         seg = {"windows": d[:, 1] - d[:, 0], "roots": d[:, 2] - d[:, 1], "rounds": d[:, 6] - d[:, 2], "final count": d[:, 3] - d[:, 6], "fill": d[:, 5] - d[:, 4]}
         for nm, v in seg.items():
             print(f"    {nm:12s} per CTA us p10/p50/p90/max", np.percentile(v, [10, 50, 90, 100]).round(1))
+        info = c[:, 7]
+        peaks, items, recs = info >> 44, (info >> 22) & 0x3FFFFF, info & 0x3FFFFF
+        cnt = d[:, 3] - d[:, 0]
+        print("    per CTA: peaks p10/p50/p90/max", np.percentile(peaks, [10, 50, 90, 100]).astype(int), " final items", np.percentile(items, [10, 50, 90, 100]).astype(int),
+              " records", np.percentile(recs, [10, 50, 90, 100]).astype(int))
+        order = np.argsort(-cnt)[:12]
+        print("    slowest count phases: us / peaks / items / records / rounds us / roots us")
+        for i in order:
+            print(f"      {cnt[i]:6.1f} {int(peaks[i]):6d} {int(items[i]):6d} {int(recs[i]):6d} {seg['rounds'][i]:6.1f} {seg['roots'][i]:6.1f}")
+        print("    corr(count us, peaks / items / records):", [round(float(np.corrcoef(cnt, x)[0, 1]), 2) for x in (peaks, items, recs)])
     if mode == 3:
         c = ctx.cta_timestamps(False).astype(np.int64)
         t0 = c[:, 0].min()
