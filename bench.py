@@ -42,9 +42,18 @@ def ncu_traffic(kernel: str, wl=None):
         return None
     try:
         doc = json.loads((ROOT / "profiles" / "traffic.json").read_text())
-        return int(doc["kernels"][kernel]["dram_bytes_per_launch"])
+        return int(_kernel_entry(doc, kernel)["dram_bytes_per_launch"])
     except Exception:
         return None
+
+
+def _kernel_entry(doc, kernel: str):
+    """The entry of `kernel` in traffic.json: exact name, else the one instance whose name starts with it."""
+    ks = doc["kernels"]
+    if kernel in ks:
+        return ks[kernel]
+    hits = [k for k in ks if k.startswith(kernel)]
+    return ks[hits[0]] if len(hits) == 1 else {}
 
 
 def ncu_metric(kernel: str, key: str, wl=None):
@@ -53,7 +62,7 @@ def ncu_metric(kernel: str, key: str, wl=None):
         return None
     try:
         doc = json.loads((ROOT / "profiles" / "traffic.json").read_text())
-        return doc["kernels"][kernel].get(key)
+        return _kernel_entry(doc, kernel).get(key)
     except Exception:
         return None
 
@@ -599,7 +608,7 @@ def main():
     dominant = max(fam + ["classify"], key=lambda k: stats[k][0])
     pass_name = {1: "k_explain_pass (level-synchronous)", 2: "k_explain_dfs (count -> scan -> fill over items in peak order)",
                  3: "k_explain_direct (counts from the composition-count table -> scan -> output-balanced fill)"}.get(pass_used, str(pass_used))
-    tkey = {1: "k_explain_pass<1>", 2: "k_explain_dfs<1, 0>", 3: "k_explain_direct<1>"}.get(pass_used, "")
+    tkey = {1: "k_explain_pass<1>", 2: "k_explain_dfs<1, 0", 3: "k_explain_direct<1>"}.get(pass_used, "")
     roofline = {"bound": "hbm", "kernel": "K3+K2b enumeration pass: " + pass_name,
                 "achieved": k2b_bytes / (k2b_ms * 1e-3) / 1e9 if k2b_ms else None, "peak": hbm_peak, "unit": "GB/s",
                 "frac": (k2b_bytes / (k2b_ms * 1e-3) / 1e9 / hbm_peak) if k2b_ms else None,
