@@ -562,7 +562,10 @@ def main():
             t1 = time.perf_counter()
             ME.explain_mass_with_table(float(wl.explain_mass[i]), dp, wl.max_modifications, threshold=float(wl.explain_thr[i]))
             t2 = time.perf_counter()
-            ME.is_valid_mass(float(wl.valid_mass[i]), dp, float(wl.valid_thr[i]))
+            try:
+                ME.is_valid_mass(float(wl.valid_mass[i]), dp, float(wl.valid_thr[i]))
+            except NotImplementedError:  # a probe beyond the table (C5's heaviest fragments): the reference raises too
+                pass
             t3 = time.perf_counter()
             te.append((t2 - t1) * 1e6)
             tv.append((t3 - t2) * 1e6)

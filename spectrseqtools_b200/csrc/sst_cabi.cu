@@ -1977,6 +1977,7 @@ int sst_explain_collect(sst_ctx* ctx, const sst_table* t, uint64_t* n_comps, int
         std::vector<uint64_t> off((size_t)pd.P + 1);
         if ((rc = sst_explain_fetch(ctx, pd.status, off.data(), pd.recs))) return rc;
         for (int64_t i = 0; i <= pd.P; i++) pd.off32[i] = (uint32_t)off[(size_t)i];
+        ctx->last_d2h_bytes = (uint64_t)pd.P + 8 * ((uint64_t)pd.P + 1) + need;  // what sst_explain_fetch copied
     }
     if (n_comps) *n_comps = ctx->n_comps;
     if (rec_width) *rec_width = ctx->rec_width;
