@@ -329,7 +329,12 @@ def block_of(wl, rank, world, dp):
 
     from spectrseqtools_b200 import sharding
 
-    eb = sharding.partition_contiguous(wl.explain_mass, wl.explain_thr, world, dp)
+    # compositions per call looked up on the device (every rank asks for the whole workload: 10^6 calls take well under a
+    # millisecond) — blocks of equal OUTPUT, known before anything is enumerated
+    from spectrseqtools_b200 import mass_explanation as ME
+
+    counts = ME.count_compositions(wl.explain_mass, dp, wl.explain_thr)
+    eb = sharding.partition_contiguous(wl.explain_mass, wl.explain_thr, world, dp, counts=counts)
     n_off = len(wl.valid_mass) // max(wl.n_peaks, 1)
     ob = [(wl.n_peaks * r) // world for r in range(world + 1)]
     mine = copy.copy(wl)

@@ -188,6 +188,14 @@ int sst_explain_cta_ns(sst_ctx* ctx, int enable, uint64_t* out, int cap_ctas, in
  * [counted, grid barrier passed, written]; after the last level [per-level peak totals summed], [placement table
  * written], [records permuted].  Right after a grid barrier that is every CTA's clock.  Unused slots are 0. */
 int sst_explain_phase_ns(const sst_ctx* ctx, uint64_t* out /* [32] */);
+/* Compositions per call WITHOUT enumerating them: counts_out[p] = what explain_mass_with_table (mass_explanation.py:92-203)
+ * would return in number for (mass[p], thr[p]; NaN / NULL = relative) when no modification budget binds — looked up in
+ * the composition-count table of the alphabet (built on first use: cnt(r, m) = cnt(r-1, m) + bit1(r, m) * cnt(r, m - w_r),
+ * the reference's own UP / LEFT recursion on integers).  ~0 when a window reaches beyond the count table (2^22 integer
+ * masses), a count saturates, or an input is not finite.  The host-side partition of a workload over the GPUs of a box
+ *  balances blocks by these. */
+int sst_count_compositions_f64(sst_ctx* ctx, sst_table* t, const double* mass, const double* thr, int64_t P, double precision,
+                               double tolerance, uint64_t* counts_out);
 /* ---- N3 + N4: ladder differences and the explanation-based alphabet reduction on a fragment frame that
  * stays on the device between the rounds (kernels: sst_ladder.cuh).
  *

@@ -38,7 +38,7 @@ EXPORTS = [
     "sst_valid_fetch", "sst_valid_stage_f64", "sst_explain", "sst_explain_stage", "sst_explain_stage_f64", "sst_explain_stage_f64_uniform", "sst_explain_rec_width", "sst_explain_phase_ns",
     "sst_explain_run", "sst_explain_fetch", "sst_classify", "sst_classify_stage", "sst_classify_run", "sst_classify_fetch", "sst_classify_launch", "sst_classify_async", "sst_classify_wait", "sst_length_bounds",
     "sst_set_pass", "sst_last_pass", "sst_explain_cta_ns", "sst_explain_submit_f64", "sst_explain_collect", "sst_classify_async_packed", "sst_host_profile", "sst_trace_ms", "sst_explain_block_layout", "sst_explain_d2h_bytes",
-    "sst_ladder_stage", "sst_ladder_round", "sst_ladder_revalidate", "sst_ladder_fetch", "sst_host_register", "sst_host_unregister",
+    "sst_ladder_stage", "sst_ladder_round", "sst_ladder_revalidate", "sst_ladder_fetch", "sst_host_register", "sst_host_unregister", "sst_count_compositions_f64",
 ]
 
 
@@ -113,6 +113,7 @@ def load() -> C.CDLL:
             "sst_explain_collect": (C.c_int, [vp, vp, C.POINTER(C.c_uint64), C.POINTER(C.c_int)]),
             "sst_host_profile": (C.c_int, [C.c_int, u64p, u64p]),
             "sst_trace_ms": (C.c_int, [vp, C.c_int, fp]),
+            "sst_count_compositions_f64": (C.c_int, [vp, vp, fp, fp, C.c_int64, C.c_double, C.c_double, u64p]),
             "sst_host_register": (C.c_int, [vp, vp, C.c_size_t]),
             "sst_host_unregister": (C.c_int, [vp, vp]),
             "sst_ladder_stage": (C.c_int, [vp, fp, fp, u8p, C.c_int64]),
@@ -378,6 +379,16 @@ class Context:
         self._check(self._lib.sst_explain_run(self._h, table._h, int(rec_width), C.c_uint64(memo_capacity), C.byref(nr), C.byref(nc)))
         self._last = (int(nr.value), int(nc.value), int(self._lib.sst_explain_rec_width(self._h)))
         return int(nr.value), int(nc.value)
+
+    def count_compositions_f64(self, table: "DeviceTable", mass, thr, precision: float, tolerance: float) -> np.ndarray:
+        """uint64[P]: compositions per call, looked up (sst_count_compositions_f64); 2**64 - 1 = not known."""
+        m = _arr(mass, np.float64)
+        h = None if thr is None else _arr(thr, np.float64)
+        if h is not None and len(h) != len(m):
+            raise ValueError("per-call arrays differ in length")
+        out = np.zeros(len(m), dtype=np.uint64)
+        self._check(self._lib.sst_count_compositions_f64(self._h, table._h, _p(m), _p(h), len(m), float(precision), float(tolerance), _p(out)))
+        return out
 
     def host_register(self, arr: np.ndarray):
         """Page-lock a caller-owned buffer (sst_host_register); ``host_unregister`` before it is freed."""

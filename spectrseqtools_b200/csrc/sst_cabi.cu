@@ -2005,6 +2005,31 @@ int sst_trace_ms(sst_ctx* ctx, int enable, float* out) {
     return SST_OK;
 }
 
+// Compositions per call without enumerating them (k_count_compositions): what the host-side partition of a workload
+// over several GPUs balances by.
+int sst_count_compositions_f64(sst_ctx* ctx, sst_table* t, const double* mass, const double* thr, int64_t P, double precision, double tolerance,
+                               uint64_t* counts_out) {
+    CK(cudaSetDevice(ctx->device));
+    if (P < 0) return fail(ctx, SST_ERR_BAD_ARG, "negative call count");
+    if (!P) return SST_OK;
+    int rc;
+    if ((rc = ensure_counts(ctx, t))) return rc;
+    if ((rc = reserve(ctx, ctx->d_vmass, (size_t)P * 8))) return rc;
+    if ((rc = reserve(ctx, ctx->d_vthrf, (size_t)P * 8))) return rc;
+    if ((rc = reserve(ctx, ctx->d_peakoff, (size_t)(P + 2) * 8))) return rc;
+    ctx->have_result = false;  // (the staging arrays and the offsets of a staged batch are overwritten)
+    ctx->R_staged = -1;
+    CK(cudaMemcpyAsync(ctx->d_vmass.p, mass, (size_t)P * 8, cudaMemcpyHostToDevice, ctx->stream));
+    if (thr) CK(cudaMemcpyAsync(ctx->d_vthrf.p, thr, (size_t)P * 8, cudaMemcpyHostToDevice, ctx->stream));
+    k_count_compositions<<<(unsigned)((P + 255) / 256), 256, 0, ctx->stream>>>(view_of(t), CountView{t->d_cnt2d, t->Mcnt}, (const double*)ctx->d_vmass.p,
+                                                                               thr ? (const double*)ctx->d_vthrf.p : nullptr, P, precision, tolerance,
+                                                                               (unsigned long long*)ctx->d_peakoff.p);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(counts_out, ctx->d_peakoff.p, (size_t)P * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return SST_OK;
+}
+
 // ---------------- N3 / N4: ladder differences and alphabet reduction on a device-resident frame (sst_ladder.cuh) ----------------
 int sst_ladder_stage(sst_ctx* ctx, const double* su, const double* obs, const uint8_t* flags, int64_t F) {
     CK(cudaSetDevice(ctx->device));

@@ -61,6 +61,43 @@ __device__ __forceinline__ uint32_t sat_add(uint32_t a, uint32_t b) {
     return s < a ? kCntSat : s;
 }
 
+// ---------------- compositions per call, looked up (no enumeration) ----------------
+// out[p] = number of compositions explain_mass_with_table returns for call p when no modification budget binds: the sum
+// of cnt(top, m) over the reachable values m of its integer window — one gather per reachable value from the top row of
+// the count table.  ~0 (all ones) when the window reaches beyond the count table or a count saturated.  Used to cut a
+// workload into blocks of equal OUTPUT before anything is enumerated (the host-side partition of SURVEY §8e).
+__global__ void __launch_bounds__(256)
+k_count_compositions(TableView tv, CountView cv, const double* __restrict__ mass, const double* __restrict__ thr, int64_t P, double precision,
+                     double tolerance, unsigned long long* __restrict__ out) {
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= P) return;
+    const double m = mass[p], th = thr ? thr[p] : nan("");
+    if (non_finite(m, th)) {
+        out[p] = ~0ULL;
+        return;
+    }
+    int64_t t, h;
+    integerise(m, th, precision, tolerance, t, h);
+    const int64_t limit = tv.C * 32;
+    const uint64_t* last = tv.tbl + (int64_t)(tv.R - 1) * tv.C;
+    const uint32_t* top = cv.c2d + (int64_t)(tv.R - 1) * cv.M;
+    const int64_t lo = t - h, hi = t + h;
+    const int64_t a = lo < 1 ? 1 : lo, b = hi < limit - 1 ? hi : limit - 1;
+    unsigned long long sum = 0ULL;
+    bool unknown = b >= cv.M && a <= b;
+    if (!unknown)
+        for_window_words(last, a, b, [&](int64_t wd, uint64_t x) {
+            while (x) {
+                const int pos = 63 - __clzll((long long)x);
+                x &= ~(1ULL << pos);
+                const uint32_t c = __ldg(top + (wd * 32 + (31 - (pos >> 1))));
+                if (c == kCntSat) unknown = true;
+                sum += c;
+            }
+        });
+    out[p] = unknown ? ~0ULL : sum;
+}
+
 // ---------------- count table, one row per launch ----------------
 __global__ void __launch_bounds__(256)
 k_count_row0(uint32_t* __restrict__ row0, int64_t M) {

@@ -237,6 +237,16 @@ def explain_masses(masses: Sequence[float], dp_table: DynamicProgrammingTable, m
     return _run_and_fetch(dp_table, dev, weights, fetch_records, copy, ctx)
 
 
+def count_compositions(masses: Sequence[float], dp_table: DynamicProgrammingTable, thresholds=None) -> np.ndarray:
+    """How many compositions ``explain_mass_with_table`` would return per mass when no modification budget binds — looked
+    up in the alphabet's composition-count table, nothing is enumerated.  uint64; ``2**64 - 1`` where the answer is not
+    known (window beyond the count table, saturated count, non-finite input).  What ``sharding.partition_contiguous``
+    balances the GPUs of a box by."""
+    masses = np.ascontiguousarray(masses, dtype=np.float64).reshape(-1)
+    dev = dp_table.device_table()
+    return dev.ctx.count_compositions_f64(dev, masses, _thr_array(thresholds, len(masses)), dp_table.precision, dp_table.tolerance)
+
+
 def _run_and_fetch(dp_table, dev, weights, fetch_records=True, copy=True, ctx=None) -> ExplanationBatch:
     ctx = ctx or dev.ctx
     cap = 0

@@ -162,14 +162,23 @@ def estimated_compositions(masses: np.ndarray, thresholds: Optional[np.ndarray],
     return 16.0 + win * (1.0 + dens[k] / width)
 
 
-def partition_contiguous(masses, thresholds, world: int, dp_table) -> List[int]:
+def partition_contiguous(masses, thresholds, world: int, dp_table, counts: Optional[np.ndarray] = None) -> List[int]:
     """Cut points [0 = c_0 <= c_1 <= ... <= c_world = n]: rank r takes calls c_r .. c_{r+1}.  Blocks are contiguous in
-    INPUT order (so gathering is a concatenation: no per-record scatter on the host) and equal in estimated work."""
+    INPUT order (so gathering is a concatenation: no per-record scatter on the host) and equal in work.
+
+    ``counts``: compositions per call looked up on the device (``mass_explanation.count_compositions``: exact when no
+    budget binds) — the work of a call is then a constant plus its compositions; calls whose count is not known
+    (2**64 - 1) and a missing ``counts`` fall back to the host-side estimate."""
     n = len(masses)
     if n == 0:
         return [0] * (world + 1)
     t = None if thresholds is None else np.asarray(thresholds, dtype=np.float64).reshape(-1)
-    cost = np.cumsum(estimated_compositions(masses, t, dp_table))
+    work = estimated_compositions(masses, t, dp_table)
+    if counts is not None:
+        c = np.asarray(counts, dtype=np.uint64)
+        known = c != np.uint64(2**64 - 1)
+        work = np.where(known, 16.0 + c.astype(np.float64), work)
+    cost = np.cumsum(work)
     cuts = [0] + [int(np.searchsorted(cost, cost[-1] * r / world)) for r in range(1, world)] + [n]
     return [int(x) for x in np.maximum.accumulate(np.minimum(cuts, n))]
 

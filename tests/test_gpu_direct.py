@@ -107,3 +107,26 @@ def test_direct_declines_binding_budgets():
         ctx.set_pass(0)
     ME.explain_masses(wl.explain_mass, dp, max_modifications=1, thresholds=wl.explain_thr)
     assert ctx.last_pass() in (1, 2)
+
+
+def test_count_compositions_equals_the_enumeration():
+    """sst_count_compositions_f64: the looked-up number of compositions of every call equals what the enumeration returns
+    (budgets that cannot bind), on ladder differences and on sparse heavy ladders; the partition it feeds is balanced."""
+    from spectrseqtools_b200 import sharding
+
+    for config, n in (("C4", 20000), ("C5", 1500)):
+        wl = S.make_workload(config, n)
+        MT.MAX_SEQ_LENGTH = wl.max_seq_length
+        try:
+            seq = MT.SequenceInformation(max_len=wl.max_len, su_mass=0.0, obs_mass=0.0, modification_rate=0.5)
+            dp = MT.DynamicProgrammingTable(S.alphabet_frame(None), 32, wl.ppm, 1e-3, seq)
+            got = ME.count_compositions(wl.explain_mass, dp, wl.explain_thr)
+            want = ME.explain_masses(wl.explain_mass, dp, max_modifications=wl.max_modifications, thresholds=wl.explain_thr).counts()
+            known = got != np.uint64(2**64 - 1)
+            assert known.mean() > 0.99
+            assert np.array_equal(got[known].astype(np.int64), want[known])
+            cuts = sharding.partition_contiguous(wl.explain_mass, wl.explain_thr, 8, dp, counts=got)
+            per = np.array([want[cuts[r]:cuts[r + 1]].sum() for r in range(8)], dtype=np.float64)
+            assert per.max() <= 1.15 * per.mean() + want.max()
+        finally:
+            MT.MAX_SEQ_LENGTH = 35
