@@ -7,7 +7,7 @@
 One step = one pass of the mass-explanation hot path over one batch: validity probes for every
 (peak x breakage offset) + enumeration for every ladder difference of the batch.
 `value` times the kernels with inputs resident in HBM; `e2e` times the public Python API with host
-buffers (H2D + kernels + D2H of all results), three batches in flight on three context slots (the copies of
+buffers (H2D + kernels + D2H of all results), four batches in flight on four context slots (the copies of
 one under the kernels of the other).  Multi-GPU: one process per GPU (torchrun).  Default `--scaling weak`:
 every rank explains its own 10^5-peak batch (no data-path collective), time = max over ranks.
 `--scaling strong`: ONE fixed workload (the C4 batch tiled `--strong-factor` times) is partitioned over the
@@ -493,11 +493,11 @@ def main():
         peaks_all, comps_all = float(wl.n_peaks), float(n_comps)
     value = peaks_all * args.steps / (total_ms * 1e-3)
 
-    # ---- e2e: public API, host buffers in, host arrays out (H2D + kernels + D2H of every result), three batches in
-    # flight on three context slots: steps i+1 and i+2 are submitted before step i is collected, so the copies of one batch run
+    # ---- e2e: public API, host buffers in, host arrays out (H2D + kernels + D2H of every result), four batches in
+    # flight on four context slots: steps i+1 .. i+3 are submitted before step i is collected, so the copies of one batch run
     # under the kernels of the other.  Strong scaling: every rank publishes its block in shared memory and rank 0
     # gathers all blocks inside the timed region.
-    gather = sharding.ShmGather(f"sstb200_{os.environ.get('MASTER_PORT', '0')}", rank, world, capacity=512 << 20) if (strong and world > 1) else None
+    gather = sharding.ShmGather(f"sstb200_{os.environ.get('MASTER_PORT', '0')}", rank, world, capacity=1 << 30) if (strong and world > 1) else None
     if gather is not None:
         gather.register(ctx)  # page-locked: the device-to-host copies land in the shared segment, the gather copies nothing
     flag_bytes = (len(wl.breakage) * ((len(observed) + 1) // 2) + 4095) & ~4095
@@ -522,7 +522,11 @@ def main():
                 return v, batch, gather.collect(seq_no)
         return v, batch, None
 
-    E2E_DEPTH = 3  # batches in flight: three context slots keep the copy engines and the SMs busy at the same time
+    E2E_DEPTH = 4  # batches in flight: four context slots keep the copy engines and the SMs busy at the same time (a batch's
+    # chain — submit, copy in, stage, pass, copy out, collect — is ~310 us long: 137 us per step with three in flight, 128
+    # with four, 120 with six, where the submitting host thread becomes the limit)
+
+    assert gather is None or E2E_DEPTH + 2 <= gather.REGIONS
 
     def e2e_loop(n, seq0):
         pend = [submit(k, seq0 + k) for k in range(min(E2E_DEPTH - 1, n))]
@@ -673,7 +677,7 @@ def main():
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "ms_per_step": 1e3 * e2e_s / args.steps,
                 "how": "public API (classify_observed + explain_masses, wait=False), pinned host inputs, results in pinned host "
-                       "arrays; three batches in flight on three context slots" + ("; every rank's results are copied by the device straight into its page-locked POSIX shared-memory segment, which rank 0 maps: gathered inside the timed region without a host copy" if gather is not None else "")},
+                       "arrays; four batches in flight on four context slots" + ("; every rank's results are copied by the device straight into its page-locked POSIX shared-memory segment, which rank 0 maps: gathered inside the timed region without a host copy" if gather is not None else "")},
         "scalar_latency_us": scalar,
         "ladder_round": ladder,
         "gpu_launches": int(launches),

@@ -24,6 +24,7 @@ import numpy as np
 from . import _cabi
 from .mass_table import DynamicProgrammingTable
 from .masses import _INT_MASS_IS_MOD, _INT_MASS_NAMES
+from .mass_table import NucleotideMass as _NucleotideMass, row_version as _row_version
 
 
 @dataclass
@@ -82,7 +83,10 @@ def _row_metadata(dp_table) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
     Cached on the table object; the key holds everything the arrays depend on (callers mutate rates and
     ``seq.max_len`` between calls, and alphabet reduction swaps the row list)."""
     rows = dp_table.masses
-    key = (id(rows), len(rows), dp_table.seq.max_len, tuple(m.modification_rate for m in rows))
+    if rows and type(rows[0]) is _NucleotideMass:
+        key = (id(rows), len(rows), dp_table.seq.max_len, _row_version())  # (any rate assignment anywhere bumps the version)
+    else:  # duck-typed rows: read the rates
+        key = (id(rows), len(rows), dp_table.seq.max_len, tuple(m.modification_rate for m in rows))
     hit = getattr(dp_table, "_row_meta", None)
     if hit is not None and hit[0] == key:
         return hit[1]

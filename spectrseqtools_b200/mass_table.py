@@ -40,12 +40,28 @@ class SequenceInformation:
     modification_rate: float
 
 
+_ROW_VERSION = 0  # bumped by every assignment to a row's mass or modification rate
+
+
+def row_version() -> int:
+    return _ROW_VERSION
+
+
 @dataclass
 class NucleotideMass:
     mass: int
     names: List[str]
     is_modification: bool
     modification_rate: float
+
+    def __setattr__(self, name, value):
+        # callers zero and restore rates in place (prediction.py, the alphabet reduction): a change bumps a module-wide
+        # version so that per-table caches of derived arrays (mass_explanation._row_metadata) notice without reading
+        # every row's rate on every call
+        if name == "modification_rate" or name == "mass":
+            global _ROW_VERSION
+            _ROW_VERSION += 1
+        object.__setattr__(self, name, value)
 
     def __eq__(self, other):
         return self.mass == other.mass

@@ -195,7 +195,7 @@ class ShmGather:
     after rank 0 has released the step that used it (``collect(seq + 1)`` releases ``seq``)."""
 
     HEADER = 4096
-    REGIONS = 4
+    REGIONS = 8  # a rank with d steps in flight needs d + 2 (the step it submits, the d - 1 behind it, the one rank 0 still reads)
     SLOT = 96  # header words per region: count + 5 per array (at most 19 arrays)
 
     def __init__(self, tag: str, rank: int, world: int, capacity: int = 256 << 20):

@@ -51,7 +51,7 @@ def loop(n, depth=2):
             pend.append(submit((i + depth - 1) % depth))
         finish(pend.pop(0))
 
-for depth, what in ((1, "ce"), (2, "ce"), (3, "ce"), (4, "ce"), (2, "e"), (3, "e"), (2, "c"), (3, "c")):
+for depth, what in ((1, "ce"), (2, "ce"), (3, "ce"), (4, "ce"), (5, "ce"), (6, "ce"), (8, "ce"), (2, "e"), (3, "e"), (5, "e"), (2, "c"), (3, "c")):
     WHAT["classify"], WHAT["explain"] = "c" in what, "e" in what
     loop(10, depth)
     for k in T: T[k] = 0.0
