@@ -194,7 +194,7 @@ class ShmGather:
     ``publish(seq, arrays)`` then ``collect(seq)`` on rank 0.  Rank 0 hands out VIEWS: a region is written again only
     after rank 0 has released the step that used it (``collect(seq + 1)`` releases ``seq``)."""
 
-    HEADER = 4096
+    HEADER = 8192
     REGIONS = 8  # a rank with d steps in flight needs d + 2 (the step it submits, the d - 1 behind it, the one rank 0 still reads)
     SLOT = 96  # header words per region: count + 5 per array (at most 19 arrays)
 
