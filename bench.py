@@ -362,6 +362,7 @@ def main():
                     help="also time the same step on the batch tiled this many times (throughput regime; 0 = skip)")
     ap.add_argument("--flush", default="write", choices=["write", "none"],
                     help="L2 between timed steps: write a 256 MiB buffer (default, the contract) or leave it warm (diagnostics)")
+    ap.add_argument("--e2e-depth", type=int, default=4, help="batches in flight in the e2e loop (context slots)")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="multi-GPU: one batch per GPU (weak, default) or ONE fixed workload partitioned over the ranks and gathered on rank 0 (strong)")
     ap.add_argument("--strong-factor", type=int, default=16, help="strong scaling: the fixed workload is the batch tiled this many times")
@@ -522,7 +523,7 @@ def main():
                 return v, batch, gather.collect(seq_no)
         return v, batch, None
 
-    E2E_DEPTH = 4  # batches in flight: four context slots keep the copy engines and the SMs busy at the same time (a batch's
+    E2E_DEPTH = args.e2e_depth  # batches in flight: four context slots keep the copy engines and the SMs busy at the same time (a batch's
     # chain — submit, copy in, stage, pass, copy out, collect — is ~310 us long: 137 us per step with three in flight, 128
     # with four, 120 with six, where the submitting host thread becomes the limit)
 

@@ -409,8 +409,14 @@ class Context:
         if len(iv) != table.R or len(im) != table.R:
             raise ValueError("ind / is_mod need one entry per table row")
         P = len(m)
-        so, oo, ro = C.c_uint64(), C.c_uint64(), C.c_uint64()
-        self._check(self._lib.sst_explain_block_layout(P, C.byref(so), C.byref(oo), C.byref(ro)))
+        lay = _BLOCK_LAYOUTS.get(P)
+        if lay is None:
+            so, oo, ro = C.c_uint64(), C.c_uint64(), C.c_uint64()
+            self._check(self._lib.sst_explain_block_layout(P, C.byref(so), C.byref(oo), C.byref(ro)))
+            if len(_BLOCK_LAYOUTS) > 64:
+                _BLOCK_LAYOUTS.clear()
+            lay = _BLOCK_LAYOUTS[P] = (so, oo, ro)
+        so, oo, ro = lay
         if out_block is not None:
             block = out_block
             if block.dtype != np.uint8 or block.ndim != 1 or block.size <= ro.value:
@@ -530,6 +536,9 @@ class Context:
         if copy:
             return status.copy(), off.copy(), None if recs is None else recs.copy()
         return status, off, recs
+
+
+_BLOCK_LAYOUTS: Dict[int, tuple] = {}  # sst_explain_block_layout(P), remembered per batch size
 
 
 class MemoFull(RuntimeError):
