@@ -111,6 +111,9 @@ int sst_valid_stage(sst_ctx* ctx, const int64_t* target, const int64_t* thr, int
  * the same IEEE operations; thr may be NULL (all relative) and a NaN entry means "threshold None" */
 int sst_valid_stage_f64(sst_ctx* ctx, const double* mass, const double* thr, int64_t P, double precision, double tolerance);
 int sst_valid_run(sst_ctx* ctx, const sst_table* t);
+/* stage + run + fetch in one call with one synchronisation (the reference-shaped is_valid_mass is a batch of one) */
+int sst_is_valid_f64(sst_ctx* ctx, const sst_table* t, const double* mass, const double* thr, int64_t P, double precision, double tolerance,
+                     uint8_t* out);
 int sst_valid_fetch(sst_ctx* ctx, uint8_t* out);
 
 /* ---- fragment classification: replaces the per-(fragment x breakage) map_elements callbacks of classify_fragments
@@ -237,7 +240,7 @@ int sst_trace_ms(sst_ctx* ctx, int enable, float* out /* [8] or NULL */);
  * stay valid until sst_explain_collect returns.  Results arrive in out_block (pinned: sst_host_alloc), laid out as
  * sst_explain_block_layout(P) says: a 512-byte header the library uses, status[P], peak offsets as uint32[P + 1],
  * records; block_bytes - recs_off bytes are available for records.  The copy carries as many records as the previous
- * batch had (+ 2 %); sst_explain_collect fetches the rest if this batch is larger.
+ * batch had (+ 2 %, environment SST_SPEC_MARGIN_PCT); sst_explain_collect fetches the rest if this batch is larger.
  *
  * Nothing looks at the host arrays: the batch is queued on the assumption that it is like the previous one (no
  * modification budget binds, compositions fit the record width of last time, a handful of compositions per peak), and

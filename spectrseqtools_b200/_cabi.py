@@ -38,7 +38,7 @@ EXPORTS = [
     "sst_valid_fetch", "sst_valid_stage_f64", "sst_explain", "sst_explain_stage", "sst_explain_stage_f64", "sst_explain_stage_f64_uniform", "sst_explain_rec_width", "sst_explain_phase_ns",
     "sst_explain_run", "sst_explain_fetch", "sst_classify", "sst_classify_stage", "sst_classify_run", "sst_classify_fetch", "sst_classify_launch", "sst_classify_async", "sst_classify_wait", "sst_length_bounds",
     "sst_set_pass", "sst_last_pass", "sst_explain_cta_ns", "sst_explain_submit_f64", "sst_explain_collect", "sst_classify_async_packed", "sst_host_profile", "sst_trace_ms", "sst_explain_block_layout", "sst_explain_d2h_bytes",
-    "sst_ladder_stage", "sst_ladder_round", "sst_ladder_revalidate", "sst_ladder_fetch", "sst_host_register", "sst_host_unregister", "sst_count_compositions_f64",
+    "sst_ladder_stage", "sst_ladder_round", "sst_ladder_revalidate", "sst_ladder_fetch", "sst_host_register", "sst_host_unregister", "sst_count_compositions_f64", "sst_is_valid_f64",
 ]
 
 
@@ -114,6 +114,7 @@ def load() -> C.CDLL:
             "sst_host_profile": (C.c_int, [C.c_int, u64p, u64p]),
             "sst_trace_ms": (C.c_int, [vp, C.c_int, fp]),
             "sst_count_compositions_f64": (C.c_int, [vp, vp, fp, fp, C.c_int64, C.c_double, C.c_double, u64p]),
+            "sst_is_valid_f64": (C.c_int, [vp, vp, fp, fp, C.c_int64, C.c_double, C.c_double, u8p]),
             "sst_host_register": (C.c_int, [vp, vp, C.c_size_t]),
             "sst_host_unregister": (C.c_int, [vp, vp]),
             "sst_ladder_stage": (C.c_int, [vp, fp, fp, u8p, C.c_int64]),
@@ -281,6 +282,16 @@ class Context:
             raise ValueError("per-probe arrays differ in length")
         self._check(self._lib.sst_valid_stage_f64(self._h, _p(m), _p(h), len(m), float(precision), float(tolerance)))
         self._staged_VP = len(m)
+
+    def is_valid_f64(self, table: "DeviceTable", mass: np.ndarray, thr: Optional[np.ndarray], precision: float, tolerance: float) -> np.ndarray:
+        """Validity codes of a (small) batch with one synchronisation (sst_is_valid_f64)."""
+        m = _arr(mass, np.float64)
+        h = None if thr is None else _arr(thr, np.float64)
+        if h is not None and len(h) != len(m):
+            raise ValueError("per-probe arrays differ in length")
+        out = np.empty(len(m), dtype=np.uint8)
+        self._check(self._lib.sst_is_valid_f64(self._h, table._h, _p(m), _p(h), len(m), float(precision), float(tolerance), _p(out)))
+        return out
 
     def explain_stage_f64(self, table: "DeviceTable", mass, thr, max_mods, ind, is_mod, precision, tolerance, with_memo):
         """``max_mods``: one int for the whole batch, or one int32 per peak."""

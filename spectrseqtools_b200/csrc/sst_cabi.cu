@@ -870,6 +870,34 @@ int sst_valid_fetch(sst_ctx* ctx, uint8_t* out) {
     return SST_OK;
 }
 
+// the three calls above in one, with ONE synchronisation: what a reference-shaped is_valid_mass (a batch of one) costs is
+// the waiting, not the kernel
+int sst_is_valid_f64(sst_ctx* ctx, const sst_table* t, const double* mass, const double* thr, int64_t P, double precision, double tolerance,
+                     uint8_t* out) {
+    CK(cudaSetDevice(ctx->device));
+    if (P < 0) return fail(ctx, SST_ERR_BAD_ARG, "negative probe count");
+    if (!P) return SST_OK;
+    int rc;
+    if ((rc = reserve(ctx, ctx->d_vmass, (size_t)P * 8))) return rc;
+    if ((rc = reserve(ctx, ctx->d_vthrf, (size_t)P * 8))) return rc;
+    if ((rc = reserve(ctx, ctx->d_vout, (size_t)P))) return rc;
+    CK(cudaMemcpyAsync(ctx->d_vmass.p, mass, (size_t)P * 8, cudaMemcpyHostToDevice, ctx->stream));
+    if (thr) CK(cudaMemcpyAsync(ctx->d_vthrf.p, thr, (size_t)P * 8, cudaMemcpyHostToDevice, ctx->stream));
+    {
+        KTimer kt(ctx, SST_K_IS_VALID);
+        k_is_valid_f64<<<(unsigned)((P + 255) / 256), 256, 0, ctx->stream>>>(view_of(t), (const double*)ctx->d_vmass.p,
+                                                                             thr ? (const double*)ctx->d_vthrf.p : nullptr, precision, tolerance, P,
+                                                                             (uint8_t*)ctx->d_vout.p);
+        kt.stop(1);
+    }
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(out, ctx->d_vout.p, (size_t)P, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    flush_timers(ctx);
+    ctx->VP = 0;  // (nothing stays staged)
+    return nf_error_codes(ctx, out, P, VALID_CODE_NAN, VALID_CODE_INF, false);
+}
+
 int sst_is_valid(sst_ctx* ctx, const sst_table* t, const int64_t* target, const int64_t* thr, int64_t P, uint8_t* out) {
     int rc = sst_valid_stage(ctx, target, thr, P);
     if (!rc) rc = sst_valid_run(ctx, t);

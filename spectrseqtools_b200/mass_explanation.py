@@ -284,6 +284,8 @@ def are_valid_masses(masses: Sequence[float], dp_table: DynamicProgrammingTable,
     thr = _thr_array(thresholds, len(masses))
     dev = dp_table.device_table()
     ctx = dev.ctx
+    if len(masses) <= 4096:  # small batches (the reference-shaped call is a batch of one): one call, one synchronisation
+        return ctx.is_valid_f64(dev, masses, thr, dp_table.precision, dp_table.tolerance)
     ctx.valid_stage_f64(masses, thr, dp_table.precision, dp_table.tolerance)
     ctx.valid_run(dev)
     return ctx.valid_fetch()
@@ -301,9 +303,11 @@ def is_valid_mass(mass: float, dp_table: DynamicProgrammingTable, threshold: flo
 def explain_mass_with_table(mass: float, dp_table: DynamicProgrammingTable, max_modifications=np.inf,
                             compression_rate=None, threshold=None, with_memo=True) -> MassExplanations:
     """Return all possible combinations of nucleosides that could sum up to the given mass."""
+    # a batch of one through the queued entry: inputs in, staging, pass and the result block out with ONE wait (the
+    # staged path waits three times; a call whose budget can bind is redone inside wait(), as for any batch)
     batch = explain_masses([mass], dp_table, max_modifications=max_modifications,
                            thresholds=None if threshold is None else [threshold], with_memo=with_memo,
-                           compression_rate=compression_rate)
+                           compression_rate=compression_rate, wait=False).wait()
     return batch.explanations(0)
 
 
