@@ -2144,8 +2144,8 @@ int sst_ladder_round(sst_ctx* ctx, const sst_table* t, double max_weight, double
     CK(cudaMemsetAsync(ctx->d_llast.p, 0, (size_t)pow2 * 4, ctx->stream));
     KeyTable kt{(unsigned long long*)ctx->d_lkeys.p, (unsigned int*)ctx->d_llast.p, (uint32_t)(pow2 - 1)};
     const unsigned gc = (unsigned)((calls + 255) / 256);
-    k_ladder_enter<<<gc, 256, 0, ctx->stream>>>((const double*)ctx->d_vmass.p, (const unsigned long long*)ctx->d_peakoff.p, calls, pairs, kt,
-                                                (uint8_t*)ctx->d_lcall.p);
+    k_ladder_enter<<<gc, 256, 0, ctx->stream>>>((const double*)ctx->d_vmass.p, (const unsigned long long*)ctx->d_peakoff.p,
+                                                (const uint8_t*)ctx->d_status.p, calls, pairs, kt, (uint8_t*)ctx->d_lcall.p, hdr);
     k_ladder_union<<<gc, 256, 0, ctx->stream>>>((const double*)ctx->d_vmass.p, (const unsigned long long*)ctx->d_peakoff.p,
                                                 (const unsigned long long*)ctx->d_recs.p, ctx->rec_width / 8, calls, kt, (uint8_t*)ctx->d_lcall.p, hdr);
     CK(cudaGetLastError());
@@ -2153,6 +2153,8 @@ int sst_ladder_round(sst_ctx* ctx, const sst_table* t, double max_weight, double
     CK(cudaStreamSynchronize(ctx->stream));
     if (mask_out) memcpy(mask_out, h + 8, 16);
     ctx->l_calls = calls;
+    if (h[14])  // explain_mass_with_table raises for such a call (mass_explanation.py:134-138), and with it the whole round upstream
+        return fail(ctx, SST_ERR_OUT_OF_TABLE, "A value of the mass window is not in the DP table. Extend its size if you want to compute larger masses.");
     return SST_OK;
 }
 

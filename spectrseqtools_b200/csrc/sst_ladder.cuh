@@ -37,7 +37,8 @@ struct LadderFrame {
 };
 
 // hdr layout (unsigned long long): [0] START fragments, [1] END fragments, [2] singletons, [3] s0 of START, [4] s0 of END,
-// [5] START pairs, [6] END pairs, [7] calls, [8..11] row mask, [12] alive fragments, [13] out-of-table flag
+// [5] START pairs, [6] END pairs, [7] calls, [8..11] row mask, [12] alive fragments, [13] out-of-table flag of the
+// re-validation, [14] a generated call's window reaches beyond the table
 constexpr int kLadderHdrWords = 16;
 
 // ---- alive fragments -> the three ordered lists (stable compaction; one CTA of kPassThreads threads)
@@ -153,10 +154,12 @@ __device__ __forceinline__ uint32_t key_slot(const KeyTable& kt, unsigned long l
     }
 }
 __global__ void __launch_bounds__(256)
-k_ladder_enter(const double* __restrict__ mass, const unsigned long long* __restrict__ peak_off, unsigned long long n_calls,
-               unsigned long long n_pairs, KeyTable kt, uint8_t* __restrict__ call_flags) {
+k_ladder_enter(const double* __restrict__ mass, const unsigned long long* __restrict__ peak_off, const uint8_t* __restrict__ status,
+               unsigned long long n_calls, unsigned long long n_pairs, KeyTable kt, uint8_t* __restrict__ call_flags,
+               unsigned long long* __restrict__ hdr) {
     const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_calls) return;
+    if (status[i] & ST_OUT_OF_TABLE) atomicOr(hdr + 14, 1ULL);  // calculate_explanations of this call raises upstream
     const bool enters = i >= n_pairs || peak_off[i + 1] > peak_off[i];  // a singleton always, a pair with >= 1 explanation
     call_flags[i] = enters ? CALL_ENTERS : 0;
     if (!enters) return;

@@ -235,6 +235,27 @@ def test_device_ladder_random_frames_equal_the_host_generator():
             assert list(got2) == list(want2), trial
 
 
+@pytest.mark.gpu
+def test_device_ladder_raises_beyond_the_table_like_upstream():
+    """A singleton whose window reaches beyond the table: calculate_explanations raises NotImplementedError upstream
+    (mass_explanation.py:134-138) in the middle of the round; the device round and the host generator raise it too."""
+    case = CASES["mods12"]
+    frame = _frame_for(set(case["alphabet"]))
+    dp = _dp(case)
+    su = np.array([329.0525, 658.105, 40000.0])
+    obs = su + 18.0105
+    brk = ["START_c/y", "START_c/y", "START_c/y"]
+    single = np.array([False, False, True])
+    with pytest.raises(NotImplementedError):
+        AR.collect_diff_explanations(su, obs, brk, single, dp, frame)
+    lad = AR.DeviceLadder(su, obs, brk, single, dp, frame)
+    with pytest.raises(NotImplementedError):
+        lad.round()
+    # without the heavy singleton the same frame goes through
+    lad = AR.DeviceLadder(su[:2], obs[:2], brk[:2], single[:2], dp, frame)
+    assert lad.round() == AR.observed_nucleotides(AR.collect_diff_explanations(su[:2], obs[:2], brk[:2], single[:2], dp, frame))
+
+
 def _reference_checkout():
     for cand in (pathlib.Path("/root/reference"), pathlib.Path(__file__).resolve().parents[1] / "baseline" / "_ref"):
         if (cand / "spectrseqtools" / "prediction.py").is_file():
