@@ -80,6 +80,7 @@ struct sst_table {
     uint32_t lam_width = 1, lam_K = 0;
     float build_ms = 0.f, transpose_ms = 0.f;
     bool built_here = false;
+    bool masks_fused = false;  // the last build wrote H itself: launch_transpose only derives the last-row summary
     // composition-count table of the direct pass (sst_direct.cuh): built on first use, dropped when the table is rebuilt
     uint32_t* d_cnt2d = nullptr;  // [R][Mcnt]
     int64_t Mcnt = 0;
@@ -309,7 +310,10 @@ void flush_timers(sst_ctx* ctx) {
     cudaGetLastError();
 }
 
+constexpr bool kFuseMasksDefault = false;  // (set by measurement: see DESIGN.md, K1)
+
 int launch_build(sst_ctx* ctx, sst_table* t) {
+    t->masks_fused = false;
     KTimer kt(ctx, SST_K_BUILD);
     cudaEvent_t e0 = ctx->tev[0], e1 = ctx->tev[1];
     CK(cudaEventRecord(e0, ctx->stream));
@@ -332,15 +336,27 @@ int launch_build(sst_ctx* ctx, sst_table* t) {
             if (grid > t->n_tiles) grid = t->n_tiles;
             if (grid < 1) grid = 1;
             void* args[] = {(void*)&t->tbl, (void*)&t->R, (void*)&t->C, (void*)&t->d_step, (void*)&t->d_shift,
-                            (void*)&t->last_mask, (void*)&t->n_tiles, (void*)&t->d_flags};
+                            (void*)&t->last_mask, (void*)&t->n_tiles, (void*)&t->d_flags, (void*)&t->H};
             return cudaLaunchCooperativeKernel((const void*)kern, dim3((unsigned)grid), dim3(nwarps * 32), args, 0, ctx->stream);
         };
+        // the build can write the mass-major row masks itself (the tile body holds every row's bit1 word): no second kernel
+        // that reads the whole table back.  SST_FUSE_MASKS=0 / 1 overrides the default.
+        bool fuse = t->H != nullptr && kFuseMasksDefault;
+        if (const char* ev = getenv("SST_FUSE_MASKS")) fuse = t->H != nullptr && atoi(ev) != 0;
         cudaError_t e;
-        if (rpw == 1) e = launch(k_build_table<1>);
-        else if (rpw == 2) e = launch(k_build_table<2>);
-        else if (rpw == 4) e = launch(k_build_table<4>);
-        else e = launch(k_build_table<8>);
+        if (fuse) {
+            if (rpw == 1) e = launch(k_build_table<1, 0, true>);
+            else if (rpw == 2) e = launch(k_build_table<2, 0, true>);
+            else if (rpw == 4) e = launch(k_build_table<4, 0, true>);
+            else e = launch(k_build_table<8, 0, true>);
+        } else {
+            if (rpw == 1) e = launch(k_build_table<1>);
+            else if (rpw == 2) e = launch(k_build_table<2>);
+            else if (rpw == 4) e = launch(k_build_table<4>);
+            else e = launch(k_build_table<8>);
+        }
         CK(e);
+        t->masks_fused = fuse;
     } else {
         k_build_table_small<<<1, 1024, 0, ctx->stream>>>(t->tbl, t->R, t->C, t->d_step, t->d_shift, t->last_mask);
         CK(cudaGetLastError());
@@ -369,7 +385,9 @@ int launch_transpose(sst_ctx* ctx, sst_table* t) {
     cudaEvent_t e0 = ctx->tev[0], e1 = ctx->tev[1];
     CK(cudaEventRecord(e0, ctx->stream));
     summary();
-    k_transpose_masks<<<(unsigned)t->n_tiles, 256, 0, ctx->stream>>>(t->tbl, t->R, t->C, t->H);
+    if (!t->masks_fused)  // (the build has written them already)
+        k_transpose_masks<<<(unsigned)t->n_tiles, 256, 0, ctx->stream>>>(t->tbl, t->R, t->C, t->H);
+    t->masks_fused = false;
     CK(cudaGetLastError());
     CK(cudaEventRecord(e1, ctx->stream));
     kt.stop(2);

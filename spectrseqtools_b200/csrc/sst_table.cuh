@@ -42,12 +42,46 @@ __device__ __forceinline__ Reach64 reach_of(uint64_t w) {
     return x;
 }
 
+// 32x32 bit transpose across a warp (lane = row).  Stage s swaps the off-diagonal s x s blocks: a lane with bit s
+// set takes (partner >> s) into the positions whose bit s is clear, a lane without it takes (partner << s) into
+// the others.  On exactly those positions a shift equals a ROTATE, so each stage is one shuffle, one funnel shift
+// by a per-lane amount and one bit-select LOP3 — amounts and masks are computed once per thread.
+struct TransposePlan {
+    uint32_t rot[5];   // rotate-left amount of stage k (s = 16 >> k)
+    uint32_t keep[5];  // bits this lane keeps from its own word in stage k
+};
+__device__ __forceinline__ TransposePlan transpose_plan(int lane) {
+    TransposePlan p;
+#pragma unroll
+    for (int k = 0; k < 5; k++) {
+        const int s = 16 >> k;
+        const uint32_t m = s == 16 ? 0x0000FFFFu : s == 8 ? 0x00FF00FFu : s == 4 ? 0x0F0F0F0Fu : s == 2 ? 0x33333333u : 0x55555555u;
+        p.rot[k] = (lane & s) ? 32 - s : s;
+        uint32_t keep = (lane & s) ? ~m : m;
+        asm volatile("mov.b32 %0, %0;" : "+r"(keep));  // keep it a register: ptxas otherwise rebuilds it as m ^ flag, 3 LOP3 per stage
+        p.keep[k] = keep;
+    }
+    return p;
+}
+__device__ __forceinline__ uint32_t warp_transpose32(uint32_t x, const TransposePlan& p) {
+#pragma unroll
+    for (int k = 0; k < 5; k++) {
+        const uint32_t y = __shfl_xor_sync(0xFFFFFFFFu, x, 16 >> k);
+        const uint32_t yr = __funnelshift_l(y, y, p.rot[k]);
+        asm("lop3.b32 %0, %1, %2, %3, 0xE4;" : "=r"(x) : "r"(x), "r"(yr), "r"(p.keep[k]));  // keep ? x : yr
+    }
+    return x;
+}
+
 // One tile of the build for one row group.  CHECKED=false is the interior fast path (every source word
 // exists, no last column); CHECKED=true handles the first tiles and the last one.
-template <int RPW, bool CHECKED>
+// FUSE: the row's "bit1" word of every (row, table word) also goes to s_c — packed like k_transpose_masks packs it,
+// P = (Thi << 1) | Tlo, masked like the table word in the last column — for the mass-major row masks the kernel writes
+// after the tile has been handed on.
+template <int RPW, bool CHECKED, bool FUSE>
 __device__ __forceinline__ void build_tile_rows(uint64_t* __restrict__ tbl, int R, int64_t C, int64_t j, int lane, int g,
                                                 const uint32_t (&src)[RPW], const int* s_step, const int* s_sh2,
-                                                uint64_t last_mask, uint64_t (*s_tot)[32], int n_data_threads) {
+                                                uint64_t last_mask, uint64_t (*s_tot)[32], int n_data_threads, uint32_t (*s_c)[33]) {
     // phase 1: gather every row's shifted reach word (independent L2 loads)
     uint64_t a[RPW], b0[RPW];
 #pragma unroll
@@ -87,6 +121,14 @@ __device__ __forceinline__ void build_tile_rows(uint64_t* __restrict__ tbl, int 
         }
         tot_lo |= Tlo[k];
         tot_hi |= Thi[k];
+        if (FUSE && r < R) {
+            uint32_t P = (Thi[k] << 1) | Tlo[k];
+            if (CHECKED) {
+                if (j >= C) P = 0u;
+                else if (j == C - 1) P &= ((uint32_t)(last_mask >> 32) & 0xAAAAAAAAu) | (((uint32_t)last_mask & 0xAAAAAAAAu) >> 1);
+            }
+            s_c[r][lane] = P;
+        }
     }
     // phase 2: prefix-OR across the row groups (data warps only)
     s_tot[g][lane] = ((uint64_t)tot_hi << 32) | tot_lo;
@@ -117,10 +159,10 @@ __device__ __forceinline__ void build_tile_rows(uint64_t* __restrict__ tbl, int 
 
 // POLICY is 0 in the product.  tools/k1_probe.cu instantiates the (incorrect) variants 1 = no polling,
 // 2 = no release fence, to measure what each mechanism costs.
-template <int RPW, int POLICY = 0>
+template <int RPW, int POLICY = 0, bool FUSE = false>
 __global__ void __launch_bounds__(kBuildMaxWarps * 32, 2)
 k_build_table(uint64_t* __restrict__ tbl, int R, int64_t C, const int32_t* __restrict__ g_step,
-              const int32_t* __restrict__ g_shift, uint64_t last_mask, int n_tiles, int* __restrict__ flags) {
+              const int32_t* __restrict__ g_shift, uint64_t last_mask, int n_tiles, int* __restrict__ flags, uint4* __restrict__ H) {
     // blockDim = 32 * nd, nd = ceil((R-1)/RPW): one warp per group of RPW rows.
     // flags[t * nd + g] = 1 once row group g of tile t is stored.  Row r only ever reads row r of earlier
     // tiles, so the hand-off is per (tile, row group): each warp polls the <= 2*RPW flags its own rows need
@@ -130,6 +172,10 @@ k_build_table(uint64_t* __restrict__ tbl, int R, int64_t C, const int32_t* __res
     // (Measured alternatives, tools/k1_probe.cu: a ticket per tile + one flag per tile, and a dedicated
     // publisher warp that takes the gpu-scope fence off the data warps, were both slower.)
     __shared__ uint64_t s_tot[2][kBuildMaxWarps][32];
+    // FUSE: the tile's packed bit1 words, [row][table word], double-buffered like s_tot: a warp that is one tile ahead writes
+    // the other buffer (it cannot be two ahead: the exchange barrier of a tile is passed by all warps together, and every
+    // warp transposes tile k before it arrives at the barrier of tile k + 1).  Rows that do not exist stay zero.
+    __shared__ uint32_t s_c[FUSE ? 2 : 1][FUSE ? kMaxRows : 1][33];
     __shared__ uint32_t s_srcoff[kMaxRows];  // r*C - step_r as a word index (R*C < 2^31, checked by the host)
     __shared__ int s_sh2[kMaxRows];
     __shared__ int s_step[kMaxRows];
@@ -140,7 +186,11 @@ k_build_table(uint64_t* __restrict__ tbl, int R, int64_t C, const int32_t* __res
         s_sh2[i] = 2 * g_shift[i];
         s_srcoff[i] = (uint32_t)((int64_t)i * C - g_step[i]);
     }
+    if (FUSE)
+        for (int i = threadIdx.x; i < 2 * kMaxRows * 33; i += blockDim.x) (&s_c[0][0][0])[i] = 0u;
     __syncthreads();
+    const TransposePlan plan = transpose_plan(lane);
+    const int mass_in_word = (lane & 1) ? 15 - (lane >> 1) : 31 - (lane >> 1);  // which mass bit `lane` of a packed word is
     const int step_max = s_step[R - 1];  // weights ascend
     // which row does this lane poll for?  lanes [0,RPW) the tile of word (j0 - step - 1), lanes [16,16+RPW) of (j0 + 31 - step)
     const int poll_k = lane & 15;
@@ -167,12 +217,25 @@ k_build_table(uint64_t* __restrict__ tbl, int R, int64_t C, const int32_t* __res
         }
         __syncwarp();
         const bool interior = (j0 - step_max - 1 >= 0) && (j0 + kTileWords < C);
-        if (interior) build_tile_rows<RPW, false>(tbl, R, C, j, lane, g, src, s_step, s_sh2, last_mask, s_tot[k & 1], nd * 32);
-        else build_tile_rows<RPW, true>(tbl, R, C, j, lane, g, src, s_step, s_sh2, last_mask, s_tot[k & 1], nd * 32);
+        if (interior) build_tile_rows<RPW, false, FUSE>(tbl, R, C, j, lane, g, src, s_step, s_sh2, last_mask, s_tot[k & 1], nd * 32, s_c[FUSE ? (k & 1) : 0]);
+        else build_tile_rows<RPW, true, FUSE>(tbl, R, C, j, lane, g, src, s_step, s_sh2, last_mask, s_tot[k & 1], nd * 32, s_c[FUSE ? (k & 1) : 0]);
         __syncwarp();
         if (lane == 0) {  // release: the group's stores (ordered before this by the warp barrier) become visible first
             if (POLICY & 2) *(volatile int*)(flags + (int64_t)t * nd + g) = 1;
             else st_release(flags + (int64_t)t * nd + g, 1);
+        }
+        if (FUSE) {  // off the dependency chain: the tile has been handed on.  Warp g takes table words g, g + nd, ... of the tile
+            uint32_t (*c)[33] = s_c[k & 1];
+            for (int l = g; l < kTileWords; l += nd) {
+                uint4 d;
+                d.x = warp_transpose32(c[lane][l], plan);
+                d.y = warp_transpose32(c[32 + lane][l], plan);
+                d.z = warp_transpose32(c[64 + lane][l], plan);
+                d.w = warp_transpose32(c[96 + lane][l], plan);
+                // lane q now holds, for bit q of the packed words, the rows that have it set; evict-first: the row masks must
+                // not push the table words the next generations read out of L2
+                if (j0 + l < C) __stcs(H + (j0 + l) * 32 + mass_in_word, d);
+            }
         }
     }
 }
@@ -219,37 +282,6 @@ k_build_table_small(uint64_t* __restrict__ tbl, int R, int64_t C, const int32_t*
 // P = (hi & 0xAAAAAAAA) | ((lo & 0xAAAAAAAA) >> 1), one shift and one LOP3 — and the permutation this leaves in
 // the bit order is undone for free in the store address: bit b of P is mass 15 - b/2 of the word if b is odd,
 // 31 - b/2 if it is even.
-
-// 32x32 bit transpose across a warp (lane = row).  Stage s swaps the off-diagonal s x s blocks: a lane with bit s
-// set takes (partner >> s) into the positions whose bit s is clear, a lane without it takes (partner << s) into
-// the others.  On exactly those positions a shift equals a ROTATE, so each stage is one shuffle, one funnel shift
-// by a per-lane amount and one bit-select LOP3 — amounts and masks are computed once per thread.
-struct TransposePlan {
-    uint32_t rot[5];   // rotate-left amount of stage k (s = 16 >> k)
-    uint32_t keep[5];  // bits this lane keeps from its own word in stage k
-};
-__device__ __forceinline__ TransposePlan transpose_plan(int lane) {
-    TransposePlan p;
-#pragma unroll
-    for (int k = 0; k < 5; k++) {
-        const int s = 16 >> k;
-        const uint32_t m = s == 16 ? 0x0000FFFFu : s == 8 ? 0x00FF00FFu : s == 4 ? 0x0F0F0F0Fu : s == 2 ? 0x33333333u : 0x55555555u;
-        p.rot[k] = (lane & s) ? 32 - s : s;
-        uint32_t keep = (lane & s) ? ~m : m;
-        asm volatile("mov.b32 %0, %0;" : "+r"(keep));  // keep it a register: ptxas otherwise rebuilds it as m ^ flag, 3 LOP3 per stage
-        p.keep[k] = keep;
-    }
-    return p;
-}
-__device__ __forceinline__ uint32_t warp_transpose32(uint32_t x, const TransposePlan& p) {
-#pragma unroll
-    for (int k = 0; k < 5; k++) {
-        const uint32_t y = __shfl_xor_sync(0xFFFFFFFFu, x, 16 >> k);
-        const uint32_t yr = __funnelshift_l(y, y, p.rot[k]);
-        asm("lop3.b32 %0, %1, %2, %3, 0xE4;" : "=r"(x) : "r"(x), "r"(yr), "r"(p.keep[k]));  // keep ? x : yr
-    }
-    return x;
-}
 
 __global__ void __launch_bounds__(256)
 k_transpose_masks(const uint64_t* __restrict__ tbl, int R, int64_t C, uint4* __restrict__ H) {

@@ -108,3 +108,22 @@ def test_uploaded_table_is_adopted():
     masks = dev.download_masks(0, dev.limit)
     H = KM.row_masks(tab)
     assert [int(m[0]) | int(m[1]) << 32 | int(m[2]) << 64 | int(m[3]) << 96 for m in masks] == H
+
+
+@pytest.mark.parametrize("n_rows", [9, 40, 104])
+def test_fused_row_masks_equal_the_transposed_ones(n_rows, monkeypatch):
+    """SST_FUSE_MASKS=1: the build writes the mass-major row masks itself (no second kernel that reads the table back).
+    Same table bytes, same masks — incl. the masked last column — as the two-kernel path, for 1, 4 and 8 rows per warp."""
+    rng = np.random.default_rng(n_rows)
+    w = [0] + sorted({int(x) for x in rng.integers(1100, 9000, size=3 * n_rows)})[:n_rows]
+    mm = max(w) * 35 + int(rng.integers(0, 31))
+    out = {}
+    for fuse in ("0", "1"):
+        monkeypatch.setenv("SST_FUSE_MASKS", fuse)
+        MT.clear_table_cache()
+        dev = MT.device_table(w, mm, 32)
+        out[fuse] = (dev.download(), dev.download_masks(0, dev.limit))
+    MT.clear_table_cache()
+    assert np.array_equal(out["0"][0], out["1"][0])
+    assert np.array_equal(out["0"][1], out["1"][1])
+    assert np.array_equal(out["1"][0], OC.build_bit_table(w, mm, 32))

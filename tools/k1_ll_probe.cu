@@ -243,7 +243,8 @@ void run_tile(Prob& p, int reps) {
     float best = 1e9;
     for (int r = 0; r < reps; r++) {
         CK(cudaMemsetAsync(p.flags, 0, (size_t)p.n_tiles * kBuildMaxWarps * sizeof(int)));
-        void* args[] = {&p.A, &p.R, &p.C, &p.d_step, &p.d_shift, &p.last_mask, &p.n_tiles, &p.flags};
+        uint4* no_masks = nullptr;
+        void* args[] = {&p.A, &p.R, &p.C, &p.d_step, &p.d_shift, &p.last_mask, &p.n_tiles, &p.flags, &no_masks};
         CK(cudaEventRecord(a));
         CK(cudaLaunchCooperativeKernel((const void*)kern, dim3(grid), dim3(nwarps * 32), args, 0, 0));
         CK(cudaEventRecord(b));

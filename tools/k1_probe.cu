@@ -22,7 +22,8 @@ float run(uint64_t* tbl, int R, int64_t C, int32_t* d_step, int32_t* d_shift, in
     float best = 1e9;
     for (int i = 0; i < reps; i++) {
         CK(cudaMemset(flags, 0, (size_t)n_tiles * kBuildMaxWarps * sizeof(int)));
-        void* args[] = {&tbl, &R, &C, &d_step, &d_shift, &last_mask, &n_tiles, &flags};
+        uint4* no_masks = nullptr;
+        void* args[] = {&tbl, &R, &C, &d_step, &d_shift, &last_mask, &n_tiles, &flags, &no_masks};
         CK(cudaEventRecord(a));
         CK(cudaLaunchCooperativeKernel((const void*)kern, dim3(grid), dim3(nwarps * 32), args, 0, 0));
         CK(cudaEventRecord(b));
