@@ -501,6 +501,17 @@ k_memo_phase_a(TableView tv, RowMeta meta, PeakBatch pk, const uint32_t* __restr
         Mask128 pend = mk(ld_nc_u4(tv.H + m));
         mask_keep_le(pend, r_in);
         mask_keep_gt(pend, top);
+        {   // the walk below visits the children one after the other, each a dependent chain of a map probe and a row-mask
+            // load: ask for all of them now (fire-and-forget, into L2), so that they are there when their turn comes
+            Mask128 ahead = pend;
+            while (!mask_empty(ahead)) {
+                const int r = mask_pop_lowest(ahead);
+                const uint32_t m2 = m - (uint32_t)s_w[r];
+                if (m2 == 0u || m2 > m) continue;
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(tv.H + m2));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(mp.keys + ((uint32_t)mix64(memo_key(p, m2)) & mp.cap_mask)));
+            }
+        }
         const int o = f.at(sp);
         f.m[o] = m; f.slot[o] = slot; f.rin[o] = (uint8_t)r_in; f.all[o] = all; f.ind[o] = ind;
         f.put(f.pend, sp, pend);
