@@ -136,11 +136,29 @@ def load() -> C.CDLL:
         return lib
 
 
+_PTRS: Dict[int, tuple] = {}  # id(array) -> (weak reference, address): see _p
+
+
 def _p(a: Optional[np.ndarray]):
-    return None if a is None else a.ctypes.data_as(C.c_void_p)
+    """Address of an array's data for a ``c_void_p`` argument.  ``ndarray.ctypes`` costs 2.5-4 us per use and a queued
+    call passes ten of them, so the address of an array object that has been seen before is remembered (a weak reference
+    guards against a recycled ``id``; arrays are not resized in place anywhere in this package)."""
+    if a is None:
+        return None
+    k = id(a)
+    hit = _PTRS.get(k)
+    if hit is not None and hit[0]() is a:
+        return hit[1]
+    ptr = a.ctypes.data
+    if len(_PTRS) > 256:
+        _PTRS.clear()
+    _PTRS[k] = (weakref.ref(a), ptr)
+    return ptr
 
 
 def _arr(x, dtype) -> np.ndarray:
+    if type(x) is np.ndarray and x.dtype == dtype and x.flags.c_contiguous:
+        return x
     return np.ascontiguousarray(x, dtype=dtype)
 
 
@@ -343,10 +361,11 @@ class Context:
         B, F = len(b), len(o)
         if packed:
             half = (F + 1) // 2
-            buf = self._pinned("classify", B * half)[: B * half] if out is None else out[: B * half]
-            if buf.size < B * half:
+            base = self._pinned("classify", B * half) if out is None else out
+            if base.size < B * half:
                 raise ValueError("out is too small for the packed flags")
-            self._check(self._lib.sst_classify_async_packed(self._h, table._h, _p(o), F, _p(b), B, float(precision), float(tolerance), _p(buf)))
+            buf = base[: B * half]
+            self._check(self._lib.sst_classify_async_packed(self._h, table._h, _p(o), F, _p(b), B, float(precision), float(tolerance), _p(base)))
             return buf.reshape(B, half)
         buf = self._pinned("classify", B * F)[: B * F]
         self._check(self._lib.sst_classify_async(self._h, table._h, _p(o), F, _p(b), B, float(precision), float(tolerance), _p(buf)))
