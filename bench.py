@@ -518,7 +518,7 @@ def main():
         v.wait()
         batch = b.wait()
         if gather is not None:
-            gather.publish(seq_no, [batch.status, batch._offsets, batch.records, v._flags])
+            gather.publish(seq_no, [batch.status, batch._offsets] + batch.raw_records() + [v._flags])
             if rank == 0:
                 return v, batch, gather.collect(seq_no)
         return v, batch, None

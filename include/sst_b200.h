@@ -254,6 +254,15 @@ int sst_explain_submit_f64(sst_ctx* ctx, const sst_table* t, const double* mass,
                            const int32_t* ind, const uint8_t* is_mod, double precision, double tolerance, int with_memo,
                            uint8_t* out_block, uint64_t block_bytes);
 int sst_explain_block_layout(int64_t P, uint64_t* status_off, uint64_t* off32_off, uint64_t* recs_off);
+/* Split records for the following submissions on this context (off by default): a batch whose compositions fit 8-byte
+ * records comes back as PLANES instead of whole records — uint32 lo[cap_n] at recs_off (the first four nucleotides of
+ * record i in lo[i], byte 0 = smallest row), then hi_planes byte planes of cap_n bytes each (plane k: nucleotide 5 + k)
+ * — with hi_planes = the previous batch's longest composition - 4: a batch of <= 5-nt ladder differences crosses the
+ * bus with 5 bytes per composition instead of 8.  cap_n = (block_bytes - recs_off) / (4 + hi_planes), rounded down to a
+ * multiple of 16.  sst_explain_rec_layout tells how the last collected submission's records are laid out (split = 0:
+ * whole records of rec_width bytes at recs_off, e.g. after a submission that was redone synchronously). */
+int sst_set_record_split(sst_ctx* ctx, int enable);
+int sst_explain_rec_layout(const sst_ctx* ctx, int* split, uint64_t* cap_n, int* hi_planes);
 /* bytes the last collected submission copied device -> host (block header, status, offsets, records incl. the margin) */
 uint64_t sst_explain_d2h_bytes(const sst_ctx* ctx);
 int sst_explain_collect(sst_ctx* ctx, const sst_table* t, uint64_t* n_comps, int* rec_width);

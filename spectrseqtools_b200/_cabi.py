@@ -38,7 +38,7 @@ EXPORTS = [
     "sst_valid_fetch", "sst_valid_stage_f64", "sst_explain", "sst_explain_stage", "sst_explain_stage_f64", "sst_explain_stage_f64_uniform", "sst_explain_rec_width", "sst_explain_phase_ns",
     "sst_explain_run", "sst_explain_fetch", "sst_classify", "sst_classify_stage", "sst_classify_run", "sst_classify_fetch", "sst_classify_launch", "sst_classify_async", "sst_classify_wait", "sst_length_bounds",
     "sst_set_pass", "sst_last_pass", "sst_explain_cta_ns", "sst_explain_submit_f64", "sst_explain_collect", "sst_classify_async_packed", "sst_host_profile", "sst_trace_ms", "sst_explain_block_layout", "sst_explain_d2h_bytes",
-    "sst_ladder_stage", "sst_ladder_round", "sst_ladder_revalidate", "sst_ladder_fetch", "sst_host_register", "sst_host_unregister", "sst_count_compositions_f64", "sst_is_valid_f64",
+    "sst_ladder_stage", "sst_ladder_round", "sst_ladder_revalidate", "sst_ladder_fetch", "sst_host_register", "sst_host_unregister", "sst_count_compositions_f64", "sst_is_valid_f64", "sst_set_record_split", "sst_explain_rec_layout",
 ]
 
 
@@ -115,6 +115,8 @@ def load() -> C.CDLL:
             "sst_trace_ms": (C.c_int, [vp, C.c_int, fp]),
             "sst_count_compositions_f64": (C.c_int, [vp, vp, fp, fp, C.c_int64, C.c_double, C.c_double, u64p]),
             "sst_is_valid_f64": (C.c_int, [vp, vp, fp, fp, C.c_int64, C.c_double, C.c_double, u8p]),
+            "sst_set_record_split": (C.c_int, [vp, C.c_int]),
+            "sst_explain_rec_layout": (C.c_int, [vp, C.POINTER(C.c_int), C.POINTER(C.c_uint64), C.POINTER(C.c_int)]),
             "sst_host_register": (C.c_int, [vp, vp, C.c_size_t]),
             "sst_host_unregister": (C.c_int, [vp, vp]),
             "sst_ladder_stage": (C.c_int, [vp, fp, fp, u8p, C.c_int64]),
@@ -174,6 +176,7 @@ class Context:
                 f"no usable sm_100 (B200) GPU at index {device} (sst_ctx_create rc={rc}); "
                 "spectrseqtools_b200 has no CPU fallback.")
         self._lib, self._h, self.device = lib, h, int(device)
+        lib.sst_set_record_split(h, 1)  # queued batches bring their records back as 4 + k byte planes (SplitRecords)
         self._finalizer = weakref.finalize(self, lib.sst_ctx_destroy, h)
 
     # -- plumbing
@@ -481,6 +484,13 @@ class Context:
         n, w = int(nc.value), int(W.value)
         self._last = (0, n, w)
         self._recs_hint = max(self.__dict__.get("_recs_hint", 0), n * w + n * w // 4)
+        if rc == SST_OK:
+            split, cap_n, hp = C.c_int(), C.c_uint64(), C.c_int()
+            self._lib.sst_explain_rec_layout(self._h, C.byref(split), C.byref(cap_n), C.byref(hp))
+            if split.value:  # planes: uint32 lo[cap_n], then hp byte planes of cap_n each
+                cn = int(cap_n.value)
+                lo = recs[: 4 * cn].view(np.uint32)[:n]
+                return status, off, SplitRecords(lo, [recs[4 * cn + k * cn: 4 * cn + k * cn + n] for k in range(hp.value)])
         return status, off, recs[: n * w].reshape(n, w)
 
     # ---- N3 / N4 on a device-resident fragment frame (sst_ladder_*)
@@ -566,6 +576,27 @@ class Context:
         if copy:
             return status.copy(), off.copy(), None if recs is None else recs.copy()
         return status, off, recs
+
+
+class SplitRecords:
+    """Records of a queued batch as they cross the bus (sst_set_record_split): ``lo`` uint32[n] holds the first four
+    nucleotides of every composition (byte 0 = smallest row), ``planes[k]`` uint8[n] nucleotide 5 + k.  ``materialize()``
+    gives the uint8[n, 8] array of whole records."""
+
+    def __init__(self, lo: np.ndarray, planes):
+        self.lo, self.planes = lo, list(planes)
+
+    def __len__(self):
+        return len(self.lo)
+
+    def materialize(self) -> np.ndarray:
+        n = len(self.lo)
+        out = np.zeros((n, 8), dtype=np.uint8)
+        if n:
+            out[:, :4] = self.lo.view(np.uint8).reshape(n, 4)
+            for k, p in enumerate(self.planes):
+                out[:, 4 + k] = p
+        return out
 
 
 _BLOCK_LAYOUTS: Dict[int, tuple] = {}  # sst_explain_block_layout(P), remembered per batch size

@@ -170,6 +170,9 @@ struct sst_ctx {
         uint8_t* recs = nullptr;
         uint64_t recs_bytes = 0, copied = 0;
         uint8_t* block = nullptr;      // the caller's result block (layout: BlockLayout)
+        bool split = false;            // records as planes: uint32 lo[capN], then hp byte planes of capN each
+        uint64_t capN = 0, copiedN = 0;
+        int hp = 0;
     } pend;
     // N3 / N4: the classified-fragment frame that stays on the device between the rounds of the alphabet reduction
     DevBuf d_lsu, d_lobs, d_lflags, d_lalive, d_lidx, d_lreach, d_lfirst, d_lhdr, d_lkeys, d_llast, d_lcall;
@@ -178,12 +181,17 @@ struct sst_ctx {
     DevBuf d_block;                    // the same block on the device: the pass writes into it, ONE copy brings it back
     uint64_t last_comps = 0;           // compositions of the last batch: sizes the speculative copy of the next one
     bool replay_attr_set = false;      // k_memo_phase_a's dynamic shared-memory limit has been raised on this device
+    bool split_records = false;        // sst_set_record_split: pipelined submissions bring 8-byte records back as 4 + k byte planes
+    int spec_hi_planes = 4;            // k of the next submission: the previous batch's longest composition - 4 (0 .. 4)
     bool spec_ok = true;               // sst_explain_submit_f64 queues blindly (the last batch it had to redo would have fitted, or none yet)
     int spec_rec_width = 8;            // with this record width
     cudaEvent_t trace_ev[8] = {nullptr};  // diagnostics (sst_trace_ms): device timeline of the last submitted batch
     bool trace_on = false;
     int spec_margin_pct = 2;           // records copied back blindly: the previous batch's plus this much (SST_SPEC_MARGIN_PCT);
                                        // every percent is bus time of every batch, a larger batch costs one more small copy
+    bool last_split = false;           // layout of the last collected submission's records (sst_explain_rec_layout)
+    uint64_t last_capN = 0;
+    int last_hp = 0;
     uint64_t last_d2h_bytes = 0;       // bytes the last collected submission brought back
     int32_t up_ind[128] = {0};         // what d_ind / d_ismod hold (the per-row budgets rarely change between batches)
     uint8_t up_ismod[128] = {0};
@@ -1428,6 +1436,8 @@ struct OutBlock {  // where a pipelined submission wants status, 32-bit offsets,
     uint8_t* base;
     BlockLayout at;
     uint64_t rec_bytes;
+    uint64_t capN;  // > 0: split records — uint32 lo[capN] at at.recs, then hp byte planes of capN each
+    int hp;
 };
 int dfs_enqueue(sst_ctx* ctx, const sst_table* t, int rec_width, const MemoMap& mp, const SpecGuard* guard = nullptr,
                 const OutBlock* ob = nullptr) {
@@ -1513,6 +1523,12 @@ int dfs_enqueue(sst_ctx* ctx, const sst_table* t, int rec_width, const MemoMap& 
             a.peak_off32 = (uint32_t*)(ob->base + ob->at.off32);
             a.recs = (unsigned long long*)(ob->base + ob->at.recs);
             a.rec_capacity = (unsigned long long)(ob->rec_bytes / rec_width);
+            if (ob->capN) {
+                a.rec_lo = (uint32_t*)(ob->base + ob->at.recs);
+                a.rec_hi = ob->base + ob->at.recs + 4 * ob->capN;
+                a.rec_hi_planes = ob->hp;
+                a.rec_capacity = ob->capN;
+            }
             a.host_out = (unsigned long long*)ob->base;
         }
         hp_mark(7);
@@ -1896,16 +1912,27 @@ int sst_explain_submit_f64(sst_ctx* ctx, const sst_table* t, const double* mass,
     // the device block: room for twice the records that are copied back blindly (a larger batch gets the rest in collect)
     uint64_t guess = (ctx->last_comps + ctx->last_comps * (uint64_t)ctx->spec_margin_pct / 100) * (uint64_t)pd.rec_width + 4096;
     if (guess > pd.recs_bytes) guess = pd.recs_bytes;
+    // split records: 4 + hp bytes per composition in planes laid out for capN compositions, the same in both blocks
+    pd.split = ctx->split_records && pd.rec_width == 8;
+    uint64_t guessN = 0;
+    if (pd.split) {
+        pd.hp = ctx->spec_hi_planes < 0 ? 0 : (ctx->spec_hi_planes > 4 ? 4 : ctx->spec_hi_planes);
+        pd.capN = (pd.recs_bytes / (uint64_t)(4 + pd.hp)) & ~15ULL;
+        guessN = ctx->last_comps + ctx->last_comps * (uint64_t)ctx->spec_margin_pct / 100 + 512;
+        if (guessN > pd.capN) guessN = pd.capN;
+        if (!pd.capN) pd.split = false;
+    }
     int rc;
     {
         uint64_t dev_recs = 2 * guess > ((uint64_t)16 << 20) ? 2 * guess : ((uint64_t)16 << 20);
         if (dev_recs < pd.recs_bytes && pd.recs_bytes <= ((uint64_t)1 << 30)) dev_recs = pd.recs_bytes;
+        if (pd.split) dev_recs = pd.recs_bytes;  // (plane offsets are the caller's)
         if ((rc = reserve(ctx, ctx->d_block, (size_t)(lay.recs + dev_recs)))) {
             pd.active = false;
             return rc;
         }
     }
-    const OutBlock ob{(uint8_t*)ctx->d_block.p, lay, (uint64_t)ctx->d_block.cap - lay.recs};
+    const OutBlock ob{(uint8_t*)ctx->d_block.p, lay, (uint64_t)ctx->d_block.cap - lay.recs, pd.split ? pd.capN : 0, pd.hp};
     rc = stage_f64_enqueue(ctx, t, mass, thr, nullptr, max_mods, P, ind, is_mod, precision, tolerance, with_memo,
                            (unsigned long long*)(ob.base + kBlockStageSummary));
     if (rc) {
@@ -1921,8 +1948,9 @@ int sst_explain_submit_f64(sst_ctx* ctx, const sst_table* t, const double* mass,
     g.summary = (const unsigned long long*)(ob.base + kBlockStageSummary);
     {
         const int64_t cap = t->C * 32 - 1;
-        const bool table_bounds = t->w_min > 0 && cap / t->w_min <= (int64_t)pd.rec_width;  // no window value of this table is deeper
-        g.max_hi = (t->w_min > 0 && !table_bounds) ? (unsigned long long)((int64_t)(pd.rec_width + 1) * t->w_min - 1) : ~0ULL;
+        const int holds = pd.split ? 4 + pd.hp : pd.rec_width;  // nucleotides a record of this submission holds
+        const bool table_bounds = t->w_min > 0 && cap / t->w_min <= (int64_t)holds;  // no window value of this table is deeper
+        g.max_hi = (t->w_min > 0 && !table_bounds) ? (unsigned long long)((int64_t)(holds + 1) * t->w_min - 1) : ~0ULL;
         ctx->max_hi = g.max_hi < (unsigned long long)cap ? (int64_t)g.max_hi : cap;
         const double heavy = kHeavyCostPerPeak * (double)P;
         g.max_cost = heavy < 1.8e19 ? (unsigned long long)heavy : ~0ULL;
@@ -1933,7 +1961,17 @@ int sst_explain_submit_f64(sst_ctx* ctx, const sst_table* t, const double* mass,
     }
     // the result block on its way back in ONE copy: summaries, status, peak offsets and as many records as the previous
     // batch had (+ spec_margin_pct); a batch that turns out larger gets the rest in sst_explain_collect
-    CK(cudaMemcpyAsync(out_block, ob.base, (size_t)(lay.recs + guess), cudaMemcpyDeviceToHost, ctx->stream));
+    if (pd.split) {  // header, status, offsets and the lo plane in one copy, then the byte planes
+        CK(cudaMemcpyAsync(out_block, ob.base, (size_t)(lay.recs + 4 * guessN), cudaMemcpyDeviceToHost, ctx->stream));
+        for (int k = 0; k < pd.hp; k++) {
+            const size_t at = (size_t)(lay.recs + 4 * pd.capN + (uint64_t)k * pd.capN);
+            CK(cudaMemcpyAsync(out_block + at, ob.base + at, (size_t)guessN, cudaMemcpyDeviceToHost, ctx->stream));
+        }
+        pd.copiedN = guessN;
+        guess = 0;
+    } else {
+        CK(cudaMemcpyAsync(out_block, ob.base, (size_t)(lay.recs + guess), cudaMemcpyDeviceToHost, ctx->stream));
+    }
     hp_mark(11);
     hp_mark(12);
     trace_mark(ctx, 4);
@@ -1943,6 +1981,18 @@ int sst_explain_submit_f64(sst_ctx* ctx, const sst_table* t, const double* mass,
 }
 
 uint64_t sst_explain_d2h_bytes(const sst_ctx* ctx) { return ctx->last_d2h_bytes; }
+
+int sst_set_record_split(sst_ctx* ctx, int enable) {
+    ctx->split_records = enable != 0;
+    return SST_OK;
+}
+
+int sst_explain_rec_layout(const sst_ctx* ctx, int* split, uint64_t* cap_n, int* hi_planes) {
+    if (split) *split = ctx->last_split ? 1 : 0;
+    if (cap_n) *cap_n = ctx->last_capN;
+    if (hi_planes) *hi_planes = ctx->last_hp;
+    return SST_OK;
+}
 
 int sst_explain_block_layout(int64_t P, uint64_t* status_off, uint64_t* off32_off, uint64_t* recs_off) {
     if (P < 0) return SST_ERR_BAD_ARG;
@@ -1978,6 +2028,7 @@ int sst_explain_collect(sst_ctx* ctx, const sst_table* t, uint64_t* n_comps, int
                 ctx->window_total = (int64_t)hs[0];
                 ctx->deepest = t->w_min > 0 ? (max_hi < cap ? max_hi : cap) / t->w_min : 0;
                 if (ctx->deepest <= 8) ctx->spec_rec_width = 8;  // (a batch of short compositions after longer ones)
+                ctx->spec_hi_planes = ctx->deepest <= 4 ? 0 : (ctx->deepest >= 8 ? 4 : (int)ctx->deepest - 4);
             }
             ctx->n_roots = roots;
             ctx->n_comps = comps;
@@ -1986,11 +2037,28 @@ int sst_explain_collect(sst_ctx* ctx, const sst_table* t, uint64_t* n_comps, int
             ctx->have_result = false;  // (delivered; nothing is left in the buffers sst_explain_fetch reads)
             ctx->last_comps = comps;
             const uint64_t need = comps * (uint64_t)pd.rec_width;
-            if (need > pd.recs_bytes) {  // the caller's block is too small: the synchronous path leaves the result on the device for sst_explain_fetch
+            ctx->last_split = pd.split;
+            ctx->last_capN = pd.capN;
+            ctx->last_hp = pd.hp;
+            if (pd.split) {  // (more compositions than capN never get here: the pass reports that the records do not fit)
+                const BlockLayout lay(pd.P);
+                if (comps > pd.copiedN) {
+                    const uint64_t n0 = pd.copiedN, dn = comps - pd.copiedN;
+                    CK(cudaMemcpyAsync(pd.block + lay.recs + 4 * n0, (const char*)ctx->d_block.p + lay.recs + 4 * n0, (size_t)(4 * dn), cudaMemcpyDeviceToHost,
+                                       ctx->stream));
+                    for (int k = 0; k < pd.hp; k++) {
+                        const size_t at = (size_t)(lay.recs + 4 * pd.capN + (uint64_t)k * pd.capN + n0);
+                        CK(cudaMemcpyAsync(pd.block + at, (const char*)ctx->d_block.p + at, (size_t)dn, cudaMemcpyDeviceToHost, ctx->stream));
+                    }
+                    CK(cudaStreamSynchronize(ctx->stream));
+                }
+                ctx->last_d2h_bytes = lay.recs + (uint64_t)(4 + pd.hp) * (comps > pd.copiedN ? comps : pd.copiedN);
+            } else if (need > pd.recs_bytes) {  // the caller's block is too small: the synchronous path leaves the result on the device for sst_explain_fetch
                 redo = true;
+            } else {
+                ctx->last_d2h_bytes = BlockLayout(pd.P).recs + (need > pd.copied ? need : pd.copied);
             }
-            ctx->last_d2h_bytes = BlockLayout(pd.P).recs + (need > pd.copied ? need : pd.copied);
-            if (need <= pd.recs_bytes && need > pd.copied) {
+            if (!pd.split && need <= pd.recs_bytes && need > pd.copied) {
                 const BlockLayout lay(pd.P);
                 CK(cudaMemcpyAsync(pd.recs + pd.copied, (const char*)ctx->d_block.p + lay.recs + pd.copied, (size_t)(need - pd.copied),
                                    cudaMemcpyDeviceToHost, ctx->stream));
@@ -2012,6 +2080,8 @@ int sst_explain_collect(sst_ctx* ctx, const sst_table* t, uint64_t* n_comps, int
         // would the speculative path have carried this batch?  Then the next submission takes it.
         ctx->spec_ok = ctx->last_pass == 2 && !ctx->n_memo && !ctx->has_exact && ctx->rec_width <= 16;
         if (ctx->spec_ok) ctx->spec_rec_width = ctx->rec_width;
+        ctx->spec_hi_planes = ctx->deepest <= 4 ? 0 : (ctx->deepest >= 8 ? 4 : (int)ctx->deepest - 4);
+        ctx->last_split = false;  // (whole records of rec_width bytes)
         if (comps >= (1ULL << 32)) return fail(ctx, SST_ERR_NOMEM, "%llu compositions: more than the 32-bit offsets of the asynchronous entry hold", (unsigned long long)comps);
         const uint64_t need = comps * (uint64_t)ctx->rec_width;
         if (n_comps) *n_comps = comps;

@@ -93,6 +93,12 @@ struct DfsArgs {
     unsigned long long* cta_info;     // [gridDim.x][3] start, length and compositions of every CTA's final list
     unsigned long long* recs;         // [rec_capacity][nw] records, final order
     unsigned long long rec_capacity;
+    // SPLIT records (pipelined submissions, 8-byte records only): the first four nucleotides of record i as rec_lo[i], the
+    // k-th further one as rec_hi[k * rec_capacity + i], k < rec_hi_planes — a batch of <= 5-nt differences crosses the bus
+    // with 5 bytes per composition instead of 8.  rec_lo == null: whole 8-byte words go to recs.
+    uint32_t* rec_lo;
+    uint8_t* rec_hi;
+    int rec_hi_planes;
     unsigned long long* peak_off;     // [P+1]
     uint32_t* peak_off32;             // [P+1] the same as uint32 (may be null; only meaningful below 2^32 compositions)
     unsigned long long* cta_tot;      // [2][gridDim.x] compositions / roots of every CTA's slice
@@ -147,6 +153,18 @@ __device__ __forceinline__ Mask128 children_of(const DfsArgs& a, const RowTables
     return c;
 }
 
+template <int NW>
+__device__ __forceinline__ void store_record(const DfsArgs& a, unsigned long long at, const unsigned long long* w) {
+    if (NW == 1 && a.rec_lo) {
+        a.rec_lo[at] = (uint32_t)w[0];
+        uint32_t hi = (uint32_t)(w[0] >> 32);
+        for (int k = 0; k < a.rec_hi_planes; k++, hi >>= 8) a.rec_hi[(unsigned long long)k * a.rec_capacity + at] = (uint8_t)hi;
+    } else {
+#pragma unroll
+        for (int q = 0; q < NW; q++) a.recs[at * NW + q] = w[q];
+    }
+}
+
 // One item, depth-first: what is left of a subtree after the split rounds.  EMIT = false: returns the number of
 // compositions below it.  EMIT = true: also stores them at recs[at...] (children in ascending row order, like the
 // reference's UP-before-LEFT walk).  `capped` is set when the walk gives up.
@@ -163,8 +181,7 @@ __device__ __noinline__ unsigned int dfs_item(const DfsArgs& a, const RowTables&
 
     auto emit = [&](const unsigned long long* w) {
         if (EMIT) {
-#pragma unroll
-            for (int q = 0; q < NW; q++) a.recs[at * NW + q] = w[q];
+            store_record<NW>(a, at, w);
             at++;
         }
         total++;
@@ -786,14 +803,12 @@ k_explain_dfs(const DfsArgs a) {
                         const uint32_t m3 = m[u] - (uint32_t)s_w[r2];
                         path_append(w, NW, r2);
                         if (m3) path_append(w, NW, leaf_row(s_leaf, s_w, a.leaf, m3, r2));
-#pragma unroll
-                        for (int q = 0; q < NW; q++) a.recs[dst * NW + q] = w[q];
+                        store_record<NW>(a, dst, w);
                         dst++;
                     }
                 } else {
                     if (kind == KIND_LEAF) path_append(path[u], NW, leaf_row(s_leaf, s_w, a.leaf, m[u], rmax));
-#pragma unroll
-                    for (int q = 0; q < NW; q++) a.recs[dst * NW + q] = path[u][q];
+                    store_record<NW>(a, dst, path[u]);
                 }
             }
         }

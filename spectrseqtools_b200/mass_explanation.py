@@ -125,10 +125,23 @@ class ExplanationBatch:
     """
 
     def __init__(self, status, offsets, records, weights, names_by_row):
-        self.status, self.records = status, records
+        self.status = status
+        self._records = records  # uint8[n, W], or the planes a queued batch crosses the bus as (_cabi.SplitRecords)
         self._offsets = offsets  # int64, or the uint32 the asynchronous entry brings back (widened on first use)
         self.weights = weights
         self._names_by_row = names_by_row
+
+    @property
+    def records(self) -> np.ndarray:
+        """uint8[n, W]: row indices ascending, 0-padded (planes are put together on first use)."""
+        if isinstance(self._records, _cabi.SplitRecords):
+            self._records = self._records.materialize()
+        return self._records
+
+    def raw_records(self):
+        """The arrays the records arrived in: [uint8[n, W]], or [lo uint32[n], plane uint8[n], ...] of a queued batch."""
+        r = self._records
+        return [r.lo] + r.planes if isinstance(r, _cabi.SplitRecords) else [r]
 
     @property
     def offsets(self) -> np.ndarray:
@@ -197,7 +210,8 @@ class PendingExplanations:
         if self._batch is None:
             status, off, recs = self._ctx.explain_collect()
             if self._copy:
-                status, off, recs = status.copy(), off.astype(np.int64), recs.copy()
+                status, off = status.copy(), off.astype(np.int64)
+                recs = recs.materialize() if isinstance(recs, _cabi.SplitRecords) else recs.copy()
             self._batch = ExplanationBatch(status, off, recs, self._weights, [m.names for m in self._dp.masses])
         return self._batch
 
