@@ -154,3 +154,49 @@ def test_speculation_recovers_after_every_kind_of_refusal():
     both(heavy_m, heavy_t, wl.max_modifications)
     both(*light)
     assert ctx.last_pass() == 2
+
+
+def test_split_records_follow_the_longest_composition():
+    """Queued batches bring their records back as planes (uint32 for the first four nucleotides + one byte plane per
+    further one, learned from the previous batch): equal to the synchronous result whatever the plane count, fewer bytes
+    across the bus for short compositions, and a longer batch after a shorter one is refused once and then carried."""
+    from spectrseqtools_b200 import _cabi
+
+    wl = S.make_workload("C4", 20000)
+    dp = _table(wl)
+    ctx = _cabi.context()
+    seen, prev = {}, None
+    w4 = sorted(x.mass for x in dp.masses if x.mass > 0)[:4]
+    rng = np.random.default_rng(3)
+    six = np.array([sum(rng.choice(w4, size=6)) for _ in range(60)], dtype=np.float64) * dp.precision  # six light nucleotides
+    for max_nt in (1, 1, 9, 9, 6, 6, 1, 9):
+        if max_nt == 6:
+            m, t = six, np.full(len(six), 2 * dp.precision)
+        else:
+            sel = wl.explain_nt <= max_nt
+            m, t = wl.explain_mass[sel], wl.explain_thr[sel]
+        want = ME.explain_masses(m, dp, max_modifications=wl.max_modifications, thresholds=t)
+        pend = ME.explain_masses(m, dp, max_modifications=wl.max_modifications, thresholds=t, wait=False, copy=False)
+        got = pend.wait()
+        raw = got.raw_records()
+        assert np.array_equal(got.status, want.status) and np.array_equal(got.offsets, want.offsets)
+        assert got.records.shape == want.records.shape and np.array_equal(got.records, want.records)
+        longest = int((want.records > 0).sum(axis=1).max())
+        if len(raw) > 1 or raw[0].dtype == np.uint32:  # planes: they hold the longest composition
+            assert 4 + (len(raw) - 1) >= longest
+            if prev == max_nt:  # (the plane count of a batch is what the batch before it needed)
+                seen[max_nt] = (len(raw) - 1, ctx.explain_d2h_bytes())
+        prev = max_nt
+    # single nucleotides need no byte plane; six-nucleotide compositions need two when they come back as planes at all (a
+    # batch the scheduler hands to the level-synchronous pass is carried out synchronously, with whole records)
+    assert seen[1][0] == 0 and seen[1][0] <= seen[9][0] <= 2
+    assert 6 not in seen or seen[6][0] == 2
+
+
+def test_split_records_materialize():
+    from spectrseqtools_b200._cabi import SplitRecords
+
+    lo = np.array([0x04030201, 0x00000009], dtype=np.uint32)
+    r = SplitRecords(lo, [np.array([5, 0], dtype=np.uint8), np.array([6, 0], dtype=np.uint8)]).materialize()
+    assert r.tolist() == [[1, 2, 3, 4, 5, 6, 0, 0], [9, 0, 0, 0, 0, 0, 0, 0]]
+    assert SplitRecords(np.zeros(0, dtype=np.uint32), []).materialize().shape == (0, 8)
