@@ -146,3 +146,30 @@ def explain(table: np.ndarray, weights, is_mod, ind, target: int, thr: int, max_
         if last_row_reach(table, v):
             sols += enumerate_root(v, mask_of, weights, is_mod, ind, max_mods, mode == "exact")
     return sols, (lo <= 0 <= hi), mode
+
+
+# ---------------------------------------------------------------- N3: the ladder window as count -> scan -> fill
+def ladder_pairs_closed_form(su: Sequence[float], max_weight: float):
+    """The pairs of ``Predictor.collect_explanations_per_side`` (reference prediction.py:296-327) the way
+    csrc/sst_ladder.cuh makes them: E(s) = last e with su[e] - su[s] <= max_weight (binary search, sorted masses), s0 =
+    first s whose E(s) is the last fragment; s <= s0 pairs with s+1 .. E(s), every later s with the last fragment only
+    (once ``end`` sits on the last fragment the reference only moves ``start``)."""
+    n = len(su)
+    reach = []
+    for s in range(n):
+        lo, hi = s, n - 1
+        while lo < hi:
+            mid = (lo + hi + 1) >> 1
+            if not (su[mid] - su[s] > max_weight):
+                lo = mid
+            else:
+                hi = mid - 1
+        reach.append(lo)
+    s0 = min([s for s in range(n) if reach[s] == n - 1 and reach[s] > s], default=n + 1)
+    pairs = []
+    for s in range(n):
+        if s <= s0:
+            pairs += [(s, e) for e in range(s + 1, reach[s] + 1)]
+        elif s < n - 1:
+            pairs.append((s, n - 1))
+    return pairs
